@@ -1,0 +1,112 @@
+"""Pins oracle/tmglow_oracle.py to the vectors produced by the REAL reference
+(tests/golden/make_golden.py).  CPU only."""
+import json
+
+import pytest
+import torch
+
+from oracle import tmglow_oracle as O
+from conftest import load_golden
+
+CASES = ["caseA_states", "caseA_nostate", "caseA_trainbn", "caseB_up4", "caseC_up1"]
+TOL = 1e-6   # observed: 0.0 (same ATen operators in the same order)
+
+
+def _close(a, b, tol=TOL):
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+
+
+def _states_close(a, b):
+    assert len(a) == len(b)
+    for s, t in zip(a, b):
+        _close(s[0], t[0]); _close(s[1], t[1])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference(name):
+    g = load_golden(name)
+    cfg = O.OracleConfig.from_dict(json.loads(g["config"]))
+    stats = {}
+    z, logp, h_out, eps = O.forward(g["state_dict"], cfg, g["x"], g["y"], g["h_in"], True,
+                                    training=g["train_bn"], stats_out=stats)
+    _close(z, g["fwd"]["z"]); _close(logp, g["fwd"]["logp"])
+    _states_close(h_out, g["fwd"]["h_out"])
+    for a, b in zip(eps, g["fwd"]["eps"]):
+        _close(a, b)
+    if g["train_bn"]:
+        for k, v in g["fwd"]["bn_after"].items():
+            _close(stats[k].float(), v.float())
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("which", ["rec", "rec2"])
+def test_reconstruct_matches_reference(name, which):
+    g = load_golden(name)
+    cfg = O.OracleConfig.from_dict(json.loads(g["config"]))
+    eps = g["fwd"]["eps"] if which == "rec" else g["rec2"]["eps"]
+    y, ld, h_out = O.reconstruct(g["state_dict"], cfg, g["x"], g["h_in"], eps, training=g["train_bn"])
+    _close(y, g[which]["y"]); _close(ld, g[which]["log_det"])
+    _states_close(h_out, g[which]["h_out"])
+
+
+def test_modules_match_reference():
+    g = load_golden("caseA_states")
+    cfg = O.OracleConfig.from_dict(json.loads(g["config"]))
+    sd, m = g["state_dict"], g["modules"]
+    z_out, c_out = O.encoder_forward(sd, cfg, g["x"])
+    _close(z_out, m["encoder"]["z_out"])
+    for a, b in zip(c_out, m["encoder"]["c_out"]):
+        _close(a, b)
+    assert torch.equal(O.squeeze_fwd(m["squeeze"]["x"]), m["squeeze"]["y"])          # bit-exact permutation
+    assert torch.equal(O.squeeze_rev(m["unsqueeze"]["y"]), m["unsqueeze"]["x"])
+    n = cfg.glow_blocks[0]
+    for s, rec in enumerate(m["steps"], start=1):
+        pre = f"glow.flow_blocks.0.revlayers.{rec['name']}."
+        kind = O._step_kind(s, n)
+        st = rec.get("state")
+        o, ld, so = O.flow_step_fwd(sd, pre, rec["x"], rec["cond"], kind, st, cfg.rec_features)
+        _close(o, rec["fwd"]); _close(ld * torch.ones(o.shape[0]), rec["fwd_logdet"])
+        r, ldr, sr = O.flow_step_rev(sd, pre, rec["x"], rec["cond"], kind, st, cfg.rec_features)
+        _close(r, rec["rev"]); _close(ldr * torch.ones(o.shape[0]), rec["rev_logdet"])
+        if kind == "lstm":
+            _states_close([so], [rec["fwd_state"]]); _states_close([sr], [rec["rev_state"]])
+            o0, ld0, so0 = O.flow_step_fwd(sd, pre, rec["x"], rec["cond"], kind, None, cfg.rec_features)
+            _close(o0, rec["fwd_nostate"]); _states_close([so0], [rec["fwd_nostate_state"]])
+    sp = m["split"]
+    z1, lp, e = O.split_fwd(sd, "glow.flow_blocks.0.split.", sp["z"])
+    _close(z1, sp["z1"]); _close(lp, sp["logp"]); _close(e, sp["eps"])
+    zr, lpr = O.split_rev(sd, "glow.flow_blocks.0.split.", sp["z1"], sp["eps"])
+    _close(zr, sp["rev_z"]); _close(lpr, sp["rev_logp"])
+    pre = "glow.flow_blocks.0.revlayers.affine_layer1.conv."
+    _close(O.conv1x1_weight(sd, pre), m["conv1x1"]["W"]); _close(O.conv1x1_inv_weight(sd, pre), m["conv1x1"]["Winv"])
+
+
+def test_invertibility_property():
+    """The reference's only known-answer property (nn/tmGlow.py:511-530): reconstruct(forward(y)) == y."""
+    g = load_golden("caseA_states")
+    cfg = O.OracleConfig.from_dict(json.loads(g["config"]))
+    z, logp, h_out, eps = O.forward(g["state_dict"], cfg, g["x"], g["y"], g["h_in"], True)
+    y, ld, _ = O.reconstruct(g["state_dict"], cfg, g["x"], g["h_in"], eps)
+    assert (y - g["y"]).abs().max().item() < 1e-4
+    # forward.logp == reconstruct.log_det + logpdf_top(z)   
+    z_out, _ = O.encoder_forward(g["state_dict"], cfg, g["x"])
+    cm, cl = O._top_prior(z_out)
+    assert torch.allclose(logp, ld + O.gaussian_logprob(z, cm, cl), rtol=1e-5, atol=1e-3)
+
+
+def test_init_lstm_states_seeded():
+    cfg = O.OracleConfig(4, 3, [2, 2], [3, 3], rec_features=8)
+    a = O.init_lstm_states(cfg, torch.tensor([3, 4]), [16, 32])
+    b = O.init_lstm_states(cfg, torch.tensor([3, 4]), [16, 32])
+    assert a[0][0].shape == (2, 8, 8, 16) and a[1][1].shape == (2, 8, 4, 8)
+    assert torch.equal(a[0][0], b[0][0]) and a[0][0].abs().max() <= 1
+
+
+def test_init_lstm_states_matches_reference():
+    g = load_golden("caseA_states")
+    cfg = O.OracleConfig.from_dict(json.loads(g["config"]))
+    B = g["x"].shape[0]
+    mine = O.init_lstm_states(cfg, torch.arange(B) + 7, list(g["y"].shape[2:]))
+    for (h, c), (hr, cr) in zip(mine, g["h_in"]):
+        assert torch.equal(h, hr) and torch.equal(c, cr)
