@@ -1,0 +1,215 @@
+// Shared declarations of libtmglow_b200 (sm_100a).  Internal layout: NHWC fp32 ("pixels x channels").
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tmglow_b200.h"
+
+namespace tmg {
+
+constexpr float kLog2Pi = 1.8378770664093453f;   // GaussianDiag.Log2PI   flowUtils.py:155
+constexpr float kLog5 = 1.6094379124341003f;     // clamp / hardtanh max  flowUtils.py:163,270
+constexpr float kLog4 = 1.3862943611198906f;     // Conv2dZeros clamp max flowUtils.py:247
+constexpr int kPixTile = 128;                    // pixels per CTA of the pointwise kernels
+constexpr int kMaxC = 64;                        // widest flow state the pointwise kernels take
+
+void set_error(const char* fmt, ...);
+extern thread_local int64_t g_launches;
+
+#define TMG_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      tmg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return TMG_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define TMG_LAUNCH_CHECK()                                                             \
+  do {                                                                                 \
+    ++tmg::g_launches;                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) {                                                          \
+      tmg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return TMG_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define TMG_TRY(expr)                 \
+  do {                                \
+    int s__ = (expr);                 \
+    if (s__ != TMG_OK) return s__;    \
+  } while (0)
+
+// ---- optional per-kernel-class timing (bench.py's roofline figures): CUDA events around launches
+enum ProfTag {
+  PROF_CONV_GATE = 0,    // ConvLSTM gate conv            (convLSTM.py:44)
+  PROF_CONV_OUT = 1,     // LSTM_out_conv                 (convLSTM.py:129)
+  PROF_CONV_ZERO = 2,    // Conv2dZeros of coupling nets  (flowUtils.py:229)
+  PROF_CONV_DENSE1 = 3,  // Cout=1 dense layers           (denseBlock.py:136)
+  PROF_CONV_SPLIT = 4,   // split prior conv
+  PROF_CONV_ENC = 5,     // encoder convs
+  PROF_POINTWISE = 6,    // fused coupling + 1x1 + ActNorm + log-det
+  PROF_LSTM_PW = 7,
+  PROF_GAUSS = 8,
+  PROF_PERMUTE = 9,
+  PROF_MISC = 10,
+  PROF_NTAGS = 11
+};
+struct ProfScope {
+  cudaStream_t st;
+  int idx;
+  ProfScope(cudaStream_t st, int tag, double flops, double bytes);
+  ~ProfScope();
+};
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ generic 3x3 convolution
+// One virtual input = channel-concatenation of up to 3 NHWC sources (torch.cat(...,1) of the
+// reference is never materialised).
+struct ConvSrc {
+  const float* p;
+  int cstride;   // floats between pixels
+  int coff;      // first channel inside the pixel
+  int nch;       // channels taken
+  int relu;      // apply ReLU while staging
+};
+
+struct ConvArgs {
+  ConvSrc src[3];
+  int nsrc;
+  const float* bn_scale;   // optional per-(concatenated)-channel affine applied before ReLU
+  const float* bn_shift;
+  const float* w;          // tap-major weights [9][cin_w][cout_w]
+  int cin_w, cout_w;
+  const float* bias;       // [cout] or null
+  const float* gain;       // scalar multiplier (exp(clamp(scale))) or null
+  int act;                 // 0 none, 1 ReLU, 2 hardtanh(-2, ln5)
+  float* out;
+  int out_cstride, out_coff, cout;
+  int B, Hin, Win, Hout, Wout, stride;
+  int pad_replicate;       // 0: zero padding, 1: replicate padding (Conv2dZeros)
+};
+int launch_conv3x3(const ConvArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ pointwise flow step
+struct PointArgs {
+  float* y;            // [B, HW, C] in/out
+  const float* hr;     // coupling-net output [B, HW, C] or null (no coupling)
+  const float* wmat;   // [C][C] row-major or null
+  const float* nw;     // ActNorm weight [C] or null
+  const float* nb;     // ActNorm bias   [C]
+  int reverse;         // 0: coupling_fwd -> norm_fwd -> W ; 1: coupling_rev -> W -> norm_rev
+  int B, HW, C;
+  float* ld_part;      // per-CTA partial sums of the coupling log-det: [B][ld_stride] (+ cta)
+  int ld_stride;
+};
+int launch_flow_pointwise(const PointArgs& a, cudaStream_t st);
+
+struct LstmArgs {
+  const float* gates;  // [B,HW,4R]  order i,f,o,g
+  const float* c_prev; // [B,HW,R] or null (zeros)
+  float* h_out;        // [B,HW,R]
+  float* c_out;
+  int64_t n;           // B*HW*R
+  int R;
+};
+int launch_lstm_pointwise(const LstmArgs& a, cudaStream_t st);
+
+struct GaussArgs {
+  const float* prm;    // NHWC [B,HW,prm_cstride]: mean at ch j, log-std at ch n+j
+  int prm_cstride;
+  float* val;          // NHWC value tensor, element (pixel, val_coff + j)
+  int val_cstride, val_coff;
+  const float* eps_in; // NCHW [B,n,HW]   (reverse: val = mean + exp(logsd)*eps)
+  float* eps_out;      // NCHW [B,n,HW] or null (forward: eps = (val-mean)/exp(logsd))
+  float* val_nchw;     // optional NCHW copy of val (user-facing z)
+  int reverse;
+  int B, HW, n;
+  float* ld_part;
+  int ld_stride;
+};
+int launch_gaussian(const GaussArgs& a, cudaStream_t st);
+
+enum PermuteMode {
+  PERM_NCHW_TO_NHWC = 0,
+  PERM_NHWC_TO_NCHW = 1,
+  PERM_SQUEEZE_NCHW_TO_NHWC = 2,    // src [B,c,2H,2W] NCHW -> dst [B,H,W,4c]
+  PERM_SQUEEZE_NHWC_TO_NHWC = 3,    // src [B,2H,2W,c]      -> dst [B,H,W,4c]
+  PERM_UNSQUEEZE_NHWC_TO_NHWC = 4,  // src [B,H,W,4c]       -> dst [B,2H,2W,c]
+  PERM_UNSQUEEZE_NHWC_TO_NCHW = 5,  // src [B,H,W,4c]       -> dst [B,c,2H,2W] NCHW
+  PERM_SQUEEZE_NCHW_TO_NCHW = 6,    // reference layout on both sides (flowUtils.py:99-121)
+  PERM_UNSQUEEZE_NCHW_TO_NCHW = 7   // (flowUtils.py:124-145)
+};
+struct PermArgs {
+  const float* src;
+  float* dst;
+  int mode;
+  int B, C, H, W;       // C,H,W of the *un-squeezed* tensor for squeeze modes, plain dims otherwise
+  int src_cstride, src_coff, dst_cstride, dst_coff;   // used for NHWC sides
+};
+int launch_permute(const PermArgs& a, cudaStream_t st);
+
+struct UpsampleArgs {
+  const float* src;    // NHWC [B,h,w,C]
+  float* dst;          // NHWC [B,h*f,w*f,C]
+  int B, h, w, C, f;
+};
+int launch_upsample(const UpsampleArgs& a, cudaStream_t st);
+
+struct BnStatArgs {
+  const float* x;      // NHWC [N, cstride]
+  int cstride, c0, n;  // channels [c0, c0+n)
+  int64_t N;           // B*h*w
+  float* mean;         // [>= c0+n]
+  float* var;          // biased
+};
+int launch_bn_stats(const BnStatArgs& a, cudaStream_t st);
+
+struct BnFoldArgs {
+  const float* mean;
+  const float* var;
+  const float* w;
+  const float* b;
+  float* run_mean;
+  float* run_var;
+  float* scale;
+  float* shift;
+  int n;
+  int64_t N;
+  float eps, momentum;
+};
+int launch_bn_fold_train(const BnFoldArgs& a, cudaStream_t st);
+
+struct LogdetArgs {
+  const float* ld_part;    // [B][ld_stride]
+  int ld_stride;
+  const float* step_const; // per flow step: sum log|w| - sum log_s
+  int n_levels;
+  int step_begin[TMG_MAX_LEVELS + 1];
+  int hw[TMG_MAX_LEVELS];
+  float* out;              // [B]
+  int B;
+};
+int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ weight packing jobs
+enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3 };
+struct PackJob {
+  int type;
+  int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n
+  int64_t src[9];        // offsets (floats) into the flat parameter buffer, -1 = absent
+                         // JOB_1X1: l,u,log_s,p,sign_s,l_mask,u_mask,eye,norm.weight
+  int64_t dst[3];        // offsets (floats) into the packed buffer
+  int opad;              // JOB_CONVW: padded O
+};
+int launch_pack(const PackJob* jobs_dev, int njobs, const float* params, float* packed, int cmax,
+                cudaStream_t st);
+
+}  // namespace tmg

@@ -1,0 +1,933 @@
+// Host side of libtmglow_b200: model description, parameter table, workspace planning and the
+// launch sequences behind the C ABI (include/tmglow_b200.h).  The sequences restate
+//   Encoder.forward            nn/tmGlow.py:104-129
+//   LSTMFLowBlock.forward/rev  nn/modules/flowLSTMBlock.py:280-361
+//   LSTMCFlowDecoder           nn/tmGlow.py:231-303
+//   TMGlow.forward/reconstruct nn/tmGlow.py:378-467
+// with every torch.cat / chunk / relu / pad tensor of the reference folded into the kernels.
+#include <cstdarg>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tmg {
+
+thread_local int64_t g_launches = 0;
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- per-class event timing
+struct ProfRec { cudaEvent_t a, b; int tag; double flops, bytes; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(cudaStream_t st_, int tag, double flops, double bytes) : st(st_), idx(-1) {
+  if (!g_prof_on) return;
+  ProfRec r{};
+  r.tag = tag; r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+}
+
+struct ParamEntry { std::string name; int64_t off; int64_t numel; int ndim; int64_t dims[4]; };
+
+struct ConvW {
+  int64_t w_param = -1;   // OIHW in the parameter buffer
+  int64_t b_param = -1;   // bias or -1
+  int64_t w_pack = -1;    // tap-major in the packed buffer
+  int O = 0, I = 0, OP = 0;
+};
+
+enum StepKind { STEP_UNNORMED = 0, STEP_PLAIN = 1, STEP_LSTM = 2 };
+
+struct StepW {
+  int kind = STEP_PLAIN;
+  int64_t norm_w = -1, norm_b = -1;
+  int64_t W = -1, Wi = -1;        // packed
+  int const_idx = -1;             // index into step_const
+  ConvW d1, d2, zc, gate, outc;
+  int64_t zc_gain = -1;           // packed
+};
+
+struct DenseW { ConvW conv; int64_t bn_w, bn_b, bn_rm, bn_rv; int64_t scale, shift; int cin; };
+
+struct LevelW {
+  int C = 0;                      // flow channels at this level (after squeeze)
+  std::vector<StepW> steps;
+  ConvW split; int64_t split_gain = -1;
+  // encoder side
+  ConvW trans; bool has_trans = false;
+  std::vector<DenseW> dense;
+  int nf_in = 0, nf_out = 0;      // dense block channels in / out
+  ConvW cond;
+};
+
+}  // namespace tmg
+
+using namespace tmg;
+
+struct tmg_model {
+  tmg_config cfg;
+  int device = 0;
+  std::vector<ParamEntry> entries;
+  int64_t n_params = 0;
+  int64_t n_packed = 0;
+  std::vector<LevelW> levels;
+  ConvW in_conv, in_conv3, out_conv;
+  int Cz = 0;
+  int n_steps = 0;
+  int cmax = 0;
+  std::vector<PackJob> jobs;
+  PackJob* jobs_dev = nullptr;
+  float* packed = nullptr;          // derived weights
+  int64_t step_const_off = 0;       // inside packed
+  float* params = nullptr;          // borrowed flat parameter buffer
+  bool ready = false;
+};
+
+namespace tmg {
+
+// ------------------------------------------------------------------ model construction
+struct Builder {
+  tmg_model& m;
+  int64_t add(const std::string& name, std::initializer_list<int64_t> shape) {
+    ParamEntry e{name, m.n_params, 1, (int)shape.size(), {1, 1, 1, 1}};
+    int k = 0;
+    for (int64_t d : shape) { e.dims[k++] = d; e.numel *= d; }
+    m.entries.push_back(e);
+    m.n_params += e.numel;
+    return e.off;
+  }
+  int64_t pack_alloc(int64_t n) {
+    int64_t o = m.n_packed;
+    m.n_packed += (n + 3) / 4 * 4;   // keep 16 B alignment
+    return o;
+  }
+  ConvW conv(const std::string& name, int O, int I, bool bias) {
+    ConvW c;
+    c.O = O; c.I = I; c.OP = (O + 3) / 4 * 4;
+    c.w_param = add(name + ".weight", {O, I, 3, 3});
+    if (bias) c.b_param = add(name + ".bias", {O});
+    c.w_pack = pack_alloc((int64_t)9 * I * c.OP);
+    PackJob j{};
+    j.type = JOB_CONVW; j.a = O; j.b = I; j.opad = c.OP;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = c.w_param; j.dst[0] = c.w_pack;
+    m.jobs.push_back(j);
+    return c;
+  }
+  int64_t gain(int64_t scale_param) {
+    int64_t o = pack_alloc(1);
+    PackJob j{};
+    j.type = JOB_GAIN;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = scale_param; j.dst[0] = o;
+    m.jobs.push_back(j);
+    return o;
+  }
+};
+
+static int build_model(tmg_model& m) {
+  const tmg_config& c = m.cfg;
+  if (c.n_levels < 1 || c.n_levels > TMG_MAX_LEVELS || c.in_features < 1 || c.out_features < 1 ||
+      c.cond_features < 1 || c.cglow_upscale < 1 || c.growth_rate < 1 || c.init_features < 2 ||
+      c.rec_features < 1) {
+    set_error("bad TMGlow configuration");
+    return TMG_ERR_BAD_CONFIG;
+  }
+  Builder B{m};
+  const int L = c.n_levels;
+  m.levels.resize(L);
+  for (const char* nm : {"in_mu", "in_std", "out_mu", "out_std"}) B.add(nm, {3});   // tmGlow.py:371-374
+
+  // ---- encoder (tmGlow.py:53-102,131-186)
+  m.in_conv = B.conv("encoder.first_encoder.In_conv", c.init_features / 2, c.in_features, false);
+  m.in_conv3 = B.conv("encoder.first_encoder.In_conv3", c.init_features, c.init_features / 2, false);
+  m.Cz = c.out_features << L;   // enc_out_features = out_features * 2^L  (tmGlow.py:348)
+  // channel bookkeeping first (out_conv is registered before the blocks in the state_dict)
+  {
+    int nf = c.init_features;
+    for (int i = 0; i < L; ++i) {
+      if (i > 0) nf = nf / 2;
+      m.levels[i].nf_in = nf;
+      nf += c.enc_blocks[i] * c.growth_rate;
+      m.levels[i].nf_out = nf;
+    }
+    m.out_conv = B.conv("encoder.out_conv.0", 2 * m.Cz, nf, false);
+  }
+  for (int i = 0; i < L; ++i) {
+    LevelW& lv = m.levels[i];
+    if (c.enc_blocks[i] < 0) { set_error("bad enc_blocks"); return TMG_ERR_BAD_CONFIG; }
+    std::string bp = "encoder.encoding_blocks." + std::to_string(i) + ".";
+    if (i > 0) {
+      lv.has_trans = true;
+      lv.trans = B.conv(bp + "encode_conv" + std::to_string(i) + ".conv1", lv.nf_in, m.levels[i - 1].nf_out, false);
+    }
+    for (int l = 1; l <= c.enc_blocks[i]; ++l) {
+      std::string lp = bp + "encode_dense_block" + std::to_string(i) + ".denselayer" + std::to_string(l) + ".";
+      DenseW d{};
+      d.cin = lv.nf_in + (l - 1) * c.growth_rate;
+      d.bn_w = B.add(lp + "norm1.weight", {d.cin});
+      d.bn_b = B.add(lp + "norm1.bias", {d.cin});
+      d.bn_rm = B.add(lp + "norm1.running_mean", {d.cin});
+      d.bn_rv = B.add(lp + "norm1.running_var", {d.cin});
+      d.conv = B.conv(lp + "conv1", c.growth_rate, d.cin, false);
+      d.scale = B.pack_alloc(d.cin);
+      d.shift = B.pack_alloc(d.cin);
+      PackJob j{};
+      j.type = JOB_BN; j.a = d.cin;
+      for (auto& s : j.src) s = -1;
+      j.src[0] = d.bn_w; j.src[1] = d.bn_b; j.src[2] = d.bn_rm; j.src[3] = d.bn_rv;
+      j.dst[0] = d.scale; j.dst[1] = d.shift;
+      m.jobs.push_back(j);
+      lv.dense.push_back(d);
+    }
+  }
+  for (int i = 0; i < L; ++i)
+    m.levels[i].cond = B.conv("encoder.cond_convs." + std::to_string(i) + ".0", c.cond_features, m.levels[i].nf_out, false);
+
+  // ---- flow blocks (flowLSTMBlock.py:244-278)
+  int C = c.out_features;
+  m.n_steps = 0;
+  for (int b = 0; b < L; ++b) {
+    LevelW& lv = m.levels[b];
+    C *= 4;
+    lv.C = C;
+    if (C % 4 != 0 || C > kMaxC) {
+      set_error("level %d has %d flow channels; supported: multiples of 4 up to %d", b, C, kMaxC);
+      return TMG_ERR_UNSUPPORTED;
+    }
+    m.cmax = C > m.cmax ? C : m.cmax;
+    const int n = c.glow_blocks[b];
+    if (n < 1) { set_error("glow_blocks[%d] must be >= 1", b); return TMG_ERR_BAD_CONFIG; }
+    const int cin_t = C / 2 + c.cond_features;
+    for (int s = 1; s <= n; ++s) {
+      StepW st;
+      st.kind = (s == n) ? STEP_LSTM : (s == 1 ? STEP_UNNORMED : STEP_PLAIN);
+      std::string sp = "glow.flow_blocks." + std::to_string(b) + ".revlayers.affine_layer" + std::to_string(s) + ".";
+      if (st.kind != STEP_UNNORMED) {
+        st.norm_w = B.add(sp + "norm.weight", {C, 1, 1});
+        st.norm_b = B.add(sp + "norm.bias", {C, 1, 1});
+      }
+      if (st.kind == STEP_LSTM) {           // declared, never used (flowLSTMBlock.py:170)
+        B.add(sp + "norm2.weight", {C, 1, 1});
+        B.add(sp + "norm2.bias", {C, 1, 1});
+      }
+      PackJob j{};
+      j.type = JOB_1X1; j.a = C;
+      j.src[0] = B.add(sp + "conv.l", {C, C});
+      j.src[1] = B.add(sp + "conv.u", {C, C});
+      j.src[2] = B.add(sp + "conv.log_s", {C});
+      j.src[3] = B.add(sp + "conv.p", {C, C});
+      j.src[4] = B.add(sp + "conv.sign_s", {C});
+      j.src[5] = B.add(sp + "conv.l_mask", {C, C});
+      j.src[6] = B.add(sp + "conv.u_mask", {C, C});
+      j.src[7] = B.add(sp + "conv.eye", {C, C});
+      B.add(sp + "conv.log_s_old", {C});       // cache key of the reference (glowConv.py:209); unused here
+      j.src[8] = st.norm_w;
+      st.W = B.pack_alloc((int64_t)C * C);
+      st.Wi = B.pack_alloc((int64_t)C * C);
+      st.const_idx = m.n_steps++;
+      j.dst[0] = st.W; j.dst[1] = st.Wi; j.dst[2] = -1;   // step_const offset patched below
+      j.b = st.const_idx;
+      m.jobs.push_back(j);
+      if (st.kind == STEP_LSTM) {
+        const int R = c.rec_features;
+        st.gate = B.conv(sp + "coupling.resid_lstm.convLSTM.conv", 4 * R, cin_t + R, true);
+        st.outc = B.conv(sp + "coupling.resid_lstm.out_seq.LSTM_out_conv", cin_t, cin_t + R, true);
+        st.d1 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
+        st.d2 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
+        int64_t sc = B.add(sp + "coupling.out_conv.zero_conv.scale", {1, 1, 1, 1});
+        st.zc = B.conv(sp + "coupling.out_conv.zero_conv.conv", C, cin_t + 2, true);
+        st.zc_gain = B.gain(sc);
+      } else {
+        st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
+        st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
+        int64_t sc = B.add(sp + "coupling.coupling_nn.zero_conv.scale", {1, 1, 1, 1});
+        st.zc = B.conv(sp + "coupling.coupling_nn.zero_conv.conv", C, cin_t + 2, true);
+        st.zc_gain = B.gain(sc);
+      }
+      lv.steps.push_back(st);
+    }
+    std::string pp = "glow.flow_blocks." + std::to_string(b) + ".split.latent_encoder.conv2d";
+    int64_t sc = B.add(pp + ".scale", {1, 1, 1, 1});
+    lv.split = B.conv(pp + ".conv", C, C / 2, true);
+    lv.split_gain = B.gain(sc);
+    C = C / 2;
+  }
+  m.step_const_off = B.pack_alloc(m.n_steps);
+  for (auto& j : m.jobs)
+    if (j.type == JOB_1X1) j.dst[2] = m.step_const_off + j.b;
+  return TMG_OK;
+}
+
+// ------------------------------------------------------------------ workspace plan
+struct Plan {
+  int B, h, w, H, W, L;
+  int eh[TMG_MAX_LEVELS], ew[TMG_MAX_LEVELS];   // encoder level sizes
+  int Hl[TMG_MAX_LEVELS], Wl[TMG_MAX_LEVELS];   // flow level sizes
+  int ctas;                                     // log-det partials per slot
+  int nslots;
+  size_t total;
+  // offsets in floats
+  size_t xn, e0, db[TMG_MAX_LEVELS], cc, cond[TMG_MAX_LEVELS], zo_pre, zout;
+  size_t bn_mean, bn_var, bn_scale, bn_shift;
+  size_t y[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
+};
+
+static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
+  const tmg_config& c = m.cfg;
+  const int L = c.n_levels;
+  if (B < 1 || h < 1 || w < 1) { set_error("bad batch/input size"); return TMG_ERR_BAD_SHAPE; }
+  p.B = B; p.h = h; p.w = w; p.L = L;
+  p.H = h * c.cglow_upscale; p.W = w * c.cglow_upscale;
+  if (p.H % (1 << L) || p.W % (1 << L)) {      // flowUtils.py:112 assert
+    set_error("high-fidelity size %dx%d not divisible by 2^%d", p.H, p.W, L);
+    return TMG_ERR_BAD_SHAPE;
+  }
+  int eh = h, ew = w;
+  for (int l = 0; l < L; ++l) {
+    eh = (eh + 1) / 2; ew = (ew + 1) / 2;       // 3x3 stride-2 pad-1 convolution
+    p.eh[l] = eh; p.ew[l] = ew;
+    p.Hl[l] = p.H >> (l + 1); p.Wl[l] = p.W >> (l + 1);
+    if (eh * c.cglow_upscale != p.Hl[l] || ew * c.cglow_upscale != p.Wl[l]) {
+      set_error("level %d: conditioning map %dx%d does not match flow map %dx%d", l,
+                eh * c.cglow_upscale, ew * c.cglow_upscale, p.Hl[l], p.Wl[l]);
+      return TMG_ERR_BAD_SHAPE;
+    }
+  }
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n, 64); return o; };
+  const size_t Bz = (size_t)B;
+  p.xn = take(Bz * h * w * c.in_features);
+  p.e0 = take(Bz * h * w * (c.init_features / 2));
+  size_t cc_max = 0, mx_y = 0, mx_g = 0, mx_u = 0, mx_pix = 0;
+  int nf_max = 0;
+  for (int l = 0; l < L; ++l) {
+    const LevelW& lv = m.levels[l];
+    p.db[l] = take(Bz * p.eh[l] * p.ew[l] * lv.nf_out);
+    p.cond[l] = take(Bz * p.Hl[l] * p.Wl[l] * c.cond_features);
+    p.y[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
+    cc_max = std::max(cc_max, Bz * p.eh[l] * p.ew[l] * c.cond_features);
+    size_t pix = Bz * p.Hl[l] * p.Wl[l];
+    mx_pix = std::max(mx_pix, pix);
+    mx_y = std::max(mx_y, pix * lv.C);
+    mx_g = std::max(mx_g, pix * 4 * c.rec_features);
+    mx_u = std::max(mx_u, pix * (lv.C / 2 + c.cond_features));
+    nf_max = std::max(nf_max, lv.nf_out);
+  }
+  p.cc = take(cc_max);
+  p.zo_pre = take(Bz * p.eh[L - 1] * p.ew[L - 1] * 2 * m.Cz);
+  p.zout = take(Bz * p.Hl[L - 1] * p.Wl[L - 1] * 2 * m.Cz);
+  p.bn_mean = take(nf_max); p.bn_var = take(nf_max);
+  p.bn_scale = take(nf_max); p.bn_shift = take(nf_max);
+  p.hr = take(mx_y);
+  p.d = take(mx_pix * 2);
+  p.gates = take(mx_g);
+  p.u0 = take(mx_u);
+  p.ctas = cdiv(p.Hl[0] * p.Wl[0], kPixTile);
+  p.nslots = 1;
+  for (int l = 0; l < L; ++l) p.nslots += c.glow_blocks[l] + 1;
+  p.ldp = take(Bz * p.nslots * p.ctas);
+  // scratch for the NCHW single-operator entry points
+  p.scratch_in = take(mx_y);
+  p.scratch_cond = take(mx_pix * c.cond_features);
+  p.scratch_out = take(mx_y);
+  p.total = off * sizeof(float);
+  return TMG_OK;
+}
+
+struct Ctx {
+  tmg_model& m;
+  Plan p;
+  float* ws;
+  cudaStream_t st;
+  const float* P() const { return m.params; }
+  const float* Q() const { return m.packed; }
+};
+
+static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int nsrc, int B, int Hin, int Win, int stride,
+                    bool replicate, int act, int64_t gain_pack, const float* bn_scale, const float* bn_shift,
+                    float* out, int out_cstride, int out_coff) {
+  ConvArgs a{};
+  for (int i = 0; i < nsrc; ++i) a.src[i] = srcs[i];
+  a.nsrc = nsrc;
+  a.bn_scale = bn_scale; a.bn_shift = bn_shift;
+  a.w = c.Q() + w.w_pack; a.cin_w = w.I; a.cout_w = w.OP;
+  a.bias = w.b_param >= 0 ? c.P() + w.b_param : nullptr;
+  a.gain = gain_pack >= 0 ? c.Q() + gain_pack : nullptr;
+  a.act = act;
+  a.out = out; a.out_cstride = out_cstride; a.out_coff = out_coff; a.cout = w.O;
+  a.B = B; a.Hin = Hin; a.Win = Win; a.stride = stride;
+  a.Hout = stride == 1 ? Hin : (Hin + 1) / 2;
+  a.Wout = stride == 1 ? Win : (Win + 1) / 2;
+  a.pad_replicate = replicate ? 1 : 0;
+  // algorithmic work: 2*M*N*K flops; bytes = read every input channel once + write the outputs
+  const double M = (double)B * a.Hout * a.Wout;
+  ProfScope ps(c.st, tag, 2.0 * M * w.O * 9.0 * w.I, 4.0 * ((double)B * Hin * Win * w.I + M * w.O));
+  return launch_conv3x3(a, c.st);
+}
+
+// ------------------------------------------------------------------ encoder
+static int run_encoder(Ctx& c, const float* x, bool bn_train) {
+  const tmg_config& g = c.m.cfg;
+  const Plan& p = c.p;
+  float* ws = c.ws;
+  const int B = p.B, L = p.L;
+  PermArgs pa{};
+  pa.src = x; pa.dst = ws + p.xn; pa.mode = PERM_NCHW_TO_NHWC;
+  pa.B = B; pa.C = g.in_features; pa.H = p.h; pa.W = p.w; pa.dst_cstride = g.in_features;
+  TMG_TRY(launch_permute(pa, c.st));
+  ConvSrc s0{ws + p.xn, g.in_features, 0, g.in_features, 0};
+  TMG_TRY(run_conv(c, PROF_CONV_ENC, c.m.in_conv, &s0, 1, B, p.h, p.w, 1, false, 0, -1, nullptr, nullptr,
+                   ws + p.e0, g.init_features / 2, 0));
+  ConvSrc s1{ws + p.e0, g.init_features / 2, 0, g.init_features / 2, 1};
+  TMG_TRY(run_conv(c, PROF_CONV_ENC, c.m.in_conv3, &s1, 1, B, p.h, p.w, 2, false, 0, -1, nullptr, nullptr,
+                   ws + p.db[0], c.m.levels[0].nf_out, 0));
+  for (int i = 0; i < L; ++i) {
+    const LevelW& lv = c.m.levels[i];
+    float* db = ws + p.db[i];
+    const int eh = p.eh[i], ew = p.ew[i];
+    if (i > 0) {
+      const LevelW& pv = c.m.levels[i - 1];
+      ConvSrc st{ws + p.db[i - 1], pv.nf_out, 0, pv.nf_out, 1};
+      TMG_TRY(run_conv(c, PROF_CONV_ENC, lv.trans, &st, 1, B, p.eh[i - 1], p.ew[i - 1], 2, false, 0, -1, nullptr, nullptr,
+                       db, lv.nf_out, 0));
+    }
+    int stats_done = 0;
+    for (size_t l = 0; l < lv.dense.size(); ++l) {
+      const DenseW& d = lv.dense[l];
+      const float* sc; const float* sh;
+      if (bn_train) {
+        BnStatArgs sa{};
+        sa.x = db; sa.cstride = lv.nf_out; sa.c0 = stats_done; sa.n = d.cin - stats_done;
+        sa.N = (int64_t)B * eh * ew; sa.mean = ws + p.bn_mean; sa.var = ws + p.bn_var;
+        TMG_TRY(launch_bn_stats(sa, c.st));
+        stats_done = d.cin;
+        BnFoldArgs fa{};
+        fa.mean = ws + p.bn_mean; fa.var = ws + p.bn_var;
+        fa.w = c.P() + d.bn_w; fa.b = c.P() + d.bn_b;
+        fa.run_mean = c.m.params + d.bn_rm; fa.run_var = c.m.params + d.bn_rv;
+        fa.scale = ws + p.bn_scale; fa.shift = ws + p.bn_shift;
+        fa.n = d.cin; fa.N = sa.N; fa.eps = 1e-5f; fa.momentum = 0.1f;
+        TMG_TRY(launch_bn_fold_train(fa, c.st));
+        sc = ws + p.bn_scale; sh = ws + p.bn_shift;
+      } else {
+        sc = c.Q() + d.scale; sh = c.Q() + d.shift;
+      }
+      ConvSrc sd{db, lv.nf_out, 0, d.cin, 1};
+      TMG_TRY(run_conv(c, PROF_CONV_ENC, d.conv, &sd, 1, B, eh, ew, 1, false, 0, -1, sc, sh, db, lv.nf_out, d.cin));
+    }
+    ConvSrc sc{db, lv.nf_out, 0, lv.nf_out, 0};
+    const bool up = g.cglow_upscale > 1;
+    TMG_TRY(run_conv(c, PROF_CONV_ENC, lv.cond, &sc, 1, B, eh, ew, 1, false, 0, -1, nullptr, nullptr,
+                     up ? ws + p.cc : ws + p.cond[i], g.cond_features, 0));
+    if (up) {
+      UpsampleArgs ua{ws + p.cc, ws + p.cond[i], B, eh, ew, g.cond_features, g.cglow_upscale};
+      TMG_TRY(launch_upsample(ua, c.st));
+    }
+    if (i == L - 1) {
+      TMG_TRY(run_conv(c, PROF_CONV_ENC, c.m.out_conv, &sc, 1, B, eh, ew, 1, false, 0, -1, nullptr, nullptr,
+                       up ? ws + p.zo_pre : ws + p.zout, 2 * c.m.Cz, 0));
+      if (up) {
+        UpsampleArgs ua{ws + p.zo_pre, ws + p.zout, B, eh, ew, 2 * c.m.Cz, g.cglow_upscale};
+        TMG_TRY(launch_upsample(ua, c.st));
+      }
+    }
+  }
+  return TMG_OK;
+}
+
+// ------------------------------------------------------------------ coupling network of one step -> HR
+static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int Wl, const float* Y,
+                           const float* cond, const float* h_in, const float* c_in, float* h_out, float* c_out) {
+  const tmg_config& g = c.m.cfg;
+  const Plan& p = c.p;
+  float* ws = c.ws;
+  const int C = c.m.levels[level].C, cf = g.cond_features, R = g.rec_features;
+  const int cin_t = C / 2 + cf;
+  float* D = ws + p.d;
+  float* HR = ws + p.hr;
+  ConvSrc src[3];
+  int nt;   // sources that make up "t"
+  if (s.kind == STEP_LSTM) {
+    if (!h_out || !c_out) { set_error("LSTM step needs h_out/c_out buffers"); return TMG_ERR_NULL; }
+    ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0}, {h_in, R, 0, R, 0}};
+    TMG_TRY(run_conv(c, PROF_CONV_GATE, s.gate, gs, h_in ? 3 : 2, B, Hl, Wl, 1, false, 0, -1, nullptr, nullptr,
+                     ws + p.gates, 4 * R, 0));
+    LstmArgs la{ws + p.gates, c_in, h_out, c_out, (int64_t)B * Hl * Wl * R, R};
+    {
+      ProfScope ps(c.st, PROF_LSTM_PW, 20.0 * la.n, 4.0 * la.n * (c_in ? 7.0 : 6.0));
+      TMG_TRY(launch_lstm_pointwise(la, c.st));
+    }
+    ConvSrc os[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0}, {h_out, R, 0, R, 0}};
+    TMG_TRY(run_conv(c, PROF_CONV_OUT, s.outc, os, 3, B, Hl, Wl, 1, false, 1, -1, nullptr, nullptr, ws + p.u0, cin_t, 0));
+    src[0] = ConvSrc{ws + p.u0, cin_t, 0, cin_t, 1};
+    nt = 1;
+  } else {
+    src[0] = ConvSrc{Y, C, 0, C / 2, 1};
+    src[1] = ConvSrc{cond, cf, 0, cf, 1};
+    nt = 2;
+  }
+  TMG_TRY(run_conv(c, PROF_CONV_DENSE1, s.d1, src, nt, B, Hl, Wl, 1, false, 0, -1, nullptr, nullptr, D, 2, 0));
+  src[nt] = ConvSrc{D, 2, 0, 1, 1};
+  TMG_TRY(run_conv(c, PROF_CONV_DENSE1, s.d2, src, nt + 1, B, Hl, Wl, 1, false, 0, -1, nullptr, nullptr, D, 2, 1));
+  src[nt] = ConvSrc{D, 2, 0, 2, 1};
+  TMG_TRY(run_conv(c, PROF_CONV_ZERO, s.zc, src, nt + 1, B, Hl, Wl, 1, true, 0, s.zc_gain, nullptr, nullptr, HR, C, 0));
+  return TMG_OK;
+}
+
+static int run_pointwise(Ctx& c, int level, float* Y, bool coupling, const StepW* mix, bool reverse,
+                         int B, int HW, float* ld_slot) {
+  PointArgs a{};
+  a.y = Y;
+  a.hr = coupling ? c.ws + c.p.hr : nullptr;
+  if (mix) {
+    a.wmat = c.Q() + (reverse ? mix->W : mix->Wi);
+    if (mix->kind != STEP_UNNORMED) { a.nw = c.P() + mix->norm_w; a.nb = c.P() + mix->norm_b; }
+  }
+  a.reverse = reverse ? 1 : 0;
+  a.B = B; a.HW = HW; a.C = c.m.levels[level].C;
+  a.ld_part = ld_slot; a.ld_stride = c.p.nslots * c.p.ctas;
+  // algorithmic bytes: read + write the flow state, read the coupling-net output
+  const double px = (double)B * HW;
+  ProfScope ps(c.st, PROF_POINTWISE, px * a.C * (mix ? 2.0 * a.C : 0.0) + px * a.C * 6.0,
+               4.0 * px * a.C * (coupling ? 3.0 : 2.0));
+  return launch_flow_pointwise(a, c.st);
+}
+
+static int run_split_prior(Ctx& c, int level, int B, int Hl, int Wl, const float* Y) {
+  const LevelW& lv = c.m.levels[level];
+  ConvSrc s{Y, lv.C, 0, lv.C / 2, 0};
+  return run_conv(c, PROF_CONV_SPLIT, lv.split, &s, 1, B, Hl, Wl, 1, true, 2, lv.split_gain, nullptr, nullptr,
+                  c.ws + c.p.hr, lv.C, 0);
+}
+
+static int finish_logdet(Ctx& c, float* out) {
+  LogdetArgs a{};
+  a.ld_part = c.ws + c.p.ldp; a.ld_stride = c.p.nslots * c.p.ctas;
+  a.step_const = c.Q() + c.m.step_const_off;
+  a.n_levels = c.p.L;
+  int k = 0;
+  for (int l = 0; l < c.p.L; ++l) {
+    a.step_begin[l] = k;
+    k += (int)c.m.levels[l].steps.size();
+    a.hw[l] = c.p.Hl[l] * c.p.Wl[l];
+  }
+  a.step_begin[c.p.L] = k;
+  a.out = out; a.B = c.p.B;
+  return launch_logdet_reduce(a, c.st);
+}
+
+static int check_common(tmg_model* m, const void* ws, size_t ws_bytes, const Plan& p) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (!m->ready) { set_error("tmg_model_refresh() has not been called"); return TMG_ERR_NOT_READY; }
+  if (!ws) { set_error("null workspace"); return TMG_ERR_NULL; }
+  if (ws_bytes < p.total) { set_error("workspace too small: %zu < %zu bytes", ws_bytes, p.total); return TMG_ERR_WORKSPACE; }
+  if (((uintptr_t)ws & 255) != 0) { set_error("workspace must be 256-byte aligned"); return TMG_ERR_BAD_SHAPE; }
+  return TMG_OK;
+}
+
+}  // namespace tmg
+
+// =================================================================== C ABI
+extern "C" {
+
+int tmg_version(void) { return 100; }
+const char* tmg_last_error(void) { return tmg::g_err; }
+
+int tmg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static const char* kProfNames[PROF_NTAGS] = {"conv_lstm_gates", "conv_lstm_out", "conv_zero", "conv_dense_cout1",
+                                              "conv_split_prior", "conv_encoder", "flow_pointwise", "lstm_pointwise",
+                                              "gaussian", "permute", "misc"};
+
+int tmg_profile_enable(int on) {
+  for (auto& r : tmg::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  tmg::g_prof.clear();
+  tmg::g_prof_on = on != 0;
+  return TMG_OK;
+}
+int tmg_profile_classes(void) { return PROF_NTAGS; }
+const char* tmg_profile_class_name(int tag) { return (tag >= 0 && tag < PROF_NTAGS) ? kProfNames[tag] : nullptr; }
+int tmg_profile_query(int tag, double* ms, int64_t* launches, double* flops, double* bytes) {
+  if (!ms || !launches || !flops || !bytes) { set_error("null argument"); return TMG_ERR_NULL; }
+  *ms = 0; *launches = 0; *flops = 0; *bytes = 0;
+  for (auto& r : tmg::g_prof) {
+    if (r.tag != tag) continue;
+    TMG_CUDA_OK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    TMG_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    *ms += t; *launches += 1; *flops += r.flops; *bytes += r.bytes;
+  }
+  return TMG_OK;
+}
+
+int64_t tmg_launch_count(int reset) {
+  int64_t v = tmg::g_launches;
+  if (reset) tmg::g_launches = 0;
+  return v;
+}
+
+int tmg_model_create(const tmg_config* cfg, tmg_model** out) {
+  if (!cfg || !out) { set_error("null argument"); return TMG_ERR_NULL; }
+  tmg_model* m = new tmg_model();
+  m->cfg = *cfg;
+  int s = build_model(*m);
+  if (s != TMG_OK) { delete m; return s; }
+  *out = m;
+  return TMG_OK;
+}
+
+void tmg_model_destroy(tmg_model* m) {
+  if (!m) return;
+  if (m->jobs_dev) cudaFree(m->jobs_dev);
+  if (m->packed) cudaFree(m->packed);
+  delete m;
+}
+
+int64_t tmg_model_param_entries(const tmg_model* m) { return m ? (int64_t)m->entries.size() : 0; }
+const char* tmg_model_param_name(const tmg_model* m, int64_t i) {
+  return (m && i >= 0 && i < (int64_t)m->entries.size()) ? m->entries[i].name.c_str() : nullptr;
+}
+int64_t tmg_model_param_offset(const tmg_model* m, int64_t i) {
+  return (m && i >= 0 && i < (int64_t)m->entries.size()) ? m->entries[i].off : -1;
+}
+int64_t tmg_model_param_numel(const tmg_model* m, int64_t i) {
+  return (m && i >= 0 && i < (int64_t)m->entries.size()) ? m->entries[i].numel : -1;
+}
+int tmg_model_param_shape(const tmg_model* m, int64_t i, int64_t dims[4]) {
+  if (!m || !dims || i < 0 || i >= (int64_t)m->entries.size()) return -1;
+  for (int k = 0; k < 4; ++k) dims[k] = m->entries[i].dims[k];
+  return m->entries[i].ndim;
+}
+int64_t tmg_model_param_total(const tmg_model* m) { return m ? m->n_params : 0; }
+
+int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
+  if (!m || !params) { set_error("null argument"); return TMG_ERR_NULL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!m->packed) {     // one-time allocation of the library-owned derived-weight cache
+    TMG_CUDA_OK(cudaGetDevice(&m->device));
+    TMG_CUDA_OK(cudaMalloc(&m->packed, (size_t)m->n_packed * sizeof(float)));
+    TMG_CUDA_OK(cudaMalloc(&m->jobs_dev, m->jobs.size() * sizeof(PackJob)));
+    TMG_CUDA_OK(cudaMemcpy(m->jobs_dev, m->jobs.data(), m->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  }
+  m->params = params;
+  TMG_TRY(launch_pack(m->jobs_dev, (int)m->jobs.size(), params, m->packed, m->cmax, st));
+  m->ready = true;
+  return TMG_OK;
+}
+
+int tmg_model_get_conv1x1(const tmg_model* m, int level, int step, int inverse, float* dst, void* stream) {
+  if (!m || !dst) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (!m->ready) { set_error("model not refreshed"); return TMG_ERR_NOT_READY; }
+  if (level < 0 || level >= m->cfg.n_levels || step < 1 || step > (int)m->levels[level].steps.size()) {
+    set_error("bad level/step"); return TMG_ERR_BAD_SHAPE;
+  }
+  const StepW& s = m->levels[level].steps[step - 1];
+  int C = m->levels[level].C;
+  TMG_CUDA_OK(cudaMemcpyAsync(dst, m->packed + (inverse ? s.Wi : s.W), (size_t)C * C * sizeof(float),
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return TMG_OK;
+}
+
+size_t tmg_workspace_bytes(const tmg_model* m, int B, int h, int w) {
+  if (!m) return 0;
+  Plan p;
+  if (make_plan(*m, B, h, w, p) != TMG_OK) return 0;
+  return p.total;
+}
+
+int tmg_encoder_forward(tmg_model* m, int B, int h, int w, const float* x, float* const* c_out, float* z_out,
+                        void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  Plan p;
+  TMG_TRY(make_plan(*m, B, h, w, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x) { set_error("null input"); return TMG_ERR_NULL; }
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
+  for (int l = 0; l < p.L && c_out; ++l) {
+    if (!c_out[l]) continue;
+    PermArgs pa{};
+    pa.src = c.ws + p.cond[l]; pa.dst = c_out[l]; pa.mode = PERM_NHWC_TO_NCHW;
+    pa.B = B; pa.C = m->cfg.cond_features; pa.H = p.Hl[l]; pa.W = p.Wl[l]; pa.src_cstride = pa.C;
+    TMG_TRY(launch_permute(pa, c.st));
+  }
+  if (z_out) {
+    PermArgs pa{};
+    pa.src = c.ws + p.zout; pa.dst = z_out; pa.mode = PERM_NHWC_TO_NCHW;
+    pa.B = B; pa.C = 2 * m->Cz; pa.H = p.Hl[p.L - 1]; pa.W = p.Wl[p.L - 1]; pa.src_cstride = pa.C;
+    TMG_TRY(launch_permute(pa, c.st));
+  }
+  return TMG_OK;
+}
+
+int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                    const float* const* c_in, const float* const* eps, float* y, float* log_det,
+                    float* const* h_out, float* const* c_out, void* workspace, size_t workspace_bytes,
+                    uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  Plan p;
+  TMG_TRY(make_plan(*m, B, h, w, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !eps || !y || !log_det || !h_out || !c_out) { set_error("null argument"); return TMG_ERR_NULL; }
+  const int L = p.L;
+  for (int l = 0; l <= L; ++l) if (!eps[l]) { set_error("eps[%d] is null", l); return TMG_ERR_NULL; }
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const int ldstride = p.nslots * p.ctas;
+  TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
+  TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
+
+  // top latent: z = cmean + exp(clamp(clog_std)) * eps[L]   (tmGlow.py:460-463); no log-prob term
+  {
+    const LevelW& lv = m->levels[L - 1];
+    GaussArgs ga{};
+    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz;
+    ga.val = ws + p.y[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
+    ga.eps_in = eps[L]; ga.reverse = 1;
+    ga.B = B; ga.HW = p.Hl[L - 1] * p.Wl[L - 1]; ga.n = m->Cz;
+    ga.ld_part = nullptr; ga.ld_stride = ldstride;
+    TMG_TRY(launch_gaussian(ga, c.st));
+  }
+  int slot = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const LevelW& lv = m->levels[l];
+    const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl;
+    float* Y = ws + p.y[l];
+    // Split.reverse (flowUtils.py:316-335)
+    TMG_TRY(run_split_prior(c, l, B, Hl, Wl, Y));
+    GaussArgs ga{};
+    ga.prm = ws + p.hr; ga.prm_cstride = lv.C;
+    ga.val = Y; ga.val_cstride = lv.C; ga.val_coff = lv.C / 2;
+    ga.eps_in = eps[l]; ga.reverse = 1; ga.B = B; ga.HW = HW; ga.n = lv.C / 2;
+    ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
+    TMG_TRY(launch_gaussian(ga, c.st));
+    // steps n..1 reversed (flowLSTMBlock.py:348-359)
+    for (int s = (int)lv.steps.size() - 1; s >= 0; --s) {
+      const StepW& st = lv.steps[s];
+      TMG_TRY(run_coupling_nn(c, l, st, B, Hl, Wl, Y, ws + p.cond[l], h_in ? h_in[l] : nullptr,
+                              c_in ? c_in[l] : nullptr, h_out[l], c_out[l]));
+      TMG_TRY(run_pointwise(c, l, Y, true, &st, true, B, HW, ws + p.ldp + (size_t)(slot++) * p.ctas));
+    }
+    // CheckerSqueeze.reverse (flowUtils.py:124-145)
+    PermArgs pa{};
+    pa.src = Y; pa.src_cstride = lv.C; pa.src_coff = 0;
+    pa.B = B; pa.C = lv.C / 4; pa.H = 2 * Hl; pa.W = 2 * Wl;
+    if (l > 0) {
+      pa.mode = PERM_UNSQUEEZE_NHWC_TO_NHWC;
+      pa.dst = ws + p.y[l - 1]; pa.dst_cstride = m->levels[l - 1].C; pa.dst_coff = 0;
+    } else {
+      pa.mode = PERM_UNSQUEEZE_NHWC_TO_NCHW;
+      pa.dst = y;
+    }
+    TMG_TRY(launch_permute(pa, c.st));
+  }
+  return finish_logdet(c, log_det);
+}
+
+int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* y, const float* const* h_in,
+                const float* const* c_in, float* z, float* logp, float* const* h_out, float* const* c_out,
+                float* const* eps_out, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  Plan p;
+  TMG_TRY(make_plan(*m, B, h, w, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !y || !z || !logp || !h_out || !c_out) { set_error("null argument"); return TMG_ERR_NULL; }
+  const int L = p.L;
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const int ldstride = p.nslots * p.ctas;
+  TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
+  TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
+  int slot = 0;
+  for (int l = 0; l < L; ++l) {
+    const LevelW& lv = m->levels[l];
+    const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl;
+    float* Y = ws + p.y[l];
+    // CheckerSqueeze.forward (flowUtils.py:99-121)
+    PermArgs pa{};
+    pa.dst = Y; pa.dst_cstride = lv.C; pa.dst_coff = 0;
+    pa.B = B; pa.C = lv.C / 4; pa.H = 2 * Hl; pa.W = 2 * Wl;
+    if (l == 0) { pa.mode = PERM_SQUEEZE_NCHW_TO_NHWC; pa.src = y; }
+    else { pa.mode = PERM_SQUEEZE_NHWC_TO_NHWC; pa.src = ws + p.y[l - 1]; pa.src_cstride = m->levels[l - 1].C; pa.src_coff = 0; }
+    TMG_TRY(launch_permute(pa, c.st));
+    // steps 1..n: [ActNorm ->] W^-1 -> coupling; the coupling of step s is fused with the
+    // ActNorm/W^-1 of step s+1 (flowLSTMBlock.py:296-308)
+    const int n = (int)lv.steps.size();
+    TMG_TRY(run_pointwise(c, l, Y, false, &lv.steps[0], false, B, HW, nullptr));
+    for (int s = 0; s < n; ++s) {
+      const StepW& st = lv.steps[s];
+      TMG_TRY(run_coupling_nn(c, l, st, B, Hl, Wl, Y, ws + p.cond[l], h_in ? h_in[l] : nullptr,
+                              c_in ? c_in[l] : nullptr, h_out[l], c_out[l]));
+      TMG_TRY(run_pointwise(c, l, Y, true, s + 1 < n ? &lv.steps[s + 1] : nullptr, false, B, HW,
+                            ws + p.ldp + (size_t)(slot++) * p.ctas));
+    }
+    // Split.forward (flowUtils.py:292-314)
+    TMG_TRY(run_split_prior(c, l, B, Hl, Wl, Y));
+    GaussArgs ga{};
+    ga.prm = ws + p.hr; ga.prm_cstride = lv.C;
+    ga.val = Y; ga.val_cstride = lv.C; ga.val_coff = lv.C / 2;
+    ga.eps_out = eps_out ? eps_out[l] : nullptr; ga.reverse = 0; ga.B = B; ga.HW = HW; ga.n = lv.C / 2;
+    ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
+    TMG_TRY(launch_gaussian(ga, c.st));
+  }
+  // top prior log p(z | cmean, clog_std) and eps0 (tmGlow.py:399-412)
+  {
+    const LevelW& lv = m->levels[L - 1];
+    GaussArgs ga{};
+    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz;
+    ga.val = ws + p.y[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
+    ga.eps_out = eps_out ? eps_out[L] : nullptr; ga.val_nchw = z; ga.reverse = 0;
+    ga.B = B; ga.HW = p.Hl[L - 1] * p.Wl[L - 1]; ga.n = m->Cz;
+    ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
+    TMG_TRY(launch_gaussian(ga, c.st));
+  }
+  return finish_logdet(c, logp);
+}
+
+// ------------------------------------------------------------------ single operators
+int tmg_squeeze_forward(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+  if (!x || !y) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (H % 2 || W % 2) { set_error("squeeze: %dx%d not divisible by 2", H, W); return TMG_ERR_BAD_SHAPE; }   // flowUtils.py:112
+  PermArgs pa{};
+  pa.src = x; pa.dst = y; pa.mode = PERM_SQUEEZE_NCHW_TO_NCHW; pa.B = B; pa.C = C; pa.H = H; pa.W = W;
+  return launch_permute(pa, (cudaStream_t)stream);
+}
+
+int tmg_squeeze_reverse(const float* y, float* x, int B, int C4, int H2, int W2, void* stream) {
+  if (!x || !y) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (C4 < 4 || C4 % 4) { set_error("unsqueeze: %d channels not divisible by 4", C4); return TMG_ERR_BAD_SHAPE; }   // flowUtils.py:136
+  PermArgs pa{};
+  pa.src = y; pa.dst = x; pa.mode = PERM_UNSQUEEZE_NCHW_TO_NCHW; pa.B = B; pa.C = C4 / 4; pa.H = 2 * H2; pa.W = 2 * W2;
+  return launch_permute(pa, (cudaStream_t)stream);
+}
+
+int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
+  if (!src || !dst) { set_error("null argument"); return TMG_ERR_NULL; }
+  PermArgs pa{};
+  pa.src = src; pa.dst = dst; pa.mode = PERM_NCHW_TO_NHWC; pa.B = B; pa.C = C; pa.H = H; pa.W = W; pa.dst_cstride = C;
+  return launch_permute(pa, (cudaStream_t)stream);
+}
+
+int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
+  if (!src || !dst) { set_error("null argument"); return TMG_ERR_NULL; }
+  PermArgs pa{};
+  pa.src = src; pa.dst = dst; pa.mode = PERM_NHWC_TO_NCHW; pa.B = B; pa.C = C; pa.H = H; pa.W = W; pa.src_cstride = C;
+  return launch_permute(pa, (cudaStream_t)stream);
+}
+
+// Plan for the single-operator entry points: the workspace is sized by tmg_workspace_bytes of
+// an LF input whose level-`level` flow map is Hl x Wl.
+static int op_plan(tmg_model* m, int level, int B, int Hl, int Wl, Plan& p) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (level < 0 || level >= m->cfg.n_levels) { set_error("bad level %d", level); return TMG_ERR_BAD_SHAPE; }
+  int H = Hl << (level + 1), W = Wl << (level + 1);
+  int up = m->cfg.cglow_upscale;
+  if (H % up || W % up) { set_error("flow map %dx%d incompatible with upscale %d", Hl, Wl, up); return TMG_ERR_BAD_SHAPE; }
+  return make_plan(*m, B, H / up, W / up, p);
+}
+
+int tmg_flow_step(tmg_model* m, int level, int step, int reverse, int B, int Hl, int Wl, const float* x,
+                  const float* cond, const float* h_in, const float* c_in, float* out, float* logdet,
+                  float* h_out, float* c_out, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan p;
+  TMG_TRY(op_plan(m, level, B, Hl, Wl, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !cond || !out || !logdet) { set_error("null argument"); return TMG_ERR_NULL; }
+  const LevelW& lv = m->levels[level];
+  if (step < 1 || step > (int)lv.steps.size()) { set_error("bad step %d", step); return TMG_ERR_BAD_SHAPE; }
+  const StepW& st = lv.steps[step - 1];
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const int HW = Hl * Wl, C = lv.C, cf = m->cfg.cond_features;
+  float* Y = ws + p.scratch_in;
+  float* CN = ws + p.scratch_cond;
+  const int ldstride = p.nslots * p.ctas;
+  TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
+  PermArgs pa{};
+  pa.src = x; pa.dst = Y; pa.mode = PERM_NCHW_TO_NHWC; pa.B = B; pa.C = C; pa.H = Hl; pa.W = Wl; pa.dst_cstride = C;
+  TMG_TRY(launch_permute(pa, c.st));
+  pa.src = cond; pa.dst = CN; pa.C = cf; pa.dst_cstride = cf;
+  TMG_TRY(launch_permute(pa, c.st));
+  if (!reverse) TMG_TRY(run_pointwise(c, level, Y, false, &st, false, B, HW, nullptr));
+  TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, h_in, c_in, h_out, c_out));
+  TMG_TRY(run_pointwise(c, level, Y, true, reverse ? &st : nullptr, reverse != 0, B, HW, ws + p.ldp));
+  PermArgs pb{};
+  pb.src = Y; pb.dst = out; pb.mode = PERM_NHWC_TO_NCHW; pb.B = B; pb.C = C; pb.H = Hl; pb.W = Wl; pb.src_cstride = C;
+  TMG_TRY(launch_permute(pb, c.st));
+  // log-det of this single step: partial sums + (sum log|w| - sum log_s) * HW
+  LogdetArgs a{};
+  a.ld_part = ws + p.ldp; a.ld_stride = ldstride;
+  a.step_const = c.Q() + m->step_const_off;
+  a.n_levels = 1; a.step_begin[0] = st.const_idx; a.step_begin[1] = st.const_idx + 1; a.hw[0] = HW;
+  a.out = logdet; a.B = B;
+  return launch_logdet_reduce(a, c.st);
+}
+
+static int split_common(tmg_model* m, int level, int B, int Hl, int Wl, const float* zin, int cin_ch,
+                        const float* eps_in, float* eps_out, float* z1_out, float* z_out, float* logp,
+                        void* workspace, size_t workspace_bytes, void* stream, bool reverse) {
+  Plan p;
+  TMG_TRY(op_plan(m, level, B, Hl, Wl, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  const LevelW& lv = m->levels[level];
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const int HW = Hl * Wl, C = lv.C;
+  float* Y = ws + p.scratch_in;
+  const int ldstride = p.nslots * p.ctas;
+  TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
+  PermArgs pa{};
+  pa.src = zin; pa.dst = Y; pa.mode = PERM_NCHW_TO_NHWC; pa.B = B; pa.C = cin_ch; pa.H = Hl; pa.W = Wl; pa.dst_cstride = C;
+  TMG_TRY(launch_permute(pa, c.st));
+  TMG_TRY(run_split_prior(c, level, B, Hl, Wl, Y));
+  GaussArgs ga{};
+  ga.prm = ws + p.hr; ga.prm_cstride = C;
+  ga.val = Y; ga.val_cstride = C; ga.val_coff = C / 2;
+  ga.eps_in = eps_in; ga.eps_out = eps_out; ga.reverse = reverse ? 1 : 0;
+  ga.B = B; ga.HW = HW; ga.n = C / 2; ga.ld_part = ws + p.ldp; ga.ld_stride = ldstride;
+  TMG_TRY(launch_gaussian(ga, c.st));
+  PermArgs pb{};
+  pb.src = Y; pb.mode = PERM_NHWC_TO_NCHW; pb.B = B; pb.H = Hl; pb.W = Wl; pb.src_cstride = C;
+  if (reverse) { pb.dst = z_out; pb.C = C; } else { pb.dst = z1_out; pb.C = C / 2; }
+  TMG_TRY(launch_permute(pb, c.st));
+  LogdetArgs a{};
+  a.ld_part = ws + p.ldp; a.ld_stride = ldstride; a.step_const = c.Q() + m->step_const_off;
+  a.n_levels = 0; a.out = logp; a.B = B;
+  return launch_logdet_reduce(a, c.st);
+}
+
+int tmg_split_forward(tmg_model* m, int level, int B, int Hl, int Wl, const float* z, float* z1, float* logp,
+                      float* eps, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !z || !z1 || !logp) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (level < 0 || level >= m->cfg.n_levels) { set_error("bad level"); return TMG_ERR_BAD_SHAPE; }
+  return split_common(m, level, B, Hl, Wl, z, m->levels[level].C, nullptr, eps, z1, nullptr, logp,
+                      workspace, workspace_bytes, stream, false);
+}
+
+int tmg_split_reverse(tmg_model* m, int level, int B, int Hl, int Wl, const float* z1, const float* eps, float* z,
+                      float* logp, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !z1 || !eps || !z || !logp) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (level < 0 || level >= m->cfg.n_levels) { set_error("bad level"); return TMG_ERR_BAD_SHAPE; }
+  return split_common(m, level, B, Hl, Wl, z1, m->levels[level].C / 2, eps, nullptr, nullptr, z, logp,
+                      workspace, workspace_bytes, stream, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Derives the kernel-side weights from the flat reference-layout parameter buffer in ONE launch:
+// one CTA per job.  Reference semantics restated:
+//   InvertibleConv1x1LU.weight / inv_weight   nn/modules/glowConv.py:151-174
+//   log-det constants                         glowConv.py:186 (forward), :206-215 (reverse), actNorm.py:66,82
+//   Conv2dZeros gain exp(clamp(scale,-4,ln4)) nn/modules/flowUtils.py:247
+//   eval-mode BatchNorm2d folded to an affine nn/modules/denseBlock.py:49
+#include "common.cuh"
+
+namespace tmg {
+
+__global__ void __launch_bounds__(256)
+pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict__ Q, int cmax) {
+  extern __shared__ __align__(16) float sm[];
+  const PackJob j = jobs[blockIdx.x];
+  const int tid = threadIdx.x;
+  if (j.type == JOB_CONVW) {
+    // OIHW [O][I][3][3]  ->  tap-major [9][I][opad]  (zero-filled padding columns)
+    const int O = j.a, I = j.b, OP = j.opad;
+    const float* s = P + j.src[0];
+    float* d = Q + j.dst[0];
+    for (int i = tid; i < 9 * I * OP; i += blockDim.x) {
+      int o = i % OP; int r = i / OP; int c = r % I; int tap = r / I;
+      d[i] = o < O ? s[((size_t)o * I + c) * 9 + tap] : 0.f;
+    }
+  } else if (j.type == JOB_GAIN) {
+    if (tid == 0) Q[j.dst[0]] = expf(fminf(fmaxf(P[j.src[0]], -4.f), kLog4));
+  } else if (j.type == JOB_BN) {
+    const float* w = P + j.src[0]; const float* b = P + j.src[1];
+    const float* rm = P + j.src[2]; const float* rv = P + j.src[3];
+    for (int c = tid; c < j.a; c += blockDim.x) {
+      float sc = w[c] * rsqrtf(rv[c] + 1e-5f);
+      Q[j.dst[0] + c] = sc;
+      Q[j.dst[1] + c] = b[c] - rm[c] * sc;
+    }
+  } else if (j.type == JOB_1X1) {
+    const int C = j.a;
+    float* L = sm;                 // L  = l*l_mask + I          (unit lower)
+    float* U = L + cmax * cmax;    // U  = u*u_mask + diag(sign*exp(log_s)) + 0.01 I
+    float* Li = U + cmax * cmax;   // L^-1
+    float* Ui = Li + cmax * cmax;  // U^-1
+    const float* pl = P + j.src[0]; const float* pu = P + j.src[1]; const float* pls = P + j.src[2];
+    const float* pp = P + j.src[3]; const float* psg = P + j.src[4]; const float* plm = P + j.src[5];
+    const float* pum = P + j.src[6]; const float* pe = P + j.src[7];
+    for (int i = tid; i < C * C; i += blockDim.x) {
+      int r = i / C, c = i % C;
+      L[i] = pl[i] * plm[i] + pe[i];
+      float dg = (r == c) ? expf(pls[r]) * psg[r] : 0.f;
+      U[i] = pu[i] * pum[i] + dg + 0.01f * pe[i];
+    }
+    __syncthreads();
+    // triangular inverses, one column per thread, accumulated in double
+    if (tid < C) {
+      const int c = tid;
+      for (int r = 0; r < C; ++r) {          // L * X = I   (forward substitution)
+        double s = (r == c) ? 1.0 : 0.0;
+        for (int k = 0; k < r; ++k) s -= (double)L[r * C + k] * (double)Li[k * C + c];
+        Li[r * C + c] = (float)(s / (double)L[r * C + r]);
+      }
+      for (int r = C - 1; r >= 0; --r) {     // U * X = I   (back substitution)
+        double s = (r == c) ? 1.0 : 0.0;
+        for (int k = r + 1; k < C; ++k) s -= (double)U[r * C + k] * (double)Ui[k * C + c];
+        Ui[r * C + c] = (float)(s / (double)U[r * C + r]);
+      }
+    }
+    __syncthreads();
+    float* W = Q + j.dst[0];
+    float* Wi = Q + j.dst[1];
+    // W = P (L U);   W^-1 = U^-1 L^-1 P^-1   (P is a permutation: P^-1 = P^T)
+    for (int i = tid; i < C * C; i += blockDim.x) {
+      int r = i / C, c = i % C;
+      // row r of P picks row `pr` of (L U)
+      double acc = 0.0;
+      for (int q = 0; q < C; ++q) {
+        float pv = pp[r * C + q];
+        if (pv != 0.f) {
+          double lu = 0.0;
+          for (int k = 0; k < C; ++k) lu += (double)L[q * C + k] * (double)U[k * C + c];
+          acc += (double)pv * lu;
+        }
+      }
+      W[i] = (float)acc;
+      double acc2 = 0.0;                      // (Ui Li)[r][q] * P^T[q][c] = (Ui Li)[r][q] * P[c][q]
+      for (int q = 0; q < C; ++q) {
+        float pv = pp[c * C + q];
+        if (pv != 0.f) {
+          double ul = 0.0;
+          for (int k = 0; k < C; ++k) ul += (double)Ui[r * C + k] * (double)Li[k * C + q];
+          acc2 += (double)pv * ul;
+        }
+      }
+      Wi[i] = (float)acc2;
+    }
+    if (tid == 0) {    // step constant: sum log|w_actnorm| - sum log_s   (multiplied by H*W at run time)
+      double s = 0.0;
+      for (int c = 0; c < C; ++c) s -= (double)pls[c];
+      if (j.src[8] >= 0) {
+        const float* nw = P + j.src[8];
+        for (int c = 0; c < C; ++c) s += log(fabs((double)nw[c]));
+      }
+      Q[j.dst[2]] = (float)s;
+    }
+  }
+}
+
+int launch_pack(const PackJob* jobs_dev, int njobs, const float* params, float* packed, int cmax,
+                cudaStream_t st) {
+  size_t smem = (size_t)4 * cmax * cmax * sizeof(float);
+  TMG_CUDA_OK(cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pack_kernel<<<njobs, 256, smem, st>>>(jobs_dev, params, packed, cmax);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+}  // namespace tmg

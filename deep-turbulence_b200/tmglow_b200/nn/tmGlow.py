@@ -1,0 +1,429 @@
+"""Drop-in ``TMGlow`` for the B200 hot path.
+
+Mirrors the public surface of the reference model (``tmglow/nn/tmGlow.py:305-509``): same
+constructor signature, ``forward`` / ``sample`` / ``reconstruct`` / ``initLSTMStates`` /
+``_num_parameters``, same attributes (``glow_blocks``, ``rec_features``, ``encoder``, ``glow``,
+``in_mu`` ...), and a ``state_dict()`` with exactly the reference's keys and shapes, so reference
+checkpoints load unchanged.  The compute is NOT PyTorch: every call goes through the C ABI of
+``libtmglow_b200.so`` (hand-written sm_100a CUDA); the sub-modules only hold parameters.  There
+is no CPU fallback -- tensors must live on a CUDA device.
+
+Inference/likelihood only in this round: outputs carry no autograd graph.
+"""
+import math
+import re
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import scipy.linalg
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+_BUFFER_SUFFIXES = ("running_mean", "running_var", "conv.p", "conv.sign_s", "conv.l_mask", "conv.u_mask",
+                    "conv.eye", "conv.log_s_old")
+_TOP_BUFFERS = ("in_mu", "in_std", "out_mu", "out_std")
+_LU_LEAF = re.compile(r"revlayers\.affine_layer\d+\.conv\.(l|u|log_s|p|sign_s|l_mask|u_mask|eye|log_s_old)$")
+
+
+def _empty_channels_last(d, device):
+    """[B,C,H,W]-shaped fp32 tensor whose memory is [B,H,W,C] (what the library reads/writes)."""
+    return torch.empty_strided(d, (d[1] * d[2] * d[3], 1, d[3] * d[1], d[1]), dtype=torch.float32, device=device)
+
+
+class _Params(nn.Module):
+    """Parameter container; its children/leaves carry the reference's names."""
+
+    def forward(self, *a, **k):   # pragma: no cover
+        raise RuntimeError("parameter container of the B200 TMGlow: call the TMGlow methods instead")
+
+
+class _EncoderHandle(_Params):
+    """``model.encoder``: holds the encoder weights; ``forward(x)`` runs the CUDA encoder
+    (reference ``Encoder.forward``, nn/tmGlow.py:104-129) and returns ``(z_out, c_out)``."""
+
+    def forward(self, x):
+        return self._owner[0].encode(x)
+
+
+def _lu_init(C, rng=np.random):
+    """Random rotation + LU factors, as the reference initialises ``InvertibleConv1x1LU``
+    (glowConv.py:123-147): numpy QR of a Gaussian matrix, scipy LU, sign/log of diag(U)."""
+    q = np.linalg.qr(rng.randn(C, C))[0].astype(np.float32)
+    p, l, u = scipy.linalg.lu(q)
+    s = np.diag(u)
+    return {
+        "l": l.astype(np.float32), "u": np.triu(u, k=1).astype(np.float32),
+        "log_s": np.log(np.abs(s)).astype(np.float32), "p": p.astype(np.float32),
+        "sign_s": np.sign(s).astype(np.float32),
+        "l_mask": np.tril(np.ones((C, C), np.float32), -1), "u_mask": np.triu(np.ones((C, C), np.float32), 1),
+        "eye": np.eye(C, dtype=np.float32), "log_s_old": (np.log(np.abs(s)) + 1.0).astype(np.float32),
+    }
+
+
+class TMGlow(nn.Module):
+    """Transient multi-fidelity Glow (drop-in for ``nn.tmGlow.TMGlow``, nn/tmGlow.py:305-509)."""
+
+    def __init__(self, in_features, out_features, enc_blocks, glow_blocks,
+                 cond_features=8, cglow_upscale=1, growth_rate=4, init_features=48, rec_features=8, bn_size=8,
+                 drop_rate=0, bottleneck=False):
+        super().__init__()
+        assert len(enc_blocks) == len(glow_blocks), 'List of conditions need to be same length as flow blocks.'
+        if bottleneck or drop_rate:
+            raise NotImplementedError("bottleneck/drop_rate are dead options in the reference (main.py:72)")
+        self.glow_blocks = list(glow_blocks)
+        self.rec_features = rec_features
+        self._cfg_dict = dict(in_features=in_features, out_features=out_features, enc_blocks=list(enc_blocks),
+                              glow_blocks=list(glow_blocks), cond_features=cond_features,
+                              cglow_upscale=cglow_upscale, growth_rate=growth_rate, init_features=init_features,
+                              rec_features=rec_features)
+        lib = _lib.load()
+        cfg = _lib.TmgConfig()
+        cfg.in_features, cfg.out_features, cfg.n_levels = in_features, out_features, len(glow_blocks)
+        for i, (e, g) in enumerate(zip(enc_blocks, glow_blocks)):
+            cfg.enc_blocks[i], cfg.glow_blocks[i] = e, g
+        cfg.cond_features, cfg.cglow_upscale, cfg.growth_rate = cond_features, cglow_upscale, growth_rate
+        cfg.init_features, cfg.rec_features = init_features, rec_features
+        self._cfg = cfg
+        self._handles = {}            # device index -> tmg_model*
+        h = self._handle("host")
+        # ---- parameter tree with the reference's names, in the library's table order
+        self._table = []              # (name, offset, numel, shape)
+        dims = (_lib.C.c_int64 * 4)()
+        for i in range(lib.tmg_model_param_entries(h)):
+            nd = lib.tmg_model_param_shape(h, i, dims)
+            self._table.append((lib.tmg_model_param_name(h, i).decode(), lib.tmg_model_param_offset(h, i),
+                                lib.tmg_model_param_numel(h, i), tuple(int(dims[k]) for k in range(nd))))
+        self._n_flat = lib.tmg_model_param_total(h)
+        self.encoder = _EncoderHandle()
+        self.glow = _Params()
+        object.__setattr__(self.encoder, "_owner", (self,))   # tuple: keep it out of the module tree
+        self._build_tree()
+        self._fix_conv_bias()
+        self._flat = None
+        self._ws = {}
+        self.assume_static_weights = False
+        self._refreshed_for = None
+        print('Total number of parameters: {}'.format(self._num_parameters()))
+
+    # ------------------------------------------------------------------ construction helpers
+    def _handle(self, key):
+        if key not in self._handles:
+            out = _lib.C.c_void_p()
+            _lib.check(_lib.load().tmg_model_create(_lib.C.byref(self._cfg), _lib.C.byref(out)))
+            self._handles[key] = out
+        return self._handles[key]
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for h in self._handles.values():
+                lib.tmg_model_destroy(h)
+        except Exception:
+            pass
+
+    def _build_tree(self):
+        lu_cache = {}
+        self._leaves = []             # (module, attr, is_param) in table order
+        for name, off, numel, shape in self._table:
+            parts = name.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, _Params())
+                mod = mod._modules[p]
+            leaf = parts[-1]
+            t, is_buf = self._init_leaf(name, shape, lu_cache)
+            if is_buf:
+                mod.register_buffer(leaf, t)
+            else:
+                mod.register_parameter(leaf, nn.Parameter(t))
+            self._leaves.append((mod, leaf, not is_buf))
+            if leaf == "running_var":     # BatchNorm2d's integer counter follows running_var
+                mod.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    @staticmethod
+    def _init_leaf(name, shape, lu_cache):
+        """Same initial distributions as the reference modules (it relies on PyTorch defaults)."""
+        leaf = name.rsplit(".", 1)[-1]
+        if name in _TOP_BUFFERS:
+            return torch.zeros(shape), True                                   # tmGlow.py:371-374
+        if _LU_LEAF.search(name):
+            key = name.rsplit(".", 1)[0]
+            if key not in lu_cache:
+                lu_cache[key] = _lu_init(shape[0])
+            return torch.from_numpy(lu_cache[key][leaf].copy()), leaf not in ("l", "u", "log_s")
+        if leaf == "running_mean":
+            return torch.zeros(shape), True
+        if leaf == "running_var":
+            return torch.ones(shape), True
+        if "norm1." in name or name.endswith(("norm.weight", "norm.bias", "norm2.weight", "norm2.bias")):
+            return (torch.ones(shape) if leaf == "weight" else torch.zeros(shape)), False   # actNorm.py:31-32
+        if "zero_conv" in name or "latent_encoder.conv2d" in name:
+            return torch.zeros(shape), False                                  # flowUtils.py:231-233
+        if leaf == "weight":                                                  # nn.Conv2d default init
+            w = torch.empty(shape)
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+            return w, False
+        if leaf == "bias":                                                    # nn.Conv2d default bias init
+            # fan_in of the sibling weight: O = shape[0]; the conv's input channels are not known
+            # from the bias alone, so the bound is filled in by _fix_conv_bias below.
+            return torch.zeros(shape), False
+        raise RuntimeError("unhandled parameter " + name)
+
+    def _fix_conv_bias(self):
+        for mod in self.modules():
+            w = mod._parameters.get("weight") if hasattr(mod, "_parameters") else None
+            b = mod._parameters.get("bias") if hasattr(mod, "_parameters") else None
+            if w is not None and b is not None and w.dim() == 4 and w.abs().sum() > 0:
+                bound = 1.0 / math.sqrt(w.shape[1] * 9)
+                with torch.no_grad():
+                    b.uniform_(-bound, bound)
+
+    # ------------------------------------------------------------------ flat parameter buffer
+    def _leaf_tensor(self, i):
+        mod, attr, is_param = self._leaves[i]
+        return mod._parameters[attr] if is_param else mod._buffers[attr]
+
+    def _sync_flat(self, device):
+        """All floating-point state lives in ONE flat buffer (the layout libtmglow_b200 reads);
+        the module's parameters/buffers are views into it.  Rebuilt whenever ``.to()``/
+        ``load_state_dict(assign=True)`` replaced the storage."""
+        ok = self._flat is not None and self._flat.device == device
+        if ok:
+            base = self._flat.data_ptr()
+            for i, (name, off, numel, shape) in enumerate(self._table):
+                t = self._leaf_tensor(i)
+                if t.data_ptr() != base + 4 * off or t.dtype != torch.float32:
+                    ok = False
+                    break
+        if ok:
+            return False
+        flat = torch.empty(self._n_flat, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for i, (name, off, numel, shape) in enumerate(self._table):
+                t = self._leaf_tensor(i)
+                view = flat[off:off + numel].view(t.shape)
+                view.copy_(t.detach().to(device=device, dtype=torch.float32))
+                t.data = view
+        self._flat = flat
+        self._refreshed_for = None
+        return True
+
+    def _prepare(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("tmglow_b200.TMGlow runs only on CUDA devices (no CPU fallback); got %s" % device)
+        lib = _lib.load()
+        changed = self._sync_flat(device)
+        h = self._handle(device.index if device.index is not None else torch.cuda.current_device())
+        if changed or not self.assume_static_weights or self._refreshed_for != (h.value, self._flat.data_ptr()):
+            st = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.tmg_model_refresh(h, self._flat.data_ptr(), st))
+            self._refreshed_for = (h.value, self._flat.data_ptr())
+        return lib, h
+
+    def _workspace(self, lib, h, B, hh, ww, device):
+        key = (device, B, hh, ww)
+        ws = self._ws.get(key)
+        if ws is None:
+            n = lib.tmg_workspace_bytes(h, B, hh, ww)
+            if n == 0:
+                raise AssertionError(lib.tmg_last_error().decode("utf-8", "replace"))
+            self._ws.clear()          # keep one workspace alive
+            ws = torch.empty(n, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ shapes
+    def _hf_size(self, x):
+        up = self._cfg.cglow_upscale
+        return x.shape[2] * up, x.shape[3] * up
+
+    def latent_shapes(self, B, H, W):
+        """Shapes of eps[0..L-1] (split noise) and eps[L] (top noise)."""
+        shapes, c = [], self._cfg.out_features
+        for _ in self.glow_blocks:
+            c, H, W = c * 4, H // 2, W // 2
+            shapes.append((B, c // 2, H, W))
+            c //= 2
+        shapes.append((B, c, H, W))
+        return shapes
+
+    def _state_dims(self, B, H, W):
+        return [(B, self.rec_features, H >> (l + 1), W >> (l + 1)) for l in range(len(self.glow_blocks))]
+
+    @staticmethod
+    def _f32c(t, device):
+        if t.device != device:
+            raise RuntimeError("tensor on %s but the model runs on %s" % (t.device, device))
+        return t.detach().to(torch.float32).contiguous()
+
+    def _states_in(self, lib, h_in, dims, device, st):
+        """LSTM states enter the library channels-last; NCHW tensors are converted by the
+        library's own permutation kernel."""
+        if h_in is None:
+            return None, None, []
+        assert len(h_in) == len(self.glow_blocks), 'List of recurrent states need to be same length as flow blocks.'
+        hs, cs, keep = [], [], []
+        for (hh, cc), d in zip(h_in, dims):
+            for t, out in ((hh, hs), (cc, cs)):
+                assert tuple(t.shape) == d, "LSTM state shape %s, expected %s" % (tuple(t.shape), d)
+                t = t.detach()
+                if t.dtype != torch.float32:
+                    t = t.float()
+                if t.device != device:
+                    raise RuntimeError("LSTM state on %s but the model runs on %s" % (t.device, device))
+                same_memory = d[1] == 1 or d[2] * d[3] == 1      # NCHW and NHWC coincide
+                if not (t.is_contiguous(memory_format=torch.channels_last) and not same_memory) and \
+                        not (same_memory and t.is_contiguous()):
+                    src = t.contiguous()
+                    t = _empty_channels_last(d, device)
+                    _lib.check(lib.tmg_nchw_to_nhwc(src.data_ptr(), t.data_ptr(), d[0], d[1], d[2], d[3], st))
+                    keep.append(src)
+                keep.append(t)
+                out.append(t.data_ptr())
+        return _lib.ptr_array(hs), _lib.ptr_array(cs), keep
+
+    @staticmethod
+    def _states_out(dims, device):
+        hs = [_empty_channels_last(d, device) for d in dims]
+        cs = [_empty_channels_last(d, device) for d in dims]
+        return hs, cs
+
+    def _flags(self):
+        return _lib.TMG_FLAG_BN_TRAIN if self.training else 0
+
+    def _bump_bn_counters(self):
+        if self.training:
+            for name, b in self.named_buffers():
+                if name.endswith("num_batches_tracked"):
+                    b += 1
+
+    # ------------------------------------------------------------------ public API (reference names)
+    def forward(self, x, y, h_in=None, return_eps=False):
+        """Encoder + flow y -> z with exact log-likelihood (reference nn/tmGlow.py:378-414).
+
+        :returns: ``z [B,Cz,H/2^L,W/2^L]``, ``log_prior + log_det [B]``, ``h_out`` (list of (h, c)),
+                  ``eps`` (list of L+1 noise tensors) or ``None``
+        """
+        device = x.device
+        lib, h = self._prepare(device)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            x = self._f32c(x, device)
+            y = self._f32c(y, device)
+            B, H, W = x.shape[0], *self._hf_size(x)
+            assert x.dim() == 4 and x.shape[1] == self._cfg.in_features, "x must be [B,%d,h,w]" % self._cfg.in_features
+            assert tuple(y.shape) == (B, self._cfg.out_features, H, W), \
+                "y must be [%d,%d,%d,%d], got %s" % (B, self._cfg.out_features, H, W, tuple(y.shape))
+            ws = self._workspace(lib, h, B, x.shape[2], x.shape[3], device)
+            dims = self._state_dims(B, H, W)
+            hp, cp, keep = self._states_in(lib, h_in, dims, device, st)
+            ho, co = self._states_out(dims, device)
+            shapes = self.latent_shapes(B, H, W)
+            z = torch.empty(shapes[-1], dtype=torch.float32, device=device)
+            logp = torch.empty(B, dtype=torch.float32, device=device)
+            eps = [torch.empty(s, dtype=torch.float32, device=device) for s in shapes] if return_eps else None
+            _lib.check(lib.tmg_forward(
+                h, B, x.shape[2], x.shape[3], x.data_ptr(), y.data_ptr(), hp, cp, z.data_ptr(), logp.data_ptr(),
+                _lib.ptr_array([t.data_ptr() for t in ho]), _lib.ptr_array([t.data_ptr() for t in co]),
+                _lib.ptr_array([t.data_ptr() for t in eps]) if return_eps else None,
+                ws.data_ptr(), ws.numel(), self._flags(), st))
+            self._bump_bn_counters()
+        return z, logp, list(zip(ho, co)), eps
+
+    def reconstruct(self, x, h_in, eps):
+        """Encoder + flow z -> y with explicit noise (reference nn/tmGlow.py:442-467): ``eps[-1]`` is the
+        top-latent noise, ``eps[:-1]`` the per-block split noise.
+
+        :returns: ``y [B,out_features,H,W]``, ``log_det [B]`` (no top-prior term, like the reference), ``h_out``
+        """
+        device = x.device
+        lib, h = self._prepare(device)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            x = self._f32c(x, device)
+            assert x.dim() == 4 and x.shape[1] == self._cfg.in_features, "x must be [B,%d,h,w]" % self._cfg.in_features
+            B, H, W = x.shape[0], *self._hf_size(x)
+            shapes = self.latent_shapes(B, H, W)
+            assert len(eps) == len(shapes), "eps must hold %d tensors" % len(shapes)
+            eps_c = []
+            for e, s in zip(eps, shapes):
+                assert tuple(e.shape) == s, "eps shape %s, expected %s" % (tuple(e.shape), s)
+                eps_c.append(self._f32c(e, device))
+            ws = self._workspace(lib, h, B, x.shape[2], x.shape[3], device)
+            dims = self._state_dims(B, H, W)
+            hp, cp, keep = self._states_in(lib, h_in, dims, device, st)
+            ho, co = self._states_out(dims, device)
+            y = torch.empty((B, self._cfg.out_features, H, W), dtype=torch.float32, device=device)
+            log_det = torch.empty(B, dtype=torch.float32, device=device)
+            _lib.check(lib.tmg_reconstruct(
+                h, B, x.shape[2], x.shape[3], x.data_ptr(), hp, cp,
+                _lib.ptr_array([t.data_ptr() for t in eps_c]), y.data_ptr(), log_det.data_ptr(),
+                _lib.ptr_array([t.data_ptr() for t in ho]), _lib.ptr_array([t.data_ptr() for t in co]),
+                ws.data_ptr(), ws.numel(), self._flags(), st))
+            self._bump_bn_counters()
+        return y, log_det, list(zip(ho, co))
+
+    def sample(self, x, h_in=None):
+        """Conditional generation (reference nn/tmGlow.py:417-440).  The Gaussian noise is drawn with
+        ``torch.randn`` in the order and shapes of the reference (top latent first, then the splits of
+        blocks L-1..0: tmGlow.py:435, flowUtils.py:206), so a seeded run consumes the RNG identically."""
+        B, (H, W) = x.shape[0], self._hf_size(x)
+        shapes = self.latent_shapes(B, H, W)
+        eps = [None] * len(shapes)
+        for i in [len(shapes) - 1] + list(range(len(shapes) - 2, -1, -1)):
+            eps[i] = torch.randn(shapes[i], dtype=torch.float32, device=x.device)
+        return self.reconstruct(x, h_in, eps)
+
+    def encode(self, x):
+        """``Encoder.forward`` (nn/tmGlow.py:104-129): returns ``(z_out, c_out)`` in NCHW."""
+        device = x.device
+        lib, h = self._prepare(device)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            x = self._f32c(x, device)
+            B, H, W = x.shape[0], *self._hf_size(x)
+            ws = self._workspace(lib, h, B, x.shape[2], x.shape[3], device)
+            L = len(self.glow_blocks)
+            c_out = [torch.empty((B, self._cfg.cond_features, H >> (l + 1), W >> (l + 1)), dtype=torch.float32,
+                                 device=device) for l in range(L)]
+            z_out = torch.empty((B, 2 * self.latent_shapes(B, H, W)[-1][1], H >> L, W >> L), dtype=torch.float32,
+                                device=device)
+            _lib.check(lib.tmg_encoder_forward(h, B, x.shape[2], x.shape[3], x.data_ptr(),
+                                               _lib.ptr_array([t.data_ptr() for t in c_out]), z_out.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), self._flags(), st))
+            self._bump_bn_counters()
+        return z_out, c_out
+
+    def _num_parameters(self):
+        """Number of trainable parameters (reference nn/tmGlow.py:469-479)."""
+        return sum(p.numel() for p in self.parameters())
+
+    def initLSTMStates(self, seeds, input_dim):
+        """Seeded initial LSTM states (reference nn/tmGlow.py:481-509): one CPU generator per sample,
+        hidden state ~ U(-1,1), cell state ~ N(0,1), moved to the model's device."""
+        device = next(self.parameters()).device
+        states = []
+        for i in range(len(self.glow_blocks)):
+            dims = [1, self.rec_features, input_dim[0] // (2 ** (i + 1)), input_dim[1] // (2 ** (i + 1))]
+            hs, cs = [], []
+            for j in range(seeds.size(0)):
+                gen = torch.Generator().manual_seed(int(seeds[j].item()))
+                hs.append(2 * torch.rand(dims, generator=gen) - 1)
+                cs.append(torch.randn(dims, generator=gen))
+            states.append((torch.cat(hs, dim=0).to(device), torch.cat(cs, dim=0).to(device)))
+        return states
+
+    # ------------------------------------------------------------------ helpers used by tests
+    def conv1x1_weight(self, level, step, inverse=False):
+        """W (or W^-1) of ``InvertibleConv1x1LU`` as derived on the device (glowConv.py:151-174)."""
+        device = next(self.parameters()).device
+        lib, h = self._prepare(device)
+        C = self._cfg.out_features * 4 * 2 ** level
+        out = torch.empty((C, C), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(lib.tmg_model_get_conv1x1(h, level, step, int(inverse), out.data_ptr(),
+                                                 torch.cuda.current_stream(device).cuda_stream))
+        return out

@@ -1,0 +1,112 @@
+"""Single operators of the flow stack through the C ABI (NCHW tensors like the reference).
+They mirror the reference sub-modules one to one and are what the parity tests call:
+
+    squeeze_forward / squeeze_reverse   CheckerSqueeze           nn/modules/flowUtils.py:99-145
+    flow_step                           *CouplingBlock.forward/.reverse   nn/modules/flowLSTMBlock.py:53-218
+    split_forward / split_reverse       Split                    nn/modules/flowUtils.py:292-335
+"""
+import torch
+
+from . import _lib
+from .nn.tmGlow import _empty_channels_last
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(t):
+    if t.device.type != "cuda":
+        raise RuntimeError("tmglow_b200 operators run only on CUDA devices (no CPU fallback)")
+
+
+def squeeze_forward(x):
+    _need_cuda(x)
+    x = x.detach().float().contiguous()
+    B, C, H, W = x.shape
+    assert H % 2 == 0 and W % 2 == 0
+    y = torch.empty((B, 4 * C, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().tmg_squeeze_forward(x.data_ptr(), y.data_ptr(), B, C, H, W, _stream(x.device)))
+    return y
+
+
+def squeeze_reverse(y):
+    _need_cuda(y)
+    y = y.detach().float().contiguous()
+    B, C, H, W = y.shape
+    assert C >= 4 and C % 4 == 0
+    x = torch.empty((B, C // 4, 2 * H, 2 * W), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().tmg_squeeze_reverse(y.data_ptr(), x.data_ptr(), B, C, H, W, _stream(y.device)))
+    return x
+
+
+def _op_workspace(model, lib, h, level, B, Hl, Wl, device):
+    up = model._cfg.cglow_upscale
+    H, W = Hl << (level + 1), Wl << (level + 1)
+    assert H % up == 0 and W % up == 0
+    return model._workspace(lib, h, B, H // up, W // up, device)
+
+
+def flow_step(model, level, step, x, cond, state=None, reverse=False):
+    """One flow step of block ``level`` (``step`` is 1-based like ``affine_layer{step}``).
+    Returns ``(out, logdet[B], state_out or None)``."""
+    _need_cuda(x)
+    device = x.device
+    lib, h = model._prepare(device)
+    x = x.detach().float().contiguous()
+    cond = cond.detach().float().contiguous()
+    B, C, Hl, Wl = x.shape
+    out = torch.empty_like(x)
+    logdet = torch.empty(B, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        st = _stream(device)
+        ws = _op_workspace(model, lib, h, level, B, Hl, Wl, device)
+        d = (B, model.rec_features, Hl, Wl)
+        is_lstm = step == model.glow_blocks[level]
+        hp = cp = None
+        keep = []
+        if state is not None:
+            ha, ca, keep = model._states_in(lib, [state], [d], device, st)
+            hp, cp = ha[0], ca[0]
+        ho = _empty_channels_last(d, device) if is_lstm else None
+        co = _empty_channels_last(d, device) if is_lstm else None
+        _lib.check(lib.tmg_flow_step(h, level, step, int(reverse), B, Hl, Wl, x.data_ptr(), cond.data_ptr(), hp, cp,
+                                     out.data_ptr(), logdet.data_ptr(),
+                                     ho.data_ptr() if is_lstm else None, co.data_ptr() if is_lstm else None,
+                                     ws.data_ptr(), ws.numel(), st))
+    return out, logdet, ((ho, co) if is_lstm else None)
+
+
+def split_forward(model, level, z, return_eps=True):
+    _need_cuda(z)
+    device = z.device
+    lib, h = model._prepare(device)
+    z = z.detach().float().contiguous()
+    B, C, Hl, Wl = z.shape
+    z1 = torch.empty((B, C // 2, Hl, Wl), dtype=torch.float32, device=device)
+    eps = torch.empty_like(z1) if return_eps else None
+    logp = torch.empty(B, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        ws = _op_workspace(model, lib, h, level, B, Hl, Wl, device)
+        _lib.check(lib.tmg_split_forward(h, level, B, Hl, Wl, z.data_ptr(), z1.data_ptr(), logp.data_ptr(),
+                                         eps.data_ptr() if return_eps else None, ws.data_ptr(), ws.numel(),
+                                         _stream(device)))
+    return z1, logp, eps
+
+
+def split_reverse(model, level, z1, eps):
+    _need_cuda(z1)
+    device = z1.device
+    lib, h = model._prepare(device)
+    z1 = z1.detach().float().contiguous()
+    eps = eps.detach().float().contiguous()
+    B, Ch, Hl, Wl = z1.shape
+    z = torch.empty((B, 2 * Ch, Hl, Wl), dtype=torch.float32, device=device)
+    logp = torch.empty(B, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        ws = _op_workspace(model, lib, h, level, B, Hl, Wl, device)
+        _lib.check(lib.tmg_split_reverse(h, level, B, Hl, Wl, z1.data_ptr(), eps.data_ptr(), z.data_ptr(),
+                                         logp.data_ptr(), ws.data_ptr(), ws.numel(), _stream(device)))
+    return z, logp

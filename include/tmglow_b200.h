@@ -1,0 +1,167 @@
+/*
+ * tmglow_b200.h -- C ABI of libtmglow_b200.so: the B200 (sm_100a) implementation of the
+ * TM-Glow conditional-flow hot path of zabaras/deep-turbulence.
+ *
+ * The reference has no FFI: its "operator API" for this path is the TMGlow nn.Module
+ * (tmglow/nn/tmGlow.py:305-509).  Each entry point below names the reference interface it
+ * replaces (file:line relative to /root/reference/tmglow).  The Python host side
+ * (deep-turbulence_b200/tmglow_b200) binds these with ctypes and keeps the reference's module
+ * API; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative tmg_status; tmg_last_error() gives text
+ *   - all pointers are DEVICE pointers to fp32 unless stated otherwise; the library never
+ *     allocates on the hot path: the caller passes a workspace of tmg_workspace_bytes()
+ *   - `stream` is a cudaStream_t passed as void* (no CUDA headers needed to bind); the call is
+ *     asynchronous and stream-ordered; buffers are borrowed until the work completes
+ *   - user-facing fields (x, y, z, eps) are NCHW like the reference; LSTM states are
+ *     channels-last ([B,H,W,rec], i.e. torch.channels_last memory of a [B,rec,H,W] tensor)
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with TMG_ERR_CUDA
+ */
+#ifndef TMGLOW_B200_H
+#define TMGLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMG_MAX_LEVELS 6
+
+typedef enum tmg_status {
+  TMG_OK = 0,
+  TMG_ERR_BAD_CONFIG = -1,   /* reference: constructor asserts */
+  TMG_ERR_BAD_SHAPE = -2,    /* reference: flowUtils.py:112,136 / tmGlow.py:249,286 asserts */
+  TMG_ERR_NULL = -3,
+  TMG_ERR_WORKSPACE = -4,    /* workspace too small */
+  TMG_ERR_CUDA = -5,         /* CUDA runtime error (text in tmg_last_error) */
+  TMG_ERR_UNSUPPORTED = -6,  /* shape/feature outside what the kernels implement */
+  TMG_ERR_NOT_READY = -7     /* tmg_model_refresh() has not been called */
+} tmg_status;
+
+/* Constructor arguments of TMGlow (nn/tmGlow.py:336-338) that shape the path. */
+typedef struct tmg_config {
+  int32_t in_features;
+  int32_t out_features;
+  int32_t n_levels;                     /* len(enc_blocks) == len(glow_blocks) */
+  int32_t enc_blocks[TMG_MAX_LEVELS];
+  int32_t glow_blocks[TMG_MAX_LEVELS];
+  int32_t cond_features;
+  int32_t cglow_upscale;
+  int32_t growth_rate;
+  int32_t init_features;
+  int32_t rec_features;
+} tmg_config;
+
+typedef struct tmg_model tmg_model;     /* opaque; owns packed weights on ONE device */
+
+/* flags for the whole-path calls */
+#define TMG_FLAG_BN_TRAIN   1u          /* encoder BatchNorm uses batch statistics and updates the
+                                           running stats in the parameter buffer (nn.Module.train()) */
+
+/* ---- library ------------------------------------------------------------------------- */
+int         tmg_version(void);
+const char* tmg_last_error(void);                 /* thread-local text of the last failure */
+int         tmg_device_count(void);               /* 0 when no CUDA device is visible */
+
+/* ---- model handle: replaces TMGlow.__init__ (nn/tmGlow.py:336-376) --------------------- */
+int  tmg_model_create(const tmg_config* cfg, tmg_model** out);   /* on the current CUDA device */
+void tmg_model_destroy(tmg_model* m);
+
+/* Parameter table: the flat fp32 parameter buffer holds every floating-point state_dict entry
+ * (parameters AND buffers, reference names) back to back in the order reported here. */
+int64_t     tmg_model_param_entries(const tmg_model* m);
+const char* tmg_model_param_name(const tmg_model* m, int64_t i);
+int64_t     tmg_model_param_offset(const tmg_model* m, int64_t i);   /* in floats */
+int64_t     tmg_model_param_numel(const tmg_model* m, int64_t i);
+int         tmg_model_param_shape(const tmg_model* m, int64_t i, int64_t dims[4]);   /* returns ndim */
+int64_t     tmg_model_param_total(const tmg_model* m);               /* floats in the flat buffer */
+
+/* Re-derive the kernel-side weights (tap-major conv weights, W and W^-1 of every
+ * InvertibleConv1x1LU -- glowConv.py:151-174 --, ActNorm/1x1 log-det sums, Conv2dZeros gains,
+ * folded eval-mode BatchNorm) from the flat parameter buffer.  Call after every parameter
+ * change.  `params` stays borrowed: BN-train calls write the running statistics back into it. */
+int tmg_model_refresh(tmg_model* m, float* params, void* stream);
+
+/* Copies of derived weights for tests (glowConv.py:151-174). dst: [C*C] device floats. */
+int tmg_model_get_conv1x1(const tmg_model* m, int level, int step /*1-based*/, int inverse,
+                          float* dst, void* stream);
+
+size_t tmg_workspace_bytes(const tmg_model* m, int B, int h, int w);   /* (h,w) = LF input size */
+
+/* ---- whole-path operators -------------------------------------------------------------- */
+/* TMGlow.reconstruct / TMGlow.sample (nn/tmGlow.py:417-467) + LSTMCFlowDecoder.reverse
+ * (:269-303).  eps[0..n_levels-1] = split noise [B,C_l/2,H_l,W_l] NCHW, eps[n_levels] = top
+ * noise [B,Cz,H_L,W_L] NCHW (TMGlow.sample = this call with eps drawn by the caller in the
+ * reference's RNG order).  h_in/c_in: n_levels pointers or NULL (zero states, convLSTM.py:66-68).
+ * Outputs: y [B,out_features,H,W] NCHW, log_det [B] (excludes the top prior, like the
+ * reference), h_out/c_out channels-last. */
+int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x,
+                    const float* const* h_in, const float* const* c_in,
+                    const float* const* eps,
+                    float* y, float* log_det, float* const* h_out, float* const* c_out,
+                    void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* TMGlow.forward (nn/tmGlow.py:378-414) + LSTMCFlowDecoder.forward (:231-267).
+ * Outputs: z [B,Cz,H_L,W_L] NCHW, logp [B] (= log prior + sum of log-dets), states, and when
+ * eps_out != NULL the n_levels+1 noise tensors (return_eps=True). */
+int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* y,
+                const float* const* h_in, const float* const* c_in,
+                float* z, float* logp, float* const* h_out, float* const* c_out,
+                float* const* eps_out,
+                void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* Encoder.forward (nn/tmGlow.py:104-129): c_out[l] [B,cond,H_l,W_l] and z_out [B,2*Cz,H_L,W_L],
+ * both written NCHW for inspection/tests. */
+int tmg_encoder_forward(tmg_model* m, int B, int h, int w, const float* x,
+                        float* const* c_out, float* z_out,
+                        void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* ---- single operators (parity tests, and building blocks for callers) ------------------ */
+/* CheckerSqueeze.forward / .reverse (flowUtils.py:99-145), NCHW in and out, bit-exact. */
+int tmg_squeeze_forward(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int tmg_squeeze_reverse(const float* y, float* x, int B, int C4, int H2, int W2, void* stream);
+
+/* One flow step of block `level` (1-based `step`), NCHW in/out:
+ * UnNormedAffineCouplingBlock / AffineCouplingBlock / LSTMCouplingBlock .forward/.reverse
+ * (flowLSTMBlock.py:53-86,116-146,180-218).  x,out: [B,C_l,Hl,Wl]; cond: [B,cond,Hl,Wl];
+ * logdet: [B]; states channels-last, used only by the LSTM step (may be NULL). */
+int tmg_flow_step(tmg_model* m, int level, int step, int reverse, int B, int Hl, int Wl,
+                  const float* x, const float* cond, const float* h_in, const float* c_in,
+                  float* out, float* logdet, float* h_out, float* c_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Split.forward / Split.reverse (flowUtils.py:292-335), NCHW.
+ * forward: z [B,C,Hl,Wl] -> z1 [B,C/2,..], logp [B], eps [B,C/2,..] (eps may be NULL)
+ * reverse: z1, eps -> z [B,C,..], logp [B] */
+int tmg_split_forward(tmg_model* m, int level, int B, int Hl, int Wl, const float* z,
+                      float* z1, float* logp, float* eps,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int tmg_split_reverse(tmg_model* m, int level, int B, int Hl, int Wl, const float* z1,
+                      const float* eps, float* z, float* logp,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* layout helpers for the LSTM states at the API boundary */
+int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
+int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
+
+/* Optional per-kernel-class timing with CUDA events (used by bench.py for the roofline figures;
+ * off by default).  tmg_profile_enable(1) starts recording on the calling thread;
+ * tmg_profile_query synchronises the recorded events and returns, for class `tag`
+ * (0..tmg_profile_classes()-1), the summed device time [ms], launch count, algorithmic FLOPs and
+ * algorithmic HBM bytes; tmg_profile_enable(0) stops and clears. */
+int         tmg_profile_enable(int on);
+int         tmg_profile_classes(void);
+const char* tmg_profile_class_name(int tag);
+int         tmg_profile_query(int tag, double* ms, int64_t* launches, double* flops, double* bytes);
+
+/* number of kernels this library launched on the calling thread since the last reset
+ * (bench.py's "gpu_launches") */
+int64_t tmg_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMGLOW_B200_H */

@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the
+real reference and against the pinned oracle on seeded inputs.  Run on the B200 box:
+    python -m pytest tests -m gpu -x -q
+Tolerances (fp32 path, stated per SURVEY.md appendix B; the reference's own fp32-vs-fp64 drift is
+6e-5 abs on latents and 2e-7 rel on logp):
+    fields / latents / states : 2e-4 abs (|values| <~ 7)
+    logp / log_det            : 1e-5 relative to |value| (+1e-3 abs)
+    squeeze / unsqueeze       : bit-exact
+"""
+import json
+
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 2e-4
+CASES = ["caseA_states", "caseA_nostate", "caseA_trainbn", "caseB_up4", "caseC_up1"]
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _model(cfg, sd, train=False):
+    from tmglow_b200 import TMGlow
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"],
+               growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    missing = m.load_state_dict(sd, strict=True)
+    m = m.to(_dev())
+    m.train(train)
+    return m
+
+
+def _field_close(a, b, tol=FIELD_TOL, what=""):
+    a = a.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= tol, "%s: max abs err %.3e > %.1e" % (what, err, tol)
+
+
+def _logp_close(a, b, what=""):
+    a = a.detach().float().cpu()
+    err = (a - b).abs()
+    assert (err <= 1e-5 * b.abs() + 1e-3).all(), "%s: %s vs %s" % (what, a.tolist(), b.tolist())
+
+
+def _states(g_states, dev):
+    return None if g_states is None else [(h.to(dev), c.to(dev)) for h, c in g_states]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_vs_reference_golden(name):
+    g = load_golden(name)
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"], g["train_bn"])
+    dev = _dev()
+    z, logp, h_out, eps = m.forward(g["x"].to(dev), g["y"].to(dev), _states(g["h_in"], dev), return_eps=True)
+    _field_close(z, g["fwd"]["z"], what="z")
+    _logp_close(logp, g["fwd"]["logp"], "logp")
+    for (h, c), (hr, cr) in zip(h_out, g["fwd"]["h_out"]):
+        _field_close(h, hr, what="h_out"); _field_close(c, cr, what="c_out")
+    for i, (e, er) in enumerate(zip(eps, g["fwd"]["eps"])):
+        _field_close(e, er, tol=5e-4, what="eps[%d]" % i)
+    if g["train_bn"]:
+        sd = m.state_dict()
+        for k, v in g["fwd"]["bn_after"].items():
+            _field_close(sd[k].float(), v.float(), tol=1e-5, what=k)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("which", ["rec", "rec2"])
+def test_reconstruct_vs_reference_golden(name, which):
+    g = load_golden(name)
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"], g["train_bn"])
+    dev = _dev()
+    eps = g["fwd"]["eps"] if which == "rec" else g["rec2"]["eps"]
+    y, ld, h_out = m.reconstruct(g["x"].to(dev), _states(g["h_in"], dev), [e.to(dev) for e in eps])
+    _field_close(y, g[which]["y"], what="y")
+    _logp_close(ld, g[which]["log_det"], "log_det")
+    for (h, c), (hr, cr) in zip(h_out, g[which]["h_out"]):
+        _field_close(h, hr, what="h_out"); _field_close(c, cr, what="c_out")
+
+
+def test_operators_vs_reference_golden():
+    from tmglow_b200 import ops
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"])
+    dev = _dev()
+    mods = g["modules"]
+    z_out, c_out = m.encoder(g["x"].to(dev))
+    _field_close(z_out, mods["encoder"]["z_out"], tol=2e-5, what="encoder z_out")
+    for a, b in zip(c_out, mods["encoder"]["c_out"]):
+        _field_close(a, b, tol=2e-5, what="encoder c_out")
+    # permutations: bit-exact, ragged channel count (5) and non-square map
+    assert torch.equal(ops.squeeze_forward(mods["squeeze"]["x"].to(dev)).cpu(), mods["squeeze"]["y"])
+    assert torch.equal(ops.squeeze_reverse(mods["unsqueeze"]["y"].to(dev)).cpu(), mods["unsqueeze"]["x"])
+    for s, rec in enumerate(mods["steps"], start=1):
+        st = rec.get("state")
+        st = None if st is None else (st[0].to(dev), st[1].to(dev))
+        o, ld, so = ops.flow_step(m, 0, s, rec["x"].to(dev), rec["cond"].to(dev), st, reverse=False)
+        _field_close(o, rec["fwd"], tol=2e-5, what="step%d fwd" % s); _logp_close(ld, rec["fwd_logdet"], "step fwd logdet")
+        r, ldr, sr = ops.flow_step(m, 0, s, rec["x"].to(dev), rec["cond"].to(dev), st, reverse=True)
+        _field_close(r, rec["rev"], tol=2e-5, what="step%d rev" % s); _logp_close(ldr, rec["rev_logdet"], "step rev logdet")
+        if st is not None:
+            _field_close(so[0], rec["fwd_state"][0], tol=2e-5, what="h"); _field_close(so[1], rec["fwd_state"][1], tol=2e-5, what="c")
+            _field_close(sr[0], rec["rev_state"][0], tol=2e-5, what="h"); _field_close(sr[1], rec["rev_state"][1], tol=2e-5, what="c")
+            o0, ld0, so0 = ops.flow_step(m, 0, s, rec["x"].to(dev), rec["cond"].to(dev), None, reverse=False)
+            _field_close(o0, rec["fwd_nostate"], tol=2e-5, what="step fwd (zero state)")
+            _field_close(so0[0], rec["fwd_nostate_state"][0], tol=2e-5, what="h0")
+    sp = mods["split"]
+    z1, lp, e = ops.split_forward(m, 0, sp["z"].to(dev))
+    _field_close(z1, sp["z1"], tol=0, what="split z1"); _logp_close(lp, sp["logp"], "split logp")
+    _field_close(e, sp["eps"], tol=2e-5, what="split eps")
+    zr, lpr = ops.split_reverse(m, 0, sp["z1"].to(dev), sp["eps"].to(dev))
+    _field_close(zr, sp["rev_z"], tol=2e-5, what="split rev z"); _logp_close(lpr, sp["rev_logp"], "split rev logp")
+    _field_close(m.conv1x1_weight(0, 1), mods["conv1x1"]["W"], tol=2e-6, what="W")
+    _field_close(m.conv1x1_weight(0, 1, inverse=True), mods["conv1x1"]["Winv"], tol=2e-5, what="Winv")
+
+
+def _default_model(seed=12345):
+    """Default architecture (args.py:116-123,135), backward-step preset, reference init plus the
+    well-conditioned perturbation of SURVEY.md appendix B (zc = 0.002)."""
+    import numpy as np
+    from tmglow_b200 import TMGlow
+    torch.manual_seed(seed); np.random.seed(seed)
+    m = TMGlow(4, 3, [4, 4, 4], [16, 16, 16], cond_features=32, cglow_upscale=2, growth_rate=4,
+               init_features=16, rec_features=64)
+    gen = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            r = torch.randn(p.shape, generator=gen)
+            if name.endswith("norm.weight"):
+                p.copy_(torch.exp(0.1 * r))
+            elif name.endswith("norm.bias"):
+                p.copy_(0.1 * r)
+            elif name.endswith("conv.log_s"):
+                p.add_(0.05 * r)
+            elif name.endswith(".scale"):
+                p.copy_(0.1 * r)
+            elif "zero_conv.conv." in name or "latent_encoder.conv2d.conv." in name:
+                p.copy_(0.002 * r)
+    m.eval()
+    return m
+
+
+def test_default_model_vs_oracle():
+    """Full default model (1.75 M parameters, 3x16 steps), backward-step geometry, vs the pinned oracle."""
+    from oracle import tmglow_oracle as O
+    dev = _dev()
+    m = _default_model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = O.OracleConfig.from_dict(m._cfg_dict)
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    x = torch.randn(B, 4, 32, 64, generator=g)
+    y = torch.randn(B, 3, 64, 128, generator=g)
+    h_in = O.init_lstm_states(cfg, torch.arange(B), [64, 128])
+    z_o, lp_o, ho_o, eps_o = O.forward(sd, cfg, x, y, h_in, True)
+    m = m.to(dev)
+    z, lp, ho, eps = m.forward(x.to(dev), y.to(dev), [(h.to(dev), c.to(dev)) for h, c in h_in], return_eps=True)
+    _field_close(z, z_o, what="z"); _logp_close(lp, lp_o, "logp")
+    for (h, c), (hr, cr) in zip(ho, ho_o):
+        _field_close(h, hr, what="h"); _field_close(c, cr, what="c")
+    y_o, ld_o, _ = O.reconstruct(sd, cfg, x, h_in, eps_o)
+    y_r, ld, _ = m.reconstruct(x.to(dev), [(h.to(dev), c.to(dev)) for h, c in h_in], [e.to(dev) for e in eps_o])
+    _field_close(y_r, y_o, what="y"); _logp_close(ld, ld_o, "log_det")
+
+
+def test_full_size_properties():
+    """Size-independent properties at a bench-like batch: invertibility (reference
+    nn/tmGlow.py:511-530), the logp identity of SURVEY appendix A.7, determinism."""
+    dev = _dev()
+    m = _default_model().to(dev)
+    B = 48
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(B, 4, 32, 64, generator=g).to(dev)
+    y = torch.randn(B, 3, 64, 128, generator=g).to(dev)
+    h_in = m.initLSTMStates(torch.arange(B), [64, 128])
+    z, logp, h_out, eps = m.forward(x, y, h_in, return_eps=True)
+    y_rec, log_det, h_out2 = m.reconstruct(x, h_in, eps)
+    assert torch.isfinite(y_rec).all() and torch.isfinite(logp).all()
+    assert (y_rec - y).abs().max().item() < 5e-4
+    for (h, c), (h2, c2) in zip(h_out, h_out2):           # states identical in both directions
+        assert (h - h2).abs().max().item() < 5e-4 and (c - c2).abs().max().item() < 5e-4
+    # forward.logp == reconstruct.log_det + log N(z; cmean, clog_std)
+    z_out, _ = m.encoder(x)
+    cmean, clog = z_out.chunk(2, 1)
+    clog = clog.clamp(-10.0, 1.6094379124341003)
+    top = (-0.5 * (1.8378770664093453 + 2 * clog + (z - cmean) ** 2 / (2 * clog).exp())).reshape(B, -1).sum(1)
+    assert torch.allclose(logp, log_det + top, rtol=2e-5, atol=0.05)
+    # same call twice -> bit-identical (no atomics in the reductions)
+    y2, ld2, _ = m.reconstruct(x, h_in, eps)
+    assert torch.equal(y2, y_rec) and torch.equal(ld2, log_det)
+    # samples are independent of the rest of the batch
+    y1, ld1, _ = m.reconstruct(x[:3], [(h[:3], c[:3]) for h, c in h_in], [e[:3] for e in eps])
+    assert torch.equal(y1, y_rec[:3])
+
+
+def test_sample_rng_order_and_shapes():
+    dev = _dev()
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"])
+    x = g["x"].to(dev)
+    torch.manual_seed(7)
+    y, ld, h = m.sample(x, None)
+    torch.manual_seed(7)
+    shapes = m.latent_shapes(x.shape[0], 16, 32)
+    eps = [None] * len(shapes)
+    for i in [len(shapes) - 1] + list(range(len(shapes) - 2, -1, -1)):
+        eps[i] = torch.randn(shapes[i], device=dev)
+    y2, ld2, _ = m.reconstruct(x, None, eps)
+    assert y.shape == (2, 3, 16, 32) and torch.equal(y, y2) and torch.equal(ld, ld2)
+
+
+def test_error_behaviour():
+    dev = _dev()
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"])
+    with pytest.raises(AssertionError):          # HF size not divisible by 2^L (flowUtils.py:112)
+        m.sample(torch.zeros(1, 4, 7, 16, device=dev))
+    with pytest.raises(AssertionError):          # wrong eps list
+        m.reconstruct(g["x"].to(dev), None, [torch.zeros(1, device=dev)])
+    with pytest.raises(RuntimeError):            # no CPU fallback
+        m.sample(g["x"])

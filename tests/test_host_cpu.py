@@ -1,0 +1,99 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol,
+the drop-in module keeps the reference's state_dict layout, argument errors, no CPU fallback."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+
+def _lib():
+    from tmglow_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib()
+    hdr = open(os.path.join(ROOT, "include", "tmglow_b200.h")).read()
+    declared = set(re.findall(r"\b(tmg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libtmglow_b200.so does not export " + name
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    assert L.load().tmg_version() >= 100
+
+
+def test_default_state_dict_layout_matches_reference():
+    from tmglow_b200 import TMGlow
+    lay = json.load(open(os.path.join(GOLDEN, "default_state_dict_layout.json")))
+    m = TMGlow(4, 3, [4, 4, 4], [16, 16, 16], cond_features=32, cglow_upscale=2, growth_rate=4,
+               init_features=16, rec_features=64)
+    mine = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert mine == lay["entries"]                 # 873 keys, same order, shapes and dtypes
+    assert m._num_parameters() == lay["n_parameters"] == 1746573
+    assert m.glow_blocks == [16, 16, 16] and m.rec_features == 64
+    assert hasattr(m, "encoder") and hasattr(m, "glow") and m.in_mu.shape == (3,)
+
+
+@pytest.mark.parametrize("name", ["caseA_states", "caseB_up4", "caseC_up1"])
+def test_reference_checkpoints_load(name):
+    from tmglow_b200 import TMGlow
+    g = load_golden(name)
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    res = m.load_state_dict(g["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, g["state_dict"][k]), k
+
+
+def test_checkpoint_with_stale_log_s_old_loads():
+    """a checkpoint saved after test() has log_s_old == log_s, which crashes a freshly
+    built reference model; the drop-in ignores the cache key."""
+    from tmglow_b200 import TMGlow
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    sd = dict(g["state_dict"])
+    for k in list(sd):
+        if k.endswith("log_s_old"):
+            sd[k] = sd[k[:-4]].clone()
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    m.load_state_dict(sd)
+
+
+def test_init_lstm_states_matches_reference():
+    from tmglow_b200 import TMGlow
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    B = g["x"].shape[0]
+    st = m.initLSTMStates(torch.arange(B) + 7, list(g["y"].shape[2:]))
+    for (h, c), (hr, cr) in zip(st, g["h_in"]):
+        assert torch.equal(h, hr) and torch.equal(c, cr)
+
+
+def test_no_cpu_fallback_and_bad_config():
+    from tmglow_b200 import TMGlow
+    m = TMGlow(4, 3, [2, 2], [3, 3], cond_features=8, cglow_upscale=2, growth_rate=4, init_features=8, rec_features=8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.sample(torch.zeros(1, 4, 8, 16))
+    with pytest.raises(AssertionError):
+        TMGlow(4, 3, [2, 2], [3], cond_features=8)
+    L = _lib()
+    assert L.load().tmg_workspace_bytes(None, 1, 8, 8) == 0
+    # product code never imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "deep-turbulence_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/", "").lower() or f == "x", f
