@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- TM-Glow hot-path benchmark (driver contract in the task statement, tier section 4).
+
+Workload (BASELINE.json configs[1]): backward-facing-step inference, default model
+(enc [4,4,4], glow [16,16,16], 1 746 573 parameters, random init + the well-conditioned
+perturbation of SURVEY.md appendix B), ONE low-fidelity snapshot x[1,4,32,64] per GPU and S
+stochastic high-fidelity samples y[S,3,64,128] per step through ``TMGlow.sample`` with the ConvLSTM
+states carried from step to step.  One "step" = one ``sample()`` call over the S samples.
+metric = HF samples/s, whole job (all ranks).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--impl b200|reference]
+
+N > 1 is launched by the driver with torch.distributed.run (one rank per GPU); samples are sharded
+over ranks with no data-path collective (weak scaling: S per GPU), NCCL is used only for the
+barrier and the max-over-ranks of the device-timed duration.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "deep-turbulence_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GEOM = dict(nic=4, h=32, w=64, noc=3, H=64, W=128)
+MODEL_KW = dict(cond_features=32, cglow_upscale=2, growth_rate=4, init_features=16, rec_features=64)
+# SURVEY.md 8(d) / BASELINE.md section 3: algorithmic work per HF sample, backward-step geometry
+ALG_FLOP_PER_SAMPLE = 2.159e9
+ALG_BYTES_PER_SAMPLE = 13.9e6
+
+
+def perturb_(model, seed):
+    """SURVEY.md appendix B recipe (zc = 0.002): non-trivial couplings/priors, well conditioned."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            r = torch.randn(p.shape, generator=gen)
+            if name.endswith("norm.weight"):
+                p.copy_(torch.exp(0.1 * r))
+            elif name.endswith("norm.bias"):
+                p.copy_(0.1 * r)
+            elif name.endswith("conv.log_s"):
+                p.add_(0.05 * r)
+            elif name.endswith(".scale"):
+                p.copy_(0.1 * r)
+            elif "zero_conv.conv." in name or "latent_encoder.conv2d.conv." in name:
+                p.copy_(0.002 * r)
+
+
+def build_model():
+    from tmglow_b200 import TMGlow
+    torch.manual_seed(12345)       # args.py:151
+    np.random.seed(12345)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TMGlow(GEOM["nic"], GEOM["noc"], [4, 4, 4], [16, 16, 16], **MODEL_KW)
+    perturb_(m, 12346)
+    m.eval()
+    return m
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_samples_per_s(sd, cfg_dict, batch, min_seconds, max_calls=50):
+    """The pinned oracle (CPU port of the reference path, torch CPU operators -- the same ATen
+    kernels the reference runs) timed on the host cores."""
+    from oracle import tmglow_oracle as O
+    cfg = O.OracleConfig.from_dict(cfg_dict)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=g).expand(batch, -1, -1, -1).contiguous()
+    h = O.init_lstm_states(cfg, torch.arange(batch), [GEOM["H"], GEOM["W"]])
+    with torch.no_grad():
+        for _ in range(2):
+            y, ld, h = O.sample(sd, cfg, x, h, g)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            y, ld, h = O.sample(sd, cfg, x, h, g)
+            n += 1
+            el = time.perf_counter() - t0
+            if el >= min_seconds or n >= max_calls:
+                break
+    return batch * n / el, threads, n, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is
+    Python (no compilable sources), /root/reference does not exist on the GPU box, so this arm
+    times the pinned oracle port (kind = "port") on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    m = build_model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    B = args.ref_batch
+    from oracle import tmglow_oracle as O
+    cfg = O.OracleConfig.from_dict(m._cfg_dict)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=g).expand(B, -1, -1, -1).contiguous()
+    h = O.init_lstm_states(cfg, torch.arange(B), [GEOM["H"], GEOM["W"]])
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y, ld, h = O.sample(sd, cfg, x, h, g)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            y, ld, h = O.sample(sd, cfg, x, h, g)
+        el = time.perf_counter() - t0
+    val = B * args.steps / el
+    line = {
+        "impl": "reference", "metric": "hf_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(B, args.gpus, note="CPU: %d samples per step (bounded sample of the workload)" % B),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps x %d HF samples, oracle.sample() on %d host threads" % (args.steps, B, threads)},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(S, n, note=None):
+    c = {"workload": "TM-Glow backward-facing-step inference: 1 LF input x %d stochastic HF samples per GPU per step "
+                     "(BASELINE.json configs[1]); x[1,4,32,64] -> y[S,3,64,128]; default model 1746573 params" % S,
+         "samples_per_gpu_per_step": S, "parallelism": "sample-parallel x%d, no collective" % n,
+         "l2_policy": "working set per step (%.1f GB of activations) far exceeds the 126 MB L2; no explicit flush" %
+                      (S * 3.5e6 / 1e9)}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--samples", type=int, default=1024, help="stochastic HF samples per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=16)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tmglow_b200 import _lib
+    lib = _lib.load()
+    model = build_model()
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    model = model.to(dev)
+    S, K, W = args.samples, args.steps, args.warmup
+
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=g).pin_memory()
+    x_dev = x_host.to(dev).expand(S, -1, -1, -1).contiguous()
+    h0 = model.initLSTMStates(torch.arange(S) + 1000 * rank, [GEOM["H"], GEOM["W"]])
+    torch.manual_seed(777 + rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident run: inputs already in HBM when the timed region starts
+    h = h0
+    for _ in range(W):
+        y, ld, h = model.sample(x_dev, h)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    lib.tmg_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        y, ld, h = model.sample(x_dev, h)
+    e1.record()
+    barrier()
+    launches = lib.tmg_launch_count(0)
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop()
+    assert torch.isfinite(y).all(), "non-finite samples"
+    value = world * S * K / (ms * 1e-3)
+
+    # ---------------- end to end through the public API with HOST buffers
+    y_host = torch.empty((S, GEOM["noc"], GEOM["H"], GEOM["W"]), dtype=torch.float32).pin_memory()
+    ld_host = torch.empty(S, dtype=torch.float32).pin_memory()
+    x_stage = torch.empty_like(x_host, device=dev)
+    h = h0
+    for _ in range(2):
+        x_stage.copy_(x_host, non_blocking=True)
+        y, ld, h = model.sample(x_stage.expand(S, -1, -1, -1), h)
+        y_host.copy_(y, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        x_stage.copy_(x_host, non_blocking=True)                       # H2D of the step's LF input
+        y, ld, h = model.sample(x_stage.expand(S, -1, -1, -1), h)
+        y_host.copy_(y, non_blocking=True)                             # D2H of the step's HF samples
+        ld_host.copy_(ld, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": world * S * K / (ms_e2e * 1e-3), "unit": "samples/s",
+           "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (y_host.numel() + ld_host.numel()) * 4}
+
+    # ---------------- per-kernel-class device times (CUDA events on the launching stream)
+    pk = peaks()
+    roof, classes = None, []
+    if rank == 0:
+        lib.tmg_profile_enable(1)
+        nprof = 2
+        for _ in range(nprof):
+            y, ld, h = model.sample(x_dev, h)
+        torch.cuda.synchronize()
+        import ctypes as C
+        tot = 0.0
+        for t in range(lib.tmg_profile_classes()):
+            msv, n, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+            _lib.check(lib.tmg_profile_query(t, C.byref(msv), C.byref(n), C.byref(fl), C.byref(by)))
+            if n.value:
+                classes.append({"class": lib.tmg_profile_class_name(t).decode(), "ms_per_step": msv.value / nprof,
+                                "launches_per_step": n.value // nprof,
+                                "tflops": fl.value / (msv.value * 1e-3) / 1e12 if msv.value else 0.0,
+                                "gbs": by.value / (msv.value * 1e-3) / 1e9 if msv.value else 0.0,
+                                "alg_flops_per_launch": fl.value / n.value, "alg_bytes_per_launch": by.value / n.value})
+                tot += msv.value / nprof
+        lib.tmg_profile_enable(0)
+        for c in classes:
+            c["share"] = c["ms_per_step"] / tot if tot else 0.0
+        if classes:
+            top = max(classes, key=lambda c: c["ms_per_step"])
+            if top["class"].startswith("conv"):
+                roof = {"kernel": top["class"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tf_sust"],
+                        "unit": "TFLOP/s", "frac": top["tflops"] / pk["tf_sust"], "traffic": None,
+                        "peak_source": pk["source"] + " (bf16 cuBLAS sustained)", "share_of_step": top["share"],
+                        "avg_launch_ms": top["ms_per_step"] / top["launches_per_step"]}
+            else:
+                roof = {"kernel": top["class"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"],
+                        "unit": "GB/s", "frac": top["gbs"] / pk["hbm"], "traffic": None,
+                        "peak_source": pk["source"], "share_of_step": top["share"],
+                        "avg_launch_ms": top["ms_per_step"] / top["launches_per_step"]}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, ncalls, el = cpu_port_samples_per_s(sd_cpu, model._cfg_dict, args.ref_batch, args.cpu_seconds)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "%d x oracle.sample() of %d HF samples (%.1f s) on %d host threads" % (ncalls, args.ref_batch, el, cores)}
+
+    if rank == 0:
+        line = {
+            "metric": "hf_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(S, world),
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu,
+            "whole_path": {"alg_tflops": value * ALG_FLOP_PER_SAMPLE / 1e12 / world,
+                           "alg_gbs": value * ALG_BYTES_PER_SAMPLE / 1e9 / world, "per": "GPU"},
+            "kernel_classes": classes,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

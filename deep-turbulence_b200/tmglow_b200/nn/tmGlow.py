@@ -259,12 +259,13 @@ class TMGlow(nn.Module):
             raise RuntimeError("tensor on %s but the model runs on %s" % (t.device, device))
         return t.detach().to(torch.float32).contiguous()
 
-    def _states_in(self, lib, h_in, dims, device, st):
+    def _states_in(self, lib, h_in, dims, device, st, check_len=True):
         """LSTM states enter the library channels-last; NCHW tensors are converted by the
         library's own permutation kernel."""
         if h_in is None:
             return None, None, []
-        assert len(h_in) == len(self.glow_blocks), 'List of recurrent states need to be same length as flow blocks.'
+        assert not check_len or len(h_in) == len(self.glow_blocks), \
+            'List of recurrent states need to be same length as flow blocks.'
         hs, cs, keep = [], [], []
         for (hh, cc), d in zip(h_in, dims):
             for t, out in ((hh, hs), (cc, cs)):

@@ -68,7 +68,7 @@ def flow_step(model, level, step, x, cond, state=None, reverse=False):
         hp = cp = None
         keep = []
         if state is not None:
-            ha, ca, keep = model._states_in(lib, [state], [d], device, st)
+            ha, ca, keep = model._states_in(lib, [state], [d], device, st, check_len=False)
             hp, cp = ha[0], ca[0]
         ho = _empty_channels_last(d, device) if is_lstm else None
         co = _empty_channels_last(d, device) if is_lstm else None
