@@ -98,6 +98,35 @@ struct ConvArgs {
 };
 int launch_conv3x3(const ConvArgs& a, cudaStream_t st);
 
+// Tensor-core (tcgen05, TF32 / 3xTF32) variant: stride 1 only, see conv3x3_tc.cu
+struct TcConvArgs {
+  ConvSrc src[3];
+  int nsrc;
+  int cin;                 // real input channels (K is walked in chunks of 16)
+  const float* wpk;        // packed weights [chunk][tap][hi|lo][plane][npad][4]
+  int npad;                // MMA N: multiple of 16, <= 256
+  const float* bias;
+  const float* gain;
+  int act;
+  float* out;
+  int out_cstride, out_coff, cout;
+  int B, H, W;
+  int pad_replicate;
+  int split3;              // 1: 3xTF32 (fp32-grade), 0: single-pass TF32
+  // fused ConvLSTM cell epilogue (gate conv): lstm_R = rec_features, else 0
+  int lstm_R;
+  const float* c_prev;
+  float* h_out;
+  float* c_out;
+};
+int launch_conv3x3_tc(const TcConvArgs& a, cudaStream_t st);
+int launch_pack_tc(const float* w_oihw, float* dst, int O, int I, int npad, cudaStream_t st);
+// floats of one conv's packed tensor-core weights: [chunk][tap][hi|lo][plane(4)][npad][4]
+__host__ __device__ inline size_t tc_packed_floats(int cin, int npad) {
+  return (size_t)((cin + 15) / 16) * 9 * 2 * 4 * npad * 4;
+}
+inline int tc_npad(int cout) { return (cout + 15) / 16 * 16; }
+
 // ------------------------------------------------------------------ pointwise flow step
 struct PointArgs {
   float* y;            // [B, HW, C] in/out
@@ -200,14 +229,15 @@ struct LogdetArgs {
 int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ weight packing jobs
-enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3 };
+enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n
   int64_t src[9];        // offsets (floats) into the flat parameter buffer, -1 = absent
                          // JOB_1X1: l,u,log_s,p,sign_s,l_mask,u_mask,eye,norm.weight
   int64_t dst[3];        // offsets (floats) into the packed buffer
-  int opad;              // JOB_CONVW: padded O
+  int opad;              // JOB_CONVW: padded O ; JOB_CONVW_TC: npad
+  int part, nparts;      // JOB_CONVW_TC: this CTA packs elements [part*chunk, (part+1)*chunk)
 };
 int launch_pack(const PackJob* jobs_dev, int njobs, const float* params, float* packed, int cmax,
                 cudaStream_t st);

@@ -46,7 +46,8 @@ struct ConvW {
   int64_t w_param = -1;   // OIHW in the parameter buffer
   int64_t b_param = -1;   // bias or -1
   int64_t w_pack = -1;    // tap-major in the packed buffer
-  int O = 0, I = 0, OP = 0;
+  int64_t w_pack_tc = -1; // tcgen05 layout (hi/lo split) in the packed buffer, -1: CUDA-core path only
+  int O = 0, I = 0, OP = 0, NP = 0;
 };
 
 enum StepKind { STEP_UNNORMED = 0, STEP_PLAIN = 1, STEP_LSTM = 2 };
@@ -94,6 +95,7 @@ struct tmg_model {
   int64_t step_const_off = 0;       // inside packed
   float* params = nullptr;          // borrowed flat parameter buffer
   bool ready = false;
+  int precision = TMG_PREC_FP32;    // which kernels run the heavy 3x3 convolutions
 };
 
 namespace tmg {
@@ -114,7 +116,7 @@ struct Builder {
     m.n_packed += (n + 3) / 4 * 4;   // keep 16 B alignment
     return o;
   }
-  ConvW conv(const std::string& name, int O, int I, bool bias) {
+  ConvW conv(const std::string& name, int O, int I, bool bias, bool tc = false) {
     ConvW c;
     c.O = O; c.I = I; c.OP = (O + 3) / 4 * 4;
     c.w_param = add(name + ".weight", {O, I, 3, 3});
@@ -125,6 +127,19 @@ struct Builder {
     for (auto& s : j.src) s = -1;
     j.src[0] = c.w_param; j.dst[0] = c.w_pack;
     m.jobs.push_back(j);
+    if (tc) {
+      c.NP = tc_npad(O);
+      const size_t total = tc_packed_floats(I, c.NP);
+      c.w_pack_tc = pack_alloc((int64_t)total);
+      const int nparts = (int)((total + 32767) / 32768);
+      for (int part = 0; part < nparts; ++part) {
+        PackJob t{};
+        t.type = JOB_CONVW_TC; t.a = O; t.b = I; t.opad = c.NP; t.part = part; t.nparts = nparts;
+        for (auto& s : t.src) s = -1;
+        t.src[0] = c.w_param; t.dst[0] = c.w_pack_tc;
+        m.jobs.push_back(t);
+      }
+    }
     return c;
   }
   int64_t gain(int64_t scale_param) {
@@ -244,18 +259,18 @@ static int build_model(tmg_model& m) {
       m.jobs.push_back(j);
       if (st.kind == STEP_LSTM) {
         const int R = c.rec_features;
-        st.gate = B.conv(sp + "coupling.resid_lstm.convLSTM.conv", 4 * R, cin_t + R, true);
-        st.outc = B.conv(sp + "coupling.resid_lstm.out_seq.LSTM_out_conv", cin_t, cin_t + R, true);
+        st.gate = B.conv(sp + "coupling.resid_lstm.convLSTM.conv", 4 * R, cin_t + R, true, 4 * R <= 256);
+        st.outc = B.conv(sp + "coupling.resid_lstm.out_seq.LSTM_out_conv", cin_t, cin_t + R, true, true);
         st.d1 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
         int64_t sc = B.add(sp + "coupling.out_conv.zero_conv.scale", {1, 1, 1, 1});
-        st.zc = B.conv(sp + "coupling.out_conv.zero_conv.conv", C, cin_t + 2, true);
+        st.zc = B.conv(sp + "coupling.out_conv.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
       } else {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
         int64_t sc = B.add(sp + "coupling.coupling_nn.zero_conv.scale", {1, 1, 1, 1});
-        st.zc = B.conv(sp + "coupling.coupling_nn.zero_conv.conv", C, cin_t + 2, true);
+        st.zc = B.conv(sp + "coupling.coupling_nn.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
       }
       lv.steps.push_back(st);
@@ -373,6 +388,18 @@ static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int ns
   a.Hout = stride == 1 ? Hin : (Hin + 1) / 2;
   a.Wout = stride == 1 ? Win : (Win + 1) / 2;
   a.pad_replicate = replicate ? 1 : 0;
+  if (c.m.precision != TMG_PREC_FP32 && w.w_pack_tc >= 0 && stride == 1 && !bn_scale && Win + 2 <= 512) {
+    TcConvArgs t{};
+    for (int i = 0; i < nsrc; ++i) t.src[i] = srcs[i];
+    t.nsrc = nsrc; t.cin = w.I; t.wpk = c.Q() + w.w_pack_tc; t.npad = w.NP;
+    t.bias = a.bias; t.gain = a.gain; t.act = act;
+    t.out = out; t.out_cstride = out_cstride; t.out_coff = out_coff; t.cout = w.O;
+    t.B = B; t.H = Hin; t.W = Win; t.pad_replicate = a.pad_replicate;
+    t.split3 = c.m.precision == TMG_PREC_TF32X3 ? 1 : 0;
+    const double M = (double)B * Hin * Win;
+    ProfScope ps(c.st, tag, 2.0 * M * w.O * 9.0 * w.I, 4.0 * ((double)B * Hin * Win * w.I + M * w.O));
+    return launch_conv3x3_tc(t, c.st);
+  }
   // algorithmic work: 2*M*N*K flops; bytes = read every input channel once + write the outputs
   const double M = (double)B * a.Hout * a.Wout;
   ProfScope ps(c.st, tag, 2.0 * M * w.O * 9.0 * w.I, 4.0 * ((double)B * Hin * Win * w.I + M * w.O));
@@ -464,10 +491,23 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
   if (s.kind == STEP_LSTM) {
     if (!h_out || !c_out) { set_error("LSTM step needs h_out/c_out buffers"); return TMG_ERR_NULL; }
     ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0}, {h_in, R, 0, R, 0}};
-    TMG_TRY(run_conv(c, PROF_CONV_GATE, s.gate, gs, h_in ? 3 : 2, B, Hl, Wl, 1, false, 0, -1, nullptr, nullptr,
-                     ws + p.gates, 4 * R, 0));
-    LstmArgs la{ws + p.gates, c_in, h_out, c_out, (int64_t)B * Hl * Wl * R, R};
-    {
+    if (c.m.precision != TMG_PREC_FP32 && s.gate.w_pack_tc >= 0 && R % 16 == 0 && Wl + 2 <= 512) {
+      // gate conv on tcgen05 with the ConvLSTM cell update fused into its epilogue (gates never touch HBM)
+      TcConvArgs t{};
+      const int ns = h_in ? 3 : 2;
+      for (int i = 0; i < ns; ++i) t.src[i] = gs[i];
+      t.nsrc = ns; t.cin = s.gate.I; t.wpk = c.Q() + s.gate.w_pack_tc; t.npad = s.gate.NP;
+      t.bias = c.P() + s.gate.b_param; t.cout = s.gate.O;
+      t.B = B; t.H = Hl; t.W = Wl; t.split3 = c.m.precision == TMG_PREC_TF32X3 ? 1 : 0;
+      t.lstm_R = R; t.c_prev = c_in; t.h_out = h_out; t.c_out = c_out;
+      const double M = (double)B * Hl * Wl;
+      ProfScope ps(c.st, PROF_CONV_GATE, 2.0 * M * s.gate.O * 9.0 * s.gate.I,
+                   4.0 * (M * s.gate.I + M * R * (c_in ? 3.0 : 2.0)));
+      TMG_TRY(launch_conv3x3_tc(t, c.st));
+    } else {
+      TMG_TRY(run_conv(c, PROF_CONV_GATE, s.gate, gs, h_in ? 3 : 2, B, Hl, Wl, 1, false, 0, -1, nullptr, nullptr,
+                       ws + p.gates, 4 * R, 0));
+      LstmArgs la{ws + p.gates, c_in, h_out, c_out, (int64_t)B * Hl * Wl * R, R};
       ProfScope ps(c.st, PROF_LSTM_PW, 20.0 * la.n, 4.0 * la.n * (c_in ? 7.0 : 6.0));
       TMG_TRY(launch_lstm_pointwise(la, c.st));
     }
@@ -600,6 +640,16 @@ void tmg_model_destroy(tmg_model* m) {
   if (m->packed) cudaFree(m->packed);
   delete m;
 }
+
+int tmg_model_set_precision(tmg_model* m, int mode) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (mode != TMG_PREC_FP32 && mode != TMG_PREC_TF32X3 && mode != TMG_PREC_TF32) {
+    set_error("unknown precision mode %d", mode); return TMG_ERR_BAD_CONFIG;
+  }
+  m->precision = mode;
+  return TMG_OK;
+}
+int tmg_model_get_precision(const tmg_model* m) { return m ? m->precision : -1; }
 
 int64_t tmg_model_param_entries(const tmg_model* m) { return m ? (int64_t)m->entries.size() : 0; }
 const char* tmg_model_param_name(const tmg_model* m, int64_t i) {
@@ -831,6 +881,52 @@ int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, v
   PermArgs pa{};
   pa.src = src; pa.dst = dst; pa.mode = PERM_NHWC_TO_NCHW; pa.B = B; pa.C = C; pa.H = H; pa.W = W; pa.src_cstride = C;
   return launch_permute(pa, (cudaStream_t)stream);
+}
+
+size_t tmg_conv3x3_workspace_bytes(int Cin, int Cout) {
+  size_t a = (size_t)9 * Cin * ((Cout + 3) / 4 * 4);
+  size_t b = tc_packed_floats(Cin, tc_npad(Cout));
+  return (a + b + 64) * sizeof(float) + sizeof(PackJob) + 256;
+}
+
+// Conv2d(k=3, s=1, p=1) (+ optional input ReLU, zero/replicate padding, bias, activation) on NHWC
+// tensors with OIHW weights: the building block behind every conv of the path, exposed so the
+// tensor-core kernel can be tested in isolation against the CUDA-core kernel and the oracle.
+int tmg_conv3x3(int mode, const float* x, int B, int H, int W, int Cin, const float* w_oihw, const float* bias,
+                int Cout, int relu_in, int pad_replicate, int act, float* out, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  if (!x || !w_oihw || !out || !workspace) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (workspace_bytes < tmg_conv3x3_workspace_bytes(Cin, Cout)) { set_error("workspace too small"); return TMG_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  ConvSrc src{x, Cin, 0, Cin, relu_in};
+  if (mode == TMG_PREC_FP32) {
+    const int OP = (Cout + 3) / 4 * 4;
+    float* wp = ws;
+    PackJob j{};
+    j.type = JOB_CONVW; j.a = Cout; j.b = Cin; j.opad = OP;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = 0; j.dst[0] = 0;
+    PackJob* jd = (PackJob*)(ws + (size_t)9 * Cin * OP + tc_packed_floats(Cin, tc_npad(Cout)) + 64);
+    TMG_CUDA_OK(cudaMemcpyAsync(jd, &j, sizeof(j), cudaMemcpyHostToDevice, st));
+    TMG_TRY(launch_pack(jd, 1, w_oihw, wp, 4, st));
+    ConvArgs a{};
+    a.src[0] = src; a.nsrc = 1; a.w = wp; a.cin_w = Cin; a.cout_w = OP; a.bias = bias; a.act = act;
+    a.out = out; a.out_cstride = Cout; a.cout = Cout; a.B = B; a.Hin = H; a.Win = W; a.Hout = H; a.Wout = W;
+    a.stride = 1; a.pad_replicate = pad_replicate;
+    return launch_conv3x3(a, st);
+  }
+  if (mode != TMG_PREC_TF32X3 && mode != TMG_PREC_TF32) { set_error("unknown mode %d", mode); return TMG_ERR_BAD_CONFIG; }
+  const int NP = tc_npad(Cout);
+  if (NP > 256) { set_error("Cout %d > 256", Cout); return TMG_ERR_UNSUPPORTED; }
+  float* wp = ws + (size_t)9 * Cin * ((Cout + 3) / 4 * 4);
+  wp = (float*)(((uintptr_t)wp + 127) & ~(uintptr_t)127);
+  TMG_TRY(launch_pack_tc(w_oihw, wp, Cout, Cin, NP, st));
+  TcConvArgs t{};
+  t.src[0] = src; t.nsrc = 1; t.cin = Cin; t.wpk = wp; t.npad = NP; t.bias = bias; t.act = act;
+  t.out = out; t.out_cstride = Cout; t.cout = Cout; t.B = B; t.H = H; t.W = W; t.pad_replicate = pad_replicate;
+  t.split3 = mode == TMG_PREC_TF32X3 ? 1 : 0;
+  return launch_conv3x3_tc(t, st);
 }
 
 // Plan for the single-operator entry points: the workspace is sized by tmg_workspace_bytes of

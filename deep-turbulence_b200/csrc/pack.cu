@@ -22,6 +22,27 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       int o = i % OP; int r = i / OP; int c = r % I; int tap = r / I;
       d[i] = o < O ? s[((size_t)o * I + c) * 9 + tap] : 0.f;
     }
+  } else if (j.type == JOB_CONVW_TC) {
+    // OIHW -> [chunk][tap][hi|lo][plane][npad][4] with the TF32 hi/lo split (conv3x3_tc.cu)
+    const int O = j.a, I = j.b, NP = j.opad;
+    const float* s = P + j.src[0];
+    float* d = Q + j.dst[0];
+    const size_t total = tc_packed_floats(I, NP);
+    const size_t per = (total + j.nparts - 1) / j.nparts;
+    const size_t lo_i = per * j.part, hi_i = lo_i + per < total ? lo_i + per : total;
+    for (size_t i = lo_i + tid; i < hi_i; i += blockDim.x) {
+      int e = i & 3;
+      size_t t = i >> 2;
+      int n = t % NP; t /= NP;
+      int plane = t & 3; t >>= 2;
+      int hl = t & 1; t >>= 1;
+      int tap = t % 9;
+      int chunk = (int)(t / 9);
+      int c = chunk * 16 + plane * 4 + e;
+      float v = (n < O && c < I) ? s[((size_t)n * I + c) * 9 + tap] : 0.f;
+      float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      d[i] = hl ? (v - hi) : hi;
+    }
   } else if (j.type == JOB_GAIN) {
     if (tid == 0) Q[j.dst[0]] = expf(fminf(fmaxf(P[j.src[0]], -4.f), kLog4));
   } else if (j.type == JOB_BN) {

@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtmglow_b200.so")
 
 TMG_MAX_LEVELS = 6
 TMG_FLAG_BN_TRAIN = 1
+PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
 
 OK, ERR_BAD_CONFIG, ERR_BAD_SHAPE, ERR_NULL, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY = \
     0, -1, -2, -3, -4, -5, -6, -7
@@ -37,6 +39,10 @@ SIGNATURES = {
     "tmg_device_count": (_I, []),
     "tmg_model_create": (_I, [C.POINTER(TmgConfig), C.POINTER(_P)]),
     "tmg_model_destroy": (None, [_P]),
+    "tmg_model_set_precision": (_I, [_P, _I]),
+    "tmg_model_get_precision": (_I, [_P]),
+    "tmg_conv3x3_workspace_bytes": (_SZ, [_I, _I]),
+    "tmg_conv3x3": (_I, [_I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "tmg_model_param_entries": (_I64, [_P]),
     "tmg_model_param_name": (C.c_char_p, [_P, _I64]),
     "tmg_model_param_offset": (_I64, [_P, _I64]),

@@ -110,3 +110,30 @@ def split_reverse(model, level, z1, eps):
         _lib.check(lib.tmg_split_reverse(h, level, B, Hl, Wl, z1.data_ptr(), eps.data_ptr(), z.data_ptr(),
                                          logp.data_ptr(), ws.data_ptr(), ws.numel(), _stream(device)))
     return z, logp
+
+
+def conv3x3(x_nchw, weight, bias=None, relu_in=False, pad_replicate=False, act=0, mode="fp32"):
+    """``nn.Conv2d(Cin, Cout, 3, padding=1)`` (+ input ReLU / replicate padding / activation) through the
+    library's convolution kernels; ``mode`` in {"fp32" (CUDA-core FMA), "tf32x3", "tf32" (tcgen05)}.
+    NCHW in/out for convenience (converted with the library's own permutation kernels)."""
+    _need_cuda(x_nchw)
+    device = x_nchw.device
+    lib = _lib.load()
+    x = x_nchw.detach().float().contiguous()
+    w = weight.detach().float().contiguous()
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, Cin, 3, 3)
+    b = None if bias is None else bias.detach().float().contiguous()
+    xh = torch.empty((B, H, W, Cin), dtype=torch.float32, device=device)
+    oh = torch.empty((B, H, W, Cout), dtype=torch.float32, device=device)
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=device)
+    ws = torch.empty(lib.tmg_conv3x3_workspace_bytes(Cin, Cout), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        st = _stream(device)
+        _lib.check(lib.tmg_nchw_to_nhwc(x.data_ptr(), xh.data_ptr(), B, Cin, H, W, st))
+        _lib.check(lib.tmg_conv3x3(_lib.PRECISIONS[mode], xh.data_ptr(), B, H, W, Cin, w.data_ptr(),
+                                   None if b is None else b.data_ptr(), Cout, int(relu_in), int(pad_replicate), act,
+                                   oh.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        _lib.check(lib.tmg_nhwc_to_nchw(oh.data_ptr(), out.data_ptr(), B, Cout, H, W, st))
+    return out

@@ -70,6 +70,17 @@ int         tmg_device_count(void);               /* 0 when no CUDA device is vi
 int  tmg_model_create(const tmg_config* cfg, tmg_model** out);   /* on the current CUDA device */
 void tmg_model_destroy(tmg_model* m);
 
+/* Which kernels run the heavy 3x3 convolutions (ConvLSTM gate/out convs, Conv2dZeros):
+ *   TMG_PREC_FP32   exact fp32 FMA on CUDA cores (default)
+ *   TMG_PREC_TF32X3 tcgen05 tensor cores, 3xTF32 operand split: fp32-grade accuracy
+ *   TMG_PREC_TF32   tcgen05 tensor cores, single-pass TF32 (what stock PyTorch/cuDNN does on
+ *                   GPU by default); looser, separately stated tolerance */
+#define TMG_PREC_FP32   0
+#define TMG_PREC_TF32X3 1
+#define TMG_PREC_TF32   2
+int tmg_model_set_precision(tmg_model* m, int mode);
+int tmg_model_get_precision(const tmg_model* m);
+
 /* Parameter table: the flat fp32 parameter buffer holds every floating-point state_dict entry
  * (parameters AND buffers, reference names) back to back in the order reported here. */
 int64_t     tmg_model_param_entries(const tmg_model* m);
@@ -142,6 +153,15 @@ int tmg_split_forward(tmg_model* m, int level, int B, int Hl, int Wl, const floa
 int tmg_split_reverse(tmg_model* m, int level, int B, int Hl, int Wl, const float* z1,
                       const float* eps, float* z, float* logp,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* nn.Conv2d(Cin, Cout, 3, stride=1, padding=1) on NHWC tensors with OIHW weights (+ optional input
+ * ReLU, replicate padding as in Conv2dZeros flowUtils.py:246, bias, activation 0 none / 1 ReLU /
+ * 2 hardtanh(-2, ln5)); `mode` is a TMG_PREC_* value.  Exposes the convolution kernels behind every
+ * conv of the path (convLSTM.py:44,129; denseBlock.py:136; flowUtils.py:229) for isolated tests. */
+size_t tmg_conv3x3_workspace_bytes(int Cin, int Cout);
+int tmg_conv3x3(int mode, const float* x_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
+                const float* bias, int Cout, int relu_in, int pad_replicate, int act, float* out_nhwc,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* layout helpers for the LSTM states at the API boundary */
 int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
