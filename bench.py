@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=1024, help="stochastic HF samples per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -229,6 +230,7 @@ def main():
     model = build_model()
     sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     model = model.to(dev)
+    model.precision = args.precision
     S, K, W = args.samples, args.steps, args.warmup
 
     g = torch.Generator().manual_seed(100 + rank)
@@ -338,8 +340,8 @@ def main():
     if rank == 0:
         line = {
             "metric": "hf_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(S, world),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)", "tf32": "tf32"}[args.precision],
+            "data": "synthetic", "config": dict(workload_config(S, world), precision=args.precision),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
             "whole_path": {"alg_tflops": value * ALG_FLOP_PER_SAMPLE / 1e12 / world,

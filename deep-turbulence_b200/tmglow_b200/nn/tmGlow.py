@@ -105,7 +105,21 @@ class TMGlow(nn.Module):
         self._ws = {}
         self.assume_static_weights = False
         self._refreshed_for = None
+        self._precision = "fp32"
         print('Total number of parameters: {}'.format(self._num_parameters()))
+
+    @property
+    def precision(self):
+        """Arithmetic of the heavy 3x3 convolutions: ``"fp32"`` (CUDA-core FMA, exact fp32),
+        ``"tf32x3"`` (tcgen05 tensor cores with the 3xTF32 split: fp32-grade accuracy) or ``"tf32"``
+        (tcgen05, single-pass TF32 -- the default arithmetic of stock PyTorch/cuDNN convolutions on GPU)."""
+        return self._precision
+
+    @precision.setter
+    def precision(self, mode):
+        if mode not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        self._precision = mode
 
     # ------------------------------------------------------------------ construction helpers
     def _handle(self, key):
@@ -221,6 +235,8 @@ class TMGlow(nn.Module):
             st = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.tmg_model_refresh(h, self._flat.data_ptr(), st))
             self._refreshed_for = (h.value, self._flat.data_ptr())
+        if lib.tmg_model_get_precision(h) != _lib.PRECISIONS[self._precision]:
+            _lib.check(lib.tmg_model_set_precision(h, _lib.PRECISIONS[self._precision]))
         return lib, h
 
     def _workspace(self, lib, h, B, hh, ww, device):

@@ -231,3 +231,53 @@ def test_error_behaviour():
         m.reconstruct(g["x"].to(dev), None, [torch.zeros(1, device=dev)])
     with pytest.raises(RuntimeError):            # no CPU fallback
         m.sample(g["x"])
+
+
+# ------------------------------------------------------------------ tensor-core precision modes
+# tf32x3: tcgen05 with the 3xTF32 operand split -> same stated fp32 tolerance as the CUDA-core path.
+# tf32  : single-pass TF32 (10-bit mantissa operands); separately stated, looser tolerance:
+#         5e-2 abs on fields (48 chained steps), 1e-3 relative on logp/log_det.
+@pytest.mark.parametrize("name", CASES)
+def test_golden_tf32x3(name):
+    g = load_golden(name)
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"], g["train_bn"])
+    m.precision = "tf32x3"
+    dev = _dev()
+    z, logp, h_out, eps = m.forward(g["x"].to(dev), g["y"].to(dev), _states(g["h_in"], dev), return_eps=True)
+    _field_close(z, g["fwd"]["z"], what="z"); _logp_close(logp, g["fwd"]["logp"], "logp")
+    for (h, c), (hr, cr) in zip(h_out, g["fwd"]["h_out"]):
+        _field_close(h, hr, what="h_out"); _field_close(c, cr, what="c_out")
+    if g["train_bn"]:
+        m.load_state_dict(g["state_dict"])
+    y, ld, h_out = m.reconstruct(g["x"].to(dev), _states(g["h_in"], dev), [e.to(dev) for e in g["rec2"]["eps"]])
+    _field_close(y, g["rec2"]["y"], what="y"); _logp_close(ld, g["rec2"]["log_det"], "log_det")
+    for (h, c), (hr, cr) in zip(h_out, g["rec2"]["h_out"]):
+        _field_close(h, hr, what="h_out"); _field_close(c, cr, what="c_out")
+
+
+def test_default_model_tensor_core_modes():
+    from oracle import tmglow_oracle as O
+    dev = _dev()
+    m = _default_model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = O.OracleConfig.from_dict(m._cfg_dict)
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    x = torch.randn(B, 4, 32, 64, generator=g)
+    y = torch.randn(B, 3, 64, 128, generator=g)
+    h_in = O.init_lstm_states(cfg, torch.arange(B), [64, 128])
+    z_o, lp_o, ho_o, eps_o = O.forward(sd, cfg, x, y, h_in, True)
+    y_o, ld_o, _ = O.reconstruct(sd, cfg, x, h_in, eps_o)
+    m = m.to(dev)
+    hd = [(h.to(dev), c.to(dev)) for h, c in h_in]
+    report = {}
+    for mode, ftol, ltol in (("tf32x3", FIELD_TOL, 1e-5), ("tf32", 5e-2, 1e-3)):
+        m.precision = mode
+        z, lp, ho, _ = m.forward(x.to(dev), y.to(dev), hd, return_eps=True)
+        yr, ld, _ = m.reconstruct(x.to(dev), hd, [e.to(dev) for e in eps_o])
+        ez = (z.cpu() - z_o).abs().max().item(); ey = (yr.cpu() - y_o).abs().max().item()
+        el = ((lp.cpu() - lp_o).abs() / lp_o.abs()).max().item(); ed = ((ld.cpu() - ld_o).abs() / ld_o.abs()).max().item()
+        report[mode] = (ez, ey, el, ed)
+        print("precision %s: |z| %.2e |y| %.2e logp %.2e log_det %.2e" % (mode, ez, ey, el, ed))
+        assert ez <= ftol and ey <= ftol and el <= ltol + 1e-7 and ed <= ltol + 1e-7, (mode, report[mode])
