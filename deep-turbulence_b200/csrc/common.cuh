@@ -58,7 +58,8 @@ enum ProfTag {
   PROF_GAUSS = 8,
   PROF_PERMUTE = 9,
   PROF_MISC = 10,
-  PROF_NTAGS = 11
+  PROF_STEP_FUSED = 11,  // coupling net + coupling + 1x1 + ActNorm in one launch (coupling_tc.cu)
+  PROF_NTAGS = 12
 };
 struct ProfScope {
   cudaStream_t st;
@@ -126,6 +127,33 @@ __host__ __device__ inline size_t tc_packed_floats(int cin, int npad) {
   return (size_t)((cin + 15) / 16) * 9 * 2 * 4 * npad * 4;
 }
 inline int tc_npad(int cout) { return (cout + 15) / 16 * 16; }
+
+// Fused flow step on tensor cores (coupling_tc.cu): coupling net + coupling + 1x1 + ActNorm + log-det
+struct CouplingArgs {
+  ConvSrc src[2];          // the coupling-net input t as 1-2 NHWC sources; each starts on a 4-channel plane
+  int nsrc;
+  const float* w1;         // dense layer 1, packed [hi|lo][plane][16 (taps)][4]
+  const float* w2;         // dense layer 2 (one more plane: d1)
+  const float* w3;         // Conv2dZeros, packed [tap][hi|lo][plane][npad][4]
+  int npad;
+  const float* bias3;
+  const float* gain3;
+  int C;
+  const float* y_in;       // [B,HW,C] flow state read by the epilogue
+  float* y_out;            // [B,HW,C] (must differ from y_in: other CTAs read y_in's halo)
+  const float* wmat;       // CxC mix or null
+  const float* nw;         // ActNorm or null
+  const float* nb;
+  int reverse;
+  float* ld_part;
+  int ld_stride;
+  int B, H, W;
+  int split3;
+};
+int launch_coupling_tc(const CouplingArgs& a, cudaStream_t st);
+int coupling_tc_tiles(int H, int W);
+// plane bookkeeping shared by host packing and the kernel: sources start on plane boundaries
+inline int cpl_planes(int nch0, int nch1) { return (nch0 + 3) / 4 + (nch1 + 3) / 4; }
 
 // ------------------------------------------------------------------ pointwise flow step
 struct PointArgs {
@@ -229,7 +257,7 @@ struct LogdetArgs {
 int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ weight packing jobs
-enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4 };
+enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n
@@ -238,6 +266,8 @@ struct PackJob {
   int64_t dst[3];        // offsets (floats) into the packed buffer
   int opad;              // JOB_CONVW: padded O ; JOB_CONVW_TC: npad
   int part, nparts;      // JOB_CONVW_TC: this CTA packs elements [part*chunk, (part+1)*chunk)
+  int nch0, nch1, nd;    // JOB_CPL_*: channels of source 0 / source 1 / d channels (concat order: src0, src1, d)
+  int nplanes;           // JOB_CPL_*: K planes in the packed tensor
 };
 int launch_pack(const PackJob* jobs_dev, int njobs, const float* params, float* packed, int cmax,
                 cudaStream_t st);

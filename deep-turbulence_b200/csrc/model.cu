@@ -59,6 +59,9 @@ struct StepW {
   int const_idx = -1;             // index into step_const
   ConvW d1, d2, zc, gate, outc;
   int64_t zc_gain = -1;           // packed
+  // fused tensor-core coupling kernel (coupling_tc.cu): packed weights and K-plane bookkeeping
+  int64_t cpl_w1 = -1, cpl_w2 = -1, cpl_w3 = -1;
+  int cpl_nch0 = 0, cpl_nch1 = 0, cpl_npad = 0;
 };
 
 struct DenseW { ConvW conv; int64_t bn_w, bn_b, bn_rm, bn_rv; int64_t scale, shift; int cin; };
@@ -141,6 +144,25 @@ struct Builder {
       }
     }
     return c;
+  }
+  void coupling_jobs(StepW& st, int nch0, int nch1, int C) {
+    const int PT = cpl_planes(nch0, nch1);
+    const int NK1 = (PT + 1) / 2 * 2, NPL = (PT + 2) / 2 * 2;
+    st.cpl_nch0 = nch0; st.cpl_nch1 = nch1; st.cpl_npad = tc_npad(C);
+    st.cpl_w1 = pack_alloc((int64_t)2 * NK1 * 16 * 4);
+    st.cpl_w2 = pack_alloc((int64_t)2 * NPL * 16 * 4);
+    st.cpl_w3 = pack_alloc((int64_t)9 * 2 * NPL * st.cpl_npad * 4);
+    auto job = [&](int type, const ConvW& w, int nplanes, int nd, int64_t dst) {
+      PackJob j{};
+      j.type = type; j.a = w.O; j.b = w.I; j.opad = st.cpl_npad; j.nplanes = nplanes;
+      j.nch0 = nch0; j.nch1 = nch1; j.nd = nd;
+      for (auto& s : j.src) s = -1;
+      j.src[0] = w.w_param; j.dst[0] = dst;
+      m.jobs.push_back(j);
+    };
+    job(JOB_CPL_W12, st.d1, NK1, 0, st.cpl_w1);
+    job(JOB_CPL_W12, st.d2, NPL, 1, st.cpl_w2);
+    job(JOB_CPL_W3, st.zc, NPL, 2, st.cpl_w3);
   }
   int64_t gain(int64_t scale_param) {
     int64_t o = pack_alloc(1);
@@ -266,12 +288,14 @@ static int build_model(tmg_model& m) {
         int64_t sc = B.add(sp + "coupling.out_conv.zero_conv.scale", {1, 1, 1, 1});
         st.zc = B.conv(sp + "coupling.out_conv.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
+        B.coupling_jobs(st, cin_t, 0, C);
       } else {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
         int64_t sc = B.add(sp + "coupling.coupling_nn.zero_conv.scale", {1, 1, 1, 1});
         st.zc = B.conv(sp + "coupling.coupling_nn.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
+        B.coupling_jobs(st, C / 2, c.cond_features, C);
       }
       lv.steps.push_back(st);
     }
@@ -298,7 +322,7 @@ struct Plan {
   // offsets in floats
   size_t xn, e0, db[TMG_MAX_LEVELS], cc, cond[TMG_MAX_LEVELS], zo_pre, zout;
   size_t bn_mean, bn_var, bn_scale, bn_shift;
-  size_t y[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
+  size_t y[TMG_MAX_LEVELS], y2[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
 };
 
 static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
@@ -334,12 +358,13 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
     p.db[l] = take(Bz * p.eh[l] * p.ew[l] * lv.nf_out);
     p.cond[l] = take(Bz * p.Hl[l] * p.Wl[l] * c.cond_features);
     p.y[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
+    p.y2[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
     cc_max = std::max(cc_max, Bz * p.eh[l] * p.ew[l] * c.cond_features);
     size_t pix = Bz * p.Hl[l] * p.Wl[l];
     mx_pix = std::max(mx_pix, pix);
     mx_y = std::max(mx_y, pix * lv.C);
     mx_g = std::max(mx_g, pix * 4 * c.rec_features);
-    mx_u = std::max(mx_u, pix * (lv.C / 2 + c.cond_features));
+    mx_u = std::max(mx_u, pix * (size_t)((lv.C / 2 + c.cond_features + 3) / 4 * 4));
     nf_max = std::max(nf_max, lv.nf_out);
   }
   p.cc = take(cc_max);
@@ -351,7 +376,7 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
   p.d = take(mx_pix * 2);
   p.gates = take(mx_g);
   p.u0 = take(mx_u);
-  p.ctas = cdiv(p.Hl[0] * p.Wl[0], kPixTile);
+  p.ctas = std::max(cdiv(p.Hl[0] * p.Wl[0], kPixTile), coupling_tc_tiles(p.Hl[0], p.Wl[0]));
   p.nslots = 1;
   for (int l = 0; l < L; ++l) p.nslots += c.glow_blocks[l] + 1;
   p.ldp = take(Bz * p.nslots * p.ctas);
@@ -478,7 +503,8 @@ static int run_encoder(Ctx& c, const float* x, bool bn_train) {
 
 // ------------------------------------------------------------------ coupling network of one step -> HR
 static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int Wl, const float* Y,
-                           const float* cond, const float* h_in, const float* c_in, float* h_out, float* c_out) {
+                           const float* cond, const float* h_in, const float* c_in, float* h_out, float* c_out,
+                           bool nn_only_lstm = false) {
   const tmg_config& g = c.m.cfg;
   const Plan& p = c.p;
   float* ws = c.ws;
@@ -512,10 +538,13 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       TMG_TRY(launch_lstm_pointwise(la, c.st));
     }
     ConvSrc os[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0}, {h_out, R, 0, R, 0}};
-    TMG_TRY(run_conv(c, PROF_CONV_OUT, s.outc, os, 3, B, Hl, Wl, 1, false, 1, -1, nullptr, nullptr, ws + p.u0, cin_t, 0));
-    src[0] = ConvSrc{ws + p.u0, cin_t, 0, cin_t, 1};
+    const int u0s = (cin_t + 3) / 4 * 4;       // padded pixel stride: 16-byte aligned planes for the fused kernel
+    TMG_TRY(run_conv(c, PROF_CONV_OUT, s.outc, os, 3, B, Hl, Wl, 1, false, 1, -1, nullptr, nullptr, ws + p.u0, u0s, 0));
+    if (nn_only_lstm) return TMG_OK;
+    src[0] = ConvSrc{ws + p.u0, u0s, 0, cin_t, 1};
     nt = 1;
   } else {
+    if (nn_only_lstm) return TMG_OK;
     src[0] = ConvSrc{Y, C, 0, C / 2, 1};
     src[1] = ConvSrc{cond, cf, 0, cf, 1};
     nt = 2;
@@ -545,6 +574,51 @@ static int run_pointwise(Ctx& c, int level, float* Y, bool coupling, const StepW
   ProfScope ps(c.st, PROF_POINTWISE, px * a.C * (mix ? 2.0 * a.C : 0.0) + px * a.C * 6.0,
                4.0 * px * a.C * (coupling ? 3.0 : 2.0));
   return launch_flow_pointwise(a, c.st);
+}
+
+// One flow step on the current flow state *Y (alternate buffer *Y2).
+//   reverse: coupling_rev(step) -> W -> ActNorm_rev            (mix = this step)
+//   forward: coupling_fwd(step) -> ActNorm_fwd -> W^-1 of `mix` (= the NEXT step, or null)
+// Tensor-core precisions run the fused kernel (one launch, result in *Y2, pointers swapped);
+// fp32 runs the CUDA-core kernels in place.
+static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool reverse, int B, int Hl, int Wl,
+                    float*& Y, float*& Y2, const float* cond, const float* h_in, const float* c_in, float* h_out,
+                    float* c_out, float* ld_slot) {
+  const tmg_config& g = c.m.cfg;
+  const int C = c.m.levels[level].C, cf = g.cond_features, HW = Hl * Wl;
+  if (c.m.precision != TMG_PREC_FP32 && st.cpl_w3 >= 0) {
+    CouplingArgs a{};
+    if (st.kind == STEP_LSTM) {
+      TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, cond, h_in, c_in, h_out, c_out, true));
+      const int cin_t = C / 2 + cf;
+      a.src[0] = ConvSrc{c.ws + c.p.u0, (cin_t + 3) / 4 * 4, 0, cin_t, 1};
+      a.nsrc = 1;
+    } else {
+      a.src[0] = ConvSrc{Y, C, 0, C / 2, 1};
+      a.src[1] = ConvSrc{cond, cf, 0, cf, 1};
+      a.nsrc = 2;
+    }
+    a.w1 = c.Q() + st.cpl_w1; a.w2 = c.Q() + st.cpl_w2; a.w3 = c.Q() + st.cpl_w3; a.npad = st.cpl_npad;
+    a.bias3 = c.P() + st.zc.b_param; a.gain3 = c.Q() + st.zc_gain;
+    a.C = C; a.y_in = Y; a.y_out = Y2;
+    if (mix) {
+      a.wmat = c.Q() + (reverse ? mix->W : mix->Wi);
+      if (mix->kind != STEP_UNNORMED) { a.nw = c.P() + mix->norm_w; a.nb = c.P() + mix->norm_b; }
+    }
+    a.reverse = reverse ? 1 : 0;
+    a.ld_part = ld_slot; a.ld_stride = c.p.nslots * c.p.ctas;
+    a.B = B; a.H = Hl; a.W = Wl; a.split3 = c.m.precision == TMG_PREC_TF32X3 ? 1 : 0;
+    const double px = (double)B * HW;
+    const int cin_t = C / 2 + cf;
+    // algorithmic work of the whole step: three convs + 1x1; bytes: read x + cond, write y
+    ProfScope ps(c.st, PROF_STEP_FUSED, 2.0 * px * 9.0 * (cin_t + (cin_t + 1) + (double)C * (cin_t + 2)) + 2.0 * px * C * C,
+                 4.0 * px * (2.0 * C + cf));
+    int rc = launch_coupling_tc(a, c.st);
+    if (rc == TMG_OK) { float* t = Y; Y = Y2; Y2 = t; }
+    return rc;
+  }
+  TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, cond, h_in, c_in, h_out, c_out));
+  return run_pointwise(c, level, Y, true, mix, reverse, B, HW, ld_slot);
 }
 
 static int run_split_prior(Ctx& c, int level, int B, int Hl, int Wl, const float* Y) {
@@ -595,7 +669,7 @@ int tmg_device_count(void) {
 
 static const char* kProfNames[PROF_NTAGS] = {"conv_lstm_gates", "conv_lstm_out", "conv_zero", "conv_dense_cout1",
                                               "conv_split_prior", "conv_encoder", "flow_pointwise", "lstm_pointwise",
-                                              "gaussian", "permute", "misc"};
+                                              "gaussian", "permute", "misc", "flow_step_fused"};
 
 int tmg_profile_enable(int on) {
   for (auto& r : tmg::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -761,6 +835,7 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const flo
     const LevelW& lv = m->levels[l];
     const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl;
     float* Y = ws + p.y[l];
+    float* Y2 = ws + p.y2[l];
     // Split.reverse (flowUtils.py:316-335)
     TMG_TRY(run_split_prior(c, l, B, Hl, Wl, Y));
     GaussArgs ga{};
@@ -772,9 +847,8 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const flo
     // steps n..1 reversed (flowLSTMBlock.py:348-359)
     for (int s = (int)lv.steps.size() - 1; s >= 0; --s) {
       const StepW& st = lv.steps[s];
-      TMG_TRY(run_coupling_nn(c, l, st, B, Hl, Wl, Y, ws + p.cond[l], h_in ? h_in[l] : nullptr,
-                              c_in ? c_in[l] : nullptr, h_out[l], c_out[l]));
-      TMG_TRY(run_pointwise(c, l, Y, true, &st, true, B, HW, ws + p.ldp + (size_t)(slot++) * p.ctas));
+      TMG_TRY(run_step(c, l, st, &st, true, B, Hl, Wl, Y, Y2, ws + p.cond[l], h_in ? h_in[l] : nullptr,
+                       c_in ? c_in[l] : nullptr, h_out[l], c_out[l], ws + p.ldp + (size_t)(slot++) * p.ctas));
     }
     // CheckerSqueeze.reverse (flowUtils.py:124-145)
     PermArgs pa{};
@@ -807,16 +881,18 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
   int slot = 0;
+  float* yfinal[TMG_MAX_LEVELS] = {nullptr};
   for (int l = 0; l < L; ++l) {
     const LevelW& lv = m->levels[l];
     const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl;
     float* Y = ws + p.y[l];
+    float* Y2 = ws + p.y2[l];
     // CheckerSqueeze.forward (flowUtils.py:99-121)
     PermArgs pa{};
     pa.dst = Y; pa.dst_cstride = lv.C; pa.dst_coff = 0;
     pa.B = B; pa.C = lv.C / 4; pa.H = 2 * Hl; pa.W = 2 * Wl;
     if (l == 0) { pa.mode = PERM_SQUEEZE_NCHW_TO_NHWC; pa.src = y; }
-    else { pa.mode = PERM_SQUEEZE_NHWC_TO_NHWC; pa.src = ws + p.y[l - 1]; pa.src_cstride = m->levels[l - 1].C; pa.src_coff = 0; }
+    else { pa.mode = PERM_SQUEEZE_NHWC_TO_NHWC; pa.src = yfinal[l - 1]; pa.src_cstride = m->levels[l - 1].C; pa.src_coff = 0; }
     TMG_TRY(launch_permute(pa, c.st));
     // steps 1..n: [ActNorm ->] W^-1 -> coupling; the coupling of step s is fused with the
     // ActNorm/W^-1 of step s+1 (flowLSTMBlock.py:296-308)
@@ -824,10 +900,9 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
     TMG_TRY(run_pointwise(c, l, Y, false, &lv.steps[0], false, B, HW, nullptr));
     for (int s = 0; s < n; ++s) {
       const StepW& st = lv.steps[s];
-      TMG_TRY(run_coupling_nn(c, l, st, B, Hl, Wl, Y, ws + p.cond[l], h_in ? h_in[l] : nullptr,
-                              c_in ? c_in[l] : nullptr, h_out[l], c_out[l]));
-      TMG_TRY(run_pointwise(c, l, Y, true, s + 1 < n ? &lv.steps[s + 1] : nullptr, false, B, HW,
-                            ws + p.ldp + (size_t)(slot++) * p.ctas));
+      TMG_TRY(run_step(c, l, st, s + 1 < n ? &lv.steps[s + 1] : nullptr, false, B, Hl, Wl, Y, Y2, ws + p.cond[l],
+                       h_in ? h_in[l] : nullptr, c_in ? c_in[l] : nullptr, h_out[l], c_out[l],
+                       ws + p.ldp + (size_t)(slot++) * p.ctas));
     }
     // Split.forward (flowUtils.py:292-314)
     TMG_TRY(run_split_prior(c, l, B, Hl, Wl, Y));
@@ -837,13 +912,14 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
     ga.eps_out = eps_out ? eps_out[l] : nullptr; ga.reverse = 0; ga.B = B; ga.HW = HW; ga.n = lv.C / 2;
     ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
     TMG_TRY(launch_gaussian(ga, c.st));
+    yfinal[l] = Y;
   }
   // top prior log p(z | cmean, clog_std) and eps0 (tmGlow.py:399-412)
   {
     const LevelW& lv = m->levels[L - 1];
     GaussArgs ga{};
     ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz;
-    ga.val = ws + p.y[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
+    ga.val = yfinal[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
     ga.eps_out = eps_out ? eps_out[L] : nullptr; ga.val_nchw = z; ga.reverse = 0;
     ga.B = B; ga.HW = p.Hl[L - 1] * p.Wl[L - 1]; ga.n = m->Cz;
     ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
@@ -962,9 +1038,10 @@ int tmg_flow_step(tmg_model* m, int level, int step, int reverse, int B, int Hl,
   TMG_TRY(launch_permute(pa, c.st));
   pa.src = cond; pa.dst = CN; pa.C = cf; pa.dst_cstride = cf;
   TMG_TRY(launch_permute(pa, c.st));
+  float* Y2 = ws + p.scratch_out;
   if (!reverse) TMG_TRY(run_pointwise(c, level, Y, false, &st, false, B, HW, nullptr));
-  TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, h_in, c_in, h_out, c_out));
-  TMG_TRY(run_pointwise(c, level, Y, true, reverse ? &st : nullptr, reverse != 0, B, HW, ws + p.ldp));
+  TMG_TRY(run_step(c, level, st, reverse ? &st : nullptr, reverse != 0, B, Hl, Wl, Y, Y2, CN, h_in, c_in, h_out, c_out,
+                   ws + p.ldp));
   PermArgs pb{};
   pb.src = Y; pb.dst = out; pb.mode = PERM_NHWC_TO_NCHW; pb.B = B; pb.C = C; pb.H = Hl; pb.W = Wl; pb.src_cstride = C;
   TMG_TRY(launch_permute(pb, c.st));

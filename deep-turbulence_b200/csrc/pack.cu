@@ -43,6 +43,35 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       d[i] = hl ? (v - hi) : hi;
     }
+  } else if (j.type == JOB_CPL_W12 || j.type == JOB_CPL_W3) {
+    // Weights of the fused coupling kernel (coupling_tc.cu).  K is laid out in 4-channel planes with
+    // every source starting on a plane boundary: [src0 planes][src1 planes][d plane][zero planes].
+    //   W12: Cout=1 dense layer, taps in N:  [hi|lo][plane][16][4],  value w[0][c][tap n] for n < 9
+    //   W3 : Conv2dZeros:                    [tap][hi|lo][plane][npad][4], value w[n][c][tap]
+    const int O = j.a, I = j.b, NPL = j.nplanes, NP = j.type == JOB_CPL_W12 ? 16 : j.opad;
+    const int p0 = (j.nch0 + 3) / 4, p1 = (j.nch1 + 3) / 4;
+    const float* s = P + j.src[0];
+    float* d = Q + j.dst[0];
+    const size_t total = (size_t)(j.type == JOB_CPL_W12 ? 1 : 9) * 2 * NPL * NP * 4;
+    for (size_t i = tid; i < total; i += blockDim.x) {
+      int e = i & 3;
+      size_t t = i >> 2;
+      int n = t % NP; t /= NP;
+      int plane = t % NPL; t /= NPL;
+      int hl = t & 1; t >>= 1;
+      int tap = (int)t;                       // W3 only
+      int c = -1;                              // concatenated input channel
+      if (plane < p0) { int q = plane * 4 + e; if (q < j.nch0) c = q; }
+      else if (plane < p0 + p1) { int q = (plane - p0) * 4 + e; if (q < j.nch1) c = j.nch0 + q; }
+      else if (plane == p0 + p1) { if (e < j.nd) c = j.nch0 + j.nch1 + e; }
+      float v = 0.f;
+      if (c >= 0 && c < I) {
+        if (j.type == JOB_CPL_W12) { if (n < 9) v = s[(size_t)c * 9 + n]; }
+        else if (n < O) v = s[((size_t)n * I + c) * 9 + tap];
+      }
+      float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      d[i] = hl ? (v - hi) : hi;
+    }
   } else if (j.type == JOB_GAIN) {
     if (tid == 0) Q[j.dst[0]] = expf(fminf(fmaxf(P[j.src[0]], -4.f), kLog4));
   } else if (j.type == JOB_BN) {

@@ -281,3 +281,23 @@ def test_default_model_tensor_core_modes():
         report[mode] = (ez, ey, el, ed)
         print("precision %s: |z| %.2e |y| %.2e logp %.2e log_det %.2e" % (mode, ez, ey, el, ed))
         assert ez <= ftol and ey <= ftol and el <= ltol + 1e-7 and ed <= ltol + 1e-7, (mode, report[mode])
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("tf32", 2e-2)])
+def test_fused_step_operators(mode, tol):
+    """Every step kind of block 0 through the fused tensor-core step kernel (coupling_tc.cu)."""
+    from tmglow_b200 import ops
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"])
+    m.precision = mode
+    dev = _dev()
+    for s, rec in enumerate(g["modules"]["steps"], start=1):
+        st = rec.get("state")
+        st = None if st is None else (st[0].to(dev), st[1].to(dev))
+        o, ld, so = ops.flow_step(m, 0, s, rec["x"].to(dev), rec["cond"].to(dev), st, reverse=False)
+        _field_close(o, rec["fwd"], tol=tol, what="%s step%d fwd" % (mode, s))
+        r, ldr, sr = ops.flow_step(m, 0, s, rec["x"].to(dev), rec["cond"].to(dev), st, reverse=True)
+        _field_close(r, rec["rev"], tol=tol, what="%s step%d rev" % (mode, s))
+        if mode == "tf32x3":
+            _logp_close(ld, rec["fwd_logdet"], "fwd logdet"); _logp_close(ldr, rec["rev_logdet"], "rev logdet")
