@@ -36,6 +36,8 @@ MODEL_KW = dict(cond_features=32, cglow_upscale=2, growth_rate=4, init_features=
 # SURVEY.md 8(d) / BASELINE.md section 3: algorithmic work per HF sample, backward-step geometry
 ALG_FLOP_PER_SAMPLE = 2.159e9
 ALG_BYTES_PER_SAMPLE = 13.9e6
+DTYPES = {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)", "tf32": "tf32",
+          "f16x3": "f32 (fp16 hi+lo tensor-core split, fp32 accumulate)", "f16": "f16 operands, f32 accumulate"}
 
 
 def perturb_(model, seed):
@@ -202,7 +204,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=1024, help="stochastic HF samples per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32", "f16x3", "f16"])
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -340,7 +342,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "hf_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)", "tf32": "tf32"}[args.precision],
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": dict(workload_config(S, world), precision=args.precision),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,

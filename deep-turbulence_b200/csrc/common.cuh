@@ -80,6 +80,7 @@ struct ConvSrc {
   int coff;      // first channel inside the pixel
   int nch;       // channels taken
   int relu;      // apply ReLU while staging
+  int bshared;   // 1: the tensor has batch 1 and is shared by every sample (one LF input, many samples)
 };
 
 struct ConvArgs {
@@ -155,6 +156,38 @@ int coupling_tc_tiles(int H, int W);
 // plane bookkeeping shared by host packing and the kernel: sources start on plane boundaries
 inline int cpl_planes(int nch0, int nch1) { return (nch0 + 3) / 4 + (nch1 + 3) / 4; }
 
+// Fused flow step, fp16-operand generation (flow_step_f16.cu): persistent + pipelined, K layout [src0 | d1 d2 | src1]
+struct Step2Args {
+  ConvSrc src[2];          // coupling-net input t (src[1] = the conditioning map, skipped when hoisted)
+  int nsrc;
+  int hoist;               // 1: src[1]'s contribution comes from the per-step tables dc / hc (same for every sample)
+  const float* dc;         // [HW][dc_stride]: cond part of d1 (+0) and d2 (+1), gathered (pre-ReLU partial sums)
+  int dc_stride;
+  const float* hc;         // [HW][hc_stride]: cond part of the Conv2dZeros output (before bias and gain)
+  int hc_stride;
+  const void* wE;          // fp16 [hl][planes][32][8]   taps of dense layers 1 (cols 0-8) and 2 (cols 16-24)
+  const void* wZ;          // fp16 [tap][hl][planes][NP][8]
+  const float* wmisc;      // [0..8] taps of layer 2's d1 input row, [9..11] inverse weight scales (w1, w2, w3)
+  const float* bias3;
+  const float* gain3;
+  int C;
+  const float* y_in;
+  float* y_out;
+  const float* wmat;
+  const float* nw;
+  const float* nb;
+  int reverse;
+  float* ld_part;
+  int ld_stride;
+  int B, H, W;
+  int x3;                  // 1: hi/lo operand split (fp32-grade), 0: single-pass fp16
+};
+int launch_step2(const Step2Args& a, cudaStream_t st);
+bool step2_supported(const Step2Args& a);
+void step2_klayout(int nch0, int nch1, int& KSy, int& KS1, int& kd);
+size_t step2_wE_floats(int nch0, int nch1);
+size_t step2_wZ_floats(int nch0, int nch1, int C);
+
 // ------------------------------------------------------------------ pointwise flow step
 struct PointArgs {
   float* y;            // [B, HW, C] in/out
@@ -182,6 +215,7 @@ int launch_lstm_pointwise(const LstmArgs& a, cudaStream_t st);
 struct GaussArgs {
   const float* prm;    // NHWC [B,HW,prm_cstride]: mean at ch j, log-std at ch n+j
   int prm_cstride;
+  int prm_bshared;     // 1: prm has batch 1, shared by every sample
   float* val;          // NHWC value tensor, element (pixel, val_coff + j)
   int val_cstride, val_coff;
   const float* eps_in; // NCHW [B,n,HW]   (reverse: val = mean + exp(logsd)*eps)
@@ -257,7 +291,8 @@ struct LogdetArgs {
 int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ weight packing jobs
-enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6 };
+enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
+                   JOB_STEP2 = 7, JOB_HOIST = 8 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n

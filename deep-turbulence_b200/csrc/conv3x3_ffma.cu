@@ -75,7 +75,7 @@ conv3x3_kernel(ConvArgs a, int plane, int rows_in_max) {
         if (cc >= s->nch && a.nsrc > 1) { cc -= s->nch; s = &a.src[1];
           if (cc >= s->nch && a.nsrc > 2) { cc -= s->nch; s = &a.src[2]; } }
         if (cc < s->nch) {
-          v = __ldg(s->p + ((size_t)(b * a.Hin + gr) * a.Win + gc) * s->cstride + s->coff + cc);
+          v = __ldg(s->p + ((size_t)((s->bshared ? 0 : b) * a.Hin + gr) * a.Win + gc) * s->cstride + s->coff + cc);
           if (a.bn_scale) v = fmaf(v, __ldg(a.bn_scale + c), __ldg(a.bn_shift + c));
           if (s->relu) v = fmaxf(v, 0.f);
         }

@@ -84,7 +84,7 @@ conv3x3_tc_kernel(TcConvArgs a, int npos_pad, int nstage, int tps, int tmem_cols
           bool inb = r >= 0 && r < a.H && cc >= 0 && cc < a.W;
           if (a.pad_replicate) { r = min(max(r, 0), a.H - 1); cc = min(max(cc, 0), a.W - 1); inb = true; }
           if (inb) {
-            const size_t pix = ((size_t)b * a.H + r) * a.W + cc;
+            const size_t pix0 = (size_t)r * a.W + cc, pixb = (size_t)b * a.H * a.W + pix0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               int ch = c0 + plane * 4 + e;
@@ -93,7 +93,7 @@ conv3x3_tc_kernel(TcConvArgs a, int npos_pad, int nstage, int tps, int tmem_cols
                 if (ch >= s->nch && a.nsrc > 1) { ch -= s->nch; s = &a.src[1];
                   if (ch >= s->nch && a.nsrc > 2) { ch -= s->nch; s = &a.src[2]; } }
                 if (ch < s->nch) {
-                  float t = __ldg(s->p + pix * s->cstride + s->coff + ch);
+                  float t = __ldg(s->p + (s->bshared ? pix0 : pixb) * s->cstride + s->coff + ch);
                   v[e] = s->relu ? fmaxf(t, 0.f) : t;
                 }
               }

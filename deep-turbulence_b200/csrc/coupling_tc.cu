@@ -97,7 +97,7 @@ coupling_tc_kernel(CouplingArgs a, CplGeom g) {
             const ConvSrc& s = a.src[s1 ? 1 : 0];
             const int ch = (s1 ? plane - g.planes0 : plane) * 4;
             const int nv = min(4, s.nch - ch);
-            const float* ptr = s.p + ((size_t)b * HW + (size_t)r * a.W + c) * s.cstride + s.coff + ch;
+            const float* ptr = s.p + ((s.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c) * s.cstride + s.coff + ch;
             float4 t;
             if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
               t = __ldg(reinterpret_cast<const float4*>(ptr));

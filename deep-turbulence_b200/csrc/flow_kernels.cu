@@ -157,7 +157,7 @@ gaussian_kernel(GaussArgs a) {
   const int p = blockIdx.x * kPixTile + threadIdx.x;
   float lsum = 0.f;
   if (p < a.HW) {
-    const float* pr = a.prm + ((size_t)b * a.HW + p) * a.prm_cstride;
+    const float* pr = a.prm + ((size_t)(a.prm_bshared ? 0 : b) * a.HW + p) * a.prm_cstride;
     float* vp = a.val + ((size_t)b * a.HW + p) * a.val_cstride + a.val_coff;
     for (int j = 0; j < a.n; ++j) {
       float mu = pr[j];

@@ -1,0 +1,568 @@
+// Fused flow step, second generation (sm_100a): persistent, software-pipelined, fp16-operand tcgen05.
+//
+// One launch = one flow step over all samples:
+//   t = cat(x1, cond) -> d1 = conv3x3(relu(t)) -> d2 = conv3x3(relu(cat(t,d1))) -> h = Conv2dZeros(relu(cat(t,d1,d2)))
+//   (flowAffine.py:49-55,73; denseBlock.py:135-150; flowUtils.py:238-247), then the coupling update, the invertible
+//   1x1 convolution, ActNorm and the per-sample log-det partial (flowAffine.py:76-81,102-107; glowConv.py:193,219;
+//   actNorm.py:66,82).
+//
+// What changed against coupling_tc.cu (measured on B200, tools/ubench_mma.cu: a tcgen05.mma with N <= 64 costs
+// ~45 cycles whatever N is, and a single issuing thread that does address arithmetic between MMAs runs at
+// 100-200 cycles per MMA):
+//   * operands are fp16 (kind::f16, K = 16 per MMA).  "x3" mode splits both operands into hi + lo halves
+//     (a = a_hi + a_lo, three MMAs: hi*hi + lo*hi + hi*lo); with weights pre-scaled by a power of two the
+//     result is fp32-grade (2^-22 relative per operand) at HALF the MMA count and HALF the shared memory of
+//     the 3xTF32 split.  Single-pass fp16 (11-bit mantissa like TF32) is the fast mode.
+//   * persistent CTAs (one per SM) loop over 16x16-pixel tiles; the step's weights stay in shared memory.
+//   * three roles run concurrently on different tiles: producer warps stage tile k+2, the MMA warp issues
+//     E(k+1) then Z(k), the epilogue warps gather d1/d2 of tile k+1 then finish tile k.
+//   * E = one un-shifted GEMM with the 9 taps of BOTH Cout=1 dense layers in N (cols 0-8: layer 1, 16-24: layer 2);
+//     the d1 -> d2 dependency (one input channel, 9 taps) is 9 FMAs per position on CUDA cores.
+//   * Z = Conv2dZeros as a tap-shifted implicit GEMM whose M tile is 16 rows x 8 columns of output pixels:
+//     the shared-memory descriptor's stride between 8-row groups (SBO) is one padded image row, so no
+//     accumulator row is wasted on halo columns.
+//   * K layout [x1 | d1 d2 | cond]: when all samples share one conditioning input (one LF snapshot, many
+//     stochastic samples) the cond K-steps are dropped and their contribution, which is the same for every
+//     sample, is read from a per-step table computed once per call ("hoisted", model.cu).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tmg {
+
+constexpr int kRP = 22;                  // padded tile pitch: 16 + 2*3
+constexpr int kNPOS = 484;               // 22 x 22 staged positions
+constexpr int kNPOSA = 512;              // allocated positions (4 E tiles of 128)
+constexpr uint32_t kPLB = kNPOSA * 16;   // bytes of one 8-channel plane
+constexpr int kS2Threads = 416;          // warps 0-7 epilogue, 8 MMA, 9-12 producers
+constexpr int kEpiThreads = 256;
+
+struct Step2Geom {
+  int KS, KSy, PLtot, kd, nbuf, pipelined;
+  int tiles_x, tiles_y, ntiles, nhl;
+  uint32_t hlA, bufA;
+  uint32_t oA, oDsc, oD1, oWE, oWZ, oWm, oBar, total;
+  uint32_t wE_hl, wZ_tap, wZ_hl;         // shared-memory strides of the weight copies
+  uint32_t gE_hl, gZ_tap, gZ_hl;         // strides of the packed (global) weights
+};
+
+__device__ __forceinline__ uint32_t idesc_f16(int n) {   // D = F32, A = B = F16, K-major, M = 128
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 -> (hi, lo) fp16 pair; |v| is clamped to the fp16 range (flow states beyond 6e4 are not meaningful)
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v, -60000.f), 60000.f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+template <int C, bool X3>
+__global__ void __launch_bounds__(kS2Threads, 1)
+flow_step_f16_kernel(Step2Args a, Step2Geom g) {
+  constexpr int NP = (C + 15) / 16 * 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = a.H * a.W;
+  const int tiles_img = g.tiles_x * g.tiles_y;
+
+  uint8_t* A = smem + g.oA;
+  float* Dsc = reinterpret_cast<float*>(smem + g.oDsc);     // [2 layers][9 taps][512]
+  float* D1 = reinterpret_cast<float*>(smem + g.oD1);       // [512] relu(d1)
+  uint8_t* WE = smem + g.oWE;
+  uint8_t* WZ = smem + g.oWZ;
+  float* Wm = reinterpret_cast<float*>(smem + g.oWm);       // C*C mix | nw | nb | bias3 | w2d[9] | inv scales[3] | red[8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.oBar);
+  uint64_t* a_full = bars;          // [3] producers (128)
+  uint64_t* a_free = bars + 3;      // [3] commit
+  uint64_t* d_ready = bars + 6;     // [3] epilogue (256)
+  uint64_t* e_full = bars + 9;      // [2] commit
+  uint64_t* e_free = bars + 11;     // [2] epilogue (256)
+  uint64_t* z_full = bars + 13;     // [2] commit
+  uint64_t* z_free = bars + 15;     // [2] epilogue (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  float* s_nw = Wm + C * C;
+  float* s_nb = s_nw + C;
+  float* s_b3 = s_nb + C;
+  float* s_w2d = s_b3 + C;
+  float* s_inv = s_w2d + 9;
+  float* s_red = s_inv + 3;
+
+  // ------------------------------------------------------------------ one-time setup
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(a_full + i, 128); mbar_init(a_free + i, 1); mbar_init(d_ready + i, kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_free + i, kEpiThreads); mbar_init(z_full + i, 1); mbar_init(z_free + i, kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  {
+    // zero every A buffer once: tail positions, padding channels and the d slots start as finite zeros
+    uint4* z4 = reinterpret_cast<uint4*>(A);
+    const int n4 = (int)((size_t)g.nbuf * g.bufA / 16);
+    for (int i = tid; i < n4; i += kS2Threads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+    // weights: packed global [hl][PLtot][..] -> shared [hl][2*KS][..] (only the K-steps this launch multiplies)
+    const int pl = 2 * g.KS;
+    const uint4* gE = reinterpret_cast<const uint4*>(a.wE);
+    for (int i = tid; i < g.nhl * pl * 32; i += kS2Threads) {
+      const int r = i % (pl * 32), hl = i / (pl * 32);
+      reinterpret_cast<uint4*>(WE + hl * g.wE_hl)[r] = __ldg(gE + (size_t)hl * (g.gE_hl / 16) + r);
+    }
+    const uint4* gZ = reinterpret_cast<const uint4*>(a.wZ);
+    const int per = pl * NP;
+    for (int i = tid; i < 9 * g.nhl * per; i += kS2Threads) {
+      const int r = i % per; int t = i / per; const int hl = t % g.nhl, tap = t / g.nhl;
+      reinterpret_cast<uint4*>(WZ + tap * g.wZ_tap + hl * g.wZ_hl)[r] =
+          __ldg(gZ + (size_t)tap * (g.gZ_tap / 16) + (size_t)hl * (g.gZ_hl / 16) + r);
+    }
+    for (int i = tid; i < C * C; i += kS2Threads) Wm[i] = a.wmat ? __ldg(a.wmat + i) : 0.f;
+    for (int i = tid; i < C; i += kS2Threads) {
+      s_nw[i] = a.nw ? __ldg(a.nw + i) : 1.f;
+      s_nb[i] = a.nw ? __ldg(a.nb + i) : 0.f;
+      s_b3[i] = __ldg(a.bias3 + i);
+    }
+    if (tid < 12) s_w2d[tid] = __ldg(a.wmisc + tid);        // w2d[9] then the three inverse scales
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp < 8) {
+    // =========================================================== epilogue warps (256 threads)
+    const int etid = tid, wg = etid >> 7, el = etid & 127;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float gain = a.gain3 ? __ldg(a.gain3) : 1.f;
+    const float inv1 = s_inv[0], inv2 = s_inv[1], inv3 = s_inv[2];
+
+    auto tile_origin = [&](int k, int& b, int& r0, int& c0, int& timg) {
+      const int t = blockIdx.x + k * gridDim.x;
+      b = t / tiles_img; timg = t - b * tiles_img;
+      r0 = (timg / g.tiles_x) * 16; c0 = (timg % g.tiles_x) * 16;
+    };
+
+    // ---- G(k): E accumulators -> d1, d2 written into the A buffer of tile k
+    auto gather = [&](int k) {
+      const int s = k & 1, u = k % g.nbuf;
+      int b, r0, c0, timg;
+      tile_origin(k, b, r0, c0, timg);
+      mbar_wait(e_full + s, (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int mt = 2 * wg + j, pos = mt * 128 + el;
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(s * 256 + mt * 32), v);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { Dsc[t * kNPOSA + pos] = v[t] * inv1; Dsc[(9 + t) * kNPOSA + pos] = v[16 + t] * inv2; }
+      }
+      tc_fence_before();
+      mbar_arrive(e_free + s);
+      named_bar_sync(1, kEpiThreads);
+      // d1 on the halo-2 region
+      for (int p = etid; p < kNPOS; p += kEpiThreads) {
+        const int rr = p / kRP, rc = p - rr * kRP;
+        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
+        if (rr >= 1 && rr <= 20 && rc >= 1 && rc <= 20 && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W) {
+          float sum = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int dr = t / 3 - 1, dc = t % 3 - 1;
+            if (ir + dr >= 0 && ir + dr < a.H && ic + dc >= 0 && ic + dc < a.W) sum += Dsc[t * kNPOSA + p + dr * kRP + dc];
+          }
+          if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride);
+          D1[p] = fmaxf(sum, 0.f);
+        }
+      }
+      named_bar_sync(1, kEpiThreads);
+      // d2 on the halo-1 region; the (d1, d2) pair goes into K slots kd, kd+1 of the A buffer
+      uint8_t* dslot = A + (size_t)u * g.bufA + (size_t)(g.kd >> 3) * kPLB + (size_t)(g.kd & 7) * 2;
+      for (int p = etid; p < kNPOS; p += kEpiThreads) {
+        const int rr = p / kRP, rc = p - rr * kRP;
+        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
+        if (rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19 && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W) {
+          float sum = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int dr = t / 3 - 1, dc = t % 3 - 1;
+            if (ir + dr >= 0 && ir + dr < a.H && ic + dc >= 0 && ic + dc < a.W) {
+              const int q = p + dr * kRP + dc;
+              sum += Dsc[(9 + t) * kNPOSA + q];
+              sum = fmaf(s_w2d[t], D1[q], sum);
+            }
+          }
+          if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride + 1);
+          const float d1 = D1[p], d2 = fmaxf(sum, 0.f);
+          __half h1, l1, h2, l2;
+          split_h(d1, h1, l1); split_h(d2, h2, l2);
+          *reinterpret_cast<uint32_t*>(dslot + (size_t)p * 16) = pack_h2(h1, h2);
+          if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)p * 16) = pack_h2(l1, l2);
+        }
+      }
+      named_bar_sync(1, kEpiThreads);
+      // replicate padding of Conv2dZeros: out-of-image positions copy the clamped pixel's pair
+      for (int p = etid; p < kNPOS; p += kEpiThreads) {
+        const int rr = p / kRP, rc = p - rr * kRP;
+        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
+        if (rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19 && (ir < 0 || ir >= a.H || ic < 0 || ic >= a.W)) {
+          const int cr = min(max(ir, 0), a.H - 1) - (r0 - 3), cc = min(max(ic, 0), a.W - 1) - (c0 - 3);
+          if (cr >= 2 && cr <= 19 && cc >= 2 && cc <= 19) {
+            const int pc = cr * kRP + cc;
+            *reinterpret_cast<uint32_t*>(dslot + (size_t)p * 16) = *reinterpret_cast<const uint32_t*>(dslot + (size_t)pc * 16);
+            if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)p * 16) =
+                        *reinterpret_cast<const uint32_t*>(dslot + g.hlA + (size_t)pc * 16);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(d_ready + u);
+    };
+
+    // ---- F(k): h -> coupling, 1x1 mix, ActNorm, store, log-det partial
+    auto finish = [&](int k) {
+      const int s = k & 1;
+      int b, r0, c0, timg;
+      tile_origin(k, b, r0, c0, timg);
+      const int ir = r0 + (el >> 3), ic = c0 + 8 * wg + (el & 7);
+      const bool valid = ir < a.H && ic < a.W;
+      const size_t pix = valid ? (size_t)b * HW + (size_t)ir * a.W + ic : 0;
+      float v[C];
+      if (valid) {
+        const float4* y4 = reinterpret_cast<const float4*>(a.y_in + pix * C);
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) { float4 t = __ldg(y4 + q); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+      }
+      mbar_wait(z_full + s, (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+      float ldsum = 0.f;
+      const uint32_t trow = tmem_base + lane_base + (uint32_t)(s * 256 + 128 + wg * NP);
+      const float* hcp = (a.hoist && valid) ? a.hc + (size_t)(ir * a.W + ic) * a.hc_stride : nullptr;
+#pragma unroll
+      for (int n0 = 0; n0 < NP; n0 += 16) {
+        float h[16];
+        tmem_ld16(trow + n0, h);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 16; q += 2) {
+            if (n0 + q < C) {
+              float hs = h[q] * inv3, hr = h[q + 1] * inv3;
+              if (hcp) { hs += __ldg(hcp + n0 + q); hr += __ldg(hcp + n0 + q + 1); }
+              const float shift = (hs + s_b3[n0 + q]) * gain;            // h[:, 0::2]
+              const float raw = (hr + s_b3[n0 + q + 1]) * gain;          // h[:, 1::2]
+              const float la = 2.f * (raw / (1.f + fabsf(raw)));
+              ldsum += la;
+              const float sc = expf(la);
+              const int j = C / 2 + (n0 + q) / 2;
+              v[j] = a.reverse ? v[j] / sc - shift : (v[j] + shift) * sc;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(z_free + s);
+      if (valid) {
+        if (!a.reverse && a.nw) {
+#pragma unroll
+          for (int q = 0; q < C; ++q) v[q] = fmaf(s_nw[q], v[q], s_nb[q]);
+        }
+        float* yo = a.y_out + pix * C;
+        if (a.wmat) {
+#pragma unroll 1
+          for (int r4 = 0; r4 < C; r4 += 4) {
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float sum = 0.f;
+              const float4* w4 = reinterpret_cast<const float4*>(Wm + (r4 + q) * C);
+#pragma unroll
+              for (int kk = 0; kk < C / 4; ++kk) {
+                const float4 w = w4[kk];
+                sum = fmaf(w.x, v[4 * kk], sum); sum = fmaf(w.y, v[4 * kk + 1], sum);
+                sum = fmaf(w.z, v[4 * kk + 2], sum); sum = fmaf(w.w, v[4 * kk + 3], sum);
+              }
+              if (a.reverse && a.nw) sum = (sum - s_nb[r4 + q]) / s_nw[r4 + q];
+              o[q] = sum;
+            }
+            *reinterpret_cast<float4*>(yo + r4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < C; q += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = (a.reverse && a.nw) ? (v[q + e] - s_nb[q + e]) / s_nw[q + e] : v[q + e];
+            *reinterpret_cast<float4*>(yo + q) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      if (a.ld_part) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
+        named_bar_sync(1, kEpiThreads);              // previous tile's reader is done with s_red
+        if (lane == 0) s_red[warp] = ldsum;
+        named_bar_sync(1, kEpiThreads);
+        if (etid == 0) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) tot += s_red[w];
+          a.ld_part[(size_t)b * a.ld_stride + timg] = tot;
+        }
+      }
+    };
+
+    if (g.pipelined) {
+      if (nmy > 0) gather(0);
+      for (int k = 0; k < nmy; ++k) { if (k + 1 < nmy) gather(k + 1); finish(k); }
+    } else {
+      for (int k = 0; k < nmy; ++k) { gather(k); finish(k); }
+    }
+  } else if (warp == 8) {
+    // =========================================================== MMA issue (one thread)
+    if (lane == 0) {
+      const uint32_t idE = idesc_f16(32), idZ = idesc_f16(NP);
+      const uint64_t bE0 = make_desc(smem_u32(WE), 512, 128);
+      const uint64_t bZ0 = make_desc(smem_u32(WZ), (uint32_t)NP * 16u, 128);
+      const uint64_t hlA16 = g.hlA >> 4, wEhl16 = g.wE_hl >> 4, wZhl16 = g.wZ_hl >> 4, wZtap16 = g.wZ_tap >> 4;
+
+      auto issue_E = [&](int k) {
+        const int s = k & 1, u = k % g.nbuf;
+        mbar_wait(a_full + u, (uint32_t)((k / g.nbuf) & 1));
+        if (k >= 2) mbar_wait(e_free + s, (uint32_t)(((k >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint64_t aE0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, 128);
+        const uint32_t tE = tmem_base + (uint32_t)(s * 256);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          uint64_t ad = aE0 + (uint64_t)(mt * 128);          // 128 positions x 16 B, in 16-byte units
+          uint64_t bd = bE0;
+          for (int ks = 0; ks < g.KS; ++ks) {
+            mma_f16(tE + (uint32_t)(mt * 32), ad, bd, idE, ks > 0 ? 1u : 0u);
+            if (X3) {
+              mma_f16(tE + (uint32_t)(mt * 32), ad + hlA16, bd, idE, 1u);
+              mma_f16(tE + (uint32_t)(mt * 32), ad, bd + wEhl16, idE, 1u);
+            }
+            ad += (uint64_t)(2 * kPLB >> 4);
+            bd += (uint64_t)(2 * 512 >> 4);
+          }
+        }
+        mma_commit(e_full + s);
+      };
+      auto issue_Z = [&](int k) {
+        const int s = k & 1, u = k % g.nbuf;
+        mbar_wait(d_ready + u, (uint32_t)((k / g.nbuf) & 1));
+        if (k >= 2) mbar_wait(z_free + s, (uint32_t)(((k >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint64_t aZ0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, kRP * 16);
+        const uint32_t tZ = tmem_base + (uint32_t)(s * 256 + 128);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            uint64_t ad = aZ0 + (uint64_t)((3 + tap / 3 - 1) * kRP + 3 + 8 * mt + tap % 3 - 1);
+            uint64_t bd = bZ0 + (uint64_t)tap * wZtap16;
+            for (int ks = 0; ks < g.KS; ++ks) {
+              const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
+              mma_f16(tZ + (uint32_t)(mt * NP), ad, bd, idZ, acc);
+              if (X3) {
+                mma_f16(tZ + (uint32_t)(mt * NP), ad + hlA16, bd, idZ, 1u);
+                mma_f16(tZ + (uint32_t)(mt * NP), ad, bd + wZhl16, idZ, 1u);
+              }
+              ad += (uint64_t)(2 * kPLB >> 4);
+              bd += (uint64_t)(2 * NP);                      // 2 planes x NP rows x 16 B, in 16-byte units
+            }
+          }
+        }
+        mma_commit(z_full + s);
+        mma_commit(a_free + u);
+      };
+      if (g.pipelined) {
+        if (nmy > 0) issue_E(0);
+        for (int k = 0; k < nmy; ++k) { if (k + 1 < nmy) issue_E(k + 1); issue_Z(k); }
+      } else {
+        for (int k = 0; k < nmy; ++k) { issue_E(k); issue_Z(k); }
+      }
+    }
+  } else {
+    // =========================================================== producers (128 threads): stage relu(t) as fp16 hi/lo
+    const int ptid = tid - 9 * 32;
+    const int npl0 = 2 * g.KSy;
+    const int npl = (!a.hoist && a.nsrc > 1) ? 2 * g.KS : npl0;
+    for (int k = 0; k < nmy; ++k) {
+      const int u = k % g.nbuf, use = k / g.nbuf;
+      const int t = blockIdx.x + k * gridDim.x;
+      const int b = t / tiles_img, timg = t - b * tiles_img;
+      const int r0 = (timg / g.tiles_x) * 16, c0 = (timg % g.tiles_x) * 16;
+      if (use >= 1) mbar_wait(a_free + u, (uint32_t)((use - 1) & 1));
+      uint8_t* Ab = A + (size_t)u * g.bufA;
+      const int items = kNPOS * npl;
+      for (int it = ptid; it < items; it += 128) {
+        const int p = it % kNPOS, plane = it / kNPOS;
+        const int rr = p / kRP, rc = p - rr * kRP;
+        const int r = min(max(r0 - 3 + rr, 0), a.H - 1), c = min(max(c0 - 3 + rc, 0), a.W - 1);
+        const bool s1 = plane >= npl0;
+        const ConvSrc& sc = a.src[s1 ? 1 : 0];
+        const int ch = (s1 ? plane - npl0 : plane) * 8;
+        const int nv = min(8, sc.nch - ch);                  // may be <= 0: pure padding / d-slot plane
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (nv > 0) {
+          const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c;
+          const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
+          if (nv == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)), t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1);
+            v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (e < nv) v[e] = __ldg(ptr + e);
+          }
+          if (sc.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+        }
+        // the d slots of this plane (if any) are owned by the epilogue warps: keep what is there
+        const bool has_d = !s1 && (g.kd >> 3) == plane;
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_h(v[e], hi[e], lo[e]);
+        uint4 ph = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+        uint8_t* dst = Ab + (size_t)plane * kPLB + (size_t)p * 16;
+        if (has_d) {        // kd & 7 == 6: the pair sits in the last 32-bit word
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+          d32[0] = ph.x; d32[1] = ph.y; d32[2] = ph.z;
+          if (X3) {
+            uint32_t* l32 = reinterpret_cast<uint32_t*>(dst + g.hlA);
+            l32[0] = pack_h2(lo[0], lo[1]); l32[1] = pack_h2(lo[2], lo[3]); l32[2] = pack_h2(lo[4], lo[5]);
+          }
+        } else {
+          *reinterpret_cast<uint4*>(dst) = ph;
+          if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) =
+                      make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(a_full + u);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------ host side
+void step2_klayout(int nch0, int nch1, int& KSy, int& KS1, int& kd) {
+  KSy = (nch0 + 2 + 15) / 16;
+  KS1 = (nch1 + 15) / 16;
+  kd = KSy * 16 - 2;
+}
+size_t step2_wE_floats(int nch0, int nch1) {
+  int KSy, KS1, kd; step2_klayout(nch0, nch1, KSy, KS1, kd);
+  return (size_t)2 * 2 * (KSy + KS1) * 32 * 16 / 4;             // [hl][planes][32][16 B]
+}
+size_t step2_wZ_floats(int nch0, int nch1, int C) {
+  int KSy, KS1, kd; step2_klayout(nch0, nch1, KSy, KS1, kd);
+  const int NP = (C + 15) / 16 * 16;
+  return (size_t)9 * 2 * 2 * (KSy + KS1) * NP * 16 / 4;         // [tap][hl][planes][NP][16 B]
+}
+
+static bool make_geom2(const Step2Args& a, Step2Geom& g) {
+  int KSy, KS1, kd;
+  const int nch0 = a.src[0].nch, nch1 = a.nsrc > 1 ? a.src[1].nch : 0;
+  step2_klayout(nch0, nch1, KSy, KS1, kd);
+  const int NP = (a.C + 15) / 16 * 16;
+  g.KSy = KSy; g.kd = kd; g.PLtot = 2 * (KSy + KS1);
+  g.KS = (a.hoist || a.nsrc < 2) ? KSy : KSy + KS1;
+  g.nhl = a.x3 ? 2 : 1;
+  g.hlA = (uint32_t)(2 * g.KS) * kPLB;
+  g.bufA = g.hlA * g.nhl;
+  g.tiles_x = cdiv(a.W, 16); g.tiles_y = cdiv(a.H, 16);
+  g.ntiles = g.tiles_x * g.tiles_y * a.B;
+  g.gE_hl = (uint32_t)g.PLtot * 512; g.gZ_hl = (uint32_t)g.PLtot * NP * 16; g.gZ_tap = 2 * g.gZ_hl;
+  g.wE_hl = (uint32_t)(2 * g.KS) * 512; g.wZ_hl = (uint32_t)(2 * g.KS) * NP * 16; g.wZ_tap = g.nhl * g.wZ_hl;
+  for (int nbuf = 3; nbuf >= 1; --nbuf) {
+    uint32_t off = 0;
+    auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
+    g.nbuf = nbuf;
+    g.oA = take((uint32_t)nbuf * g.bufA);
+    g.oDsc = take(18u * kNPOSA * 4);
+    g.oD1 = take(kNPOSA * 4);
+    g.oWE = take(g.nhl * g.wE_hl);
+    g.oWZ = take(9u * g.wZ_tap);
+    g.oWm = take((uint32_t)(a.C * a.C + 3 * a.C + 9 + 3 + 8) * 4);
+    g.oBar = take(17 * 8 + 16);
+    g.total = off;
+    if (g.total <= 227 * 1024) { g.pipelined = nbuf >= 2; return true; }
+  }
+  return false;
+}
+
+bool step2_supported(const Step2Args& a) {
+  Step2Geom g{};
+  return a.C % 4 == 0 && a.C <= kMaxC && (a.src[0].nch + 2 + 15) / 16 * 16 - 2 >= a.src[0].nch && make_geom2(a, g);
+}
+
+int launch_step2(const Step2Args& a, cudaStream_t st) {
+  if (a.B <= 0) return TMG_OK;
+  Step2Geom g{};
+  if (a.C % 4 || a.C > kMaxC || !make_geom2(a, g)) {
+    set_error("fused fp16 flow step: unsupported shape (C=%d, %dx%d)", a.C, a.H, a.W);
+    return TMG_ERR_UNSUPPORTED;
+  }
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  static int cached_sm[64] = {0};
+  if (dev < 64) {
+    if (!cached_sm[dev]) cudaDeviceGetAttribute(&cached_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    nsm = cached_sm[dev] > 0 ? cached_sm[dev] : 148;
+  }
+  const int grid = std::min(g.ntiles, nsm);
+#define TMG_S2(CC, XX)                                                                                                       \
+  {                                                                                                                          \
+    TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    flow_step_f16_kernel<CC, XX><<<grid, kS2Threads, g.total, st>>>(a, g);                                                   \
+  }
+#define TMG_S2C(CC) case CC: if (a.x3) TMG_S2(CC, true) else TMG_S2(CC, false) break;
+  switch (a.C) {
+    TMG_S2C(4) TMG_S2C(8) TMG_S2C(12) TMG_S2C(16) TMG_S2C(24) TMG_S2C(32) TMG_S2C(48) TMG_S2C(64)
+    default:
+      set_error("fused fp16 flow step: %d channels not supported", a.C);
+      return TMG_ERR_UNSUPPORTED;
+  }
+#undef TMG_S2C
+#undef TMG_S2
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+}  // namespace tmg

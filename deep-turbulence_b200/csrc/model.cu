@@ -62,6 +62,9 @@ struct StepW {
   // fused tensor-core coupling kernel (coupling_tc.cu): packed weights and K-plane bookkeeping
   int64_t cpl_w1 = -1, cpl_w2 = -1, cpl_w3 = -1;
   int cpl_nch0 = 0, cpl_nch1 = 0, cpl_npad = 0;
+  // fp16 fused step (flow_step_f16.cu)
+  int64_t s2_wE = -1, s2_wZ = -1, s2_misc = -1;
+  int s2_nch0 = 0, s2_nch1 = 0;
 };
 
 struct DenseW { ConvW conv; int64_t bn_w, bn_b, bn_rm, bn_rv; int64_t scale, shift; int cin; };
@@ -75,6 +78,9 @@ struct LevelW {
   std::vector<DenseW> dense;
   int nf_in = 0, nf_out = 0;      // dense block channels in / out
   ConvW cond;
+  // hoisted conditioning tables (one LF input shared by all samples): packed weight slices [9][cond][OP]
+  int64_t hoist_wd = -1, hoist_wh = -1;
+  int hoist_opd = 0, hoist_oph = 0;
 };
 
 }  // namespace tmg
@@ -163,6 +169,18 @@ struct Builder {
     job(JOB_CPL_W12, st.d1, NK1, 0, st.cpl_w1);
     job(JOB_CPL_W12, st.d2, NPL, 1, st.cpl_w2);
     job(JOB_CPL_W3, st.zc, NPL, 2, st.cpl_w3);
+  }
+  void step2_jobs(StepW& st, int nch0, int nch1, int C) {
+    st.s2_nch0 = nch0; st.s2_nch1 = nch1;
+    st.s2_wE = pack_alloc((int64_t)step2_wE_floats(nch0, nch1));
+    st.s2_wZ = pack_alloc((int64_t)step2_wZ_floats(nch0, nch1, C));
+    st.s2_misc = pack_alloc(16);
+    PackJob j{};
+    j.type = JOB_STEP2; j.a = C; j.b = st.d1.I; j.opad = tc_npad(C); j.nch0 = nch0; j.nch1 = nch1;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = st.d1.w_param; j.src[1] = st.d2.w_param; j.src[2] = st.zc.w_param;
+    j.dst[0] = st.s2_wE; j.dst[1] = st.s2_wZ; j.dst[2] = st.s2_misc;
+    m.jobs.push_back(j);
   }
   int64_t gain(int64_t scale_param) {
     int64_t o = pack_alloc(1);
@@ -289,6 +307,7 @@ static int build_model(tmg_model& m) {
         st.zc = B.conv(sp + "coupling.out_conv.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
         B.coupling_jobs(st, cin_t, 0, C);
+        B.step2_jobs(st, cin_t, 0, C);
       } else {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
@@ -296,8 +315,27 @@ static int build_model(tmg_model& m) {
         st.zc = B.conv(sp + "coupling.coupling_nn.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
         B.coupling_jobs(st, C / 2, c.cond_features, C);
+        B.step2_jobs(st, C / 2, c.cond_features, C);
       }
       lv.steps.push_back(st);
+    }
+    // hoisted conditioning tables: one weight slice per plain step, concatenated along Cout
+    lv.hoist_opd = (2 * n + 3) / 4 * 4;
+    lv.hoist_oph = (n * C + 3) / 4 * 4;
+    lv.hoist_wd = B.pack_alloc((int64_t)9 * c.cond_features * lv.hoist_opd);
+    lv.hoist_wh = B.pack_alloc((int64_t)9 * c.cond_features * lv.hoist_oph);
+    for (int s = 0; s < n; ++s) {
+      const StepW& st = lv.steps[s];
+      if (st.kind == STEP_LSTM) continue;       // its coupling net reads the LSTM output, not cond
+      for (int kind = 0; kind < 2; ++kind) {
+        PackJob j{};
+        j.type = JOB_HOIST; j.a = C; j.b = c.cond_features; j.nch0 = C / 2; j.nd = kind; j.part = s; j.nparts = n;
+        j.opad = kind ? lv.hoist_oph : lv.hoist_opd;
+        for (auto& q : j.src) q = -1;
+        j.src[0] = st.d1.w_param; j.src[1] = st.d2.w_param; j.src[2] = st.zc.w_param;
+        j.dst[0] = kind ? lv.hoist_wh : lv.hoist_wd;
+        m.jobs.push_back(j);
+      }
     }
     std::string pp = "glow.flow_blocks." + std::to_string(b) + ".split.latent_encoder.conv2d";
     int64_t sc = B.add(pp + ".scale", {1, 1, 1, 1});
@@ -313,7 +351,8 @@ static int build_model(tmg_model& m) {
 
 // ------------------------------------------------------------------ workspace plan
 struct Plan {
-  int B, h, w, H, W, L;
+  int B, Bx, h, w, H, W, L;     // Bx: batch of the LF input / encoder (1 when one input is shared by all samples)
+  int shared;
   int eh[TMG_MAX_LEVELS], ew[TMG_MAX_LEVELS];   // encoder level sizes
   int Hl[TMG_MAX_LEVELS], Wl[TMG_MAX_LEVELS];   // flow level sizes
   int ctas;                                     // log-det partials per slot
@@ -323,13 +362,15 @@ struct Plan {
   size_t xn, e0, db[TMG_MAX_LEVELS], cc, cond[TMG_MAX_LEVELS], zo_pre, zout;
   size_t bn_mean, bn_var, bn_scale, bn_shift;
   size_t y[TMG_MAX_LEVELS], y2[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
+  size_t dc_all[TMG_MAX_LEVELS], hc_all[TMG_MAX_LEVELS];
 };
 
-static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
+static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shared = false) {
   const tmg_config& c = m.cfg;
   const int L = c.n_levels;
   if (B < 1 || h < 1 || w < 1) { set_error("bad batch/input size"); return TMG_ERR_BAD_SHAPE; }
   p.B = B; p.h = h; p.w = w; p.L = L;
+  p.shared = shared ? 1 : 0; p.Bx = shared ? 1 : B;
   p.H = h * c.cglow_upscale; p.W = w * c.cglow_upscale;
   if (p.H % (1 << L) || p.W % (1 << L)) {      // flowUtils.py:112 assert
     set_error("high-fidelity size %dx%d not divisible by 2^%d", p.H, p.W, L);
@@ -348,18 +389,20 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
   }
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n, 64); return o; };
-  const size_t Bz = (size_t)B;
-  p.xn = take(Bz * h * w * c.in_features);
-  p.e0 = take(Bz * h * w * (c.init_features / 2));
+  const size_t Bz = (size_t)B, Bx = (size_t)p.Bx;
+  p.xn = take(Bx * h * w * c.in_features);
+  p.e0 = take(Bx * h * w * (c.init_features / 2));
   size_t cc_max = 0, mx_y = 0, mx_g = 0, mx_u = 0, mx_pix = 0;
   int nf_max = 0;
   for (int l = 0; l < L; ++l) {
     const LevelW& lv = m.levels[l];
-    p.db[l] = take(Bz * p.eh[l] * p.ew[l] * lv.nf_out);
-    p.cond[l] = take(Bz * p.Hl[l] * p.Wl[l] * c.cond_features);
+    p.db[l] = take(Bx * p.eh[l] * p.ew[l] * lv.nf_out);
+    p.cond[l] = take(Bx * p.Hl[l] * p.Wl[l] * c.cond_features);
+    p.dc_all[l] = take((size_t)p.Hl[l] * p.Wl[l] * lv.hoist_opd);
+    p.hc_all[l] = take((size_t)p.Hl[l] * p.Wl[l] * lv.hoist_oph);
     p.y[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
     p.y2[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
-    cc_max = std::max(cc_max, Bz * p.eh[l] * p.ew[l] * c.cond_features);
+    cc_max = std::max(cc_max, Bx * p.eh[l] * p.ew[l] * c.cond_features);
     size_t pix = Bz * p.Hl[l] * p.Wl[l];
     mx_pix = std::max(mx_pix, pix);
     mx_y = std::max(mx_y, pix * lv.C);
@@ -368,8 +411,8 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
     nf_max = std::max(nf_max, lv.nf_out);
   }
   p.cc = take(cc_max);
-  p.zo_pre = take(Bz * p.eh[L - 1] * p.ew[L - 1] * 2 * m.Cz);
-  p.zout = take(Bz * p.Hl[L - 1] * p.Wl[L - 1] * 2 * m.Cz);
+  p.zo_pre = take(Bx * p.eh[L - 1] * p.ew[L - 1] * 2 * m.Cz);
+  p.zout = take(Bx * p.Hl[L - 1] * p.Wl[L - 1] * 2 * m.Cz);
   p.bn_mean = take(nf_max); p.bn_var = take(nf_max);
   p.bn_scale = take(nf_max); p.bn_shift = take(nf_max);
   p.hr = take(mx_y);
@@ -388,11 +431,16 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p) {
   return TMG_OK;
 }
 
+static inline bool prec_tc(int p) { return p != TMG_PREC_FP32; }
+static inline bool prec_split(int p) { return p == TMG_PREC_TF32X3 || p == TMG_PREC_F16X3; }
+static inline bool prec_f16(int p) { return p == TMG_PREC_F16X3 || p == TMG_PREC_F16; }
+
 struct Ctx {
   tmg_model& m;
   Plan p;
   float* ws;
   cudaStream_t st;
+  bool hoist_ready = false;     // the per-step conditioning tables dc_all / hc_all of this call are filled
   const float* P() const { return m.params; }
   const float* Q() const { return m.packed; }
 };
@@ -420,7 +468,7 @@ static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int ns
     t.bias = a.bias; t.gain = a.gain; t.act = act;
     t.out = out; t.out_cstride = out_cstride; t.out_coff = out_coff; t.cout = w.O;
     t.B = B; t.H = Hin; t.W = Win; t.pad_replicate = a.pad_replicate;
-    t.split3 = c.m.precision == TMG_PREC_TF32X3 ? 1 : 0;
+    t.split3 = prec_split(c.m.precision) ? 1 : 0;
     const double M = (double)B * Hin * Win;
     ProfScope ps(c.st, tag, 2.0 * M * w.O * 9.0 * w.I, 4.0 * ((double)B * Hin * Win * w.I + M * w.O));
     return launch_conv3x3_tc(t, c.st);
@@ -436,7 +484,7 @@ static int run_encoder(Ctx& c, const float* x, bool bn_train) {
   const tmg_config& g = c.m.cfg;
   const Plan& p = c.p;
   float* ws = c.ws;
-  const int B = p.B, L = p.L;
+  const int B = p.Bx, L = p.L;
   PermArgs pa{};
   pa.src = x; pa.dst = ws + p.xn; pa.mode = PERM_NCHW_TO_NHWC;
   pa.B = B; pa.C = g.in_features; pa.H = p.h; pa.W = p.w; pa.dst_cstride = g.in_features;
@@ -516,7 +564,8 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
   int nt;   // sources that make up "t"
   if (s.kind == STEP_LSTM) {
     if (!h_out || !c_out) { set_error("LSTM step needs h_out/c_out buffers"); return TMG_ERR_NULL; }
-    ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0}, {h_in, R, 0, R, 0}};
+    const int sh = c.p.shared;
+    ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_in, R, 0, R, 0}};
     if (c.m.precision != TMG_PREC_FP32 && s.gate.w_pack_tc >= 0 && R % 16 == 0 && Wl + 2 <= 512) {
       // gate conv on tcgen05 with the ConvLSTM cell update fused into its epilogue (gates never touch HBM)
       TcConvArgs t{};
@@ -524,7 +573,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       for (int i = 0; i < ns; ++i) t.src[i] = gs[i];
       t.nsrc = ns; t.cin = s.gate.I; t.wpk = c.Q() + s.gate.w_pack_tc; t.npad = s.gate.NP;
       t.bias = c.P() + s.gate.b_param; t.cout = s.gate.O;
-      t.B = B; t.H = Hl; t.W = Wl; t.split3 = c.m.precision == TMG_PREC_TF32X3 ? 1 : 0;
+      t.B = B; t.H = Hl; t.W = Wl; t.split3 = prec_split(c.m.precision) ? 1 : 0;
       t.lstm_R = R; t.c_prev = c_in; t.h_out = h_out; t.c_out = c_out;
       const double M = (double)B * Hl * Wl;
       ProfScope ps(c.st, PROF_CONV_GATE, 2.0 * M * s.gate.O * 9.0 * s.gate.I,
@@ -537,7 +586,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       ProfScope ps(c.st, PROF_LSTM_PW, 20.0 * la.n, 4.0 * la.n * (c_in ? 7.0 : 6.0));
       TMG_TRY(launch_lstm_pointwise(la, c.st));
     }
-    ConvSrc os[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0}, {h_out, R, 0, R, 0}};
+    ConvSrc os[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_out, R, 0, R, 0}};
     const int u0s = (cin_t + 3) / 4 * 4;       // padded pixel stride: 16-byte aligned planes for the fused kernel
     TMG_TRY(run_conv(c, PROF_CONV_OUT, s.outc, os, 3, B, Hl, Wl, 1, false, 1, -1, nullptr, nullptr, ws + p.u0, u0s, 0));
     if (nn_only_lstm) return TMG_OK;
@@ -546,7 +595,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
   } else {
     if (nn_only_lstm) return TMG_OK;
     src[0] = ConvSrc{Y, C, 0, C / 2, 1};
-    src[1] = ConvSrc{cond, cf, 0, cf, 1};
+    src[1] = ConvSrc{cond, cf, 0, cf, 1, c.p.shared};
     nt = 2;
   }
   TMG_TRY(run_conv(c, PROF_CONV_DENSE1, s.d1, src, nt, B, Hl, Wl, 1, false, 0, -1, nullptr, nullptr, D, 2, 0));
@@ -586,6 +635,45 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
                     float* c_out, float* ld_slot) {
   const tmg_config& g = c.m.cfg;
   const int C = c.m.levels[level].C, cf = g.cond_features, HW = Hl * Wl;
+  if (prec_f16(c.m.precision) && st.s2_wE >= 0) {
+    Step2Args a{};
+    if (st.kind == STEP_LSTM) {
+      const int cin_t = C / 2 + cf;
+      a.src[0] = ConvSrc{c.ws + c.p.u0, (cin_t + 3) / 4 * 4, 0, cin_t, 1};
+      a.nsrc = 1;
+    } else {
+      a.src[0] = ConvSrc{Y, C, 0, C / 2, 1};
+      a.src[1] = ConvSrc{cond, cf, 0, cf, 1, c.p.shared};
+      a.nsrc = 2;
+      if (c.p.shared && c.hoist_ready) {
+        const LevelW& lv = c.m.levels[level];
+        const int sidx = (int)(&st - lv.steps.data());
+        a.hoist = 1;
+        a.dc = c.ws + c.p.dc_all[level] + 2 * sidx; a.dc_stride = lv.hoist_opd;
+        a.hc = c.ws + c.p.hc_all[level] + (size_t)sidx * C; a.hc_stride = lv.hoist_oph;
+      }
+    }
+    a.wE = c.Q() + st.s2_wE; a.wZ = c.Q() + st.s2_wZ; a.wmisc = c.Q() + st.s2_misc;
+    a.bias3 = c.P() + st.zc.b_param; a.gain3 = c.Q() + st.zc_gain;
+    a.C = C; a.y_in = Y; a.y_out = Y2;
+    if (mix) {
+      a.wmat = c.Q() + (reverse ? mix->W : mix->Wi);
+      if (mix->kind != STEP_UNNORMED) { a.nw = c.P() + mix->norm_w; a.nb = c.P() + mix->norm_b; }
+    }
+    a.reverse = reverse ? 1 : 0;
+    a.ld_part = ld_slot; a.ld_stride = c.p.nslots * c.p.ctas;
+    a.B = B; a.H = Hl; a.W = Wl; a.x3 = prec_split(c.m.precision) ? 1 : 0;
+    if (step2_supported(a)) {
+      if (st.kind == STEP_LSTM) TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, cond, h_in, c_in, h_out, c_out, true));
+      const double px = (double)B * HW;
+      const int cin_t = C / 2 + cf;
+      ProfScope ps(c.st, PROF_STEP_FUSED, 2.0 * px * 9.0 * (cin_t + (cin_t + 1) + (double)C * (cin_t + 2)) + 2.0 * px * C * C,
+                   4.0 * px * (2.0 * C + cf));
+      int rc = launch_step2(a, c.st);
+      if (rc == TMG_OK) { float* t = Y; Y = Y2; Y2 = t; }
+      return rc;
+    }
+  }
   if (c.m.precision != TMG_PREC_FP32 && st.cpl_w3 >= 0) {
     CouplingArgs a{};
     if (st.kind == STEP_LSTM) {
@@ -595,7 +683,7 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
       a.nsrc = 1;
     } else {
       a.src[0] = ConvSrc{Y, C, 0, C / 2, 1};
-      a.src[1] = ConvSrc{cond, cf, 0, cf, 1};
+      a.src[1] = ConvSrc{cond, cf, 0, cf, 1, c.p.shared};
       a.nsrc = 2;
     }
     a.w1 = c.Q() + st.cpl_w1; a.w2 = c.Q() + st.cpl_w2; a.w3 = c.Q() + st.cpl_w3; a.npad = st.cpl_npad;
@@ -607,7 +695,7 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
     }
     a.reverse = reverse ? 1 : 0;
     a.ld_part = ld_slot; a.ld_stride = c.p.nslots * c.p.ctas;
-    a.B = B; a.H = Hl; a.W = Wl; a.split3 = c.m.precision == TMG_PREC_TF32X3 ? 1 : 0;
+    a.B = B; a.H = Hl; a.W = Wl; a.split3 = prec_split(c.m.precision) ? 1 : 0;
     const double px = (double)B * HW;
     const int cin_t = C / 2 + cf;
     // algorithmic work of the whole step: three convs + 1x1; bytes: read x + cond, write y
@@ -626,6 +714,33 @@ static int run_split_prior(Ctx& c, int level, int B, int Hl, int Wl, const float
   ConvSrc s{Y, lv.C, 0, lv.C / 2, 0};
   return run_conv(c, PROF_CONV_SPLIT, lv.split, &s, 1, B, Hl, Wl, 1, true, 2, lv.split_gain, nullptr, nullptr,
                   c.ws + c.p.hr, lv.C, 0);
+}
+
+// One LF input shared by every sample: the conditioning map's contribution to every plain step's coupling net
+// is the same for all samples.  Two exact-fp32 convolutions per level fill, for all steps at once,
+//   dc_all[pix][2s], [2s+1] = conv3x3_zero-pad(relu(cond), w1_s / w2_s cond rows)
+//   hc_all[pix][s*C + n]    = conv3x3_replicate(relu(cond), zero_conv_s cond rows)       (before bias and gain)
+static int run_hoist(Ctx& c) {
+  const tmg_config& g = c.m.cfg;
+  for (int l = 0; l < c.p.L; ++l) {
+    const LevelW& lv = c.m.levels[l];
+    for (int kind = 0; kind < 2; ++kind) {
+      ConvArgs a{};
+      a.src[0] = ConvSrc{c.ws + c.p.cond[l], g.cond_features, 0, g.cond_features, 1, 1};
+      a.nsrc = 1;
+      a.w = c.Q() + (kind ? lv.hoist_wh : lv.hoist_wd);
+      a.cin_w = g.cond_features; a.cout_w = kind ? lv.hoist_oph : lv.hoist_opd;
+      a.out = c.ws + (kind ? c.p.hc_all[l] : c.p.dc_all[l]);
+      a.out_cstride = a.cout_w; a.out_coff = 0; a.cout = a.cout_w;
+      a.B = 1; a.Hin = c.p.Hl[l]; a.Win = c.p.Wl[l]; a.Hout = a.Hin; a.Wout = a.Win; a.stride = 1;
+      a.pad_replicate = kind;
+      const double M = (double)a.Hin * a.Win;
+      ProfScope ps(c.st, PROF_MISC, 2.0 * M * a.cout * 9.0 * a.cin_w, 4.0 * M * (a.cin_w + a.cout));
+      TMG_TRY(launch_conv3x3(a, c.st));
+    }
+  }
+  c.hoist_ready = true;
+  return TMG_OK;
 }
 
 static int finish_logdet(Ctx& c, float* out) {
@@ -658,7 +773,7 @@ static int check_common(tmg_model* m, const void* ws, size_t ws_bytes, const Pla
 // =================================================================== C ABI
 extern "C" {
 
-int tmg_version(void) { return 100; }
+int tmg_version(void) { return 110; }
 const char* tmg_last_error(void) { return tmg::g_err; }
 
 int tmg_device_count(void) {
@@ -717,7 +832,7 @@ void tmg_model_destroy(tmg_model* m) {
 
 int tmg_model_set_precision(tmg_model* m, int mode) {
   if (!m) { set_error("null model"); return TMG_ERR_NULL; }
-  if (mode != TMG_PREC_FP32 && mode != TMG_PREC_TF32X3 && mode != TMG_PREC_TF32) {
+  if (mode < TMG_PREC_FP32 || mode > TMG_PREC_F16) {
     set_error("unknown precision mode %d", mode); return TMG_ERR_BAD_CONFIG;
   }
   m->precision = mode;
@@ -748,6 +863,7 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
   if (!m->packed) {     // one-time allocation of the library-owned derived-weight cache
     TMG_CUDA_OK(cudaGetDevice(&m->device));
     TMG_CUDA_OK(cudaMalloc(&m->packed, (size_t)m->n_packed * sizeof(float)));
+    TMG_CUDA_OK(cudaMemset(m->packed, 0, (size_t)m->n_packed * sizeof(float)));
     TMG_CUDA_OK(cudaMalloc(&m->jobs_dev, m->jobs.size() * sizeof(PackJob)));
     TMG_CUDA_OK(cudaMemcpy(m->jobs_dev, m->jobs.data(), m->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
   }
@@ -808,7 +924,9 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const flo
                     uint32_t flags, void* stream) {
   if (!m) { set_error("null model"); return TMG_ERR_NULL; }
   Plan p;
-  TMG_TRY(make_plan(*m, B, h, w, p));
+  const bool shared = (flags & TMG_FLAG_SHARED_X) != 0;
+  if (shared && (flags & TMG_FLAG_BN_TRAIN)) { set_error("TMG_FLAG_SHARED_X cannot be combined with train-mode BatchNorm"); return TMG_ERR_BAD_CONFIG; }
+  TMG_TRY(make_plan(*m, B, h, w, p, shared));
   TMG_TRY(check_common(m, workspace, workspace_bytes, p));
   if (!x || !eps || !y || !log_det || !h_out || !c_out) { set_error("null argument"); return TMG_ERR_NULL; }
   const int L = p.L;
@@ -818,12 +936,13 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const flo
   const int ldstride = p.nslots * p.ctas;
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
+  if (shared && prec_f16(m->precision)) TMG_TRY(run_hoist(c));
 
   // top latent: z = cmean + exp(clamp(clog_std)) * eps[L]   (tmGlow.py:460-463); no log-prob term
   {
     const LevelW& lv = m->levels[L - 1];
     GaussArgs ga{};
-    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz;
+    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz; ga.prm_bshared = p.shared;
     ga.val = ws + p.y[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
     ga.eps_in = eps[L]; ga.reverse = 1;
     ga.B = B; ga.HW = p.Hl[L - 1] * p.Wl[L - 1]; ga.n = m->Cz;
@@ -871,7 +990,9 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
                 float* const* eps_out, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
   if (!m) { set_error("null model"); return TMG_ERR_NULL; }
   Plan p;
-  TMG_TRY(make_plan(*m, B, h, w, p));
+  const bool shared = (flags & TMG_FLAG_SHARED_X) != 0;
+  if (shared && (flags & TMG_FLAG_BN_TRAIN)) { set_error("TMG_FLAG_SHARED_X cannot be combined with train-mode BatchNorm"); return TMG_ERR_BAD_CONFIG; }
+  TMG_TRY(make_plan(*m, B, h, w, p, shared));
   TMG_TRY(check_common(m, workspace, workspace_bytes, p));
   if (!x || !y || !z || !logp || !h_out || !c_out) { set_error("null argument"); return TMG_ERR_NULL; }
   const int L = p.L;
@@ -880,6 +1001,7 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
   const int ldstride = p.nslots * p.ctas;
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
+  if (shared && prec_f16(m->precision)) TMG_TRY(run_hoist(c));
   int slot = 0;
   float* yfinal[TMG_MAX_LEVELS] = {nullptr};
   for (int l = 0; l < L; ++l) {
@@ -918,7 +1040,7 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
   {
     const LevelW& lv = m->levels[L - 1];
     GaussArgs ga{};
-    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz;
+    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz; ga.prm_bshared = p.shared;
     ga.val = yfinal[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
     ga.eps_out = eps_out ? eps_out[L] : nullptr; ga.val_nchw = z; ga.reverse = 0;
     ga.B = B; ga.HW = p.Hl[L - 1] * p.Wl[L - 1]; ga.n = m->Cz;

@@ -4,6 +4,8 @@
 //   log-det constants                         glowConv.py:186 (forward), :206-215 (reverse), actNorm.py:66,82
 //   Conv2dZeros gain exp(clamp(scale,-4,ln4)) nn/modules/flowUtils.py:247
 //   eval-mode BatchNorm2d folded to an affine nn/modules/denseBlock.py:49
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace tmg {
@@ -71,6 +73,98 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       }
       float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       d[i] = hl ? (v - hi) : hi;
+    }
+  } else if (j.type == JOB_STEP2) {
+    // Weights of the fp16 fused flow step (flow_step_f16.cu).  K layout: [src0 | pad | d1 d2][src1 | pad], 16 per
+    // K-step, 8 per plane.  Each conv is scaled by a power of two so that max|w| lands in [2^10, 2^11): the hi/lo
+    // fp16 pair then carries 22 mantissa bits of every weight within 2^13 of the largest one.
+    //   wE [hl][plane][32][8]: col n < 9 -> dense layer 1 tap n, 16 <= n < 25 -> dense layer 2 tap n-16 (t rows only)
+    //   wZ [tap][hl][plane][NP][8]: Conv2dZeros, col n < C
+    //   wmisc: [0..8] layer 2's d1 row (fp32, applied on CUDA cores), [9..11] inverse scales
+    const int C = j.a, I1 = j.b, NP = j.opad, nch0 = j.nch0, nch1 = j.nch1;
+    int KSy, KS1, kd;
+    KSy = (nch0 + 2 + 15) / 16; KS1 = (nch1 + 15) / 16; kd = KSy * 16 - 2;
+    const int PL = 2 * (KSy + KS1);
+    const float* w1 = P + j.src[0]; const float* w2 = P + j.src[1]; const float* w3 = P + j.src[2];
+    const int n1 = 9 * I1, n2 = 9 * (I1 + 1), n3 = 9 * C * (I1 + 2);
+    float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    for (int i = tid; i < n1; i += blockDim.x) m1 = fmaxf(m1, fabsf(w1[i]));
+    for (int i = tid; i < n2; i += blockDim.x) m2 = fmaxf(m2, fabsf(w2[i]));
+    for (int i = tid; i < n3; i += blockDim.x) m3 = fmaxf(m3, fabsf(w3[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+    }
+    if ((tid & 31) == 0) { sm[(tid >> 5) * 3] = m1; sm[(tid >> 5) * 3 + 1] = m2; sm[(tid >> 5) * 3 + 2] = m3; }
+    __syncthreads();
+    float sc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float m = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sm[w * 3 + q]);
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) frexpf(m, &e);                // m = f * 2^e, f in [0.5, 1)
+      sc[q] = m > 0.f ? ldexpf(1.f, min(max(11 - e, -20), 40)) : 1.f;   // scaled max in [2^10, 2^11)
+    }
+    auto chan = [&](int k) -> int {          // K index -> concatenated input channel (or -1)
+      if (k < KSy * 16) {
+        if (k < nch0) return k;
+        if (k == kd) return nch0 + nch1;
+        if (k == kd + 1) return nch0 + nch1 + 1;
+        return -1;
+      }
+      const int q = k - KSy * 16;
+      return q < nch1 ? nch0 + q : -1;
+    };
+    __half* dE = reinterpret_cast<__half*>(Q + j.dst[0]);
+    const int totE = 2 * PL * 32 * 8;
+    for (int i = tid; i < totE; i += blockDim.x) {
+      const int e = i & 7; int t = i >> 3; const int n = t & 31; t >>= 5; const int plane = t % PL, hl = t / PL;
+      const int c = chan(plane * 8 + e);
+      float v = 0.f;
+      if (c >= 0 && c < I1) {
+        if (n < 9) v = w1[(size_t)c * 9 + n] * sc[0];
+        else if (n >= 16 && n < 25) v = w2[(size_t)c * 9 + (n - 16)] * sc[1];
+      }
+      const __half hi = __float2half_rn(v);
+      dE[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    __half* dZ = reinterpret_cast<__half*>(Q + j.dst[1]);
+    const int totZ = 9 * 2 * PL * NP * 8;
+    for (int i = tid; i < totZ; i += blockDim.x) {
+      const int e = i & 7; int t = i >> 3; const int n = t % NP; t /= NP; const int plane = t % PL; t /= PL;
+      const int hl = t & 1, tap = t >> 1;
+      const int c = chan(plane * 8 + e);
+      float v = 0.f;
+      if (c >= 0 && c < I1 + 2 && n < C) v = w3[((size_t)n * (I1 + 2) + c) * 9 + tap] * sc[2];
+      const __half hi = __float2half_rn(v);
+      dZ[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    float* dm = Q + j.dst[2];
+    if (tid < 9) dm[tid] = w2[(size_t)I1 * 9 + tid];
+    if (tid >= 9 && tid < 12) dm[tid] = 1.f / sc[tid - 9];
+  } else if (j.type == JOB_HOIST) {
+    // Conditioning-only weight slices of every plain step of one level, concatenated along Cout, tap-major
+    // [9][cond][opad] for conv3x3_ffma: the cond contribution to d1/d2 (kind 0: col 2s, 2s+1) or to the
+    // Conv2dZeros output (kind 1: col s*C + n) of step s.  a = C, b = cond channels, nch0 = C/2 (first cond row),
+    // nd = kind, part = step index, nparts = steps.  One job per step.
+    const int C = j.a, CF = j.b, OP = j.opad, s = j.part, row0 = j.nch0;
+    float* d = Q + j.dst[0];
+    if (j.nd == 0) {
+      const float* w1 = P + j.src[0]; const float* w2 = P + j.src[1];
+      for (int i = tid; i < 9 * CF * 2; i += blockDim.x) {
+        const int which = i & 1; int t = i >> 1; const int c = t % CF, tap = t / CF;
+        d[((size_t)tap * CF + c) * OP + 2 * s + which] = (which ? w2 : w1)[(size_t)(row0 + c) * 9 + tap];
+      }
+    } else {
+      const float* w3 = P + j.src[2];
+      const int I3 = row0 + CF + 2;
+      for (int i = tid; i < 9 * CF * C; i += blockDim.x) {
+        const int n = i % C; int t = i / C; const int c = t % CF, tap = t / CF;
+        d[((size_t)tap * CF + c) * OP + s * C + n] = w3[((size_t)n * I3 + row0 + c) * 9 + tap];
+      }
     }
   } else if (j.type == JOB_GAIN) {
     if (tid == 0) Q[j.dst[0]] = expf(fminf(fmaxf(P[j.src[0]], -4.f), kLog4));

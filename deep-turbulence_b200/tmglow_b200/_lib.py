@@ -11,8 +11,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtmglow_b200.so")
 
 TMG_MAX_LEVELS = 6
 TMG_FLAG_BN_TRAIN = 1
-PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+TMG_FLAG_SHARED_X = 2
+PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_F16X3, PREC_F16 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "f16x3": PREC_F16X3, "f16": PREC_F16}
 
 OK, ERR_BAD_CONFIG, ERR_BAD_SHAPE, ERR_NULL, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY = \
     0, -1, -2, -3, -4, -5, -6, -7

@@ -111,8 +111,10 @@ class TMGlow(nn.Module):
     @property
     def precision(self):
         """Arithmetic of the heavy 3x3 convolutions: ``"fp32"`` (CUDA-core FMA, exact fp32),
-        ``"tf32x3"`` (tcgen05 tensor cores with the 3xTF32 split: fp32-grade accuracy) or ``"tf32"``
-        (tcgen05, single-pass TF32 -- the default arithmetic of stock PyTorch/cuDNN convolutions on GPU)."""
+        ``"tf32x3"`` (tcgen05 tensor cores with the 3xTF32 split: fp32-grade accuracy), ``"tf32"``
+        (tcgen05, single-pass TF32 -- the default arithmetic of stock PyTorch/cuDNN convolutions on GPU),
+        ``"f16x3"`` (tcgen05, fp16 hi+lo operand split with power-of-two weight scaling: fp32-grade accuracy,
+        persistent fused flow-step kernel) or ``"f16"`` (single-pass fp16 operands, fp32 accumulation)."""
         return self._precision
 
     @precision.setter
@@ -308,8 +310,19 @@ class TMGlow(nn.Module):
         cs = [_empty_channels_last(d, device) for d in dims]
         return hs, cs
 
-    def _flags(self):
-        return _lib.TMG_FLAG_BN_TRAIN if self.training else 0
+    def _flags(self, shared=False):
+        return (_lib.TMG_FLAG_BN_TRAIN if self.training else 0) | (_lib.TMG_FLAG_SHARED_X if shared else 0)
+
+    def _x_arg(self, x, device):
+        """The LF input as the library wants it.  A batch-expanded view (``x1.expand(S, -1, -1, -1)``: one
+        low-fidelity snapshot, S stochastic samples -- the uncertainty-quantification loop of
+        trainFlowParallel.py:345-358 folded into the batch dimension) is passed as ONE input with
+        TMG_FLAG_SHARED_X: the encoder runs once and the conditioning maps are shared by all samples.
+        Results are those of the materialised batch.  Not used in train mode (BatchNorm batch statistics)."""
+        shared = x.dim() == 4 and x.shape[0] > 1 and x.stride(0) == 0 and not self.training
+        if shared:
+            return self._f32c(x[:1], device), True
+        return self._f32c(x, device), False
 
     def _bump_bn_counters(self):
         if self.training:
@@ -328,10 +341,10 @@ class TMGlow(nn.Module):
         lib, h = self._prepare(device)
         with torch.cuda.device(device):
             st = torch.cuda.current_stream(device).cuda_stream
-            x = self._f32c(x, device)
-            y = self._f32c(y, device)
             B, H, W = x.shape[0], *self._hf_size(x)
             assert x.dim() == 4 and x.shape[1] == self._cfg.in_features, "x must be [B,%d,h,w]" % self._cfg.in_features
+            x, shared = self._x_arg(x, device)
+            y = self._f32c(y, device)
             assert tuple(y.shape) == (B, self._cfg.out_features, H, W), \
                 "y must be [%d,%d,%d,%d], got %s" % (B, self._cfg.out_features, H, W, tuple(y.shape))
             ws = self._workspace(lib, h, B, x.shape[2], x.shape[3], device)
@@ -346,7 +359,7 @@ class TMGlow(nn.Module):
                 h, B, x.shape[2], x.shape[3], x.data_ptr(), y.data_ptr(), hp, cp, z.data_ptr(), logp.data_ptr(),
                 _lib.ptr_array([t.data_ptr() for t in ho]), _lib.ptr_array([t.data_ptr() for t in co]),
                 _lib.ptr_array([t.data_ptr() for t in eps]) if return_eps else None,
-                ws.data_ptr(), ws.numel(), self._flags(), st))
+                ws.data_ptr(), ws.numel(), self._flags(shared), st))
             self._bump_bn_counters()
         return z, logp, list(zip(ho, co)), eps
 
@@ -360,9 +373,9 @@ class TMGlow(nn.Module):
         lib, h = self._prepare(device)
         with torch.cuda.device(device):
             st = torch.cuda.current_stream(device).cuda_stream
-            x = self._f32c(x, device)
             assert x.dim() == 4 and x.shape[1] == self._cfg.in_features, "x must be [B,%d,h,w]" % self._cfg.in_features
             B, H, W = x.shape[0], *self._hf_size(x)
+            x, shared = self._x_arg(x, device)
             shapes = self.latent_shapes(B, H, W)
             assert len(eps) == len(shapes), "eps must hold %d tensors" % len(shapes)
             eps_c = []
@@ -379,7 +392,7 @@ class TMGlow(nn.Module):
                 h, B, x.shape[2], x.shape[3], x.data_ptr(), hp, cp,
                 _lib.ptr_array([t.data_ptr() for t in eps_c]), y.data_ptr(), log_det.data_ptr(),
                 _lib.ptr_array([t.data_ptr() for t in ho]), _lib.ptr_array([t.data_ptr() for t in co]),
-                ws.data_ptr(), ws.numel(), self._flags(), st))
+                ws.data_ptr(), ws.numel(), self._flags(shared), st))
             self._bump_bn_counters()
         return y, log_det, list(zip(ho, co))
 

@@ -60,6 +60,10 @@ typedef struct tmg_model tmg_model;     /* opaque; owns packed weights on ONE de
 /* flags for the whole-path calls */
 #define TMG_FLAG_BN_TRAIN   1u          /* encoder BatchNorm uses batch statistics and updates the
                                            running stats in the parameter buffer (nn.Module.train()) */
+#define TMG_FLAG_SHARED_X   2u          /* x holds ONE low-fidelity input [1,nic,h,w] shared by all B samples
+                                           (uncertainty quantification: many stochastic samples of one input,
+                                           trainFlowParallel.py:345-358): the encoder runs once and the flow steps
+                                           reuse the conditioning maps.  Same results as x.expand(B,...) */
 
 /* ---- library ------------------------------------------------------------------------- */
 int         tmg_version(void);
@@ -78,6 +82,12 @@ void tmg_model_destroy(tmg_model* m);
 #define TMG_PREC_FP32   0
 #define TMG_PREC_TF32X3 1
 #define TMG_PREC_TF32   2
+/*   TMG_PREC_F16X3  tcgen05, fp16 operands split into hi + lo halves with power-of-two weight scaling
+ *                   (three MMAs, fp32 accumulation): fp32-grade accuracy at half the tensor work and half the
+ *                   shared memory of the 3xTF32 split; persistent fused flow-step kernel (flow_step_f16.cu)
+ *   TMG_PREC_F16    tcgen05, single-pass fp16 operands (11-bit mantissa like TF32); looser tolerance */
+#define TMG_PREC_F16X3  3
+#define TMG_PREC_F16    4
 int tmg_model_set_precision(tmg_model* m, int mode);
 int tmg_model_get_precision(const tmg_model* m);
 

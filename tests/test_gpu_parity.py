@@ -237,12 +237,15 @@ def test_error_behaviour():
 # tf32x3: tcgen05 with the 3xTF32 operand split -> same stated fp32 tolerance as the CUDA-core path.
 # tf32  : single-pass TF32 (10-bit mantissa operands); separately stated, looser tolerance:
 #         5e-2 abs on fields (48 chained steps), 1e-3 relative on logp/log_det.
+# f16x3 : tcgen05 kind::f16 with the hi+lo fp16 operand split and power-of-two weight scaling -> fp32 tolerance.
+# f16   : single-pass fp16 operands (11-bit mantissa), same looser tolerance as tf32.
+@pytest.mark.parametrize("mode", ["tf32x3", "f16x3"])
 @pytest.mark.parametrize("name", CASES)
-def test_golden_tf32x3(name):
+def test_golden_tf32x3(name, mode):
     g = load_golden(name)
     cfg = json.loads(g["config"])
     m = _model(cfg, g["state_dict"], g["train_bn"])
-    m.precision = "tf32x3"
+    m.precision = mode
     dev = _dev()
     z, logp, h_out, eps = m.forward(g["x"].to(dev), g["y"].to(dev), _states(g["h_in"], dev), return_eps=True)
     _field_close(z, g["fwd"]["z"], what="z"); _logp_close(logp, g["fwd"]["logp"], "logp")
@@ -272,7 +275,7 @@ def test_default_model_tensor_core_modes():
     m = m.to(dev)
     hd = [(h.to(dev), c.to(dev)) for h, c in h_in]
     report = {}
-    for mode, ftol, ltol in (("tf32x3", FIELD_TOL, 1e-5), ("tf32", 5e-2, 1e-3)):
+    for mode, ftol, ltol in (("tf32x3", FIELD_TOL, 1e-5), ("tf32", 5e-2, 1e-3), ("f16x3", FIELD_TOL, 1e-5), ("f16", 5e-2, 1e-3)):
         m.precision = mode
         z, lp, ho, _ = m.forward(x.to(dev), y.to(dev), hd, return_eps=True)
         yr, ld, _ = m.reconstruct(x.to(dev), hd, [e.to(dev) for e in eps_o])
@@ -283,7 +286,7 @@ def test_default_model_tensor_core_modes():
         assert ez <= ftol and ey <= ftol and el <= ltol + 1e-7 and ed <= ltol + 1e-7, (mode, report[mode])
 
 
-@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("tf32", 2e-2)])
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("tf32", 2e-2), ("f16x3", 2e-5), ("f16", 2e-2)])
 def test_fused_step_operators(mode, tol):
     """Every step kind of block 0 through the fused tensor-core step kernel (coupling_tc.cu)."""
     from tmglow_b200 import ops
@@ -299,5 +302,63 @@ def test_fused_step_operators(mode, tol):
         _field_close(o, rec["fwd"], tol=tol, what="%s step%d fwd" % (mode, s))
         r, ldr, sr = ops.flow_step(m, 0, s, rec["x"].to(dev), rec["cond"].to(dev), st, reverse=True)
         _field_close(r, rec["rev"], tol=tol, what="%s step%d rev" % (mode, s))
-        if mode == "tf32x3":
+        if mode in ("tf32x3", "f16x3"):
             _logp_close(ld, rec["fwd_logdet"], "fwd logdet"); _logp_close(ldr, rec["rev_logdet"], "rev logdet")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "f16x3"])
+def test_shared_input_equals_materialised_batch(mode):
+    """One LF input expanded over S samples (x.expand: TMG_FLAG_SHARED_X, encoder once, and in the f16 modes the
+    hoisted conditioning tables) must give what the materialised batch gives, and what the oracle gives."""
+    from oracle import tmglow_oracle as O
+    dev = _dev()
+    m = _default_model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = O.OracleConfig.from_dict(m._cfg_dict)
+    g = torch.Generator().manual_seed(11)
+    S = 3
+    x1 = torch.randn(1, 4, 32, 64, generator=g)
+    h_in = O.init_lstm_states(cfg, torch.arange(S), [64, 128])
+    m = m.to(dev)
+    m.precision = mode
+    eps = [torch.randn(s, generator=g) for s in m.latent_shapes(S, 64, 128)]
+    y_o, ld_o, ho_o = O.reconstruct(sd, cfg, x1.expand(S, -1, -1, -1).contiguous(), h_in, eps)
+    hd = [(h.to(dev), c.to(dev)) for h, c in h_in]
+    ed = [e.to(dev) for e in eps]
+    xs = x1.to(dev).expand(S, -1, -1, -1)
+    assert xs.stride(0) == 0
+    y_s, ld_s, ho_s = m.reconstruct(xs, hd, ed)                      # shared path
+    y_m, ld_m, ho_m = m.reconstruct(xs.contiguous(), hd, ed)         # materialised batch
+    _field_close(y_s, y_o, what="shared y vs oracle"); _logp_close(ld_s, ld_o, "shared log_det vs oracle")
+    _field_close(y_s, y_m.cpu(), tol=2e-5, what="shared vs materialised")
+    for (h, c), (hr, cr) in zip(ho_s, ho_o):
+        _field_close(h, hr, what="h"); _field_close(c, cr, what="c")
+    # forward direction through the shared path
+    z_o, lp_o, _, _ = O.forward(sd, cfg, x1.expand(S, -1, -1, -1).contiguous(), y_o, h_in, False)
+    z_s, lp_s, _, _ = m.forward(xs, y_o.to(dev), hd)
+    _field_close(z_s, z_o, what="shared z"); _logp_close(lp_s, lp_o, "shared logp")
+
+
+def test_f16x3_full_size_properties():
+    """The persistent fp16x3 step kernel at a bench-like batch: many tiles per CTA, all pipeline stages
+    wrap around; invertibility, bit-reproducibility and batch independence."""
+    dev = _dev()
+    m = _default_model().to(dev)
+    m.precision = "f16x3"
+    B = 160
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(B, 4, 32, 64, generator=g).to(dev)
+    y = torch.randn(B, 3, 64, 128, generator=g).to(dev)
+    h_in = m.initLSTMStates(torch.arange(B), [64, 128])
+    z, logp, h_out, eps = m.forward(x, y, h_in, return_eps=True)
+    y_rec, log_det, _ = m.reconstruct(x, h_in, eps)
+    assert torch.isfinite(y_rec).all() and torch.isfinite(logp).all()
+    assert (y_rec - y).abs().max().item() < 5e-4
+    y2, ld2, _ = m.reconstruct(x, h_in, eps)
+    assert torch.equal(y2, y_rec) and torch.equal(ld2, log_det)
+    y1, ld1, _ = m.reconstruct(x[:3], [(h[:3], c[:3]) for h, c in h_in], [e[:3] for e in eps])
+    assert torch.equal(y1, y_rec[:3])
+    m.precision = "fp32"
+    y3, ld3, _ = m.reconstruct(x, h_in, eps)
+    assert (y3 - y_rec).abs().max().item() < 2e-4
+    assert ((ld3 - log_det).abs() <= 1e-5 * ld3.abs() + 1e-3).all()
