@@ -237,7 +237,9 @@ def main():
 
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=g).pin_memory()
-    x_dev = x_host.to(dev).expand(S, -1, -1, -1).contiguous()
+    # ONE LF input, S stochastic samples: the batch-expanded view is what a UQ caller passes (the model detects
+    # the zero batch stride, runs the encoder once and shares the conditioning maps)
+    x_dev = x_host.to(dev).expand(S, -1, -1, -1)
     h0 = model.initLSTMStates(torch.arange(S) + 1000 * rank, [GEOM["H"], GEOM["W"]])
     torch.manual_seed(777 + rank)
 

@@ -184,6 +184,7 @@ struct Step2Args {
 };
 int launch_step2(const Step2Args& a, cudaStream_t st);
 bool step2_supported(const Step2Args& a);
+int step2_ld_slots(int H, int W);   // log-det partial slots per sample: 8 (epilogue warps) per 16x16 tile
 void step2_klayout(int nch0, int nch1, int& KSy, int& KS1, int& kd);
 size_t step2_wE_floats(int nch0, int nch1);
 size_t step2_wZ_floats(int nch0, int nch1, int C);

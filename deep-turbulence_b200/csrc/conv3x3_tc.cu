@@ -168,8 +168,8 @@ conv3x3_tc_kernel(TcConvArgs a, int npos_pad, int nstage, int tps, int tmem_cols
       }
     }
   } else if (warp == 4) {
-    // ============================ MMA issue (one thread) ============================
-    if (lane == 0) {
+    // ============================ MMA issue (one elected lane) ============================
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(a.npad);
       const uint32_t lbo_b = (uint32_t)a.npad * 16u;
       uint32_t acc = 0;

@@ -282,7 +282,7 @@ coupling_tc_kernel(CouplingArgs a, CplGeom g) {
     }
   } else if (warp == 4) {
     // ===================================================== MMA issue
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc16 = make_idesc_tf32(16);
       const uint32_t a_base = smem_u32(A);
       mbar_wait(t_full, 0);

@@ -94,11 +94,12 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   const int tiles_img = g.tiles_x * g.tiles_y;
 
   uint8_t* A = smem + g.oA;
-  float* Dsc = reinterpret_cast<float*>(smem + g.oDsc);     // [2 layers][9 taps][512]
+  float* Ds1 = reinterpret_cast<float*>(smem + g.oDsc) + 32 * 9;          // [rows -32..543][9] dense layer 1 tap partials
+  float* Ds2 = Ds1 + (kNPOSA + 64) * 9;                                 // same for dense layer 2
   float* D1 = reinterpret_cast<float*>(smem + g.oD1);       // [512] relu(d1)
   uint8_t* WE = smem + g.oWE;
   uint8_t* WZ = smem + g.oWZ;
-  float* Wm = reinterpret_cast<float*>(smem + g.oWm);       // C*C mix | nw | nb | bias3 | w2d[9] | inv scales[3] | red[8]
+  float* Wm = reinterpret_cast<float*>(smem + g.oWm);       // C*C mix | nw | nb | bias3 | w2d[9] | inv scales[3] | 1/nw
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.oBar);
   uint64_t* a_full = bars;          // [3] producers (128)
   uint64_t* a_free = bars + 3;      // [3] commit
@@ -114,7 +115,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   float* s_b3 = s_nb + C;
   float* s_w2d = s_b3 + C;
   float* s_inv = s_w2d + 9;
-  float* s_red = s_inv + 3;
+  float* s_rnw = s_inv + 3;                                 // 1 / ActNorm weight
 
   // ------------------------------------------------------------------ one-time setup
   if (tid == 0) {
@@ -147,6 +148,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       s_nw[i] = a.nw ? __ldg(a.nw + i) : 1.f;
       s_nb[i] = a.nw ? __ldg(a.nb + i) : 0.f;
       s_b3[i] = __ldg(a.bias3 + i);
+      s_rnw[i] = a.nw ? 1.f / __ldg(a.nw + i) : 1.f;
     }
     if (tid < 12) s_w2d[tid] = __ldg(a.wmisc + tid);        // w2d[9] then the three inverse scales
     fence_proxy_async();
@@ -171,6 +173,9 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
     };
 
     // ---- G(k): E accumulators -> d1, d2 written into the A buffer of tile k
+    // Dsc holds the tap partials PRE-SHIFTED: the partial of tap t computed at position q is stored in row
+    // q - off(t), so row p holds the nine terms of the 3x3 sum at p; out-of-image q store zeros (zero padding of
+    // the dense layers), so the sums below need no masks.
     auto gather = [&](int k) {
       const int s = k & 1, u = k % g.nbuf;
       int b, r0, c0, timg;
@@ -179,67 +184,68 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int mt = 2 * wg + j, pos = mt * 128 + el;
+        const int mt = 2 * wg + j, q = mt * 128 + el;
         float v[32];
         tmem_ld32(tmem_base + lane_base + (uint32_t)(s * 256 + mt * 32), v);
+        const int rr = q / kRP, rc = q - rr * kRP;
+        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
+        const bool in = q < kNPOS && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W;
+        const float m1 = in ? inv1 : 0.f, m2 = in ? inv2 : 0.f;
+        float* d1p = Ds1 + q * 9;
+        float* d2p = Ds2 + q * 9;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) { Dsc[t * kNPOSA + pos] = v[t] * inv1; Dsc[(9 + t) * kNPOSA + pos] = v[16 + t] * inv2; }
+        for (int t = 0; t < 9; ++t) {
+          const int off = (t / 3 - 1) * kRP + (t % 3 - 1);
+          d1p[t - off * 9] = v[t] * m1;
+          d2p[t - off * 9] = v[16 + t] * m2;
+        }
       }
       tc_fence_before();
       mbar_arrive(e_free + s);
       named_bar_sync(1, kEpiThreads);
-      // d1 on the halo-2 region
-      for (int p = etid; p < kNPOS; p += kEpiThreads) {
+      // d1 = relu(sum) on the halo-2 region (zero outside the image)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p = etid + j * kEpiThreads;
         const int rr = p / kRP, rc = p - rr * kRP;
         const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
-        if (rr >= 1 && rr <= 20 && rc >= 1 && rc <= 20 && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W) {
-          float sum = 0.f;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int dr = t / 3 - 1, dc = t % 3 - 1;
-            if (ir + dr >= 0 && ir + dr < a.H && ic + dc >= 0 && ic + dc < a.W) sum += Dsc[t * kNPOSA + p + dr * kRP + dc];
+        if (p < kNPOS && rr >= 1 && rr <= 20 && rc >= 1 && rc <= 20) {
+          float val = 0.f;
+          if (ir >= 0 && ir < a.H && ic >= 0 && ic < a.W) {
+            const float* e = Ds1 + p * 9;
+            float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
+            float sum = ((s0 + s1) + (s2 + s3)) + e[8];
+            if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride);
+            val = fmaxf(sum, 0.f);
           }
-          if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride);
-          D1[p] = fmaxf(sum, 0.f);
+          D1[p] = val;
         }
       }
       named_bar_sync(1, kEpiThreads);
-      // d2 on the halo-1 region; the (d1, d2) pair goes into K slots kd, kd+1 of the A buffer
+      // d2 on the halo-1 region, evaluated at the replicate-clamped pixel (Conv2dZeros pads by replication);
+      // the (d1, d2) pair goes into K slots kd, kd+1 of the A buffer
       uint8_t* dslot = A + (size_t)u * g.bufA + (size_t)(g.kd >> 3) * kPLB + (size_t)(g.kd & 7) * 2;
-      for (int p = etid; p < kNPOS; p += kEpiThreads) {
-        const int rr = p / kRP, rc = p - rr * kRP;
-        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
-        if (rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19 && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W) {
-          float sum = 0.f;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int dr = t / 3 - 1, dc = t % 3 - 1;
-            if (ir + dr >= 0 && ir + dr < a.H && ic + dc >= 0 && ic + dc < a.W) {
-              const int q = p + dr * kRP + dc;
-              sum += Dsc[(9 + t) * kNPOSA + q];
-              sum = fmaf(s_w2d[t], D1[q], sum);
-            }
-          }
-          if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride + 1);
-          const float d1 = D1[p], d2 = fmaxf(sum, 0.f);
-          __half h1, l1, h2, l2;
-          split_h(d1, h1, l1); split_h(d2, h2, l2);
-          *reinterpret_cast<uint32_t*>(dslot + (size_t)p * 16) = pack_h2(h1, h2);
-          if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)p * 16) = pack_h2(l1, l2);
-        }
-      }
-      named_bar_sync(1, kEpiThreads);
-      // replicate padding of Conv2dZeros: out-of-image positions copy the clamped pixel's pair
-      for (int p = etid; p < kNPOS; p += kEpiThreads) {
+      for (int j = 0; j < 2; ++j) {
+        const int p = etid + j * kEpiThreads;
         const int rr = p / kRP, rc = p - rr * kRP;
-        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
-        if (rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19 && (ir < 0 || ir >= a.H || ic < 0 || ic >= a.W)) {
-          const int cr = min(max(ir, 0), a.H - 1) - (r0 - 3), cc = min(max(ic, 0), a.W - 1) - (c0 - 3);
-          if (cr >= 2 && cr <= 19 && cc >= 2 && cc <= 19) {
-            const int pc = cr * kRP + cc;
-            *reinterpret_cast<uint32_t*>(dslot + (size_t)p * 16) = *reinterpret_cast<const uint32_t*>(dslot + (size_t)pc * 16);
-            if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)p * 16) =
-                        *reinterpret_cast<const uint32_t*>(dslot + g.hlA + (size_t)pc * 16);
+        if (p < kNPOS && rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19) {
+          const int ir = min(max(r0 - 3 + rr, 0), a.H - 1), ic = min(max(c0 - 3 + rc, 0), a.W - 1);
+          const int pc = (ir - (r0 - 3)) * kRP + (ic - (c0 - 3));
+          if (pc >= 2 * kRP + 2 && pc < 20 * kRP) {         // the clamped pixel lies inside this tile's halo-1 region
+            const float* e = Ds2 + pc * 9;
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const int off = (t / 3 - 1) * kRP + (t % 3 - 1);
+              sum += fmaf(s_w2d[t], D1[pc + off], e[t]);
+            }
+            if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride + 1);
+            const float d1 = D1[pc], d2 = fmaxf(sum, 0.f);
+            __half h1, l1, h2, l2;
+            split_h(d1, h1, l1); split_h(d2, h2, l2);
+            *reinterpret_cast<uint32_t*>(dslot + (size_t)p * 16) = pack_h2(h1, h2);
+            if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)p * 16) = pack_h2(l1, l2);
           }
         }
       }
@@ -265,24 +271,28 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       tc_fence_after();
       float ldsum = 0.f;
       const uint32_t trow = tmem_base + lane_base + (uint32_t)(s * 256 + 128 + wg * NP);
-      const float* hcp = (a.hoist && valid) ? a.hc + (size_t)(ir * a.W + ic) * a.hc_stride : nullptr;
+      const float4* hcp = (a.hoist && valid) ? reinterpret_cast<const float4*>(a.hc + (size_t)(ir * a.W + ic) * a.hc_stride) : nullptr;
 #pragma unroll
       for (int n0 = 0; n0 < NP; n0 += 16) {
         float h[16];
         tmem_ld16(trow + n0, h);
         if (valid) {
 #pragma unroll
-          for (int q = 0; q < 16; q += 2) {
+          for (int q = 0; q < 16; q += 4) {
             if (n0 + q < C) {
-              float hs = h[q] * inv3, hr = h[q + 1] * inv3;
-              if (hcp) { hs += __ldg(hcp + n0 + q); hr += __ldg(hcp + n0 + q + 1); }
-              const float shift = (hs + s_b3[n0 + q]) * gain;            // h[:, 0::2]
-              const float raw = (hr + s_b3[n0 + q + 1]) * gain;          // h[:, 1::2]
-              const float la = 2.f * (raw / (1.f + fabsf(raw)));
-              ldsum += la;
-              const float sc = expf(la);
-              const int j = C / 2 + (n0 + q) / 2;
-              v[j] = a.reverse ? v[j] / sc - shift : (v[j] + shift) * sc;
+              float4 hc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (hcp) hc4 = __ldg(hcp + (n0 + q) / 4);
+              const float hv[4] = {fmaf(h[q], inv3, hc4.x), fmaf(h[q + 1], inv3, hc4.y), fmaf(h[q + 2], inv3, hc4.z),
+                                   fmaf(h[q + 3], inv3, hc4.w)};
+#pragma unroll
+              for (int e = 0; e < 4; e += 2) {
+                const float shift = (hv[e] + s_b3[n0 + q + e]) * gain;            // h[:, 0::2]
+                const float raw = (hv[e + 1] + s_b3[n0 + q + e + 1]) * gain;      // h[:, 1::2]
+                const float la = 2.f * (raw / (1.f + fabsf(raw)));
+                ldsum += la;
+                const int j = C / 2 + (n0 + q + e) / 2;
+                v[j] = a.reverse ? fmaf(v[j], expf(-la), -shift) : (v[j] + shift) * expf(la);
+              }
             }
           }
         }
@@ -309,7 +319,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
                 sum = fmaf(w.x, v[4 * kk], sum); sum = fmaf(w.y, v[4 * kk + 1], sum);
                 sum = fmaf(w.z, v[4 * kk + 2], sum); sum = fmaf(w.w, v[4 * kk + 3], sum);
               }
-              if (a.reverse && a.nw) sum = (sum - s_nb[r4 + q]) / s_nw[r4 + q];
+              if (a.reverse && a.nw) sum = (sum - s_nb[r4 + q]) * s_rnw[r4 + q];
               o[q] = sum;
             }
             *reinterpret_cast<float4*>(yo + r4) = make_float4(o[0], o[1], o[2], o[3]);
@@ -319,23 +329,15 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
           for (int q = 0; q < C; q += 4) {
             float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = (a.reverse && a.nw) ? (v[q + e] - s_nb[q + e]) / s_nw[q + e] : v[q + e];
+            for (int e = 0; e < 4; ++e) o[e] = (a.reverse && a.nw) ? (v[q + e] - s_nb[q + e]) * s_rnw[q + e] : v[q + e];
             *reinterpret_cast<float4*>(yo + q) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
       }
-      if (a.ld_part) {
+      if (a.ld_part) {          // one partial per epilogue warp: slot = tile * 8 + warp (summed in fixed order later)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
-        named_bar_sync(1, kEpiThreads);              // previous tile's reader is done with s_red
-        if (lane == 0) s_red[warp] = ldsum;
-        named_bar_sync(1, kEpiThreads);
-        if (etid == 0) {
-          float tot = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) tot += s_red[w];
-          a.ld_part[(size_t)b * a.ld_stride + timg] = tot;
-        }
+        if (lane == 0) a.ld_part[(size_t)b * a.ld_stride + timg * 8 + warp] = ldsum;
       }
     };
 
@@ -346,8 +348,8 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       for (int k = 0; k < nmy; ++k) { gather(k); finish(k); }
     }
   } else if (warp == 8) {
-    // =========================================================== MMA issue (one thread)
-    if (lane == 0) {
+    // =========================================================== MMA issue (one elected lane of a converged warp)
+    if (elect_one()) {
       const uint32_t idE = idesc_f16(32), idZ = idesc_f16(NP);
       const uint64_t bE0 = make_desc(smem_u32(WE), 512, 128);
       const uint64_t bZ0 = make_desc(smem_u32(WZ), (uint32_t)NP * 16u, 128);
@@ -515,17 +517,19 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g) {
     auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
     g.nbuf = nbuf;
     g.oA = take((uint32_t)nbuf * g.bufA);
-    g.oDsc = take(18u * kNPOSA * 4);
+    g.oDsc = take(2u * (kNPOSA + 64) * 9 * 4);
     g.oD1 = take(kNPOSA * 4);
     g.oWE = take(g.nhl * g.wE_hl);
     g.oWZ = take(9u * g.wZ_tap);
-    g.oWm = take((uint32_t)(a.C * a.C + 3 * a.C + 9 + 3 + 8) * 4);
+    g.oWm = take((uint32_t)(a.C * a.C + 4 * a.C + 9 + 3) * 4);
     g.oBar = take(17 * 8 + 16);
     g.total = off;
     if (g.total <= 227 * 1024) { g.pipelined = nbuf >= 2; return true; }
   }
   return false;
 }
+
+int step2_ld_slots(int H, int W) { return 8 * cdiv(H, 16) * cdiv(W, 16); }
 
 bool step2_supported(const Step2Args& a) {
   Step2Geom g{};

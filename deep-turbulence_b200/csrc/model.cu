@@ -420,6 +420,7 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
   p.gates = take(mx_g);
   p.u0 = take(mx_u);
   p.ctas = std::max(cdiv(p.Hl[0] * p.Wl[0], kPixTile), coupling_tc_tiles(p.Hl[0], p.Wl[0]));
+  p.ctas = std::max(p.ctas, step2_ld_slots(p.Hl[0], p.Wl[0]));
   p.nslots = 1;
   for (int l = 0; l < L; ++l) p.nslots += c.glow_blocks[l] + 1;
   p.ldp = take(Bz * p.nslots * p.ctas);

@@ -100,6 +100,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a fully converged warp (what CUTLASS calls elect_one_sync): code under this predicate keeps its
+// warp-uniform values in uniform registers, so tcgen05.mma descriptors are not shuffled through R2UR/ELECT loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
