@@ -181,6 +181,7 @@ struct Step2Args {
   int ld_stride;
   int B, H, W;
   int x3;                  // 1: hi/lo operand split (fp32-grade), 0: single-pass fp16
+  long long* prof;         // developer profiling (TMG_STEP2_PROF=1): per-CTA cycle counters per role, else null
 };
 int launch_step2(const Step2Args& a, cudaStream_t st);
 bool step2_supported(const Step2Args& a);

@@ -25,6 +25,7 @@
 //     stochastic samples) the cond K-steps are dropped and their contribution, which is the same for every
 //     sample, is read from a per-step table computed once per call ("hoisted", model.cu).
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -35,14 +36,14 @@ constexpr int kRP = 22;                  // padded tile pitch: 16 + 2*3
 constexpr int kNPOS = 484;               // 22 x 22 staged positions
 constexpr int kNPOSA = 512;              // allocated positions (4 E tiles of 128)
 constexpr uint32_t kPLB = kNPOSA * 16;   // bytes of one 8-channel plane
-constexpr int kS2Threads = 416;          // warps 0-7 epilogue, 8 MMA, 9-12 producers
 constexpr int kEpiThreads = 256;
 
 struct Step2Geom {
   int KS, KSy, PLtot, kd, nbuf, pipelined;
   int tiles_x, tiles_y, ntiles, nhl;
-  uint32_t hlA, bufA;
-  uint32_t oA, oDsc, oD1, oWE, oWZ, oWm, oBar, total;
+  int step_b, step_t; uint32_t inv_tx; int ngroups;
+  uint32_t hlA, bufA, scratch;
+  uint32_t oA, oDsc, oWE, oWZ, oWm, oBar, total;
   uint32_t wE_hl, wZ_tap, wZ_hl;         // shared-memory strides of the weight copies
   uint32_t gE_hl, gZ_tap, gZ_hl;         // strides of the packed (global) weights
 };
@@ -84,30 +85,52 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-template <int C, bool X3>
-__global__ void __launch_bounds__(kS2Threads, 1)
+// developer profiling: cycles between marks, accumulated per role (written by one thread per role at the end)
+#define PROF_DECL long long pt_ = 0, pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const bool prof_on_ = a.prof != nullptr; if (prof_on_) pt_ = clock64();
+#define PROF_MARK(i) if (prof_on_) { const long long n_ = clock64(); pacc_[i] += n_ - pt_; pt_ = n_; }
+#define PROF_FLUSH(base) if (prof_on_) { for (int i_ = 0; i_ < 8; ++i_) a.prof[(size_t)blockIdx.x * 32 + (base) + i_] = pacc_[i_]; }
+
+// Tile bookkeeping without per-tile integer divisions: tile t = blockIdx.x + k * gridDim.x  ->  (sample, tile in image)
+struct TileIt {
+  int b, timg;
+  __device__ __forceinline__ void init(int t, int tiles_img) { b = t / tiles_img; timg = t - b * tiles_img; }
+  __device__ __forceinline__ void advance(const Step2Geom& g, int tiles_img) {
+    timg += g.step_t; b += g.step_b;
+    if (timg >= tiles_img) { timg -= tiles_img; ++b; }
+  }
+  __device__ __forceinline__ void origin(const Step2Geom& g, int& r0, int& c0) const {
+    const int ty = (int)(((uint32_t)timg * g.inv_tx) >> 16);
+    r0 = ty * 16; c0 = (timg - ty * g.tiles_x) * 16;
+  }
+};
+
+// NG epilogue groups of 256 threads (8 warps); warps 8*NG .. 8*NG+2 issue the MMAs (E, Z of M tile 0, Z of M tile 1:
+// three issuers on three schedulers -- a lone issuing warp that shares its scheduler with busy epilogue warps runs
+// at ~100 cycles per MMA instead of 40, tools/ubench_mma.cu); the next 4 warps are producers.
+template <int C, bool X3, int NG>
+__global__ void __launch_bounds__(NG * 256 + 224, 1)
 flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   constexpr int NP = (C + 15) / 16 * 16;
+  constexpr int kThreads = NG * 256 + 224;
+  constexpr int kMmaWarp = 8 * NG;        // E issuer (+ TMEM owner); kMmaWarp+1, +2: Z issuers
+  constexpr int kProdWarp = 8 * NG + 3;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W;
   const int tiles_img = g.tiles_x * g.tiles_y;
 
   uint8_t* A = smem + g.oA;
-  float* Ds1 = reinterpret_cast<float*>(smem + g.oDsc) + 32 * 9;          // [rows -32..543][9] dense layer 1 tap partials
-  float* Ds2 = Ds1 + (kNPOSA + 64) * 9;                                 // same for dense layer 2
-  float* D1 = reinterpret_cast<float*>(smem + g.oD1);       // [512] relu(d1)
   uint8_t* WE = smem + g.oWE;
   uint8_t* WZ = smem + g.oWZ;
   float* Wm = reinterpret_cast<float*>(smem + g.oWm);       // C*C mix | nw | nb | bias3 | w2d[9] | inv scales[3] | 1/nw
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.oBar);
   uint64_t* a_full = bars;          // [3] producers (128)
   uint64_t* a_free = bars + 3;      // [3] commit
-  uint64_t* d_ready = bars + 6;     // [3] epilogue (256)
+  uint64_t* d_ready = bars + 6;     // [3] epilogue group (256)
   uint64_t* e_full = bars + 9;      // [2] commit
-  uint64_t* e_free = bars + 11;     // [2] epilogue (256)
+  uint64_t* e_free = bars + 11;     // [2] epilogue group (256)
   uint64_t* z_full = bars + 13;     // [2] commit
-  uint64_t* z_free = bars + 15;     // [2] epilogue (256)
+  uint64_t* z_free = bars + 15;     // [2] epilogue group (256)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   float* s_nw = Wm + C * C;
@@ -119,32 +142,32 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
 
   // ------------------------------------------------------------------ one-time setup
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(a_full + i, 128); mbar_init(a_free + i, 1); mbar_init(d_ready + i, kEpiThreads); }
-    for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_free + i, kEpiThreads); mbar_init(z_full + i, 1); mbar_init(z_free + i, kEpiThreads); }
+    for (int i = 0; i < 3; ++i) { mbar_init(a_full + i, 128); mbar_init(a_free + i, 3); mbar_init(d_ready + i, kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_free + i, kEpiThreads); mbar_init(z_full + i, 2); mbar_init(z_free + i, kEpiThreads); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   {
     // zero every A buffer once: tail positions, padding channels and the d slots start as finite zeros
     uint4* z4 = reinterpret_cast<uint4*>(A);
     const int n4 = (int)((size_t)g.nbuf * g.bufA / 16);
-    for (int i = tid; i < n4; i += kS2Threads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < n4; i += kThreads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
     // weights: packed global [hl][PLtot][..] -> shared [hl][2*KS][..] (only the K-steps this launch multiplies)
     const int pl = 2 * g.KS;
     const uint4* gE = reinterpret_cast<const uint4*>(a.wE);
-    for (int i = tid; i < g.nhl * pl * 32; i += kS2Threads) {
+    for (int i = tid; i < g.nhl * pl * 32; i += kThreads) {
       const int r = i % (pl * 32), hl = i / (pl * 32);
       reinterpret_cast<uint4*>(WE + hl * g.wE_hl)[r] = __ldg(gE + (size_t)hl * (g.gE_hl / 16) + r);
     }
     const uint4* gZ = reinterpret_cast<const uint4*>(a.wZ);
     const int per = pl * NP;
-    for (int i = tid; i < 9 * g.nhl * per; i += kS2Threads) {
+    for (int i = tid; i < 9 * g.nhl * per; i += kThreads) {
       const int r = i % per; int t = i / per; const int hl = t % g.nhl, tap = t / g.nhl;
       reinterpret_cast<uint4*>(WZ + tap * g.wZ_tap + hl * g.wZ_hl)[r] =
           __ldg(gZ + (size_t)tap * (g.gZ_tap / 16) + (size_t)hl * (g.gZ_hl / 16) + r);
     }
-    for (int i = tid; i < C * C; i += kS2Threads) Wm[i] = a.wmat ? __ldg(a.wmat + i) : 0.f;
-    for (int i = tid; i < C; i += kS2Threads) {
+    for (int i = tid; i < C * C; i += kThreads) Wm[i] = a.wmat ? __ldg(a.wmat + i) : 0.f;
+    for (int i = tid; i < C; i += kThreads) {
       s_nw[i] = a.nw ? __ldg(a.nw + i) : 1.f;
       s_nb[i] = a.nw ? __ldg(a.nb + i) : 0.f;
       s_b3[i] = __ldg(a.bias3 + i);
@@ -159,28 +182,51 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   const uint32_t tmem_base = *tmem_slot;
   const int nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp < 8) {
-    // =========================================================== epilogue warps (256 threads)
-    const int etid = tid, wg = etid >> 7, el = etid & 127;
+  if (warp < kMmaWarp) {
+    // =========================================================== epilogue groups (256 threads each)
+    const int grp = warp >> 3;
+    const int etid = tid & 255, wg = etid >> 7, el = etid & 127;
+    const int bar_id = 1 + grp;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float gain = a.gain3 ? __ldg(a.gain3) : 1.f;
     const float inv1 = s_inv[0], inv2 = s_inv[1], inv3 = s_inv[2];
+    float* Ds1 = reinterpret_cast<float*>(smem + g.oDsc + (size_t)grp * g.scratch) + 32 * 9;   // [rows -32..543][9]
+    float* Ds2 = Ds1 + (kNPOSA + 64) * 9;
+    float* D1 = Ds2 + (kNPOSA + 32) * 9;                                                      // [512] relu(d1)
+    PROF_DECL
 
-    auto tile_origin = [&](int k, int& b, int& r0, int& c0, int& timg) {
-      const int t = blockIdx.x + k * gridDim.x;
-      b = t / tiles_img; timg = t - b * tiles_img;
-      r0 = (timg / g.tiles_x) * 16; c0 = (timg % g.tiles_x) * 16;
-    };
-
-    // ---- G(k): E accumulators -> d1, d2 written into the A buffer of tile k
-    // Dsc holds the tap partials PRE-SHIFTED: the partial of tap t computed at position q is stored in row
-    // q - off(t), so row p holds the nine terms of the 3x3 sum at p; out-of-image q store zeros (zero padding of
-    // the dense layers), so the sums below need no masks.
-    auto gather = [&](int k) {
+    // ---- G(k): E accumulators -> d1, d2 written into the A buffer of tile k.
+    // The tap partials are stored PRE-SHIFTED: the partial of tap t computed at position q goes to row q - off(t),
+    // so row p holds the nine terms of the 3x3 sum at p; out-of-image q store zeros (zero padding of the dense
+    // layers), so the sums need no masks.
+    auto gather = [&](int k, const TileIt& it) {
       const int s = k & 1, u = k % g.nbuf;
-      int b, r0, c0, timg;
-      tile_origin(k, b, r0, c0, timg);
+      int r0, c0;
+      it.origin(g, r0, c0);
+      // positions of this thread in the d1 / d2 passes and the hoisted conditioning terms (prefetched)
+      int pd[2], pcl[2];
+      bool ok1[2], in1[2], ok2[2];
+      float dcv1[2] = {0.f, 0.f}, dcv2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p = etid + j * kEpiThreads;
+        const int rr = p / kRP, rc = p - rr * kRP;
+        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
+        pd[j] = p;
+        ok1[j] = p < kNPOS && rr >= 1 && rr <= 20 && rc >= 1 && rc <= 20;
+        in1[j] = ir >= 0 && ir < a.H && ic >= 0 && ic < a.W;
+        ok2[j] = p < kNPOS && rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19;
+        const int irc = min(max(ir, 0), a.H - 1), icc = min(max(ic, 0), a.W - 1);
+        pcl[j] = (irc - (r0 - 3)) * kRP + (icc - (c0 - 3));
+        ok2[j] = ok2[j] && pcl[j] >= 2 * kRP + 2 && pcl[j] < 20 * kRP;
+        if (a.hoist) {
+          if (ok1[j] && in1[j]) dcv1[j] = __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride);
+          if (ok2[j]) dcv2[j] = __ldg(a.dc + (size_t)(irc * a.W + icc) * a.dc_stride + 1);
+        }
+      }
+      PROF_MARK(0)
       mbar_wait(e_full + s, (uint32_t)((k >> 1) & 1));
+      PROF_MARK(1)
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -202,76 +248,76 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       }
       tc_fence_before();
       mbar_arrive(e_free + s);
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(bar_id, kEpiThreads);
       // d1 = relu(sum) on the halo-2 region (zero outside the image)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int p = etid + j * kEpiThreads;
-        const int rr = p / kRP, rc = p - rr * kRP;
-        const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
-        if (p < kNPOS && rr >= 1 && rr <= 20 && rc >= 1 && rc <= 20) {
+        if (ok1[j]) {
           float val = 0.f;
-          if (ir >= 0 && ir < a.H && ic >= 0 && ic < a.W) {
-            const float* e = Ds1 + p * 9;
-            float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
-            float sum = ((s0 + s1) + (s2 + s3)) + e[8];
-            if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride);
-            val = fmaxf(sum, 0.f);
+          if (in1[j]) {
+            const float* e = Ds1 + pd[j] * 9;
+            const float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
+            val = fmaxf(((s0 + s1) + (s2 + s3)) + e[8] + dcv1[j], 0.f);
           }
-          D1[p] = val;
+          D1[pd[j]] = val;
         }
       }
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(bar_id, kEpiThreads);
       // d2 on the halo-1 region, evaluated at the replicate-clamped pixel (Conv2dZeros pads by replication);
       // the (d1, d2) pair goes into K slots kd, kd+1 of the A buffer
       uint8_t* dslot = A + (size_t)u * g.bufA + (size_t)(g.kd >> 3) * kPLB + (size_t)(g.kd & 7) * 2;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int p = etid + j * kEpiThreads;
-        const int rr = p / kRP, rc = p - rr * kRP;
-        if (p < kNPOS && rr >= 2 && rr <= 19 && rc >= 2 && rc <= 19) {
-          const int ir = min(max(r0 - 3 + rr, 0), a.H - 1), ic = min(max(c0 - 3 + rc, 0), a.W - 1);
-          const int pc = (ir - (r0 - 3)) * kRP + (ic - (c0 - 3));
-          if (pc >= 2 * kRP + 2 && pc < 20 * kRP) {         // the clamped pixel lies inside this tile's halo-1 region
-            const float* e = Ds2 + pc * 9;
-            float sum = 0.f;
+        if (ok2[j]) {
+          const int pc = pcl[j];
+          const float* e = Ds2 + pc * 9;
+          float sa = dcv2[j], sb = 0.f;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const int off = (t / 3 - 1) * kRP + (t % 3 - 1);
-              sum += fmaf(s_w2d[t], D1[pc + off], e[t]);
-            }
-            if (a.hoist) sum += __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride + 1);
-            const float d1 = D1[pc], d2 = fmaxf(sum, 0.f);
-            __half h1, l1, h2, l2;
-            split_h(d1, h1, l1); split_h(d2, h2, l2);
-            *reinterpret_cast<uint32_t*>(dslot + (size_t)p * 16) = pack_h2(h1, h2);
-            if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)p * 16) = pack_h2(l1, l2);
+          for (int t = 0; t < 9; ++t) {
+            const int off = (t / 3 - 1) * kRP + (t % 3 - 1);
+            if (t & 1) sb += fmaf(s_w2d[t], D1[pc + off], e[t]);
+            else sa += fmaf(s_w2d[t], D1[pc + off], e[t]);
           }
+          const float d1 = D1[pc], d2 = fmaxf(sa + sb, 0.f);
+          __half h1, l1, h2, l2;
+          split_h(d1, h1, l1); split_h(d2, h2, l2);
+          *reinterpret_cast<uint32_t*>(dslot + (size_t)pd[j] * 16) = pack_h2(h1, h2);
+          if (X3) *reinterpret_cast<uint32_t*>(dslot + g.hlA + (size_t)pd[j] * 16) = pack_h2(l1, l2);
         }
       }
       fence_proxy_async();
       mbar_arrive(d_ready + u);
+      PROF_MARK(2)
     };
 
     // ---- F(k): h -> coupling, 1x1 mix, ActNorm, store, log-det partial
-    auto finish = [&](int k) {
+    auto finish = [&](int k, const TileIt& it) {
       const int s = k & 1;
-      int b, r0, c0, timg;
-      tile_origin(k, b, r0, c0, timg);
+      int r0, c0;
+      it.origin(g, r0, c0);
+      const int b = it.b;
       const int ir = r0 + (el >> 3), ic = c0 + 8 * wg + (el & 7);
       const bool valid = ir < a.H && ic < a.W;
       const size_t pix = valid ? (size_t)b * HW + (size_t)ir * a.W + ic : 0;
       float v[C];
+      constexpr int NHC = C <= 24 ? C / 4 : 1;
+      float4 hcv[NHC];
+      const float4* hcp = (a.hoist && valid) ? reinterpret_cast<const float4*>(a.hc + (size_t)(ir * a.W + ic) * a.hc_stride) : nullptr;
       if (valid) {
         const float4* y4 = reinterpret_cast<const float4*>(a.y_in + pix * C);
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) { float4 t = __ldg(y4 + q); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
       }
+      if (C <= 24) {
+#pragma unroll
+        for (int q = 0; q < NHC; ++q) hcv[q] = hcp ? __ldg(hcp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      PROF_MARK(3)
       mbar_wait(z_full + s, (uint32_t)((k >> 1) & 1));
+      PROF_MARK(4)
       tc_fence_after();
       float ldsum = 0.f;
       const uint32_t trow = tmem_base + lane_base + (uint32_t)(s * 256 + 128 + wg * NP);
-      const float4* hcp = (a.hoist && valid) ? reinterpret_cast<const float4*>(a.hc + (size_t)(ir * a.W + ic) * a.hc_stride) : nullptr;
 #pragma unroll
       for (int n0 = 0; n0 < NP; n0 += 16) {
         float h[16];
@@ -280,8 +326,9 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
 #pragma unroll
           for (int q = 0; q < 16; q += 4) {
             if (n0 + q < C) {
-              float4 hc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (hcp) hc4 = __ldg(hcp + (n0 + q) / 4);
+              float4 hc4;
+              if (C <= 24) hc4 = hcv[(n0 + q) / 4 < NHC ? (n0 + q) / 4 : 0];
+              else hc4 = hcp ? __ldg(hcp + (n0 + q) / 4) : make_float4(0.f, 0.f, 0.f, 0.f);
               const float hv[4] = {fmaf(h[q], inv3, hc4.x), fmaf(h[q + 1], inv3, hc4.y), fmaf(h[q + 2], inv3, hc4.z),
                                    fmaf(h[q + 3], inv3, hc4.w)};
 #pragma unroll
@@ -337,149 +384,205 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       if (a.ld_part) {          // one partial per epilogue warp: slot = tile * 8 + warp (summed in fixed order later)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ldsum += __shfl_xor_sync(0xffffffffu, ldsum, o);
-        if (lane == 0) a.ld_part[(size_t)b * a.ld_stride + timg * 8 + warp] = ldsum;
+        if (lane == 0) a.ld_part[(size_t)b * a.ld_stride + it.timg * 8 + (warp & 7)] = ldsum;
       }
+      PROF_MARK(5)
     };
 
-    if (g.pipelined) {
-      if (nmy > 0) gather(0);
-      for (int k = 0; k < nmy; ++k) { if (k + 1 < nmy) gather(k + 1); finish(k); }
+    if (NG == 2) {
+      TileIt it;
+      it.init(blockIdx.x + grp * gridDim.x, tiles_img);
+      for (int k = grp; k < nmy; k += 2) {
+        gather(k, it);
+        finish(k, it);
+        it.advance(g, tiles_img); it.advance(g, tiles_img);
+      }
+    } else if (g.pipelined) {
+      TileIt itf, itg;
+      itf.init(blockIdx.x, tiles_img); itg = itf;
+      if (nmy > 0) gather(0, itg);
+      for (int k = 0; k < nmy; ++k) {
+        itg.advance(g, tiles_img);
+        if (k + 1 < nmy) gather(k + 1, itg);
+        finish(k, itf);
+        itf.advance(g, tiles_img);
+      }
     } else {
-      for (int k = 0; k < nmy; ++k) { gather(k); finish(k); }
+      TileIt it;
+      it.init(blockIdx.x, tiles_img);
+      for (int k = 0; k < nmy; ++k) { gather(k, it); finish(k, it); it.advance(g, tiles_img); }
     }
-  } else if (warp == 8) {
-    // =========================================================== MMA issue (one elected lane of a converged warp)
+    if (etid == 0 && grp == 0) { PROF_FLUSH(0) }
+  } else if (warp < kProdWarp) {
+    // =========================================================== MMA issue: one elected lane per issuer warp
+    const int role = warp - kMmaWarp;         // 0: E, 1: Z of M tile 0 (columns 0-7), 2: Z of M tile 1 (columns 8-15)
     if (elect_one()) {
-      const uint32_t idE = idesc_f16(32), idZ = idesc_f16(NP);
-      const uint64_t bE0 = make_desc(smem_u32(WE), 512, 128);
-      const uint64_t bZ0 = make_desc(smem_u32(WZ), (uint32_t)NP * 16u, 128);
-      const uint64_t hlA16 = g.hlA >> 4, wEhl16 = g.wE_hl >> 4, wZhl16 = g.wZ_hl >> 4, wZtap16 = g.wZ_tap >> 4;
-
-      auto issue_E = [&](int k) {
-        const int s = k & 1, u = k % g.nbuf;
-        mbar_wait(a_full + u, (uint32_t)((k / g.nbuf) & 1));
-        if (k >= 2) mbar_wait(e_free + s, (uint32_t)(((k >> 1) - 1) & 1));
-        tc_fence_after();
-        const uint64_t aE0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, 128);
-        const uint32_t tE = tmem_base + (uint32_t)(s * 256);
+      const uint64_t hlA16 = g.hlA >> 4;
+      PROF_DECL
+      if (role == 0) {
+        const uint32_t idE = idesc_f16(32);
+        const uint64_t bE0 = make_desc(smem_u32(WE), 512, 128);
+        const uint64_t wEhl16 = g.wE_hl >> 4;
+        for (int k = 0; k < nmy; ++k) {
+          const int s = k & 1, u = k % g.nbuf;
+          PROF_MARK(0)
+          mbar_wait(a_full + u, (uint32_t)((k / g.nbuf) & 1));
+          PROF_MARK(1)
+          if (k >= 2) mbar_wait(e_free + s, (uint32_t)(((k >> 1) - 1) & 1));
+          PROF_MARK(2)
+          tc_fence_after();
+          const uint64_t aE0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, 128);
+          const uint32_t tE = tmem_base + (uint32_t)(s * 256);
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          uint64_t ad = aE0 + (uint64_t)(mt * 128);          // 128 positions x 16 B, in 16-byte units
-          uint64_t bd = bE0;
-          for (int ks = 0; ks < g.KS; ++ks) {
-            mma_f16(tE + (uint32_t)(mt * 32), ad, bd, idE, ks > 0 ? 1u : 0u);
-            if (X3) {
-              mma_f16(tE + (uint32_t)(mt * 32), ad + hlA16, bd, idE, 1u);
-              mma_f16(tE + (uint32_t)(mt * 32), ad, bd + wEhl16, idE, 1u);
+          for (int mt = 0; mt < 4; ++mt) {
+            uint64_t ad = aE0 + (uint64_t)(mt * 128);          // 128 positions x 16 B, in 16-byte units
+            uint64_t bd = bE0;
+            for (int ks = 0; ks < g.KS; ++ks) {
+              mma_f16(tE + (uint32_t)(mt * 32), ad, bd, idE, ks > 0 ? 1u : 0u);
+              if (X3) {
+                mma_f16(tE + (uint32_t)(mt * 32), ad + hlA16, bd, idE, 1u);
+                mma_f16(tE + (uint32_t)(mt * 32), ad, bd + wEhl16, idE, 1u);
+              }
+              ad += (uint64_t)(2 * kPLB >> 4);
+              bd += (uint64_t)(2 * 512 >> 4);
             }
-            ad += (uint64_t)(2 * kPLB >> 4);
-            bd += (uint64_t)(2 * 512 >> 4);
           }
+          mma_commit(e_full + s);
+          mma_commit(a_free + u);
+          PROF_MARK(3)
         }
-        mma_commit(e_full + s);
-      };
-      auto issue_Z = [&](int k) {
-        const int s = k & 1, u = k % g.nbuf;
-        mbar_wait(d_ready + u, (uint32_t)((k / g.nbuf) & 1));
-        if (k >= 2) mbar_wait(z_free + s, (uint32_t)(((k >> 1) - 1) & 1));
-        tc_fence_after();
-        const uint64_t aZ0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, kRP * 16);
-        const uint32_t tZ = tmem_base + (uint32_t)(s * 256 + 128);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        PROF_FLUSH(8)
+      } else {
+        const int mt = role - 1;
+        const uint32_t idZ = idesc_f16(NP);
+        const uint64_t bZ0 = make_desc(smem_u32(WZ), (uint32_t)NP * 16u, 128);
+        const uint64_t wZhl16 = g.wZ_hl >> 4, wZtap16 = g.wZ_tap >> 4;
+        for (int k = 0; k < nmy; ++k) {
+          const int s = k & 1, u = k % g.nbuf;
+          PROF_MARK(0)
+          mbar_wait(d_ready + u, (uint32_t)((k / g.nbuf) & 1));
+          PROF_MARK(4)
+          if (k >= 2) mbar_wait(z_free + s, (uint32_t)(((k >> 1) - 1) & 1));
+          PROF_MARK(5)
+          tc_fence_after();
+          const uint64_t aZ0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, kRP * 16) + (uint64_t)(8 * mt);
+          const uint32_t tZ = tmem_base + (uint32_t)(s * 256 + 128 + mt * NP);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            uint64_t ad = aZ0 + (uint64_t)((3 + tap / 3 - 1) * kRP + 3 + 8 * mt + tap % 3 - 1);
+            uint64_t ad = aZ0 + (uint64_t)((3 + tap / 3 - 1) * kRP + 3 + tap % 3 - 1);
             uint64_t bd = bZ0 + (uint64_t)tap * wZtap16;
             for (int ks = 0; ks < g.KS; ++ks) {
               const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
-              mma_f16(tZ + (uint32_t)(mt * NP), ad, bd, idZ, acc);
+              mma_f16(tZ, ad, bd, idZ, acc);
               if (X3) {
-                mma_f16(tZ + (uint32_t)(mt * NP), ad + hlA16, bd, idZ, 1u);
-                mma_f16(tZ + (uint32_t)(mt * NP), ad, bd + wZhl16, idZ, 1u);
+                mma_f16(tZ, ad + hlA16, bd, idZ, 1u);
+                mma_f16(tZ, ad, bd + wZhl16, idZ, 1u);
               }
               ad += (uint64_t)(2 * kPLB >> 4);
-              bd += (uint64_t)(2 * NP);                      // 2 planes x NP rows x 16 B, in 16-byte units
+              bd += (uint64_t)(2 * NP);                        // 2 planes x NP rows x 16 B, in 16-byte units
             }
           }
+          mma_commit(z_full + s);
+          mma_commit(a_free + u);
+          PROF_MARK(6)
         }
-        mma_commit(z_full + s);
-        mma_commit(a_free + u);
-      };
-      if (g.pipelined) {
-        if (nmy > 0) issue_E(0);
-        for (int k = 0; k < nmy; ++k) { if (k + 1 < nmy) issue_E(k + 1); issue_Z(k); }
-      } else {
-        for (int k = 0; k < nmy; ++k) { issue_E(k); issue_Z(k); }
+        if (role == 1) { PROF_FLUSH(24) }
       }
     }
   } else {
     // =========================================================== producers (128 threads): stage relu(t) as fp16 hi/lo
-    const int ptid = tid - 9 * 32;
+    const int ptid = tid - kProdWarp * 32;
     const int npl0 = 2 * g.KSy;
-    const int npl = (!a.hoist && a.nsrc > 1) ? 2 * g.KS : npl0;
+    const int nst0 = (a.src[0].nch + 7) / 8;                                     // staged planes of src0
+    const int nstage = nst0 + ((!a.hoist && a.nsrc > 1) ? (a.src[1].nch + 7) / 8 : 0);
+    TileIt it;
+    it.init(blockIdx.x, tiles_img);
+    PROF_DECL
     for (int k = 0; k < nmy; ++k) {
       const int u = k % g.nbuf, use = k / g.nbuf;
-      const int t = blockIdx.x + k * gridDim.x;
-      const int b = t / tiles_img, timg = t - b * tiles_img;
-      const int r0 = (timg / g.tiles_x) * 16, c0 = (timg % g.tiles_x) * 16;
+      const int b = it.b;
+      int r0, c0;
+      it.origin(g, r0, c0);
+      it.advance(g, tiles_img);
+      PROF_MARK(0)
       if (use >= 1) mbar_wait(a_free + u, (uint32_t)((use - 1) & 1));
+      PROF_MARK(1)
       uint8_t* Ab = A + (size_t)u * g.bufA;
-      const int items = kNPOS * npl;
-      for (int it = ptid; it < items; it += 128) {
-        const int p = it % kNPOS, plane = it / kNPOS;
-        const int rr = p / kRP, rc = p - rr * kRP;
-        const int r = min(max(r0 - 3 + rr, 0), a.H - 1), c = min(max(c0 - 3 + rc, 0), a.W - 1);
-        const bool s1 = plane >= npl0;
-        const ConvSrc& sc = a.src[s1 ? 1 : 0];
-        const int ch = (s1 ? plane - npl0 : plane) * 8;
-        const int nv = min(8, sc.nch - ch);                  // may be <= 0: pure padding / d-slot plane
-        float v[8];
+      // planes that hold source channels (pure padding / d-slot planes were zeroed once and are never staged)
+      const int items = kNPOS * nstage;
+      for (int it0 = ptid; it0 < items; it0 += 128 * 4) {
+        float v[4][8];
+        int pos[4], pln[4];
+        bool relu[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (nv > 0) {
-          const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c;
-          const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
-          if (nv == 8 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)), t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1);
-            v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-          } else {
+        for (int q = 0; q < 4; ++q) {
+          const int itx = it0 + q * 128;
+          pos[q] = -1; pln[q] = 0; relu[q] = true;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) if (e < nv) v[e] = __ldg(ptr + e);
-          }
-          if (sc.relu) {
+          for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+          if (itx < items) {
+            const int p = itx % kNPOS, sp = itx / kNPOS;
+            const bool s1 = sp >= nst0;
+            const int plane = s1 ? npl0 + (sp - nst0) : sp;
+            const int rr = p / kRP, rc = p - rr * kRP;
+            const int r = min(max(r0 - 3 + rr, 0), a.H - 1), c = min(max(c0 - 3 + rc, 0), a.W - 1);
+            const ConvSrc& sc = a.src[s1 ? 1 : 0];
+            const int ch = (s1 ? sp - nst0 : sp) * 8;
+            const int nv = min(8, sc.nch - ch);
+            pos[q] = p; pln[q] = plane; relu[q] = sc.relu != 0;
+            const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c;
+            const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
+            if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (nv & 1) == 0) {
+              if (nv >= 4) { const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; v[q][2] = t0.z; v[q][3] = t0.w; }
+              else { const float2 t0 = __ldg(reinterpret_cast<const float2*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; }
+              if (nv == 8) { const float4 t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1); v[q][4] = t1.x; v[q][5] = t1.y; v[q][6] = t1.z; v[q][7] = t1.w; }
+              else if (nv == 6) { const float2 t1 = __ldg(reinterpret_cast<const float2*>(ptr) + 2); v[q][4] = t1.x; v[q][5] = t1.y; }
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+              for (int e = 0; e < 8; ++e) if (e < nv) v[q][e] = __ldg(ptr + e);
+            }
           }
         }
-        // the d slots of this plane (if any) are owned by the epilogue warps: keep what is there
-        const bool has_d = !s1 && (g.kd >> 3) == plane;
-        __half hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_h(v[e], hi[e], lo[e]);
-        uint4 ph = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-        uint8_t* dst = Ab + (size_t)plane * kPLB + (size_t)p * 16;
-        if (has_d) {        // kd & 7 == 6: the pair sits in the last 32-bit word
-          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-          d32[0] = ph.x; d32[1] = ph.y; d32[2] = ph.z;
-          if (X3) {
-            uint32_t* l32 = reinterpret_cast<uint32_t*>(dst + g.hlA);
-            l32[0] = pack_h2(lo[0], lo[1]); l32[1] = pack_h2(lo[2], lo[3]); l32[2] = pack_h2(lo[4], lo[5]);
+        for (int q = 0; q < 4; ++q) {
+          if (pos[q] < 0) continue;
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float y0 = fminf(v[q][2 * e], 60000.f), y1 = fminf(v[q][2 * e + 1], 60000.f);
+            y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
+            const __half2 h2 = __floats2half2_rn(y0, y1);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+            ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-        } else {
-          *reinterpret_cast<uint4*>(dst) = ph;
-          if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) =
-                      make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+          // the d slots of this plane (if any) are owned by the epilogue warps: keep what is there
+          const bool has_d = (g.kd >> 3) == pln[q];
+          uint8_t* dst = Ab + (size_t)pln[q] * kPLB + (size_t)pos[q] * 16;
+          if (has_d) {        // kd & 7 == 6: the pair sits in the last 32-bit word
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+            d32[0] = ph[0]; d32[1] = ph[1]; d32[2] = ph[2];
+            if (X3) {
+              uint32_t* l32 = reinterpret_cast<uint32_t*>(dst + g.hlA);
+              l32[0] = pl[0]; l32[1] = pl[1]; l32[2] = pl[2];
+            }
+          } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
         }
       }
       fence_proxy_async();
       mbar_arrive(a_full + u);
+      PROF_MARK(2)
     }
+    if (ptid == 0) { PROF_FLUSH(16) }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -498,7 +601,18 @@ size_t step2_wZ_floats(int nch0, int nch1, int C) {
   return (size_t)9 * 2 * 2 * (KSy + KS1) * NP * 16 / 4;         // [tap][hl][planes][NP][16 B]
 }
 
-static bool make_geom2(const Step2Args& a, Step2Geom& g) {
+static int sm_count() {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  static int cached_sm[64] = {0};
+  if (dev >= 0 && dev < 64) {
+    if (!cached_sm[dev]) cudaDeviceGetAttribute(&cached_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (cached_sm[dev] > 0) nsm = cached_sm[dev];
+  }
+  return nsm;
+}
+
+static bool make_geom2(const Step2Args& a, Step2Geom& g, int grid) {
   int KSy, KS1, kd;
   const int nch0 = a.src[0].nch, nch1 = a.nsrc > 1 ? a.src[1].nch : 0;
   step2_klayout(nch0, nch1, KSy, KS1, kd);
@@ -509,22 +623,30 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g) {
   g.hlA = (uint32_t)(2 * g.KS) * kPLB;
   g.bufA = g.hlA * g.nhl;
   g.tiles_x = cdiv(a.W, 16); g.tiles_y = cdiv(a.H, 16);
-  g.ntiles = g.tiles_x * g.tiles_y * a.B;
+  const int tiles_img = g.tiles_x * g.tiles_y;
+  g.ntiles = tiles_img * a.B;
+  if (grid <= 0) grid = std::min(g.ntiles, sm_count());
+  g.step_b = grid / tiles_img; g.step_t = grid % tiles_img;
+  g.inv_tx = (uint32_t)((65536 + g.tiles_x - 1) / g.tiles_x);      // exact floor(t / tiles_x) for t < 4096
+  if (tiles_img >= 4096) return false;
   g.gE_hl = (uint32_t)g.PLtot * 512; g.gZ_hl = (uint32_t)g.PLtot * NP * 16; g.gZ_tap = 2 * g.gZ_hl;
   g.wE_hl = (uint32_t)(2 * g.KS) * 512; g.wZ_hl = (uint32_t)(2 * g.KS) * NP * 16; g.wZ_tap = g.nhl * g.wZ_hl;
-  for (int nbuf = 3; nbuf >= 1; --nbuf) {
-    uint32_t off = 0;
-    auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
-    g.nbuf = nbuf;
-    g.oA = take((uint32_t)nbuf * g.bufA);
-    g.oDsc = take(2u * (kNPOSA + 64) * 9 * 4);
-    g.oD1 = take(kNPOSA * 4);
-    g.oWE = take(g.nhl * g.wE_hl);
-    g.oWZ = take(9u * g.wZ_tap);
-    g.oWm = take((uint32_t)(a.C * a.C + 4 * a.C + 9 + 3) * 4);
-    g.oBar = take(17 * 8 + 16);
-    g.total = off;
-    if (g.total <= 227 * 1024) { g.pipelined = nbuf >= 2; return true; }
+  g.scratch = (uint32_t)(2 * (kNPOSA + 64) * 9 + kNPOSA) * 4;
+  // preference: two epilogue groups (narrow levels only: register budget) with the deepest A ring that fits
+  for (int ng = (a.C <= 24 ? 2 : 1); ng >= 1; --ng) {
+    for (int nbuf = 3; nbuf >= (ng == 2 ? 2 : 1); --nbuf) {
+      uint32_t off = 0;
+      auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
+      g.nbuf = nbuf; g.ngroups = ng;
+      g.oA = take((uint32_t)nbuf * g.bufA);
+      g.oDsc = take((uint32_t)ng * g.scratch);
+      g.oWE = take(g.nhl * g.wE_hl);
+      g.oWZ = take(9u * g.wZ_tap);
+      g.oWm = take((uint32_t)(a.C * a.C + 4 * a.C + 9 + 3) * 4);
+      g.oBar = take(17 * 8 + 16);
+      g.total = off;
+      if (g.total <= 227 * 1024) { g.pipelined = nbuf >= 2; return true; }
+    }
   }
   return false;
 }
@@ -533,39 +655,61 @@ int step2_ld_slots(int H, int W) { return 8 * cdiv(H, 16) * cdiv(W, 16); }
 
 bool step2_supported(const Step2Args& a) {
   Step2Geom g{};
-  return a.C % 4 == 0 && a.C <= kMaxC && (a.src[0].nch + 2 + 15) / 16 * 16 - 2 >= a.src[0].nch && make_geom2(a, g);
+  return a.C % 4 == 0 && a.C <= kMaxC && make_geom2(a, g, 148);
 }
 
-int launch_step2(const Step2Args& a, cudaStream_t st) {
-  if (a.B <= 0) return TMG_OK;
+int launch_step2(const Step2Args& a_in, cudaStream_t st) {
+  if (a_in.B <= 0) return TMG_OK;
+  Step2Args a = a_in;
+  static const bool prof_env = getenv("TMG_STEP2_PROF") != nullptr;
+  static long long* prof_buf = nullptr;
+  static int prof_left = 0;
+  if (prof_env && !prof_buf) { cudaMalloc(&prof_buf, 148 * 32 * sizeof(long long)); prof_left = atoi(getenv("TMG_STEP2_PROF")); }
+  if (prof_env && prof_left > 0) { cudaMemsetAsync(prof_buf, 0, 148 * 32 * sizeof(long long), st); a.prof = prof_buf; }
   Step2Geom g{};
-  if (a.C % 4 || a.C > kMaxC || !make_geom2(a, g)) {
+  const int tiles = cdiv(a.W, 16) * cdiv(a.H, 16) * a.B;
+  const int grid = std::min(tiles, sm_count());
+  if (a.C % 4 || a.C > kMaxC || !make_geom2(a, g, grid)) {
     set_error("fused fp16 flow step: unsupported shape (C=%d, %dx%d)", a.C, a.H, a.W);
     return TMG_ERR_UNSUPPORTED;
   }
-  int dev = 0, nsm = 148;
-  cudaGetDevice(&dev);
-  static int cached_sm[64] = {0};
-  if (dev < 64) {
-    if (!cached_sm[dev]) cudaDeviceGetAttribute(&cached_sm[dev], cudaDevAttrMultiProcessorCount, dev);
-    nsm = cached_sm[dev] > 0 ? cached_sm[dev] : 148;
+#define TMG_S2(CC, XX, GG)                                                                                                       \
+  {                                                                                                                              \
+    TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    flow_step_f16_kernel<CC, XX, GG><<<grid, GG * 256 + 224, g.total, st>>>(a, g);                                               \
   }
-  const int grid = std::min(g.ntiles, nsm);
-#define TMG_S2(CC, XX)                                                                                                       \
-  {                                                                                                                          \
-    TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-    flow_step_f16_kernel<CC, XX><<<grid, kS2Threads, g.total, st>>>(a, g);                                                   \
-  }
-#define TMG_S2C(CC) case CC: if (a.x3) TMG_S2(CC, true) else TMG_S2(CC, false) break;
+#define TMG_S2N(CC)                                                                              \
+  case CC:                                                                                       \
+    if (g.ngroups == 2) { if (a.x3) TMG_S2(CC, true, 2) else TMG_S2(CC, false, 2) }              \
+    else { if (a.x3) TMG_S2(CC, true, 1) else TMG_S2(CC, false, 1) }                             \
+    break;
+#define TMG_S2W(CC) case CC: if (a.x3) TMG_S2(CC, true, 1) else TMG_S2(CC, false, 1) break;
   switch (a.C) {
-    TMG_S2C(4) TMG_S2C(8) TMG_S2C(12) TMG_S2C(16) TMG_S2C(24) TMG_S2C(32) TMG_S2C(48) TMG_S2C(64)
+    TMG_S2N(4) TMG_S2N(8) TMG_S2N(12) TMG_S2N(16) TMG_S2N(24) TMG_S2W(32) TMG_S2W(48) TMG_S2W(64)
     default:
       set_error("fused fp16 flow step: %d channels not supported", a.C);
       return TMG_ERR_UNSUPPORTED;
   }
-#undef TMG_S2C
+#undef TMG_S2W
+#undef TMG_S2N
 #undef TMG_S2
   TMG_LAUNCH_CHECK();
+  if (a.prof) {      // developer profiling: average cycles per role and phase over the CTAs of this launch
+    --prof_left;
+    static long long h[148 * 32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    double s[32] = {0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 32; ++i) s[i] += (double)h[b * 32 + i] / grid;
+    const double tiles = (double)g.ntiles / grid;
+    fprintf(stderr, "[step2 prof] C=%d x3=%d hoist=%d KS=%d nbuf=%d ng=%d tiles/CTA=%.1f | cycles per tile: "
+            "EPI(g0) pre %.0f wait_e %.0f gather %.0f pre_f %.0f wait_z %.0f finish %.0f | "
+            "MMA gap %.0f wait_a %.0f wait_efree %.0f issueE %.0f wait_d %.0f wait_zfree %.0f issueZ %.0f | PROD gap %.0f wait_free %.0f stage %.0f\n",
+            a.C, a.x3, a.hoist, g.KS, g.nbuf, g.ngroups, tiles,
+            s[0] / tiles * g.ngroups, s[1] / tiles * g.ngroups, s[2] / tiles * g.ngroups, s[3] / tiles * g.ngroups, s[4] / tiles * g.ngroups, s[5] / tiles * g.ngroups,
+            (s[8] + s[24]) / tiles, s[9] / tiles, s[10] / tiles, s[11] / tiles, s[28] / tiles, s[29] / tiles, s[30] / tiles,
+            s[16] / tiles, s[17] / tiles, s[18] / tiles);
+  }
   return TMG_OK;
 }
 

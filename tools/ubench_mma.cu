@@ -99,6 +99,86 @@ void run_lean(long long* d) {
          (double)h[0] / iters, (double)h[1] / iters);
 }
 
+
+// Same issue loop with (a) a strided M mapping (SBO = 352 B, as the 16x8-pixel tiles of flow_step_f16.cu), (b) the
+// hi/lo x3 descriptor pattern, (c) NOISE other warps streaming shared memory (LDS + STS) meanwhile.
+template <int N, int SBO, int X3, int NOISE>
+__global__ void __launch_bounds__(32 + 32 * (NOISE > 0 ? NOISE : 1), 1) k_real(int iters, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int stop;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); stop = 0; }
+  if (tid < 32) tmem_alloc(&slot, 512);
+  fence_proxy_async();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (tid < 32) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(N, 1);
+      // A: [hl 2][2 planes][512 pos][16 B] = 32 KB; B: [9 taps][hl 2][2 planes][N][16 B]
+      const uint64_t a0 = make_desc(smem_u32(smem), 8192, SBO), b0 = make_desc(smem_u32(smem + 64 * 1024), (uint32_t)N * 16u, 128);
+      long long t0 = clock64();
+      for (int i = 0; i < iters; i += 18) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t ad = a0 + (uint64_t)((3 + tap / 3 - 1) * 22 + 3 + 8 * mt + tap % 3 - 1);
+            const uint64_t bd = b0 + (uint64_t)(tap * 2 * 2 * N);
+            mma_f16(tm + mt * N, ad, bd, idesc, 1);
+            if (X3) { mma_f16(tm + mt * N, ad + 1024, bd, idesc, 1); mma_f16(tm + mt * N, ad, bd + 2 * N, idesc, 1); }
+          }
+        }
+      }
+      long long t1 = clock64();
+      mma_commit(&bar);
+      mbar_wait(&bar, 0);
+      long long t2 = clock64();
+      out[0] = t1 - t0; out[1] = t2 - t0;
+      stop = 1;
+    }
+  } else if (NOISE > 0) {
+    float* f = reinterpret_cast<float*>(smem + 100 * 1024);
+    float acc = 0.f;
+    int it = 0;
+    float c0 = tid, c1 = 1.f, c2 = 2.f, c3 = 3.f, c4 = 4.f, c5 = 5.f, c6 = 6.f, c7 = 7.f;
+    while (!stop && it < 200000) {
+      if (SBO == 128) {      // ALU-heavy noise: 8 independent FMA chains per thread (scheduler contention, no smem)
+#pragma unroll 16
+        for (int j = 0; j < 16; ++j) {
+          c0 = fmaf(c0, 1.0001f, 0.5f); c1 = fmaf(c1, 1.0001f, 0.5f); c2 = fmaf(c2, 1.0001f, 0.5f); c3 = fmaf(c3, 1.0001f, 0.5f);
+          c4 = fmaf(c4, 1.0001f, 0.5f); c5 = fmaf(c5, 1.0001f, 0.5f); c6 = fmaf(c6, 1.0001f, 0.5f); c7 = fmaf(c7, 1.0001f, 0.5f);
+        }
+      } else {               // shared-memory noise: independent 16-byte loads and stores
+        float4* f4 = reinterpret_cast<float4*>(f);
+#pragma unroll 8
+        for (int j = 0; j < 8; ++j) { float4 t = f4[(tid + j * 67 + it) & 2047]; acc += t.x; f4[(tid + j * 131 + it * 3) & 2047] = t; }
+      }
+      ++it;
+    }
+    acc += c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+    if (acc == 123.456f) out[2] = 1;
+  }
+  tc_fence_before(); __syncthreads();
+  if (tid < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+template <int N, int SBO, int X3, int NOISE>
+void run_real(long long* d) {
+  long long h[2];
+  const int iters = 18 * 40;
+  cudaFuncSetAttribute(k_real<N, SBO, X3, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_real<N, SBO, X3, NOISE><<<1, 32 + 32 * (NOISE > 0 ? NOISE : 1), 160 * 1024>>>(iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+  cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  const int n = iters * (X3 ? 3 : 1);
+  printf("real N=%3d SBO=%3d x3=%d noise_warps=%2d : issue %.1f cyc/mma, complete %.1f cyc/mma\n", N, SBO, X3, NOISE,
+         (double)h[0] / n, (double)h[1] / n);
+}
+
 // truncation test: D = A*B with A row r = (1 + r*2^-20) in channel 0, B col 0 = 1 at k=0
 __global__ void __launch_bounds__(128, 1) k_trunc(float* out) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -154,6 +234,8 @@ int main() {
   run_lean<48, 1, 4>(d);
   run_lean<64, 1, 4>(d);
   run_lean<128, 1, 4>(d);
+  run_real<16, 128, 0, 0>(d); run_real<16, 352, 0, 0>(d); run_real<16, 352, 1, 0>(d);
+  run_real<16, 352, 1, 8>(d); run_real<16, 352, 1, 20>(d); run_real<32, 352, 1, 20>(d); run_real<16, 128, 1, 20>(d);
   float* o; cudaMalloc(&o, 512);
   k_trunc<<<1, 128, 16 * 1024>>>(o);
   cudaDeviceSynchronize();
