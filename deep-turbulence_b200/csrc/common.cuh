@@ -129,6 +129,31 @@ __host__ __device__ inline size_t tc_packed_floats(int cin, int npad) {
 }
 inline int tc_npad(int cout) { return (cout + 15) / 16 * 16; }
 
+// fp16-operand persistent conv (conv3x3_f16.cu): stride 1, sources start on 8-channel plane boundaries
+struct ConvF16Args {
+  ConvSrc src[3];
+  int nsrc;
+  const void* wpk;         // fp16 [kstep][tap][hl][2 planes][npad][8]
+  const float* inv_scale;  // 1 / (power-of-two weight scale)
+  int npad;                // MMA N: multiple of 16, <= 256
+  const float* bias;
+  const float* gain;
+  int act;
+  float* out;
+  int out_cstride, out_coff, cout;
+  int B, H, W;
+  int pad_replicate;
+  int x3;
+  int lstm_R;              // fused ConvLSTM cell epilogue when > 0 (multiple of 32, 4*R == npad)
+  const float* c_prev;
+  float* h_out;
+  float* c_out;
+};
+int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st);
+bool convf16_supported(const ConvF16Args& a);
+int convf16_ksteps(const int* nch, int nsrc);
+size_t convf16_packed_floats(const int* nch, int nsrc, int npad);
+
 // Fused flow step on tensor cores (coupling_tc.cu): coupling net + coupling + 1x1 + ActNorm + log-det
 struct CouplingArgs {
   ConvSrc src[2];          // the coupling-net input t as 1-2 NHWC sources; each starts on a 4-channel plane
@@ -294,7 +319,7 @@ int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
-                   JOB_STEP2 = 7, JOB_HOIST = 8 };
+                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n

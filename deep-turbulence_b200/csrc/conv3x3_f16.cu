@@ -1,0 +1,413 @@
+// 3x3 convolution (stride 1) as a persistent fp16-operand tcgen05 implicit GEMM (sm_100a), second generation of
+// conv3x3_tc.cu.  Used for the two heavy convolutions of the LSTM flow step
+//   ConvLSTM gate conv   nn/modules/convLSTM.py:44,74   (N = 4*rec = 256, ConvLSTM cell update fused in the epilogue)
+//   LSTM_out_conv        nn/modules/convLSTM.py:129     (N = C/2+cond, bias + ReLU)
+// and for any other stride-1 conv of the path (bias / gain / activation epilogue).
+//
+//   * CTA tile = 16x16 output pixels = two MMA M tiles of 16 rows x 8 columns: the A descriptor's stride between
+//     8-row groups (SBO) is one padded row of the staged tile, so the 1-pixel halo costs (18*18)/256 = 1.27x
+//     staging instead of the 2.05x of the linear-index trick, and no accumulator row is wasted.
+//   * operands are fp16 (kind::f16, K = 16 per MMA); "x3" splits both operands into hi + lo halves
+//     (hi*hi + lo*hi + hi*lo, fp32 accumulate, weights pre-scaled by a power of two): fp32-grade results at half
+//     the tensor work of the 3xTF32 split.
+//   * persistent CTAs, warp-specialised: 4 producer warps stage activation K-steps (16 channels) into a ring,
+//     one warp streams packed weights per (K-step, tap) with cp.async.bulk, two warps issue the MMAs (one per
+//     M tile, elect.sync), eight warps run the epilogue (exp2/rcp based sigmoid/tanh for the LSTM cell).
+//   * every source of the virtual concatenation starts on an 8-channel plane boundary (weights packed to match),
+//     so staging is vector loads + cvt, no per-channel source selection.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tmg {
+
+constexpr int kCvRP = 18;                 // staged tile pitch: 16 + 2
+constexpr int kCvNPOS = 324;
+constexpr int kCvNPOSA = 328;
+constexpr uint32_t kCvPLB = kCvNPOSA * 16;        // bytes of one 8-channel plane of a K-step
+constexpr int kCvThreads = 480;           // warps 0-7 epilogue, 8-9 MMA, 10 weights, 11-14 producers
+constexpr int kCvNA = 3;                  // activation K-step ring
+constexpr int kCvMaxNB = 8;               // weight stage ring (upper bound)
+
+struct ConvF16Geom {
+  int KS;                 // K-steps of 16 channels
+  int nhl, nb;
+  int tiles_x, tiles_y, ntiles, step_b, step_t;
+  uint32_t inv_tx;
+  uint32_t hlA, bufA;     // bytes: hi->lo distance inside an A K-step buffer, buffer size
+  uint32_t stageB, hlB;   // bytes of one weight stage (hi [+ lo]); hi->lo distance
+  uint32_t gstageB;       // bytes between packed (global) stages (always hi + lo)
+  uint32_t oA, oB, oMisc, oBar, total;
+  int plane0[3];          // first 8-channel plane of each source
+  int nplanes[3];
+};
+
+__device__ __forceinline__ uint32_t cv_idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void cv_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// sigmoid / tanh from ex2.approx + rcp.approx (2 ulp each): abs error ~2e-7, far inside the stated 2e-4
+__device__ __forceinline__ float fast_sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+struct CvTileIt {
+  int b, timg;
+  __device__ __forceinline__ void init(int t, int tiles_img) { b = t / tiles_img; timg = t - b * tiles_img; }
+  __device__ __forceinline__ void advance(const ConvF16Geom& g, int tiles_img) {
+    timg += g.step_t; b += g.step_b;
+    if (timg >= tiles_img) { timg -= tiles_img; ++b; }
+  }
+  __device__ __forceinline__ void origin(const ConvF16Geom& g, int& r0, int& c0) const {
+    const int ty = (int)(((uint32_t)timg * g.inv_tx) >> 16);
+    r0 = ty * 16; c0 = (timg - ty * g.tiles_x) * 16;
+  }
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = a.H * a.W;
+  const int tiles_img = g.tiles_x * g.tiles_y;
+  const int NP = a.npad;
+
+  uint8_t* As = smem + g.oA;                 // kCvNA K-step buffers [hl][2 planes][NPOSA][16 B]
+  uint8_t* Bs = smem + g.oB;                 // nb weight stages [hl][2 planes][NP][16 B]
+  float* s_bias = reinterpret_cast<float*>(smem + g.oMisc);      // [NP]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.oBar);
+  uint64_t* a_full = bars;                   // [3]  producers (128)
+  uint64_t* a_free = bars + 3;               // [3]  2 commits
+  uint64_t* b_full = bars + 6;               // [8]  tx
+  uint64_t* b_free = bars + 14;              // [8]  2 commits
+  uint64_t* acc_full = bars + 22;            // 2 commits
+  uint64_t* acc_free = bars + 23;            // epilogue (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  if (tid == 0) {
+    for (int i = 0; i < kCvNA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_free + i, 2); }
+    for (int i = 0; i < kCvMaxNB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_free + i, 2); }
+    mbar_init(acc_full, 2); mbar_init(acc_free, 256);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < NP; i += kCvThreads) s_bias[i] = (a.bias && i < a.cout) ? __ldg(a.bias + i) : 0.f;
+  {   // zero the A ring once (positions >= 324 of every plane stay zero)
+    uint4* z4 = reinterpret_cast<uint4*>(As);
+    const int n4 = (int)((size_t)kCvNA * g.bufA / 16);
+    for (int i = tid; i < n4; i += kCvThreads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nstage_tile = g.KS * 9;
+
+  if (warp < 8) {
+    // =========================================================== epilogue (256 threads)
+    const int el = tid & 127, half = tid >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float inv = a.inv_scale ? __ldg(a.inv_scale) : 1.f;
+    const float gain = a.gain ? __ldg(a.gain) : 1.f;
+    CvTileIt it;
+    it.init(blockIdx.x, tiles_img);
+    for (int k = 0; k < nmy; ++k) {
+      int r0, c0;
+      it.origin(g, r0, c0);
+      const int b = it.b;
+      it.advance(g, tiles_img);
+      mbar_wait(acc_full, (uint32_t)(k & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int ir = r0 + (el >> 3), ic = c0 + 8 * mt + (el & 7);
+        const bool valid = ir < a.H && ic < a.W;
+        const size_t pix = valid ? (size_t)b * HW + (size_t)ir * a.W + ic : 0;
+        const uint32_t trow = tmem_base + lane_base + (uint32_t)(mt * 256);
+        if (a.lstm_R > 0) {
+          // fused ConvLSTM cell (convLSTM.py:76-83): gates i,f,o,g at columns [0,R),[R,2R),[2R,3R),[3R,4R);
+          // this thread owns recurrent channels [half*R/2, (half+1)*R/2) of its pixel
+          const int R = a.lstm_R, Rh = R >> 1, rb = half * Rh;
+          for (int q0 = 0; q0 < Rh; q0 += 16) {
+            float gi[16], gf[16], go[16], gg[16], cp[16];
+            tmem_ld16(trow + rb + q0, gi);
+            tmem_ld16(trow + R + rb + q0, gf);
+            tmem_ld16(trow + 2 * R + rb + q0, go);
+            tmem_ld16(trow + 3 * R + rb + q0, gg);
+            if (valid) {
+              if (a.c_prev) {
+                const float4* c4 = reinterpret_cast<const float4*>(a.c_prev + pix * R + rb + q0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float4 t = __ldg(c4 + e); cp[4 * e] = t.x; cp[4 * e + 1] = t.y; cp[4 * e + 2] = t.z; cp[4 * e + 3] = t.w; }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) cp[e] = 0.f;
+              }
+              float hn[16], cn[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int r = rb + q0 + e;
+                const float i_ = fast_sigm(fmaf(gi[e], inv, s_bias[r]));
+                const float f_ = fast_sigm(fmaf(gf[e], inv, s_bias[R + r]));
+                const float o_ = fast_sigm(fmaf(go[e], inv, s_bias[2 * R + r]));
+                const float g_ = fast_tanh(fmaf(gg[e], inv, s_bias[3 * R + r]));
+                cn[e] = fmaf(f_, cp[e], i_ * g_);
+                hn[e] = o_ * fast_tanh(cn[e]);
+              }
+              float4* co = reinterpret_cast<float4*>(a.c_out + pix * R + rb + q0);
+              float4* ho = reinterpret_cast<float4*>(a.h_out + pix * R + rb + q0);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                co[e] = make_float4(cn[4 * e], cn[4 * e + 1], cn[4 * e + 2], cn[4 * e + 3]);
+                ho[e] = make_float4(hn[4 * e], hn[4 * e + 1], hn[4 * e + 2], hn[4 * e + 3]);
+              }
+            }
+          }
+        } else {
+          // columns split between the two halves in chunks of 16
+          for (int n0 = half * 16; n0 < NP; n0 += 32) {
+            float v[16];
+            tmem_ld16(trow + n0, v);
+            if (valid) {
+              float* op = a.out + pix * a.out_cstride + a.out_coff + n0;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                if (n0 + e < a.cout) {
+                  float t = fmaf(v[e], inv, s_bias[n0 + e]);
+                  if (a.gain) t *= gain;
+                  if (a.act == 1) t = fmaxf(t, 0.f);
+                  else if (a.act == 2) t = fminf(fmaxf(t, -2.f), kLog5);
+                  op[e] = t;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_free);
+    }
+  } else if (warp < 10) {
+    // =========================================================== MMA issue: warp 8 -> M tile 0, warp 9 -> M tile 1
+    const int mt = warp - 8;
+    if (elect_one()) {
+      const uint32_t idesc = cv_idesc_f16(NP);
+      const uint64_t hlA16 = g.hlA >> 4, hlB16 = g.hlB >> 4;
+      const uint32_t tacc = tmem_base + (uint32_t)(mt * 256);
+      int ja = 0, jb = 0;                      // running K-step / weight-stage counters
+      for (int k = 0; k < nmy; ++k) {
+        if (k >= 1) mbar_wait(acc_free, (uint32_t)((k - 1) & 1));
+        tc_fence_after();
+        for (int ks = 0; ks < g.KS; ++ks, ++ja) {
+          const int ua = ja % kCvNA;
+          mbar_wait(a_full + ua, (uint32_t)((ja / kCvNA) & 1));
+          tc_fence_after();
+          const uint64_t a0 = make_desc(smem_u32(As + (size_t)ua * g.bufA), kCvPLB, kCvRP * 16) + (uint64_t)(8 * mt);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap, ++jb) {
+            const int ub = jb % g.nb;
+            mbar_wait(b_full + ub, (uint32_t)((jb / g.nb) & 1));
+            tc_fence_after();
+            const uint64_t ad = a0 + (uint64_t)((1 + tap / 3 - 1) * kCvRP + 1 + tap % 3 - 1);
+            const uint64_t bd = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)NP * 16u, 128);
+            cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+            if (X3) {
+              cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
+              cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
+            }
+            mma_commit(b_free + ub);
+          }
+          mma_commit(a_free + ua);
+        }
+        mma_commit(acc_full);
+      }
+    }
+  } else if (warp == 10) {
+    // =========================================================== weight streaming (one lane, cp.async.bulk)
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk);
+      int jb = 0;
+      for (int k = 0; k < nmy; ++k) {
+        for (int st = 0; st < nstage_tile; ++st, ++jb) {
+          const int ub = jb % g.nb, use = jb / g.nb;
+          if (use >= 1) mbar_wait(b_free + ub, (uint32_t)((use - 1) & 1));
+          mbar_expect_tx(b_full + ub, g.stageB);
+          bulk_g2s(Bs + (size_t)ub * g.stageB, wsrc + (size_t)st * g.gstageB, g.stageB, b_full + ub);
+        }
+      }
+    }
+  } else {
+    // =========================================================== producers (128 threads): activation K-steps
+    const int ptid = tid - 11 * 32;
+    CvTileIt it;
+    it.init(blockIdx.x, tiles_img);
+    int ja = 0;
+    for (int k = 0; k < nmy; ++k) {
+      int r0, c0;
+      it.origin(g, r0, c0);
+      const int b = it.b;
+      it.advance(g, tiles_img);
+      for (int ks = 0; ks < g.KS; ++ks, ++ja) {
+        const int ua = ja % kCvNA, use = ja / kCvNA;
+        if (use >= 1) mbar_wait(a_free + ua, (uint32_t)((use - 1) & 1));
+        uint8_t* Ab = As + (size_t)ua * g.bufA;
+        // 2 planes x 324 positions; 3 batches of up to 2 items per thread, loads first
+        for (int it0 = ptid; it0 < 2 * kCvNPOS; it0 += 256) {
+          float v[2][8];
+          int pos[2], pln[2];
+          bool relu[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int itx = it0 + q * 128;
+            pos[q] = -1; pln[q] = 0; relu[q] = false;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+            if (itx < 2 * kCvNPOS) {
+              const int lp = itx >= kCvNPOS ? 1 : 0, p = itx - lp * kCvNPOS;
+              const int plane = 2 * ks + lp;
+              pos[q] = p; pln[q] = lp;
+              const int rr = p / kCvRP, rc = p - rr * kCvRP;
+              int r = r0 - 1 + rr, c = c0 - 1 + rc;
+              bool inb = r >= 0 && r < a.H && c >= 0 && c < a.W;
+              if (a.pad_replicate) { r = min(max(r, 0), a.H - 1); c = min(max(c, 0), a.W - 1); inb = true; }
+              // which source owns this plane
+              int si = 0;
+              if (a.nsrc > 1 && plane >= g.plane0[1]) si = 1;
+              if (a.nsrc > 2 && plane >= g.plane0[2]) si = 2;
+              const ConvSrc& sc = a.src[si];
+              const int ch = (plane - g.plane0[si]) * 8;
+              const int nv = min(8, sc.nch - ch);
+              relu[q] = sc.relu != 0;
+              if (inb && nv > 0 && sc.p != nullptr) {
+                const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c;
+                const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
+                if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (nv & 1) == 0) {
+                  if (nv >= 4) { const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; v[q][2] = t0.z; v[q][3] = t0.w; }
+                  else { const float2 t0 = __ldg(reinterpret_cast<const float2*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; }
+                  if (nv == 8) { const float4 t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1); v[q][4] = t1.x; v[q][5] = t1.y; v[q][6] = t1.z; v[q][7] = t1.w; }
+                  else if (nv == 6) { const float2 t1 = __ldg(reinterpret_cast<const float2*>(ptr) + 2); v[q][4] = t1.x; v[q][5] = t1.y; }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (e < nv) v[q][e] = __ldg(ptr + e);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (pos[q] < 0) continue;
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float y0 = fminf(v[q][2 * e], 60000.f), y1 = fminf(v[q][2 * e + 1], 60000.f);
+              y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
+              const __half2 h2 = __floats2half2_rn(y0, y1);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+              ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            uint8_t* dst = Ab + (size_t)pln[q] * kCvPLB + (size_t)pos[q] * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full + ua);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------ host side
+int convf16_ksteps(const int* nch, int nsrc) {
+  int planes = 0;
+  for (int i = 0; i < nsrc; ++i) planes += (nch[i] + 7) / 8;
+  return (planes + 1) / 2;
+}
+size_t convf16_packed_floats(const int* nch, int nsrc, int npad) {     // [ks][tap][hl][2 planes][npad][8 halves]
+  return (size_t)convf16_ksteps(nch, nsrc) * 9 * 2 * 2 * npad * 16 / 4;
+}
+
+static int cv_sm_count() {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  static int cached[64] = {0};
+  if (dev >= 0 && dev < 64) {
+    if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (cached[dev] > 0) nsm = cached[dev];
+  }
+  return nsm;
+}
+
+static bool cv_geom(const ConvF16Args& a, ConvF16Geom& g, int grid) {
+  if (a.npad % 16 || a.npad < 16 || a.npad > 256 || a.nsrc < 1 || a.nsrc > 3) return false;
+  int pl = 0;
+  for (int i = 0; i < 3; ++i) {
+    g.plane0[i] = pl;
+    g.nplanes[i] = i < a.nsrc ? (a.src[i].nch + 7) / 8 : 0;
+    pl += g.nplanes[i];
+  }
+  g.KS = (pl + 1) / 2;
+  g.nhl = a.x3 ? 2 : 1;
+  g.hlA = 2 * kCvPLB; g.bufA = g.hlA * g.nhl;
+  g.hlB = (uint32_t)2 * a.npad * 16; g.stageB = g.hlB * g.nhl; g.gstageB = 2 * g.hlB;
+  g.tiles_x = cdiv(a.W, 16); g.tiles_y = cdiv(a.H, 16);
+  const int tiles_img = g.tiles_x * g.tiles_y;
+  if (tiles_img >= 4096) return false;
+  g.ntiles = tiles_img * a.B;
+  g.step_b = grid / tiles_img; g.step_t = grid % tiles_img;
+  g.inv_tx = (uint32_t)((65536 + g.tiles_x - 1) / g.tiles_x);
+  uint32_t off = 0;
+  auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
+  g.oA = take((uint32_t)kCvNA * g.bufA);
+  g.oMisc = take((uint32_t)a.npad * 4);
+  g.oBar = take(25 * 8 + 16);
+  const uint32_t fixed = off;
+  int nb = (int)((220u * 1024u - fixed) / ((g.stageB + 127) / 128 * 128));
+  nb = std::min(nb, kCvMaxNB);
+  if (nb < 2) return false;
+  g.nb = nb;
+  g.oB = take((uint32_t)nb * g.stageB);
+  g.total = off;
+  return g.total <= 227 * 1024;
+}
+
+bool convf16_supported(const ConvF16Args& a) {
+  ConvF16Geom g{};
+  return cv_geom(a, g, 148) && (a.lstm_R == 0 || (a.lstm_R % 32 == 0 && 4 * a.lstm_R == a.npad));
+}
+
+int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st) {
+  if (a.B <= 0 || a.H <= 0 || a.W <= 0) return TMG_OK;
+  const int tiles = cdiv(a.W, 16) * cdiv(a.H, 16) * a.B;
+  const int grid = std::min(tiles, cv_sm_count());
+  ConvF16Geom g{};
+  if (!cv_geom(a, g, grid) || (a.lstm_R != 0 && (a.lstm_R % 32 != 0 || 4 * a.lstm_R != a.npad))) {
+    set_error("fp16 conv: unsupported shape (N=%d, %dx%d, %d sources)", a.npad, a.H, a.W, a.nsrc);
+    return TMG_ERR_UNSUPPORTED;
+  }
+  if (a.x3) {
+    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    conv3x3_f16_kernel<true><<<grid, kCvThreads, g.total, st>>>(a, g);
+  } else {
+    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    conv3x3_f16_kernel<false><<<grid, kCvThreads, g.total, st>>>(a, g);
+  }
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+}  // namespace tmg

@@ -47,6 +47,7 @@ struct ConvW {
   int64_t b_param = -1;   // bias or -1
   int64_t w_pack = -1;    // tap-major in the packed buffer
   int64_t w_pack_tc = -1; // tcgen05 layout (hi/lo split) in the packed buffer, -1: CUDA-core path only
+  int64_t w_pack_f16 = -1, inv_f16 = -1;   // fp16 hi/lo layout of conv3x3_f16.cu + inverse weight scale
   int O = 0, I = 0, OP = 0, NP = 0;
 };
 
@@ -150,6 +151,19 @@ struct Builder {
       }
     }
     return c;
+  }
+  void conv_f16_job(ConvW& c, int n0, int n1, int n2) {
+    const int nch[3] = {n0, n1, n2};
+    const int nsrc = n2 > 0 ? 3 : (n1 > 0 ? 2 : 1);
+    const int NP = tc_npad(c.O);
+    c.NP = NP;
+    c.w_pack_f16 = pack_alloc((int64_t)convf16_packed_floats(nch, nsrc, NP));
+    c.inv_f16 = pack_alloc(1);
+    PackJob j{};
+    j.type = JOB_CONV_F16; j.a = c.O; j.b = c.I; j.opad = NP; j.nch0 = n0; j.nch1 = n1; j.nd = n2;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16; j.dst[1] = c.inv_f16;
+    m.jobs.push_back(j);
   }
   void coupling_jobs(StepW& st, int nch0, int nch1, int C) {
     const int PT = cpl_planes(nch0, nch1);
@@ -301,6 +315,8 @@ static int build_model(tmg_model& m) {
         const int R = c.rec_features;
         st.gate = B.conv(sp + "coupling.resid_lstm.convLSTM.conv", 4 * R, cin_t + R, true, 4 * R <= 256);
         st.outc = B.conv(sp + "coupling.resid_lstm.out_seq.LSTM_out_conv", cin_t, cin_t + R, true, true);
+        if (4 * R <= 256) B.conv_f16_job(st.gate, C / 2, c.cond_features, R);
+        B.conv_f16_job(st.outc, C / 2, c.cond_features, R);
         st.d1 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
         int64_t sc = B.add(sp + "coupling.out_conv.zero_conv.scale", {1, 1, 1, 1});
@@ -340,6 +356,7 @@ static int build_model(tmg_model& m) {
     std::string pp = "glow.flow_blocks." + std::to_string(b) + ".split.latent_encoder.conv2d";
     int64_t sc = B.add(pp + ".scale", {1, 1, 1, 1});
     lv.split = B.conv(pp + ".conv", C, C / 2, true);
+    B.conv_f16_job(lv.split, C / 2, 0, 0);
     lv.split_gain = B.gain(sc);
     C = C / 2;
   }
@@ -567,7 +584,44 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
     if (!h_out || !c_out) { set_error("LSTM step needs h_out/c_out buffers"); return TMG_ERR_NULL; }
     const int sh = c.p.shared;
     ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_in, R, 0, R, 0}};
-    if (c.m.precision != TMG_PREC_FP32 && s.gate.w_pack_tc >= 0 && R % 16 == 0 && Wl + 2 <= 512) {
+    bool gate_done = false, out_done = false;
+    const int u0s_f = (cin_t + 3) / 4 * 4;
+    if (prec_f16(c.m.precision) && s.gate.w_pack_f16 >= 0) {
+      ConvF16Args t{};
+      const int ns = h_in ? 3 : 2;
+      for (int i = 0; i < 3; ++i) t.src[i] = gs[i];
+      if (!h_in) t.src[2].p = nullptr;        // zero states: the plane is staged as zeros
+      t.nsrc = 3; (void)ns;
+      t.wpk = c.Q() + s.gate.w_pack_f16; t.inv_scale = c.Q() + s.gate.inv_f16; t.npad = s.gate.NP;
+      t.bias = c.P() + s.gate.b_param; t.cout = s.gate.O;
+      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+      t.lstm_R = R; t.c_prev = c_in; t.h_out = h_out; t.c_out = c_out;
+      if (convf16_supported(t)) {
+        const double M = (double)B * Hl * Wl;
+        ProfScope ps(c.st, PROF_CONV_GATE, 2.0 * M * s.gate.O * 9.0 * s.gate.I, 4.0 * (M * s.gate.I + M * R * (c_in ? 3.0 : 2.0)));
+        TMG_TRY(launch_conv3x3_f16(t, c.st));
+        gate_done = true;
+      }
+    }
+    if (gate_done) {
+      ConvF16Args t{};
+      ConvSrc os2[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_out, R, 0, R, 0}};
+      for (int i = 0; i < 3; ++i) t.src[i] = os2[i];
+      t.nsrc = 3;
+      t.wpk = c.Q() + s.outc.w_pack_f16; t.inv_scale = c.Q() + s.outc.inv_f16; t.npad = s.outc.NP;
+      t.bias = c.P() + s.outc.b_param; t.cout = s.outc.O; t.act = 1;
+      t.out = ws + p.u0; t.out_cstride = u0s_f; t.out_coff = 0;
+      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+      if (s.outc.w_pack_f16 >= 0 && convf16_supported(t)) {
+        const double M = (double)B * Hl * Wl;
+        ProfScope ps(c.st, PROF_CONV_OUT, 2.0 * M * s.outc.O * 9.0 * s.outc.I, 4.0 * (M * s.outc.I + M * s.outc.O));
+        TMG_TRY(launch_conv3x3_f16(t, c.st));
+        out_done = true;
+      }
+    }
+    if (gate_done) {
+      // fall through to the output conv below if it was not done
+    } else if (c.m.precision != TMG_PREC_FP32 && s.gate.w_pack_tc >= 0 && R % 16 == 0 && Wl + 2 <= 512) {
       // gate conv on tcgen05 with the ConvLSTM cell update fused into its epilogue (gates never touch HBM)
       TcConvArgs t{};
       const int ns = h_in ? 3 : 2;
@@ -589,7 +643,8 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
     }
     ConvSrc os[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_out, R, 0, R, 0}};
     const int u0s = (cin_t + 3) / 4 * 4;       // padded pixel stride: 16-byte aligned planes for the fused kernel
-    TMG_TRY(run_conv(c, PROF_CONV_OUT, s.outc, os, 3, B, Hl, Wl, 1, false, 1, -1, nullptr, nullptr, ws + p.u0, u0s, 0));
+    if (!out_done)
+      TMG_TRY(run_conv(c, PROF_CONV_OUT, s.outc, os, 3, B, Hl, Wl, 1, false, 1, -1, nullptr, nullptr, ws + p.u0, u0s, 0));
     if (nn_only_lstm) return TMG_OK;
     src[0] = ConvSrc{ws + p.u0, u0s, 0, cin_t, 1};
     nt = 1;
@@ -713,6 +768,19 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
 static int run_split_prior(Ctx& c, int level, int B, int Hl, int Wl, const float* Y) {
   const LevelW& lv = c.m.levels[level];
   ConvSrc s{Y, lv.C, 0, lv.C / 2, 0};
+  if (prec_f16(c.m.precision) && lv.split.w_pack_f16 >= 0) {
+    ConvF16Args t{};
+    t.src[0] = s; t.nsrc = 1;
+    t.wpk = c.Q() + lv.split.w_pack_f16; t.inv_scale = c.Q() + lv.split.inv_f16; t.npad = lv.split.NP;
+    t.bias = c.P() + lv.split.b_param; t.gain = c.Q() + lv.split_gain; t.act = 2; t.cout = lv.split.O;
+    t.out = c.ws + c.p.hr; t.out_cstride = lv.C; t.out_coff = 0;
+    t.B = B; t.H = Hl; t.W = Wl; t.pad_replicate = 1; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+    if (convf16_supported(t)) {
+      const double M = (double)B * Hl * Wl;
+      ProfScope ps(c.st, PROF_CONV_SPLIT, 2.0 * M * lv.split.O * 9.0 * lv.split.I, 4.0 * (M * lv.split.I + M * lv.split.O));
+      return launch_conv3x3_f16(t, c.st);
+    }
+  }
   return run_conv(c, PROF_CONV_SPLIT, lv.split, &s, 1, B, Hl, Wl, 1, true, 2, lv.split_gain, nullptr, nullptr,
                   c.ws + c.p.hr, lv.C, 0);
 }

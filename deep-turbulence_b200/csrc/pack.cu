@@ -166,6 +166,45 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
         d[((size_t)tap * CF + c) * OP + s * C + n] = w3[((size_t)n * I3 + row0 + c) * 9 + tap];
       }
     }
+  } else if (j.type == JOB_CONV_F16) {
+    // OIHW -> fp16 [kstep][tap][hl][2 planes][npad][8] for conv3x3_f16.cu.  The input channels are the
+    // concatenation of up to three sources (nch0, nch1, nd), each padded to a multiple of 8 in the K layout.
+    // Scaled by a power of two so that max|w| lands in [2^10, 2^11); dst[1] receives the inverse scale.
+    const int O = j.a, I = j.b, NP = j.opad;
+    const int nch[3] = {j.nch0, j.nch1, j.nd};
+    int pl0[4]; pl0[0] = 0;
+    for (int q = 0; q < 3; ++q) pl0[q + 1] = pl0[q] + (nch[q] + 7) / 8;
+    const int KS = (pl0[3] + 1) / 2;
+    const float* w = P + j.src[0];
+    float m = 0.f;
+    for (int i = tid; i < O * I * 9; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) sm[tid >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm[q]);
+    int ex = 0;
+    if (m > 0.f && m < 3.0e38f) frexpf(m, &ex);
+    const float sc = m > 0.f ? ldexpf(1.f, min(max(11 - ex, -20), 40)) : 1.f;
+    __half* d = reinterpret_cast<__half*>(Q + j.dst[0]);
+    const size_t total = (size_t)KS * 9 * 2 * 2 * NP * 8;
+    for (size_t i = tid; i < total; i += blockDim.x) {
+      const int e = (int)(i & 7); size_t t = i >> 3; const int n = (int)(t % NP); t /= NP;
+      const int lp = (int)(t & 1); t >>= 1; const int hl = (int)(t & 1); t >>= 1;
+      const int tap = (int)(t % 9); const int ks = (int)(t / 9);
+      const int plane = 2 * ks + lp;
+      int c = -1;
+      for (int q = 0, base = 0; q < 3; ++q) {
+        if (plane >= pl0[q] && plane < pl0[q + 1]) { const int ch = (plane - pl0[q]) * 8 + e; if (ch < nch[q]) c = base + ch; }
+        base += nch[q];
+      }
+      float v = 0.f;
+      if (c >= 0 && c < I && n < O) v = w[((size_t)n * I + c) * 9 + tap] * sc;
+      const __half hi = __float2half_rn(v);
+      d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    if (tid == 0) Q[j.dst[1]] = 1.f / sc;
   } else if (j.type == JOB_GAIN) {
     if (tid == 0) Q[j.dst[0]] = expf(fminf(fmaxf(P[j.src[0]], -4.f), kLog4));
   } else if (j.type == JOB_BN) {

@@ -103,7 +103,7 @@ class TMGlow(nn.Module):
         self._fix_conv_bias()
         self._flat = None
         self._ws = {}
-        self.assume_static_weights = False
+        self.always_refresh_weights = False
         self._refreshed_for = None
         self._precision = "fp32"
         print('Total number of parameters: {}'.format(self._num_parameters()))
@@ -202,6 +202,9 @@ class TMGlow(nn.Module):
         mod, attr, is_param = self._leaves[i]
         return mod._parameters[attr] if is_param else mod._buffers[attr]
 
+    def _leaf_tensors(self):
+        return [mod._parameters[attr] if is_param else mod._buffers[attr] for mod, attr, is_param in self._leaves]
+
     def _sync_flat(self, device):
         """All floating-point state lives in ONE flat buffer (the layout libtmglow_b200 reads);
         the module's parameters/buffers are views into it.  Rebuilt whenever ``.to()``/
@@ -233,13 +236,23 @@ class TMGlow(nn.Module):
         lib = _lib.load()
         changed = self._sync_flat(device)
         h = self._handle(device.index if device.index is not None else torch.cuda.current_device())
-        if changed or not self.assume_static_weights or self._refreshed_for != (h.value, self._flat.data_ptr()):
+        # Derived weights (packed conv weights, W / W^-1 of the 1x1 convolutions, log-det constants) are re-derived
+        # when the flat parameter buffer was replaced or any parameter/buffer was written in place since the last call
+        # (optimizers, load_state_dict, copy_ bump the tensors' version counters; their sum only grows).
+        # Writes through ``p.data`` bypass the counter: call ``refresh_weights()`` after those, or set
+        # ``always_refresh_weights = True``.
+        key = (h.value, self._flat.data_ptr(), sum(t._version for t in self._leaf_tensors()))
+        if changed or self.always_refresh_weights or self._refreshed_for != key:
             st = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.tmg_model_refresh(h, self._flat.data_ptr(), st))
-            self._refreshed_for = (h.value, self._flat.data_ptr())
+            self._refreshed_for = key
         if lib.tmg_model_get_precision(h) != _lib.PRECISIONS[self._precision]:
             _lib.check(lib.tmg_model_set_precision(h, _lib.PRECISIONS[self._precision]))
         return lib, h
+
+    def refresh_weights(self):
+        """Force the kernel-side weights to be re-derived on the next call (after writes through ``.data``)."""
+        self._refreshed_for = None
 
     def _workspace(self, lib, h, B, hh, ww, device):
         key = (device, B, hh, ww)
@@ -326,6 +339,7 @@ class TMGlow(nn.Module):
 
     def _bump_bn_counters(self):
         if self.training:
+            self._refreshed_for = None      # the library updated the BatchNorm running statistics in place
             for name, b in self.named_buffers():
                 if name.endswith("num_batches_tracked"):
                     b += 1
