@@ -17,7 +17,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "lts__t_bytes.sum", "l1tex__t_bytes.sum"]
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
 
 
 def short(name):
@@ -66,10 +68,23 @@ def rep(tag, which):
                 if k in idx:
                     f.write("   %-75s %-12s %s\n" % (k, units[idx[k]], d[idx[k]]))
     print(open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.txt" % (tag, which))).read()[:6000])
+    # dram traffic per launch of the captured kernel, for bench.py's roofline.traffic
+    if data and "dram__bytes_read.sum" in idx:
+        def num(d, k):
+            v, u = float(d[idx[k]].replace(",", "")), units[idx[k]]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        return num(data[0], "dram__bytes_read.sum") + num(data[0], "dram__bytes_write.sum")
 
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     launches(tag)
+    import json
+    traffic = {}
     for which in sys.argv[2:] or ["conv", "pointwise"]:
-        rep(tag, which)
+        t = rep(tag, which)
+        if t is not None:
+            traffic[{"step": "flow_step_fused", "gate": "conv_lstm_gates"}.get(which, which)] = t
+    if traffic:
+        json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+        print("traffic.json:", traffic)
