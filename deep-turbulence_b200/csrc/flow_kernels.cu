@@ -249,9 +249,46 @@ __global__ void permute_kernel(PermArgs a, int64_t total) {
   }
 }
 
+// CheckerSqueeze.reverse into the user-facing NCHW field (flowUtils.py:124-145): one thread per squeezed pixel reads
+// its 4C contiguous channels (float4) and writes, per channel and output row, the two adjacent columns as one float2:
+// a warp reads 32*4C*4 contiguous bytes and writes 256 contiguous bytes per (channel, row).
+template <int C>
+__global__ void __launch_bounds__(256)
+unsqueeze_nchw_kernel(PermArgs a, int64_t npix) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const int H2 = a.H / 2, W2 = a.W / 2;
+  const int x = (int)(i % W2); int64_t t = i / W2; const int y = (int)(t % H2); const int b = (int)(t / H2);
+  float v[4 * C];
+  const float4* s4 = reinterpret_cast<const float4*>(a.src + i * a.src_cstride + a.src_coff);
+#pragma unroll
+  for (int q = 0; q < C; ++q) { const float4 f = __ldg(s4 + q); v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w; }
+  // channel groups k = 0..3 hold offsets (dr,dc) = (0,0),(1,0),(1,1),(0,1)
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float* d = a.dst + (((int64_t)b * C + c) * a.H + 2 * y) * a.W + 2 * x;
+    *reinterpret_cast<float2*>(d) = make_float2(v[c], v[3 * C + c]);                 // row 2y  : (0,0), (0,1)
+    *reinterpret_cast<float2*>(d + a.W) = make_float2(v[C + c], v[2 * C + c]);       // row 2y+1: (1,0), (1,1)
+  }
+}
+
 int launch_permute(const PermArgs& a, cudaStream_t st) {
   int64_t total = (int64_t)a.B * a.C * a.H * a.W;
   if (total == 0) return TMG_OK;
+  if (a.mode == PERM_UNSQUEEZE_NHWC_TO_NCHW && a.src_cstride % 4 == 0 && a.src_coff % 4 == 0 && a.W % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dst) & 7) == 0 &&
+      (a.C == 3 || a.C == 1 || a.C == 2 || a.C == 4)) {
+    const int64_t npix = total / (4 * a.C);
+    const unsigned grid = (unsigned)((npix + 255) / 256);
+    switch (a.C) {
+      case 1: unsqueeze_nchw_kernel<1><<<grid, 256, 0, st>>>(a, npix); break;
+      case 2: unsqueeze_nchw_kernel<2><<<grid, 256, 0, st>>>(a, npix); break;
+      case 3: unsqueeze_nchw_kernel<3><<<grid, 256, 0, st>>>(a, npix); break;
+      default: unsqueeze_nchw_kernel<4><<<grid, 256, 0, st>>>(a, npix); break;
+    }
+    TMG_LAUNCH_CHECK();
+    return TMG_OK;
+  }
   int thr = 256;
   permute_kernel<<<(unsigned)((total + thr - 1) / thr), thr, 0, st>>>(a, total);
   TMG_LAUNCH_CHECK();
@@ -342,21 +379,28 @@ int launch_bn_fold_train(const BnFoldArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------ per-sample log-det assembly
 __global__ void logdet_reduce_kernel(LogdetArgs a) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per sample; every lane sums a fixed strided subset in fp64, then a fixed butterfly: the order of
+  // additions depends only on (ld_stride), so results are bit-reproducible run to run
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (b >= a.B) return;
   double s = 0.0;
   const float* p = a.ld_part + (size_t)b * a.ld_stride;
-  for (int i = 0; i < a.ld_stride; ++i) s += p[i];
-  for (int l = 0; l < a.n_levels; ++l) {
-    double cs = 0.0;
-    for (int k = a.step_begin[l]; k < a.step_begin[l + 1]; ++k) cs += a.step_const[k];
-    s += cs * (double)a.hw[l];
+  for (int i = lane; i < a.ld_stride; i += 32) s += (double)p[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    for (int l = 0; l < a.n_levels; ++l) {
+      double cs = 0.0;
+      for (int k = a.step_begin[l]; k < a.step_begin[l + 1]; ++k) cs += a.step_const[k];
+      s += cs * (double)a.hw[l];
+    }
+    a.out[b] = (float)s;
   }
-  a.out[b] = (float)s;
 }
 
 int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st) {
-  logdet_reduce_kernel<<<cdiv(a.B, 64), 64, 0, st>>>(a);
+  logdet_reduce_kernel<<<cdiv(a.B * 32, 128), 128, 0, st>>>(a);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }

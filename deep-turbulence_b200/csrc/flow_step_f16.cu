@@ -236,7 +236,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         const int rr = q / kRP, rc = q - rr * kRP;
         const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
         const bool in = q < kNPOS && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W;
-        const float m1 = in ? inv1 : 0.f, m2 = in ? inv2 : 0.f;
+        const float m1 = in ? 1.f : 0.f, m2 = m1;
         float* d1p = Ds1 + q * 9;
         float* d2p = Ds2 + q * 9;
 #pragma unroll
@@ -257,7 +257,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
           if (in1[j]) {
             const float* e = Ds1 + pd[j] * 9;
             const float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
-            val = fmaxf(((s0 + s1) + (s2 + s3)) + e[8] + dcv1[j], 0.f);
+            val = fmaxf(fmaf(((s0 + s1) + (s2 + s3)) + e[8], inv1, dcv1[j]), 0.f);
           }
           D1[pd[j]] = val;
         }
@@ -271,14 +271,14 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         if (ok2[j]) {
           const int pc = pcl[j];
           const float* e = Ds2 + pc * 9;
-          float sa = dcv2[j], sb = 0.f;
+          float sa = 0.f, sb = 0.f, da = dcv2[j], db = 0.f;          // sa/sb: scaled tensor-core partials, da/db: fp32 d1 taps
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int off = (t / 3 - 1) * kRP + (t % 3 - 1);
-            if (t & 1) sb += fmaf(s_w2d[t], D1[pc + off], e[t]);
-            else sa += fmaf(s_w2d[t], D1[pc + off], e[t]);
+            if (t & 1) { sb += e[t]; db = fmaf(s_w2d[t], D1[pc + off], db); }
+            else { sa += e[t]; da = fmaf(s_w2d[t], D1[pc + off], da); }
           }
-          const float d1 = D1[pc], d2 = fmaxf(sa + sb, 0.f);
+          const float d1 = D1[pc], d2 = fmaxf(fmaf(sa + sb, inv2, da + db), 0.f);
           __half h1, l1, h2, l2;
           split_h(d1, h1, l1); split_h(d2, h2, l2);
           *reinterpret_cast<uint32_t*>(dslot + (size_t)pd[j] * 16) = pack_h2(h1, h2);
@@ -335,10 +335,10 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
               for (int e = 0; e < 4; e += 2) {
                 const float shift = (hv[e] + s_b3[n0 + q + e]) * gain;            // h[:, 0::2]
                 const float raw = (hv[e + 1] + s_b3[n0 + q + e + 1]) * gain;      // h[:, 1::2]
-                const float la = 2.f * (raw / (1.f + fabsf(raw)));
+                const float la = 2.f * __fdividef(raw, 1.f + fabsf(raw));      // 2*softsign; rcp.approx, 2 ulp
                 ldsum += la;
                 const int j = C / 2 + (n0 + q + e) / 2;
-                v[j] = a.reverse ? fmaf(v[j], expf(-la), -shift) : (v[j] + shift) * expf(la);
+                v[j] = a.reverse ? fmaf(v[j], __expf(-la), -shift) : (v[j] + shift) * __expf(la);   // |la| <= 2: ex2.approx, 2 ulp
               }
             }
           }

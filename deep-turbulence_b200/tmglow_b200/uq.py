@@ -1,0 +1,109 @@
+"""Sample-parallel uncertainty quantification on top of ``TMGlow.sample``.
+
+The reference draws stochastic high-fidelity samples of one low-fidelity sequence with a Python loop over
+samples around the loop over time steps (``utils/utils.py:197-222`` ``modelPred``, ``nn/trainFlowParallel.py:345-367``
+``TrainFlow.test``), one ``model.sample`` call per (sample, time step).  Here the sample loop is folded into the batch
+dimension: one call per time step produces all S samples of this rank from ONE low-fidelity snapshot (passed as a
+batch-expanded view, so the encoder runs once and the conditioning maps are shared), the ConvLSTM states stay on the
+device, and only per-time-step moments (mean / variance over samples) leave the step.
+
+Multi-GPU: samples are independent (own noise, own LSTM state), so the S samples are sharded
+over the ranks with no data-path collective; the only communication is one all-reduce of the moment sums per
+sequence (``combine_moments``), which also works on the gloo backend (tests/test_parallel_cpu.py).
+"""
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition of ``range(total)``: ranks below ``total % world`` get one extra item."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %d/%d" % (rank, world))
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sample_seeds(base_seed: int, sequence: int, lo: int, hi: int) -> torch.Tensor:
+    """LSTM-state seeds of samples [lo, hi) of one LF sequence: a function of the GLOBAL sample index only, so a run
+    sharded over any number of ranks draws the states a single-rank run draws (``initLSTMStates`` seeds one CPU
+    generator per sample, tmGlow.py:481-509)."""
+    idx = torch.arange(lo, hi, dtype=torch.long)
+    return (base_seed + 1000003 * sequence + idx) % (2 ** 31 - 1)
+
+
+def combine_moments(s1: torch.Tensor, s2: torch.Tensor, n: int, group=None):
+    """All-reduce the per-rank sums, sums of squares and counts -> (mean, unbiased variance, total count)."""
+    import torch.distributed as dist
+    cnt = torch.tensor([float(n)], dtype=torch.float64, device=s1.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        s1 = s1.clone(); s2 = s2.clone()
+        dist.all_reduce(s1, group=group)
+        dist.all_reduce(s2, group=group)
+        dist.all_reduce(cnt, group=group)
+    ntot = int(cnt.item())
+    mean = s1 / ntot
+    var = (s2 - ntot * mean * mean) / max(ntot - 1, 1)
+    return mean, var.clamp_(min=0), ntot
+
+
+def mix_states(states, key, weight=0.5):
+    """Average the running LSTM states with the initial ("key") states, as the reference does every 10 (test) or 20
+    (modelPred) time steps: trainFlowParallel.py:360-366, utils.py:216-222."""
+    return [(weight * h + (1 - weight) * hk, weight * c + (1 - weight) * ck) for (h, c), (hk, ck) in zip(states, key)]
+
+
+@torch.no_grad()
+def sample_sequence(model, x_seq: torch.Tensor, samples: int, *, base_seed: int = 0, sequence: int = 0,
+                    state_mix_every: int = 10, rank: int = 0, world: int = 1, group=None,
+                    unnormalise: bool = True, keep_samples: bool = False,
+                    sampler: Optional[Callable] = None, init_states: Optional[Callable] = None):
+    """S stochastic HF samples of one LF sequence ``x_seq [T, nic, h, w]``.
+
+    Returns ``(mean [T,C,H,W], var [T,C,H,W], n_total, samples or None)``; ``samples`` ([S_rank,T,C,H,W], this rank's
+    shard) only when ``keep_samples``.  ``sampler(x, h) -> (y, log_det, h)`` and ``init_states(seeds, [H,W])`` default
+    to ``model.sample`` / ``model.initLSTMStates`` (tests substitute CPU stand-ins).
+    """
+    sampler = sampler or model.sample
+    init_states = init_states or model.initLSTMStates
+    T = x_seq.shape[0]
+    lo, hi = shard_range(samples, rank, world)
+    S = hi - lo
+    dev = x_seq.device
+    out_mu = out_std = None
+    if unnormalise and getattr(model, "out_mu", None) is not None:
+        out_mu = model.out_mu.to(dev).view(1, -1, 1, 1)
+        out_std = model.out_std.to(dev).view(1, -1, 1, 1)
+        if float(out_std.abs().sum()) == 0.0:      # buffers never set by a data loader (dataLoader.py:159-164)
+            out_mu = out_std = None
+    s1 = s2 = None
+    kept: List[torch.Tensor] = []
+    if S > 0:
+        up = getattr(getattr(model, "_cfg", None), "cglow_upscale", None)
+        H, W = (x_seq.shape[-2] * up, x_seq.shape[-1] * up) if up else (None, None)
+        key = init_states(sample_seeds(base_seed, sequence, lo, hi), [H, W])
+        h = key
+    for t in range(T):
+        if S > 0:
+            x = x_seq[t:t + 1].expand(S, -1, -1, -1)          # ONE input, S samples: shared-input fast path
+            y, _, h = sampler(x, h)
+            if out_mu is not None:
+                y = out_std * y + out_mu
+            y64 = y.double()
+            m1, m2 = y64.sum(0), (y64 * y64).sum(0)
+            if keep_samples:
+                kept.append(y)
+            if state_mix_every and t % state_mix_every == 0:
+                h = mix_states(h, key)
+        else:
+            m1 = m2 = None
+        if s1 is None and m1 is not None:
+            s1 = torch.zeros((T,) + tuple(m1.shape), dtype=torch.float64, device=dev)
+            s2 = torch.zeros_like(s1)
+        if m1 is not None:
+            s1[t], s2[t] = m1, m2
+    if s1 is None:       # a rank without samples still takes part in the reduction
+        raise ValueError("rank %d of %d has no samples: use samples >= world" % (rank, world))
+    mean, var, ntot = combine_moments(s1, s2, S, group)
+    return mean.float(), var.float(), ntot, (torch.stack(kept, 1) if keep_samples else None)

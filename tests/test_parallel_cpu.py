@@ -1,0 +1,109 @@
+"""Host-side logic of the N > 1 (sample-parallel) path on CPU: world_size-2 gloo processes.
+
+The CUDA path cannot run here; what shards samples over ranks, seeds the LSTM states, streams the per-time-step
+moments and combines them with ONE all-reduce per sequence (tmglow_b200/uq.py) is plain host code and is exercised
+with a CPU stand-in for ``TMGlow.sample`` whose output depends on the per-sample seed, so any sharding or
+reduction mistake changes the result.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "deep-turbulence_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _init_states(seeds, dims):
+    hs = []
+    for sd in seeds.tolist():
+        g = torch.Generator().manual_seed(int(sd))
+        hs.append(torch.rand(1, 2, 2, 2, generator=g))
+    h = torch.cat(hs, 0)
+    return [(h, h.clone())]
+
+
+def _sampler(x, h):
+    """y depends on the LF input, on the per-sample state and on a state-dependent 'noise'."""
+    (hh, cc), = h
+    base = x.mean(dim=(1, 2, 3), keepdim=True)
+    y = base + hh.mean(dim=(1, 2, 3)).view(-1, 1, 1, 1) * torch.ones(x.shape[0], 3, 4, 4) + 0.1 * cc.sum(dim=(1, 2, 3)).view(-1, 1, 1, 1)
+    h2 = [(0.9 * hh + 0.05, cc + 0.01 * hh)]
+    return y, torch.zeros(x.shape[0]), h2
+
+
+def _run_rank(rank, world, port, samples, out):
+    import torch.distributed as dist
+    from tmglow_b200 import uq
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    x_seq = torch.randn(5, 4, 2, 2, generator=g)
+    mean, var, ntot, kept = uq.sample_sequence(None, x_seq, samples, base_seed=7, rank=rank, world=world,
+                                               state_mix_every=2, unnormalise=False, keep_samples=True,
+                                               sampler=_sampler, init_states=_init_states)
+    if rank == 0:
+        torch.save({"mean": mean, "var": var, "n": ntot, "kept": kept.shape[0]}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    from tmglow_b200 import uq
+    for total in (0, 1, 7, 8, 1000, 1023):
+        for world in (1, 2, 3, 8):
+            parts = [uq.shard_range(total, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        uq.shard_range(4, 2, 2)
+
+
+def test_seeds_depend_on_global_index_only():
+    from tmglow_b200 import uq
+    full = uq.sample_seeds(11, 3, 0, 10)
+    assert torch.equal(torch.cat([uq.sample_seeds(11, 3, 0, 4), uq.sample_seeds(11, 3, 4, 10)]), full)
+    assert len(set(full.tolist())) == 10
+    assert not torch.equal(uq.sample_seeds(11, 4, 0, 10), full)
+
+
+@pytest.mark.parametrize("samples", [8, 7])
+def test_two_rank_gloo_matches_single_process(tmp_path, samples):
+    from tmglow_b200 import uq
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_run_rank, args=(2, _free_port(), samples, out), nprocs=2, join=True)
+    got = torch.load(out)
+    g = torch.Generator().manual_seed(0)
+    x_seq = torch.randn(5, 4, 2, 2, generator=g)
+    mean, var, ntot, kept = uq.sample_sequence(None, x_seq, samples, base_seed=7, state_mix_every=2, unnormalise=False,
+                                               keep_samples=True, sampler=_sampler, init_states=_init_states)
+    assert got["n"] == samples == ntot
+    assert got["kept"] == (samples + 1) // 2            # rank 0 holds the larger shard
+    assert torch.allclose(got["mean"], mean, rtol=0, atol=1e-6)
+    assert torch.allclose(got["var"], var, rtol=1e-5, atol=1e-7)
+    # the moments are those of the kept samples
+    assert torch.allclose(mean, kept.mean(0), atol=1e-5)
+    assert torch.allclose(var, kept.var(0, unbiased=True), atol=1e-5)
+
+
+def test_bench_sharding_is_weak_scaling():
+    """bench.py gives every rank its own LF input and S samples (weak scaling, no data-path collective): the
+    whole-job value is world * S * K / max-over-ranks time."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.workload_config(1024, 8)
+    assert c["samples_per_gpu_per_step"] == 1024 and "x8" in c["parallelism"] and "no collective" in c["parallelism"]
