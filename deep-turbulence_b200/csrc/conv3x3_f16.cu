@@ -26,13 +26,14 @@ constexpr int kCvRP = 18;                 // staged tile pitch: 16 + 2
 constexpr int kCvNPOS = 324;
 constexpr int kCvNPOSA = 328;
 constexpr uint32_t kCvPLB = kCvNPOSA * 16;        // bytes of one 8-channel plane of a K-step
-constexpr int kCvThreads = 480;           // warps 0-7 epilogue, 8-9 MMA, 10 weights, 11-14 producers
+// warps 0-7 epilogue, 8-9 MMA, 10 weights, 11.. producers (NPW warps: 4 when the MMAs dominate (wide N), 8 when the
+// activation staging does (narrow N))
 constexpr int kCvNA = 3;                  // activation K-step ring
 constexpr int kCvMaxNB = 8;               // weight stage ring (upper bound)
 
 struct ConvF16Geom {
   int KS;                 // K-steps of 16 channels
-  int nhl, nb;
+  int nhl, nb, tps;       // weight ring depth; taps per weight stage (1, 3 or 9)
   int tiles_x, tiles_y, ntiles, step_b, step_t;
   uint32_t inv_tx;
   uint32_t hlA, bufA;     // bytes: hi->lo distance inside an A K-step buffer, buffer size
@@ -69,9 +70,11 @@ struct CvTileIt {
   }
 };
 
-template <bool X3>
-__global__ void __launch_bounds__(kCvThreads, 1)
+template <bool X3, int NPW>
+__global__ void __launch_bounds__((11 + NPW) * 32, 1)
 conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
+  constexpr int kCvThreads = (11 + NPW) * 32;
+  constexpr int kNPT = NPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W;
@@ -91,7 +94,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   if (tid == 0) {
-    for (int i = 0; i < kCvNA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_free + i, 2); }
+    for (int i = 0; i < kCvNA; ++i) { mbar_init(a_full + i, kNPT); mbar_init(a_free + i, 2); }
     for (int i = 0; i < kCvMaxNB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_free + i, 2); }
     mbar_init(acc_full, 2); mbar_init(acc_free, 256);
     fence_barrier_init();
@@ -200,7 +203,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     const int mt = warp - 8;
     if (elect_one()) {
       const uint32_t idesc = cv_idesc_f16(NP);
-      const uint64_t hlA16 = g.hlA >> 4, hlB16 = g.hlB >> 4;
+      const uint64_t hlA16 = g.hlA >> 4, hlB16 = g.hlB >> 4, tapB16 = (uint64_t)(g.nhl * g.hlB) >> 4;
       const uint32_t tacc = tmem_base + (uint32_t)(mt * 256);
       int ja = 0, jb = 0;                      // running K-step / weight-stage counters
       for (int k = 0; k < nmy; ++k) {
@@ -211,17 +214,21 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
           mbar_wait(a_full + ua, (uint32_t)((ja / kCvNA) & 1));
           tc_fence_after();
           const uint64_t a0 = make_desc(smem_u32(As + (size_t)ua * g.bufA), kCvPLB, kCvRP * 16) + (uint64_t)(8 * mt);
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap, ++jb) {
+          for (int sg = 0; sg < 9; sg += g.tps, ++jb) {
             const int ub = jb % g.nb;
             mbar_wait(b_full + ub, (uint32_t)((jb / g.nb) & 1));
             tc_fence_after();
-            const uint64_t ad = a0 + (uint64_t)((1 + tap / 3 - 1) * kCvRP + 1 + tap % 3 - 1);
-            const uint64_t bd = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)NP * 16u, 128);
-            cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
-            if (X3) {
-              cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
-              cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
+            const uint64_t bd0 = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)NP * 16u, 128);
+            for (int t = 0; t < g.tps; ++t) {
+              const int tap = sg + t;
+              const int dr = tap / 3, dc = tap - 3 * dr;
+              const uint64_t ad = a0 + (uint64_t)(dr * kCvRP + dc);
+              const uint64_t bd = bd0 + (uint64_t)t * tapB16;
+              cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+              if (X3) {
+                cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
+                cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
+              }
             }
             mma_commit(b_free + ub);
           }
@@ -235,12 +242,18 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     if (lane == 0) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk);
       int jb = 0;
+      const uint32_t tapB = g.nhl * g.hlB;
       for (int k = 0; k < nmy; ++k) {
-        for (int st = 0; st < nstage_tile; ++st, ++jb) {
+        for (int st = 0; st < nstage_tile; st += g.tps, ++jb) {
           const int ub = jb % g.nb, use = jb / g.nb;
           if (use >= 1) mbar_wait(b_free + ub, (uint32_t)((use - 1) & 1));
           mbar_expect_tx(b_full + ub, g.stageB);
-          bulk_g2s(Bs + (size_t)ub * g.stageB, wsrc + (size_t)st * g.gstageB, g.stageB, b_full + ub);
+          uint8_t* dst = Bs + (size_t)ub * g.stageB;
+          if (X3) {          // hi and lo of consecutive taps are contiguous in the packed layout
+            bulk_g2s(dst, wsrc + (size_t)st * g.gstageB, g.stageB, b_full + ub);
+          } else {
+            for (int t = 0; t < g.tps; ++t) bulk_g2s(dst + (size_t)t * tapB, wsrc + (size_t)(st + t) * g.gstageB, tapB, b_full + ub);
+          }
         }
       }
     }
@@ -259,14 +272,14 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
         const int ua = ja % kCvNA, use = ja / kCvNA;
         if (use >= 1) mbar_wait(a_free + ua, (uint32_t)((use - 1) & 1));
         uint8_t* Ab = As + (size_t)ua * g.bufA;
-        // 2 planes x 324 positions; 3 batches of up to 2 items per thread, loads first
-        for (int it0 = ptid; it0 < 2 * kCvNPOS; it0 += 256) {
+        // 2 planes x 324 positions; batches of up to 2 items per thread, loads first
+        for (int it0 = ptid; it0 < 2 * kCvNPOS; it0 += 2 * kNPT) {
           float v[2][8];
           int pos[2], pln[2];
           bool relu[2];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const int itx = it0 + q * 128;
+            const int itx = it0 + q * kNPT;
             pos[q] = -1; pln[q] = 0; relu[q] = false;
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
@@ -363,7 +376,11 @@ static bool cv_geom(const ConvF16Args& a, ConvF16Geom& g, int grid) {
   g.KS = (pl + 1) / 2;
   g.nhl = a.x3 ? 2 : 1;
   g.hlA = 2 * kCvPLB; g.bufA = g.hlA * g.nhl;
-  g.hlB = (uint32_t)2 * a.npad * 16; g.stageB = g.hlB * g.nhl; g.gstageB = 2 * g.hlB;
+  g.hlB = (uint32_t)2 * a.npad * 16; g.gstageB = 2 * g.hlB;
+  // a weight stage holds 9, 3 or 1 taps: narrow-N convs have too little MMA work per tap to hide the barrier round
+  // trip of a per-tap stage
+  g.tps = g.hlB * g.nhl * 9 <= 32 * 1024 ? 9 : (g.hlB * g.nhl * 3 <= 32 * 1024 ? 3 : 1);
+  g.stageB = g.hlB * g.nhl * g.tps;
   g.tiles_x = cdiv(a.W, 16); g.tiles_y = cdiv(a.H, 16);
   const int tiles_img = g.tiles_x * g.tiles_y;
   if (tiles_img >= 4096) return false;
@@ -377,7 +394,7 @@ static bool cv_geom(const ConvF16Args& a, ConvF16Geom& g, int grid) {
   g.oBar = take(25 * 8 + 16);
   const uint32_t fixed = off;
   int nb = (int)((220u * 1024u - fixed) / ((g.stageB + 127) / 128 * 128));
-  nb = std::min(nb, kCvMaxNB);
+  nb = std::min(nb, g.tps == 1 ? kCvMaxNB : 4);
   if (nb < 2) return false;
   g.nb = nb;
   g.oB = take((uint32_t)nb * g.stageB);
@@ -399,13 +416,15 @@ int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st) {
     set_error("fp16 conv: unsupported shape (N=%d, %dx%d, %d sources)", a.npad, a.H, a.W, a.nsrc);
     return TMG_ERR_UNSUPPORTED;
   }
-  if (a.x3) {
-    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    conv3x3_f16_kernel<true><<<grid, kCvThreads, g.total, st>>>(a, g);
-  } else {
-    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    conv3x3_f16_kernel<false><<<grid, kCvThreads, g.total, st>>>(a, g);
+#define TMG_CV(XX, PW)                                                                                                      \
+  {                                                                                                                         \
+    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_f16_kernel<XX, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    conv3x3_f16_kernel<XX, PW><<<grid, (11 + PW) * 32, g.total, st>>>(a, g);                                                \
   }
+  const bool wide = a.npad > 96 || a.lstm_R > 0;
+  if (a.x3) { if (wide) TMG_CV(true, 4) else TMG_CV(true, 8) }
+  else { if (wide) TMG_CV(false, 4) else TMG_CV(false, 8) }
+#undef TMG_CV
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }

@@ -169,6 +169,9 @@ static int launch_t(const ConvArgs& a, cudaStream_t st) {
 int launch_conv3x3(const ConvArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.Hout <= 0 || a.Wout <= 0) return TMG_OK;
   if (a.cout_w % 4 != 0) { set_error("conv3x3: packed cout %d not a multiple of 4", a.cout_w); return TMG_ERR_BAD_SHAPE; }
+  // small problems (the encoder and the hoisted conditioning tables at batch 1): a grid of a few CTAs is latency
+  // bound, so split the output channels four at a time over blockIdx.z and use 128-pixel tiles
+  if ((long long)cdiv(a.Hout * a.Wout, 256) * a.B * cdiv(a.cout, 16) < 256) return launch_t<4, 1>(a, st);
   if (a.cout <= 4) return launch_t<4, 2>(a, st);
   if (a.cout <= 16) return launch_t<16, 2>(a, st);
   if (a.cout <= 32) return launch_t<32, 2>(a, st);
