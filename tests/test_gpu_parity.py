@@ -362,3 +362,28 @@ def test_f16x3_full_size_properties():
     y3, ld3, _ = m.reconstruct(x, h_in, eps)
     assert (y3 - y_rec).abs().max().item() < 2e-4
     assert ((ld3 - log_det).abs() <= 1e-5 * ld3.abs() + 1e-3).all()
+
+
+def test_uq_driver_moments_and_shared_path():
+    """tmglow_b200.uq.sample_sequence on the GPU: the streamed moments are those of the samples it drew, and the
+    driver (batch-expanded LF input -> shared-input path) reproduces a hand-written loop with the same seeds."""
+    from tmglow_b200 import uq
+    dev = _dev()
+    m = _default_model().to(dev)
+    m.precision = "f16x3"
+    g = torch.Generator().manual_seed(21)
+    T, S = 3, 6
+    x_seq = torch.randn(T, 4, 32, 64, generator=g).to(dev)
+    torch.manual_seed(5)
+    mean, var, n, kept = uq.sample_sequence(m, x_seq, S, base_seed=3, state_mix_every=2, keep_samples=True)
+    assert n == S and kept.shape == (S, T, 3, 64, 128)
+    assert torch.allclose(mean, kept.mean(0), atol=1e-4) and torch.allclose(var, kept.var(0), atol=1e-3, rtol=1e-3)
+    # the same thing by hand, materialised batch
+    torch.manual_seed(5)
+    key = m.initLSTMStates(uq.sample_seeds(3, 0, 0, S), [64, 128])
+    h = key
+    for t in range(T):
+        y, _, h = m.sample(x_seq[t:t + 1].expand(S, -1, -1, -1).contiguous(), h)
+        assert (y - kept[:, t]).abs().max().item() < 2e-4
+        if t % 2 == 0:
+            h = uq.mix_states(h, key)
