@@ -108,10 +108,16 @@ struct TileIt {
 // three issuers on three schedulers -- a lone issuing warp that shares its scheduler with busy epilogue warps runs
 // at ~100 cycles per MMA instead of 40, tools/ubench_mma.cu); the next 4 warps are producers.
 template <int C, bool X3, int NG>
-__global__ void __launch_bounds__(NG * 256 + 224, 1)
+__global__ void __launch_bounds__(NG * 256 + 96 + (NG == 2 ? 192 : 128), 1)
 flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   constexpr int NP = (C + 15) / 16 * 16;
-  constexpr int kThreads = NG * 256 + 224;
+  // TMEM: E accumulators (4 M tiles x 32 columns) in two slots [0,256), released as soon as the gather read them;
+  // Z accumulators (2 M tiles x NP columns) in NZ slots from column 256 on, released after the finishing epilogue.
+  // Four Z slots (C <= 32) let each epilogue group gather its NEXT tile while the Z MMAs of its current one run.
+  constexpr int ZW = 2 * NP;
+  constexpr int NZ = (4 * ZW <= 256) ? 4 : 2;
+  constexpr int kProdThreads = NG == 2 ? 192 : 128;       // producer warps: 6 with two epilogue groups, else 4
+  constexpr int kThreads = NG * 256 + 96 + kProdThreads;
   constexpr int kMmaWarp = 8 * NG;        // E issuer (+ TMEM owner); kMmaWarp+1, +2: Z issuers
   constexpr int kProdWarp = 8 * NG + 3;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -129,9 +135,9 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   uint64_t* d_ready = bars + 6;     // [3] epilogue group (256)
   uint64_t* e_full = bars + 9;      // [2] commit
   uint64_t* e_free = bars + 11;     // [2] epilogue group (256)
-  uint64_t* z_full = bars + 13;     // [2] commit
-  uint64_t* z_free = bars + 15;     // [2] epilogue group (256)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* z_full = bars + 13;     // [4] commit
+  uint64_t* z_free = bars + 17;     // [4] epilogue group (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   float* s_nw = Wm + C * C;
   float* s_nb = s_nw + C;
@@ -142,8 +148,9 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
 
   // ------------------------------------------------------------------ one-time setup
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(a_full + i, 128); mbar_init(a_free + i, 3); mbar_init(d_ready + i, kEpiThreads); }
-    for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_free + i, kEpiThreads); mbar_init(z_full + i, 2); mbar_init(z_free + i, kEpiThreads); }
+    for (int i = 0; i < 3; ++i) { mbar_init(a_full + i, kProdThreads); mbar_init(a_free + i, 3); mbar_init(d_ready + i, kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_free + i, kEpiThreads); }
+    for (int i = 0; i < 4; ++i) { mbar_init(z_full + i, 2); mbar_init(z_free + i, kEpiThreads); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
@@ -232,7 +239,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       for (int j = 0; j < 2; ++j) {
         const int mt = 2 * wg + j, q = mt * 128 + el;
         float v[32];
-        tmem_ld32(tmem_base + lane_base + (uint32_t)(s * 256 + mt * 32), v);
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(s * 128 + mt * 32), v);
         const int rr = q / kRP, rc = q - rr * kRP;
         const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
         const bool in = q < kNPOS && ir >= 0 && ir < a.H && ic >= 0 && ic < a.W;
@@ -292,7 +299,8 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
 
     // ---- F(k): h -> coupling, 1x1 mix, ActNorm, store, log-det partial
     auto finish = [&](int k, const TileIt& it) {
-      const int s = k & 1;
+      const int s = k & (NZ - 1);
+      const uint32_t zpar = (uint32_t)((k / NZ) & 1);
       int r0, c0;
       it.origin(g, r0, c0);
       const int b = it.b;
@@ -313,11 +321,11 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         for (int q = 0; q < NHC; ++q) hcv[q] = hcp ? __ldg(hcp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       PROF_MARK(3)
-      mbar_wait(z_full + s, (uint32_t)((k >> 1) & 1));
+      mbar_wait(z_full + s, zpar);
       PROF_MARK(4)
       tc_fence_after();
       float ldsum = 0.f;
-      const uint32_t trow = tmem_base + lane_base + (uint32_t)(s * 256 + 128 + wg * NP);
+      const uint32_t trow = tmem_base + lane_base + (uint32_t)(256 + s * ZW + wg * NP);
 #pragma unroll
       for (int n0 = 0; n0 < NP; n0 += 16) {
         float h[16];
@@ -390,12 +398,22 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
     };
 
     if (NG == 2) {
-      TileIt it;
-      it.init(blockIdx.x + grp * gridDim.x, tiles_img);
-      for (int k = grp; k < nmy; k += 2) {
-        gather(k, it);
-        finish(k, it);
-        it.advance(g, tiles_img); it.advance(g, tiles_img);
+      TileIt itf, itg;
+      itf.init(blockIdx.x + grp * gridDim.x, tiles_img); itg = itf;
+      if (NZ == 4 && g.nbuf >= 3) {          // gather of this group's next tile overlaps the Z MMAs of the current one
+        if (grp < nmy) gather(grp, itg);
+        for (int k = grp; k < nmy; k += 2) {
+          itg.advance(g, tiles_img); itg.advance(g, tiles_img);
+          if (k + 2 < nmy) gather(k + 2, itg);
+          finish(k, itf);
+          itf.advance(g, tiles_img); itf.advance(g, tiles_img);
+        }
+      } else {
+        for (int k = grp; k < nmy; k += 2) {
+          gather(k, itf);
+          finish(k, itf);
+          itf.advance(g, tiles_img); itf.advance(g, tiles_img);
+        }
       }
     } else if (g.pipelined) {
       TileIt itf, itg;
@@ -432,7 +450,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
           PROF_MARK(2)
           tc_fence_after();
           const uint64_t aE0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, 128);
-          const uint32_t tE = tmem_base + (uint32_t)(s * 256);
+          const uint32_t tE = tmem_base + (uint32_t)(s * 128);
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt) {
             uint64_t ad = aE0 + (uint64_t)(mt * 128);          // 128 positions x 16 B, in 16-byte units
@@ -458,15 +476,15 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         const uint64_t bZ0 = make_desc(smem_u32(WZ), (uint32_t)NP * 16u, 128);
         const uint64_t wZhl16 = g.wZ_hl >> 4, wZtap16 = g.wZ_tap >> 4;
         for (int k = 0; k < nmy; ++k) {
-          const int s = k & 1, u = k % g.nbuf;
+          const int s = k & (NZ - 1), u = k % g.nbuf;
           PROF_MARK(0)
           mbar_wait(d_ready + u, (uint32_t)((k / g.nbuf) & 1));
           PROF_MARK(4)
-          if (k >= 2) mbar_wait(z_free + s, (uint32_t)(((k >> 1) - 1) & 1));
+          if (k >= NZ) mbar_wait(z_free + s, (uint32_t)(((k / NZ) - 1) & 1));
           PROF_MARK(5)
           tc_fence_after();
           const uint64_t aZ0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, kRP * 16) + (uint64_t)(8 * mt);
-          const uint32_t tZ = tmem_base + (uint32_t)(s * 256 + 128 + mt * NP);
+          const uint32_t tZ = tmem_base + (uint32_t)(256 + s * ZW + mt * NP);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             uint64_t ad = aZ0 + (uint64_t)((3 + tap / 3 - 1) * kRP + 3 + tap % 3 - 1);
@@ -510,13 +528,13 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       uint8_t* Ab = A + (size_t)u * g.bufA;
       // planes that hold source channels (pure padding / d-slot planes were zeroed once and are never staged)
       const int items = kNPOS * nstage;
-      for (int it0 = ptid; it0 < items; it0 += 128 * 4) {
+      for (int it0 = ptid; it0 < items; it0 += kProdThreads * 4) {
         float v[4][8];
         int pos[4], pln[4];
         bool relu[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int itx = it0 + q * 128;
+          const int itx = it0 + q * kProdThreads;
           pos[q] = -1; pln[q] = 0; relu[q] = true;
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
@@ -643,7 +661,7 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g, int grid) {
       g.oWE = take(g.nhl * g.wE_hl);
       g.oWZ = take(9u * g.wZ_tap);
       g.oWm = take((uint32_t)(a.C * a.C + 4 * a.C + 9 + 3) * 4);
-      g.oBar = take(17 * 8 + 16);
+      g.oBar = take(21 * 8 + 16);
       g.total = off;
       if (g.total <= 227 * 1024) { g.pipelined = nbuf >= 2; return true; }
     }
@@ -676,7 +694,7 @@ int launch_step2(const Step2Args& a_in, cudaStream_t st) {
 #define TMG_S2(CC, XX, GG)                                                                                                       \
   {                                                                                                                              \
     TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-    flow_step_f16_kernel<CC, XX, GG><<<grid, GG * 256 + 224, g.total, st>>>(a, g);                                               \
+    flow_step_f16_kernel<CC, XX, GG><<<grid, GG * 256 + 96 + (GG == 2 ? 192 : 128), g.total, st>>>(a, g);                                               \
   }
 #define TMG_S2N(CC)                                                                              \
   case CC:                                                                                       \
