@@ -354,7 +354,51 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       }
       tc_fence_before();
       mbar_arrive(z_free + s);
-      if (valid) {
+      // Wide levels on short images (C >= 32, H <= 8: the lower half of every 16-row M tile is outside the image):
+      // the C x C mix of a pixel is split between its own thread (output rows [0, C/2)) and the idle thread 64 lanes
+      // up (rows [C/2, C)); the post-coupling state goes through shared memory (the gather scratch is free here).
+      const bool split_mix = C >= 32 && a.H <= 8 && a.wmat != nullptr;
+      if (split_mix) {
+        constexpr int VP = C + 4;
+        float* Vx = Ds1 - 32 * 9;
+        if (valid) {
+          if (!a.reverse && a.nw) {
+#pragma unroll
+            for (int q = 0; q < C; ++q) v[q] = fmaf(s_nw[q], v[q], s_nb[q]);
+          }
+          float4* vd = reinterpret_cast<float4*>(Vx + (wg * 64 + (el & 63)) * VP);
+#pragma unroll
+          for (int q = 0; q < C / 4; ++q) vd[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        named_bar_sync(bar_id, kEpiThreads);
+        const int px = el & 63, part = el >> 6;
+        const int ir2 = r0 + (px >> 3), ic2 = c0 + 8 * wg + (px & 7);
+        if (ir2 < a.H && ic2 < a.W) {
+          const float4* vs = reinterpret_cast<const float4*>(Vx + (wg * 64 + px) * VP);
+#pragma unroll
+          for (int q = 0; q < C / 4; ++q) { const float4 t = vs[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+          float* yo = a.y_out + ((size_t)b * HW + (size_t)ir2 * a.W + ic2) * C;
+#pragma unroll 1
+          for (int r4 = part * (C / 2); r4 < (part + 1) * (C / 2); r4 += 4) {
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float sum = 0.f;
+              const float4* w4 = reinterpret_cast<const float4*>(Wm + (r4 + q) * C);
+#pragma unroll
+              for (int kk = 0; kk < C / 4; ++kk) {
+                const float4 w = w4[kk];
+                sum = fmaf(w.x, v[4 * kk], sum); sum = fmaf(w.y, v[4 * kk + 1], sum);
+                sum = fmaf(w.z, v[4 * kk + 2], sum); sum = fmaf(w.w, v[4 * kk + 3], sum);
+              }
+              if (a.reverse && a.nw) sum = (sum - s_nb[r4 + q]) * s_rnw[r4 + q];
+              o[q] = sum;
+            }
+            *reinterpret_cast<float4*>(yo + r4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        named_bar_sync(bar_id, kEpiThreads);       // the scratch goes back to the next gather
+      } else if (valid) {
         if (!a.reverse && a.nw) {
 #pragma unroll
           for (int q = 0; q < C; ++q) v[q] = fmaf(s_nw[q], v[q], s_nb[q]);
