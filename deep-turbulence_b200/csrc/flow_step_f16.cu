@@ -21,6 +21,10 @@
 //   * Z = Conv2dZeros as a tap-shifted implicit GEMM whose M tile is 16 rows x 8 columns of output pixels:
 //     the shared-memory descriptor's stride between 8-row groups (SBO) is one padded image row, so no
 //     accumulator row is wasted on halo columns.
+//   * the A operand lives in a ring of K-step slots (16 channels of one tile each).  A tile's chunks are staged
+//     conditioning first, the x1+d chunk last: E and the d-independent part of Z consume (and release) the
+//     conditioning chunks while the gather of d1/d2 is still running, so the un-hoisted path (distinct LF inputs,
+//     LSTM tail, forward likelihood) pipelines across tiles with 3-4 slots instead of whole-tile double buffers.
 //   * K layout [x1 | d1 d2 | cond]: when all samples share one conditioning input (one LF snapshot, many
 //     stochastic samples) the cond K-steps are dropped and their contribution, which is the same for every
 //     sample, is read from a per-step table computed once per call ("hoisted", model.cu).
@@ -39,10 +43,10 @@ constexpr uint32_t kPLB = kNPOSA * 16;   // bytes of one 8-channel plane
 constexpr int kEpiThreads = 256;
 
 struct Step2Geom {
-  int KS, KSy, PLtot, kd, nbuf, pipelined;
+  int KS, KSy, PLtot, kd, nbuf, pipelined;   // nbuf: slots of the K-step ring (one slot = 16 channels of one tile)
   int tiles_x, tiles_y, ntiles, nhl;
   int step_b, step_t; uint32_t inv_tx; int ngroups;
-  uint32_t hlA, bufA, scratch;
+  uint32_t hlA, bufA, scratch;               // hlA: hi->lo distance inside a ring slot, bufA: slot size
   uint32_t oA, oDsc, oWE, oWZ, oWm, oBar, total;
   uint32_t wE_hl, wZ_tap, wZ_hl;         // shared-memory strides of the weight copies
   uint32_t gE_hl, gZ_tap, gZ_hl;         // strides of the packed (global) weights
@@ -130,14 +134,14 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   uint8_t* WZ = smem + g.oWZ;
   float* Wm = reinterpret_cast<float*>(smem + g.oWm);       // C*C mix | nw | nb | bias3 | w2d[9] | inv scales[3] | 1/nw
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.oBar);
-  uint64_t* a_full = bars;          // [3] producers (128)
-  uint64_t* a_free = bars + 3;      // [3] commit
-  uint64_t* d_ready = bars + 6;     // [3] epilogue group (256)
-  uint64_t* e_full = bars + 9;      // [2] commit
-  uint64_t* e_free = bars + 11;     // [2] epilogue group (256)
-  uint64_t* z_full = bars + 13;     // [4] commit
-  uint64_t* z_free = bars + 17;     // [4] epilogue group (256)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* a_full = bars;          // [4] ring slots: producers
+  uint64_t* a_free = bars + 4;      // [4] ring slots: 3 commits (E issuer + 2 Z issuers)
+  uint64_t* d_ready = bars + 8;     // [4] tiles in flight: epilogue group (256)
+  uint64_t* e_full = bars + 12;     // [2] commit
+  uint64_t* e_free = bars + 14;     // [2] epilogue group (256)
+  uint64_t* z_full = bars + 16;     // [4] commit
+  uint64_t* z_free = bars + 20;     // [4] epilogue group (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   float* s_nw = Wm + C * C;
   float* s_nb = s_nw + C;
@@ -148,7 +152,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
 
   // ------------------------------------------------------------------ one-time setup
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(a_full + i, kProdThreads); mbar_init(a_free + i, 3); mbar_init(d_ready + i, kEpiThreads); }
+    for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, kProdThreads); mbar_init(a_free + i, 3); mbar_init(d_ready + i, kEpiThreads); }
     for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_free + i, kEpiThreads); }
     for (int i = 0; i < 4; ++i) { mbar_init(z_full + i, 2); mbar_init(z_free + i, kEpiThreads); }
     fence_barrier_init();
@@ -207,7 +211,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
     // so row p holds the nine terms of the 3x3 sum at p; out-of-image q store zeros (zero padding of the dense
     // layers), so the sums need no masks.
     auto gather = [&](int k, const TileIt& it) {
-      const int s = k & 1, u = k % g.nbuf;
+      const int s = k & 1, u = (k * g.KS + g.KS - 1) % g.nbuf;      // u: ring slot of this tile's x1+d chunk
       int r0, c0;
       it.origin(g, r0, c0);
       // positions of this thread in the d1 / d2 passes and the hoisted conditioning terms (prefetched)
@@ -272,7 +276,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       named_bar_sync(bar_id, kEpiThreads);
       // d2 on the halo-1 region, evaluated at the replicate-clamped pixel (Conv2dZeros pads by replication);
       // the (d1, d2) pair goes into K slots kd, kd+1 of the A buffer
-      uint8_t* dslot = A + (size_t)u * g.bufA + (size_t)(g.kd >> 3) * kPLB + (size_t)(g.kd & 7) * 2;
+      uint8_t* dslot = A + (size_t)u * g.bufA + kPLB + (size_t)(g.kd & 7) * 2;      // second plane of the chunk, channels 6,7
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (ok2[j]) {
@@ -293,7 +297,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         }
       }
       fence_proxy_async();
-      mbar_arrive(d_ready + u);
+      mbar_arrive(d_ready + (k & 3));
       PROF_MARK(2)
     };
 
@@ -444,7 +448,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
     if (NG == 2) {
       TileIt itf, itg;
       itf.init(blockIdx.x + grp * gridDim.x, tiles_img); itg = itf;
-      if (NZ == 4 && g.nbuf >= 3) {          // gather of this group's next tile overlaps the Z MMAs of the current one
+      if (NZ == 4 && g.pipelined) {          // gather of this group's next tile overlaps the Z MMAs of the current one
         if (grp < nmy) gather(grp, itg);
         for (int k = grp; k < nmy; k += 2) {
           itg.advance(g, tiles_img); itg.advance(g, tiles_img);
@@ -480,37 +484,38 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
     const int role = warp - kMmaWarp;         // 0: E, 1: Z of M tile 0 (columns 0-7), 2: Z of M tile 1 (columns 8-15)
     if (elect_one()) {
       const uint64_t hlA16 = g.hlA >> 4;
+      const int nsrc1 = g.KS - g.KSy;            // conditioning chunks staged (and consumed) before the x1+d chunks
       PROF_DECL
       if (role == 0) {
         const uint32_t idE = idesc_f16(32);
         const uint64_t bE0 = make_desc(smem_u32(WE), 512, 128);
         const uint64_t wEhl16 = g.wE_hl >> 4;
+        int c = 0;                                // running chunk counter
         for (int k = 0; k < nmy; ++k) {
-          const int s = k & 1, u = k % g.nbuf;
+          const int s = k & 1;
           PROF_MARK(0)
-          mbar_wait(a_full + u, (uint32_t)((k / g.nbuf) & 1));
-          PROF_MARK(1)
           if (k >= 2) mbar_wait(e_free + s, (uint32_t)(((k >> 1) - 1) & 1));
           PROF_MARK(2)
-          tc_fence_after();
-          const uint64_t aE0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, 128);
           const uint32_t tE = tmem_base + (uint32_t)(s * 128);
+          for (int j = 0; j < g.KS; ++j, ++c) {
+            const int u = c % g.nbuf;
+            const int wk = j < nsrc1 ? g.KSy + j : j - nsrc1;        // K-step of the packed weights
+            mbar_wait(a_full + u, (uint32_t)((c / g.nbuf) & 1));
+            tc_fence_after();
+            const uint64_t aE0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, 128);
+            const uint64_t bd = bE0 + (uint64_t)wk * (uint64_t)(2 * 512 >> 4);
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            uint64_t ad = aE0 + (uint64_t)(mt * 128);          // 128 positions x 16 B, in 16-byte units
-            uint64_t bd = bE0;
-            for (int ks = 0; ks < g.KS; ++ks) {
-              mma_f16(tE + (uint32_t)(mt * 32), ad, bd, idE, ks > 0 ? 1u : 0u);
+            for (int mt = 0; mt < 4; ++mt) {
+              const uint64_t ad = aE0 + (uint64_t)(mt * 128);          // 128 positions x 16 B, in 16-byte units
+              mma_f16(tE + (uint32_t)(mt * 32), ad, bd, idE, j > 0 ? 1u : 0u);
               if (X3) {
                 mma_f16(tE + (uint32_t)(mt * 32), ad + hlA16, bd, idE, 1u);
                 mma_f16(tE + (uint32_t)(mt * 32), ad, bd + wEhl16, idE, 1u);
               }
-              ad += (uint64_t)(2 * kPLB >> 4);
-              bd += (uint64_t)(2 * 512 >> 4);
             }
+            mma_commit(a_free + u);
           }
           mma_commit(e_full + s);
-          mma_commit(a_free + u);
           PROF_MARK(3)
         }
         PROF_FLUSH(8)
@@ -519,33 +524,38 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         const uint32_t idZ = idesc_f16(NP);
         const uint64_t bZ0 = make_desc(smem_u32(WZ), (uint32_t)NP * 16u, 128);
         const uint64_t wZhl16 = g.wZ_hl >> 4, wZtap16 = g.wZ_tap >> 4;
+        int c = 0;
         for (int k = 0; k < nmy; ++k) {
-          const int s = k & (NZ - 1), u = k % g.nbuf;
+          const int s = k & (NZ - 1);
           PROF_MARK(0)
-          mbar_wait(d_ready + u, (uint32_t)((k / g.nbuf) & 1));
-          PROF_MARK(4)
           if (k >= NZ) mbar_wait(z_free + s, (uint32_t)(((k / NZ) - 1) & 1));
           PROF_MARK(5)
-          tc_fence_after();
-          const uint64_t aZ0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, kRP * 16) + (uint64_t)(8 * mt);
           const uint32_t tZ = tmem_base + (uint32_t)(256 + s * ZW + mt * NP);
+          for (int j = 0; j < g.KS; ++j, ++c) {
+            const int u = c % g.nbuf;
+            const int wk = j < nsrc1 ? g.KSy + j : j - nsrc1;
+            mbar_wait(a_full + u, (uint32_t)((c / g.nbuf) & 1));
+            if (j == g.KS - 1) {                   // the chunk that carries d1, d2: wait for the gather of this tile
+              PROF_MARK(6)
+              mbar_wait(d_ready + (k & 3), (uint32_t)((k >> 2) & 1));
+              PROF_MARK(4)
+            }
+            tc_fence_after();
+            const uint64_t aZ0 = make_desc(smem_u32(A + (size_t)u * g.bufA), kPLB, kRP * 16) + (uint64_t)(8 * mt);
+            const uint64_t bk = bZ0 + (uint64_t)wk * (uint64_t)(2 * NP);   // 2 planes x NP rows x 16 B, in 16-byte units
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            uint64_t ad = aZ0 + (uint64_t)((3 + tap / 3 - 1) * kRP + 3 + tap % 3 - 1);
-            uint64_t bd = bZ0 + (uint64_t)tap * wZtap16;
-            for (int ks = 0; ks < g.KS; ++ks) {
-              const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
-              mma_f16(tZ, ad, bd, idZ, acc);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t ad = aZ0 + (uint64_t)((3 + tap / 3 - 1) * kRP + 3 + tap % 3 - 1);
+              const uint64_t bd = bk + (uint64_t)tap * wZtap16;
+              mma_f16(tZ, ad, bd, idZ, (tap > 0 || j > 0) ? 1u : 0u);
               if (X3) {
                 mma_f16(tZ, ad + hlA16, bd, idZ, 1u);
                 mma_f16(tZ, ad, bd + wZhl16, idZ, 1u);
               }
-              ad += (uint64_t)(2 * kPLB >> 4);
-              bd += (uint64_t)(2 * NP);                        // 2 planes x NP rows x 16 B, in 16-byte units
             }
+            mma_commit(a_free + u);
           }
           mma_commit(z_full + s);
-          mma_commit(a_free + u);
           PROF_MARK(6)
         }
         if (role == 1) { PROF_FLUSH(24) }
@@ -555,89 +565,94 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
     // =========================================================== producers (128 threads): stage relu(t) as fp16 hi/lo
     const int ptid = tid - kProdWarp * 32;
     const int npl0 = 2 * g.KSy;
-    const int nst0 = (a.src[0].nch + 7) / 8;                                     // staged planes of src0
-    const int nstage = nst0 + ((!a.hoist && a.nsrc > 1) ? (a.src[1].nch + 7) / 8 : 0);
+    const int nsrc1 = g.KS - g.KSy;
     TileIt it;
     it.init(blockIdx.x, tiles_img);
     PROF_DECL
+    int c = 0;                                    // running chunk counter
     for (int k = 0; k < nmy; ++k) {
-      const int u = k % g.nbuf, use = k / g.nbuf;
       const int b = it.b;
       int r0, c0;
       it.origin(g, r0, c0);
       it.advance(g, tiles_img);
-      PROF_MARK(0)
-      if (use >= 1) mbar_wait(a_free + u, (uint32_t)((use - 1) & 1));
-      PROF_MARK(1)
-      uint8_t* Ab = A + (size_t)u * g.bufA;
-      // planes that hold source channels (pure padding / d-slot planes were zeroed once and are never staged)
-      const int items = kNPOS * nstage;
-      for (int it0 = ptid; it0 < items; it0 += kProdThreads * 4) {
-        float v[4][8];
-        int pos[4], pln[4];
-        bool relu[4];
+      for (int j = 0; j < g.KS; ++j, ++c) {
+        const int u = c % g.nbuf, use = c / g.nbuf;
+        const int wk = j < nsrc1 ? g.KSy + j : j - nsrc1;            // K-step in the K layout [src0 + d | src1]
+        PROF_MARK(0)
+        if (use >= 1) mbar_wait(a_free + u, (uint32_t)((use - 1) & 1));
+        PROF_MARK(1)
+        uint8_t* Ab = A + (size_t)u * g.bufA;
+        // 2 planes x 484 positions; batches of up to 4 items per thread, loads first
+        for (int it0 = ptid; it0 < 2 * kNPOS; it0 += kProdThreads * 4) {
+          float v[4][8];
+          int pos[4], lpl[4];
+          bool relu[4], hasd[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int itx = it0 + q * kProdThreads;
-          pos[q] = -1; pln[q] = 0; relu[q] = true;
+          for (int q = 0; q < 4; ++q) {
+            const int itx = it0 + q * kProdThreads;
+            pos[q] = -1; lpl[q] = 0; relu[q] = true; hasd[q] = false;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
-          if (itx < items) {
-            const int p = itx % kNPOS, sp = itx / kNPOS;
-            const bool s1 = sp >= nst0;
-            const int plane = s1 ? npl0 + (sp - nst0) : sp;
-            const int rr = p / kRP, rc = p - rr * kRP;
-            const int r = min(max(r0 - 3 + rr, 0), a.H - 1), c = min(max(c0 - 3 + rc, 0), a.W - 1);
-            const ConvSrc& sc = a.src[s1 ? 1 : 0];
-            const int ch = (s1 ? sp - nst0 : sp) * 8;
-            const int nv = min(8, sc.nch - ch);
-            pos[q] = p; pln[q] = plane; relu[q] = sc.relu != 0;
-            const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c;
-            const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
-            if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (nv & 1) == 0) {
-              if (nv >= 4) { const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; v[q][2] = t0.z; v[q][3] = t0.w; }
-              else { const float2 t0 = __ldg(reinterpret_cast<const float2*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; }
-              if (nv == 8) { const float4 t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1); v[q][4] = t1.x; v[q][5] = t1.y; v[q][6] = t1.z; v[q][7] = t1.w; }
-              else if (nv == 6) { const float2 t1 = __ldg(reinterpret_cast<const float2*>(ptr) + 2); v[q][4] = t1.x; v[q][5] = t1.y; }
+            for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+            if (itx < 2 * kNPOS) {
+              const int lp = itx >= kNPOS ? 1 : 0, p = itx - lp * kNPOS;
+              const int plane = 2 * wk + lp;                          // plane in the K layout
+              const bool s1 = plane >= npl0;
+              const ConvSrc& sc = a.src[s1 ? 1 : 0];
+              const int ch = (s1 ? plane - npl0 : plane) * 8;
+              const int nv = min(8, sc.nch - ch);                     // <= 0: pure padding (or the d-slot plane)
+              pos[q] = p; lpl[q] = lp; relu[q] = sc.relu != 0;
+              hasd[q] = !s1 && (g.kd >> 3) == plane;
+              if (nv <= 0 && g.KS == 1) pos[q] = -1;      // one chunk type only: its padding plane was zeroed once and stays zero
+              if (nv > 0) {
+                const int rr = p / kRP, rc = p - rr * kRP;
+                const int r = min(max(r0 - 3 + rr, 0), a.H - 1), cc = min(max(c0 - 3 + rc, 0), a.W - 1);
+                const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + cc;
+                const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
+                if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (nv & 1) == 0) {
+                  if (nv >= 4) { const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; v[q][2] = t0.z; v[q][3] = t0.w; }
+                  else { const float2 t0 = __ldg(reinterpret_cast<const float2*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; }
+                  if (nv == 8) { const float4 t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1); v[q][4] = t1.x; v[q][5] = t1.y; v[q][6] = t1.z; v[q][7] = t1.w; }
+                  else if (nv == 6) { const float2 t1 = __ldg(reinterpret_cast<const float2*>(ptr) + 2); v[q][4] = t1.x; v[q][5] = t1.y; }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (e < nv) v[q][e] = __ldg(ptr + e);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (pos[q] < 0) continue;
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float y0 = fminf(v[q][2 * e], 60000.f), y1 = fminf(v[q][2 * e + 1], 60000.f);
+              y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
+              const __half2 h2 = __floats2half2_rn(y0, y1);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+              ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            // the d slots (last 32-bit word of their plane) are owned by the epilogue warps
+            uint8_t* dst = Ab + (size_t)lpl[q] * kPLB + (size_t)pos[q] * 16;
+            if (hasd[q]) {
+              uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+              d32[0] = ph[0]; d32[1] = ph[1]; d32[2] = ph[2];
+              if (X3) {
+                uint32_t* l32 = reinterpret_cast<uint32_t*>(dst + g.hlA);
+                l32[0] = pl[0]; l32[1] = pl[1]; l32[2] = pl[2];
+              }
             } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) if (e < nv) v[q][e] = __ldg(ptr + e);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (pos[q] < 0) continue;
-          uint32_t ph[4], pl[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float y0 = fminf(v[q][2 * e], 60000.f), y1 = fminf(v[q][2 * e + 1], 60000.f);
-            y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
-            const __half2 h2 = __floats2half2_rn(y0, y1);
-            const float2 hf = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
-            ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
-            pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
-          }
-          // the d slots of this plane (if any) are owned by the epilogue warps: keep what is there
-          const bool has_d = (g.kd >> 3) == pln[q];
-          uint8_t* dst = Ab + (size_t)pln[q] * kPLB + (size_t)pos[q] * 16;
-          if (has_d) {        // kd & 7 == 6: the pair sits in the last 32-bit word
-            uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-            d32[0] = ph[0]; d32[1] = ph[1]; d32[2] = ph[2];
-            if (X3) {
-              uint32_t* l32 = reinterpret_cast<uint32_t*>(dst + g.hlA);
-              l32[0] = pl[0]; l32[1] = pl[1]; l32[2] = pl[2];
-            }
-          } else {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-          }
-        }
+        fence_proxy_async();
+        mbar_arrive(a_full + u);
+        PROF_MARK(2)
       }
-      fence_proxy_async();
-      mbar_arrive(a_full + u);
-      PROF_MARK(2)
     }
     if (ptid == 0) { PROF_FLUSH(16) }
   }
@@ -682,7 +697,7 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g, int grid) {
   g.KSy = KSy; g.kd = kd; g.PLtot = 2 * (KSy + KS1);
   g.KS = (a.hoist || a.nsrc < 2) ? KSy : KSy + KS1;
   g.nhl = a.x3 ? 2 : 1;
-  g.hlA = (uint32_t)(2 * g.KS) * kPLB;
+  g.hlA = 2 * kPLB;                 // one ring slot = one K-step: [hi | lo][2 planes][512 positions][16 B]
   g.bufA = g.hlA * g.nhl;
   g.tiles_x = cdiv(a.W, 16); g.tiles_y = cdiv(a.H, 16);
   const int tiles_img = g.tiles_x * g.tiles_y;
@@ -694,9 +709,10 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g, int grid) {
   g.gE_hl = (uint32_t)g.PLtot * 512; g.gZ_hl = (uint32_t)g.PLtot * NP * 16; g.gZ_tap = 2 * g.gZ_hl;
   g.wE_hl = (uint32_t)(2 * g.KS) * 512; g.wZ_hl = (uint32_t)(2 * g.KS) * NP * 16; g.wZ_tap = g.nhl * g.wZ_hl;
   g.scratch = (uint32_t)(2 * (kNPOSA + 64) * 9 + kNPOSA) * 4;
-  // preference: two epilogue groups (narrow levels only: register budget) with the deepest A ring that fits
+  // preference: two epilogue groups (narrow levels only: register budget) with the deepest K-step ring that fits
+  // (at most 4 slots; at least KS so that a whole tile can be resident)
   for (int ng = (a.C <= 24 ? 2 : 1); ng >= 1; --ng) {
-    for (int nbuf = 3; nbuf >= (ng == 2 ? 2 : 1); --nbuf) {
+    for (int nbuf = 4; nbuf >= std::max(g.KS, 2); --nbuf) {
       uint32_t off = 0;
       auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
       g.nbuf = nbuf; g.ngroups = ng;
@@ -705,9 +721,10 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g, int grid) {
       g.oWE = take(g.nhl * g.wE_hl);
       g.oWZ = take(9u * g.wZ_tap);
       g.oWm = take((uint32_t)(a.C * a.C + 4 * a.C + 9 + 3) * 4);
-      g.oBar = take(21 * 8 + 16);
+      g.oBar = take(24 * 8 + 16);
       g.total = off;
-      if (g.total <= 227 * 1024) { g.pipelined = nbuf >= 2; return true; }
+      // pipelining across tiles needs room for the next tile's chunks while this tile's x1+d chunk is held
+      if (g.total <= 227 * 1024) { g.pipelined = nbuf >= g.KS + 1; return true; }
     }
   }
   return false;
