@@ -190,6 +190,7 @@ struct Step2Args {
   int dc_stride;
   const float* hc;         // [HW][hc_stride]: cond part of the Conv2dZeros output (before bias and gain)
   int hc_stride;
+  int hoist_bstride;       // 0: one table shared by all samples; 1: tables per sample ([B][HW][stride])
   const void* wE;          // fp16 [hl][planes][32][8]   taps of dense layers 1 (cols 0-8) and 2 (cols 16-24)
   const void* wZ;          // fp16 [tap][hl][planes][NP][8]
   const float* wmisc;      // [0..8] taps of layer 2's d1 input row, [9..11] inverse weight scales (w1, w2, w3)

@@ -120,6 +120,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float inv = a.inv_scale ? __ldg(a.inv_scale) : 1.f;
     const float gain = a.gain ? __ldg(a.gain) : 1.f;
+    const bool vec_ok = (a.out_cstride & 3) == 0 && (a.out_coff & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
     CvTileIt it;
     it.init(blockIdx.x, tiles_img);
     for (int k = 0; k < nmy; ++k) {
@@ -183,13 +184,18 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
               float* op = a.out + pix * a.out_cstride + a.out_coff + n0;
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                if (n0 + e < a.cout) {
-                  float t = fmaf(v[e], inv, s_bias[n0 + e]);
-                  if (a.gain) t *= gain;
-                  if (a.act == 1) t = fmaxf(t, 0.f);
-                  else if (a.act == 2) t = fminf(fmaxf(t, -2.f), kLog5);
-                  op[e] = t;
-                }
+                float t = fmaf(v[e], inv, s_bias[n0 + e]);
+                if (a.gain) t *= gain;
+                if (a.act == 1) t = fmaxf(t, 0.f);
+                else if (a.act == 2) t = fminf(fmaxf(t, -2.f), kLog5);
+                v[e] = t;
+              }
+              if (vec_ok && n0 + 16 <= a.cout) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) if (n0 + e < a.cout) op[e] = v[e];
               }
             }
           }

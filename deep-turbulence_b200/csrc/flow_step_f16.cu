@@ -231,8 +231,9 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
         pcl[j] = (irc - (r0 - 3)) * kRP + (icc - (c0 - 3));
         ok2[j] = ok2[j] && pcl[j] >= 2 * kRP + 2 && pcl[j] < 20 * kRP;
         if (a.hoist) {
-          if (ok1[j] && in1[j]) dcv1[j] = __ldg(a.dc + (size_t)(ir * a.W + ic) * a.dc_stride);
-          if (ok2[j]) dcv2[j] = __ldg(a.dc + (size_t)(irc * a.W + icc) * a.dc_stride + 1);
+          const size_t hb = a.hoist_bstride ? (size_t)it.b * HW : 0;
+          if (ok1[j] && in1[j]) dcv1[j] = __ldg(a.dc + (hb + (size_t)(ir * a.W + ic)) * a.dc_stride);
+          if (ok2[j]) dcv2[j] = __ldg(a.dc + (hb + (size_t)(irc * a.W + icc)) * a.dc_stride + 1);
         }
       }
       PROF_MARK(0)
@@ -314,7 +315,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       float v[C];
       constexpr int NHC = C <= 24 ? C / 4 : 1;
       float4 hcv[NHC];
-      const float4* hcp = (a.hoist && valid) ? reinterpret_cast<const float4*>(a.hc + (size_t)(ir * a.W + ic) * a.hc_stride) : nullptr;
+      const float4* hcp = (a.hoist && valid) ? reinterpret_cast<const float4*>(a.hc + ((a.hoist_bstride ? (size_t)b * HW : 0) + (size_t)(ir * a.W + ic)) * a.hc_stride) : nullptr;
       if (valid) {
         const float4* y4 = reinterpret_cast<const float4*>(a.y_in + pix * C);
 #pragma unroll

@@ -82,6 +82,10 @@ struct LevelW {
   // hoisted conditioning tables (one LF input shared by all samples): packed weight slices [9][cond][OP]
   int64_t hoist_wd = -1, hoist_wh = -1;
   int hoist_opd = 0, hoist_oph = 0;
+  int64_t hoist_od = -1, hoist_oh = -1;            // the same slices as OIHW (phase 1) ...
+  struct HoistChunk { ConvW w; int col0; };
+  std::vector<HoistChunk> hoist_f16[2];            // ... packed for conv3x3_f16 in phase 2 (per-sample hoisting),
+                                                   // in column chunks of at most 256 outputs
 };
 
 }  // namespace tmg
@@ -101,6 +105,8 @@ struct tmg_model {
   int cmax = 0;
   std::vector<PackJob> jobs;
   PackJob* jobs_dev = nullptr;
+  std::vector<PackJob> jobs2;       // phase 2: sources are in the packed buffer (written by phase 1)
+  PackJob* jobs2_dev = nullptr;
   float* packed = nullptr;          // derived weights
   int64_t step_const_off = 0;       // inside packed
   float* params = nullptr;          // borrowed flat parameter buffer
@@ -340,6 +346,29 @@ static int build_model(tmg_model& m) {
     lv.hoist_oph = (n * C + 3) / 4 * 4;
     lv.hoist_wd = B.pack_alloc((int64_t)9 * c.cond_features * lv.hoist_opd);
     lv.hoist_wh = B.pack_alloc((int64_t)9 * c.cond_features * lv.hoist_oph);
+    lv.hoist_od = B.pack_alloc((int64_t)9 * c.cond_features * lv.hoist_opd);
+    lv.hoist_oh = B.pack_alloc((int64_t)9 * c.cond_features * lv.hoist_oph);
+    for (int kind = 0; kind < 2; ++kind) {        // phase-2 fp16 packing of the concatenated slices (conv3x3_f16.cu)
+      const int total = kind ? n * C : 2 * n;       // real columns (the 4-padding columns are never read)
+      const int unit = kind ? C : 2;                // keep a step's columns in one chunk
+      const int per = std::max(unit, 256 / unit * unit);
+      for (int col0 = 0; col0 < total; col0 += per) {
+        LevelW::HoistChunk hc{};
+        hc.col0 = col0;
+        ConvW& cw = hc.w;
+        cw.O = std::min(per, total - col0); cw.I = c.cond_features; cw.NP = tc_npad(cw.O);
+        const int nch[3] = {c.cond_features, 0, 0};
+        cw.w_pack_f16 = B.pack_alloc((int64_t)convf16_packed_floats(nch, 1, cw.NP));
+        cw.inv_f16 = B.pack_alloc(1);
+        PackJob j{};
+        j.type = JOB_CONV_F16; j.a = cw.O; j.b = cw.I; j.opad = cw.NP; j.nch0 = c.cond_features; j.nch1 = 0; j.nd = 0;
+        for (auto& q : j.src) q = -1;
+        j.src[0] = (kind ? lv.hoist_oh : lv.hoist_od) + (int64_t)col0 * c.cond_features * 9;   // offset into the PACKED buffer
+        j.dst[0] = cw.w_pack_f16; j.dst[1] = cw.inv_f16;
+        m.jobs2.push_back(j);
+        lv.hoist_f16[kind].push_back(hc);
+      }
+    }
     for (int s = 0; s < n; ++s) {
       const StepW& st = lv.steps[s];
       if (st.kind == STEP_LSTM) continue;       // its coupling net reads the LSTM output, not cond
@@ -350,6 +379,7 @@ static int build_model(tmg_model& m) {
         for (auto& q : j.src) q = -1;
         j.src[0] = st.d1.w_param; j.src[1] = st.d2.w_param; j.src[2] = st.zc.w_param;
         j.dst[0] = kind ? lv.hoist_wh : lv.hoist_wd;
+        j.dst[1] = kind ? lv.hoist_oh : lv.hoist_od;
         m.jobs.push_back(j);
       }
     }
@@ -415,8 +445,8 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
     const LevelW& lv = m.levels[l];
     p.db[l] = take(Bx * p.eh[l] * p.ew[l] * lv.nf_out);
     p.cond[l] = take(Bx * p.Hl[l] * p.Wl[l] * c.cond_features);
-    p.dc_all[l] = take((size_t)p.Hl[l] * p.Wl[l] * lv.hoist_opd);
-    p.hc_all[l] = take((size_t)p.Hl[l] * p.Wl[l] * lv.hoist_oph);
+    p.dc_all[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.hoist_opd);
+    p.hc_all[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.hoist_oph);
     p.y[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
     p.y2[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
     cc_max = std::max(cc_max, Bx * p.eh[l] * p.ew[l] * c.cond_features);
@@ -701,12 +731,13 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
       a.src[0] = ConvSrc{Y, C, 0, C / 2, 1};
       a.src[1] = ConvSrc{cond, cf, 0, cf, 1, c.p.shared};
       a.nsrc = 2;
-      if (c.p.shared && c.hoist_ready) {
+      if (c.hoist_ready) {
         const LevelW& lv = c.m.levels[level];
         const int sidx = (int)(&st - lv.steps.data());
         a.hoist = 1;
         a.dc = c.ws + c.p.dc_all[level] + 2 * sidx; a.dc_stride = lv.hoist_opd;
         a.hc = c.ws + c.p.hc_all[level] + (size_t)sidx * C; a.hc_stride = lv.hoist_oph;
+        a.hoist_bstride = c.p.shared ? 0 : 1;          // tables per sample (distinct LF inputs) or shared by all
       }
     }
     a.wE = c.Q() + st.s2_wE; a.wZ = c.Q() + st.s2_wZ; a.wmisc = c.Q() + st.s2_misc;
@@ -791,6 +822,32 @@ static int run_split_prior(Ctx& c, int level, int B, int Hl, int Wl, const float
 //   hc_all[pix][s*C + n]    = conv3x3_replicate(relu(cond), zero_conv_s cond rows)       (before bias and gain)
 static int run_hoist(Ctx& c) {
   const tmg_config& g = c.m.cfg;
+  if (!c.p.shared) {
+    // distinct LF inputs: the same tables per sample, as two tensor-core convolutions per level (N = all steps at
+    // once) -- the conditioning K-steps leave the 15 step kernels of the level and run as one well-shaped GEMM
+    for (int l = 0; l < c.p.L; ++l) {
+      const LevelW& lv = c.m.levels[l];
+      for (int kind = 0; kind < 2; ++kind) {
+        for (const auto& hc : lv.hoist_f16[kind]) {
+          const ConvW& cw = hc.w;
+          ConvF16Args t{};
+          t.src[0] = ConvSrc{c.ws + c.p.cond[l], g.cond_features, 0, g.cond_features, 1, 0};
+          t.nsrc = 1;
+          t.wpk = c.Q() + cw.w_pack_f16; t.inv_scale = c.Q() + cw.inv_f16; t.npad = cw.NP; t.cout = cw.O;
+          t.out = c.ws + (kind ? c.p.hc_all[l] : c.p.dc_all[l]);
+          t.out_cstride = kind ? lv.hoist_oph : lv.hoist_opd; t.out_coff = hc.col0;
+          t.B = c.p.B; t.H = c.p.Hl[l]; t.W = c.p.Wl[l]; t.pad_replicate = kind;
+          t.x3 = prec_split(c.m.precision) ? 1 : 0;
+          if (!convf16_supported(t)) { set_error("hoisted conditioning conv: unsupported shape"); return TMG_ERR_UNSUPPORTED; }
+          const double M = (double)t.B * t.H * t.W;
+          ProfScope ps(c.st, PROF_MISC, 2.0 * M * cw.O * 9.0 * cw.I, 4.0 * M * (cw.I + cw.O));
+          TMG_TRY(launch_conv3x3_f16(t, c.st));
+        }
+      }
+    }
+    c.hoist_ready = true;
+    return TMG_OK;
+  }
   for (int l = 0; l < c.p.L; ++l) {
     const LevelW& lv = c.m.levels[l];
     for (int kind = 0; kind < 2; ++kind) {
@@ -895,6 +952,7 @@ int tmg_model_create(const tmg_config* cfg, tmg_model** out) {
 void tmg_model_destroy(tmg_model* m) {
   if (!m) return;
   if (m->jobs_dev) cudaFree(m->jobs_dev);
+  if (m->jobs2_dev) cudaFree(m->jobs2_dev);
   if (m->packed) cudaFree(m->packed);
   delete m;
 }
@@ -935,9 +993,14 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
     TMG_CUDA_OK(cudaMemset(m->packed, 0, (size_t)m->n_packed * sizeof(float)));
     TMG_CUDA_OK(cudaMalloc(&m->jobs_dev, m->jobs.size() * sizeof(PackJob)));
     TMG_CUDA_OK(cudaMemcpy(m->jobs_dev, m->jobs.data(), m->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    if (!m->jobs2.empty()) {
+      TMG_CUDA_OK(cudaMalloc(&m->jobs2_dev, m->jobs2.size() * sizeof(PackJob)));
+      TMG_CUDA_OK(cudaMemcpy(m->jobs2_dev, m->jobs2.data(), m->jobs2.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    }
   }
   m->params = params;
   TMG_TRY(launch_pack(m->jobs_dev, (int)m->jobs.size(), params, m->packed, m->cmax, st));
+  if (!m->jobs2.empty()) TMG_TRY(launch_pack(m->jobs2_dev, (int)m->jobs2.size(), m->packed, m->packed, m->cmax, st));
   m->ready = true;
   return TMG_OK;
 }
@@ -1005,7 +1068,7 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const flo
   const int ldstride = p.nslots * p.ctas;
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
-  if (shared && prec_f16(m->precision)) TMG_TRY(run_hoist(c));
+  if (prec_f16(m->precision)) TMG_TRY(run_hoist(c));
 
   // top latent: z = cmean + exp(clamp(clog_std)) * eps[L]   (tmGlow.py:460-463); no log-prob term
   {
@@ -1070,7 +1133,7 @@ int tmg_forward(tmg_model* m, int B, int h, int w, const float* x, const float* 
   const int ldstride = p.nslots * p.ctas;
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
-  if (shared && prec_f16(m->precision)) TMG_TRY(run_hoist(c));
+  if (prec_f16(m->precision)) TMG_TRY(run_hoist(c));
   int slot = 0;
   float* yfinal[TMG_MAX_LEVELS] = {nullptr};
   for (int l = 0; l < L; ++l) {

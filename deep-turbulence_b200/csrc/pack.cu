@@ -152,18 +152,23 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
     // nd = kind, part = step index, nparts = steps.  One job per step.
     const int C = j.a, CF = j.b, OP = j.opad, s = j.part, row0 = j.nch0;
     float* d = Q + j.dst[0];
+    float* d2 = Q + j.dst[1];          // the same slice as OIHW [OP][CF][3][3] (source of the phase-2 fp16 packing)
     if (j.nd == 0) {
       const float* w1 = P + j.src[0]; const float* w2 = P + j.src[1];
       for (int i = tid; i < 9 * CF * 2; i += blockDim.x) {
         const int which = i & 1; int t = i >> 1; const int c = t % CF, tap = t / CF;
-        d[((size_t)tap * CF + c) * OP + 2 * s + which] = (which ? w2 : w1)[(size_t)(row0 + c) * 9 + tap];
+        const float v = (which ? w2 : w1)[(size_t)(row0 + c) * 9 + tap];
+        d[((size_t)tap * CF + c) * OP + 2 * s + which] = v;
+        d2[((size_t)(2 * s + which) * CF + c) * 9 + tap] = v;
       }
     } else {
       const float* w3 = P + j.src[2];
       const int I3 = row0 + CF + 2;
       for (int i = tid; i < 9 * CF * C; i += blockDim.x) {
         const int n = i % C; int t = i / C; const int c = t % CF, tap = t / CF;
-        d[((size_t)tap * CF + c) * OP + s * C + n] = w3[((size_t)n * I3 + row0 + c) * 9 + tap];
+        const float v = w3[((size_t)n * I3 + row0 + c) * 9 + tap];
+        d[((size_t)tap * CF + c) * OP + s * C + n] = v;
+        d2[((size_t)(s * C + n) * CF + c) * 9 + tap] = v;
       }
     }
   } else if (j.type == JOB_CONV_F16) {

@@ -15,3 +15,18 @@ for name, fn in (("sample(distinct x)", lambda h: m.sample(x, h)[2]), ("forward(
     for _ in range(5): hh = fn(hh)
     e1.record(); torch.cuda.synchronize()
     print(name, m.precision, "%.1f ms/call  %.0f samples/s" % (e0.elapsed_time(e1) / 5, B * 5 / (e0.elapsed_time(e1) * 1e-3)))
+
+# per-kernel-class device times of one un-shared sample() call
+import ctypes as C
+from tmglow_b200 import _lib
+lib = _lib.load()
+lib.tmg_profile_enable(1)
+hh = m.sample(x, h)[2]
+torch.cuda.synchronize()
+for t in range(lib.tmg_profile_classes()):
+    msv, n, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+    lib.tmg_profile_query(t, C.byref(msv), C.byref(n), C.byref(fl), C.byref(by))
+    if n.value:
+        print("   %-18s %7.3f ms  %3d launches  %7.1f TFLOP/s  %7.1f GB/s" % (lib.tmg_profile_class_name(t).decode(), msv.value, n.value,
+              fl.value / (msv.value * 1e-3) / 1e12, by.value / (msv.value * 1e-3) / 1e9))
+lib.tmg_profile_enable(0)
