@@ -97,6 +97,10 @@ struct ConvArgs {
   int out_cstride, out_coff, cout;
   int B, Hin, Win, Hout, Wout, stride;
   int pad_replicate;       // 0: zero padding, 1: replicate padding (Conv2dZeros)
+  // backward use (data gradient = the same kernel on flipped/transposed weights): gate the result with the sign of
+  // the forward input (ReLU) and accumulate into the destination
+  const float* mask;       // same layout as out (out_cstride, out_coff): result kept where mask > 0, or null
+  int accum;               // 1: out += result
 };
 int launch_conv3x3(const ConvArgs& a, cudaStream_t st);
 
@@ -317,6 +321,37 @@ struct LogdetArgs {
   int B;
 };
 int launch_logdet_reduce(const LogdetArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ backward building blocks (backward.cu)
+// Weight gradient of a 3x3 stride-1 convolution: gw[o][c][tap] = sum_{b,p} g[b,p,o] * xin[b,p+off(tap),c] with xin the
+// forward input (virtual concat, ReLU / padding applied while staging).  Deterministic: partial sums per pixel
+// split, reduced in a fixed order.
+struct WgradArgs {
+  ConvSrc src[3];
+  int nsrc;
+  int cin;                 // channels of the concatenation
+  const float* g;          // output gradient [B,HW,g_cstride], channels [g_coff, g_coff + cout)
+  int g_cstride, g_coff, cout;
+  int B, H, W;
+  int pad_replicate;
+  float* gw;               // OIHW [cout][cin][3][3], accumulated into (+=) when accum
+  float* gbias;            // [cout] column sums of g (+= when accum) or null
+  int accum;
+  float* scratch;          // >= wgrad_scratch_floats(...)
+};
+size_t wgrad_scratch_floats(int cout, int cin, int B, int H, int W);
+int launch_wgrad(const WgradArgs& a, cudaStream_t st);
+// tap-major transposed + flipped weights for the data gradient: wt[tap][o][c (padded to 4)] = w[o][c][8 - tap]
+int launch_pack_dgrad(const float* w_oihw, float* wt, int O, int I, cudaStream_t st);
+// replicate padding: adds the gradient of the out-of-image ring to the clamped border pixels
+struct RingArgs {
+  const float* g; int g_cstride, g_coff, cout;
+  const float* w_oihw; int cin_total, c0, nch;      // weight rows [c0, c0+nch) of the concatenation
+  const float* mask;                                  // forward input of this source (ReLU gate) or null
+  float* gx; int gx_cstride, gx_coff;
+  int B, H, W;
+};
+int launch_dgrad_ring(const RingArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,

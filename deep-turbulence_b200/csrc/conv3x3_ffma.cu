@@ -127,6 +127,7 @@ conv3x3_kernel(ConvArgs a, int plane, int rows_in_max) {
     if (!valid[j]) continue;
     int p = p0 + tid + j * kThreads;
     float* op = a.out + ((size_t)b * HWo + p) * a.out_cstride + a.out_coff + n0;
+    const float* mp = a.mask ? a.mask + ((size_t)b * HWo + p) * a.out_cstride + a.out_coff + n0 : nullptr;
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
       if (n0 + n < a.cout) {
@@ -135,7 +136,8 @@ conv3x3_kernel(ConvArgs a, int plane, int rows_in_max) {
         if (a.gain) v *= gain;
         if (a.act == 1) v = fmaxf(v, 0.f);
         else if (a.act == 2) v = fminf(fmaxf(v, -2.f), kLog5);
-        op[n] = v;
+        if (mp && !(__ldg(mp + n) > 0.f)) v = 0.f;
+        op[n] = a.accum ? op[n] + v : v;
       }
     }
   }

@@ -1283,6 +1283,53 @@ int tmg_conv3x3(int mode, const float* x, int B, int H, int W, int Cin, const fl
   return launch_conv3x3_tc(t, st);
 }
 
+// Backward of nn.Conv2d(Cin, Cout, 3, padding=1) (+ input ReLU, zero / replicate padding) on NHWC tensors: data
+// gradient, weight gradient (OIHW) and bias gradient.  Building block of the training path (autograd of every conv of
+// the flow, nn/trainFlowParallel.py:277 loss.backward()); exposed for gradient parity tests.
+size_t tmg_conv3x3_backward_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+  return ((size_t)9 * Cout * ((Cin + 3) / 4 * 4) + wgrad_scratch_floats(Cout, Cin, B, H, W) + 128) * sizeof(float);
+}
+
+int tmg_conv3x3_backward(const float* x, int B, int H, int W, int Cin, const float* w_oihw, int Cout, int relu_in,
+                         int pad_replicate, const float* gout, float* gx, float* gw, float* gbias, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!x || !w_oihw || !gout || !workspace) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (workspace_bytes < tmg_conv3x3_backward_workspace_bytes(B, H, W, Cin, Cout)) { set_error("workspace too small"); return TMG_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  const int Ip = (Cin + 3) / 4 * 4;
+  float* wt = ws;
+  float* scratch = ws + (size_t)9 * Cout * Ip + 64;
+  scratch = (float*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+  if (gw) {
+    WgradArgs wa{};
+    wa.src[0] = ConvSrc{x, Cin, 0, Cin, relu_in}; wa.nsrc = 1; wa.cin = Cin;
+    wa.g = gout; wa.g_cstride = Cout; wa.g_coff = 0; wa.cout = Cout;
+    wa.B = B; wa.H = H; wa.W = W; wa.pad_replicate = pad_replicate;
+    wa.gw = gw; wa.gbias = gbias; wa.accum = 0; wa.scratch = scratch;
+    TMG_TRY(launch_wgrad(wa, st));
+  }
+  if (gx) {
+    TMG_TRY(launch_pack_dgrad(w_oihw, wt, Cout, Cin, st));
+    ConvArgs a{};
+    a.src[0] = ConvSrc{gout, Cout, 0, Cout, 0}; a.nsrc = 1;
+    a.w = wt; a.cin_w = Cout; a.cout_w = Ip; a.cout = Cin;
+    a.out = gx; a.out_cstride = Cin; a.out_coff = 0;
+    a.B = B; a.Hin = H; a.Win = W; a.Hout = H; a.Wout = W; a.stride = 1;
+    a.mask = relu_in ? x : nullptr; a.accum = 0;
+    TMG_TRY(launch_conv3x3(a, st));
+    if (pad_replicate) {
+      RingArgs r{};
+      r.g = gout; r.g_cstride = Cout; r.g_coff = 0; r.cout = Cout;
+      r.w_oihw = w_oihw; r.cin_total = Cin; r.c0 = 0; r.nch = Cin;
+      r.mask = relu_in ? x : nullptr;
+      r.gx = gx; r.gx_cstride = Cin; r.gx_coff = 0; r.B = B; r.H = H; r.W = W;
+      TMG_TRY(launch_dgrad_ring(r, st));
+    }
+  }
+  return TMG_OK;
+}
+
 // Plan for the single-operator entry points: the workspace is sized by tmg_workspace_bytes of
 // an LF input whose level-`level` flow map is Hl x Wl.
 static int op_plan(tmg_model* m, int level, int B, int Hl, int Wl, Plan& p) {

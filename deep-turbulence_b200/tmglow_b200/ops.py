@@ -137,3 +137,32 @@ def conv3x3(x_nchw, weight, bias=None, relu_in=False, pad_replicate=False, act=0
                                    oh.data_ptr(), ws.data_ptr(), ws.numel(), st))
         _lib.check(lib.tmg_nhwc_to_nchw(oh.data_ptr(), out.data_ptr(), B, Cout, H, W, st))
     return out
+
+
+def conv3x3_backward(x_nchw, weight, gout_nchw, relu_in=False, pad_replicate=False):
+    """Gradients of ``F.conv2d(pad(relu?(x)), weight, bias)`` w.r.t. x, weight and bias through the library's backward
+    kernels (exact fp32): returns ``(gx [B,Cin,H,W], gw [Cout,Cin,3,3], gbias [Cout])``."""
+    _need_cuda(x_nchw)
+    device = x_nchw.device
+    lib = _lib.load()
+    x = x_nchw.detach().float().contiguous()
+    w = weight.detach().float().contiguous()
+    g = gout_nchw.detach().float().contiguous()
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    xh = torch.empty((B, H, W, Cin), dtype=torch.float32, device=device)
+    gh = torch.empty((B, H, W, Cout), dtype=torch.float32, device=device)
+    gxh = torch.empty((B, H, W, Cin), dtype=torch.float32, device=device)
+    gx = torch.empty_like(x)
+    gw = torch.empty_like(w)
+    gb = torch.empty(Cout, dtype=torch.float32, device=device)
+    ws = torch.empty(lib.tmg_conv3x3_backward_workspace_bytes(B, H, W, Cin, Cout), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        st = _stream(device)
+        _lib.check(lib.tmg_nchw_to_nhwc(x.data_ptr(), xh.data_ptr(), B, Cin, H, W, st))
+        _lib.check(lib.tmg_nchw_to_nhwc(g.data_ptr(), gh.data_ptr(), B, Cout, H, W, st))
+        _lib.check(lib.tmg_conv3x3_backward(xh.data_ptr(), B, H, W, Cin, w.data_ptr(), Cout, int(relu_in), int(pad_replicate),
+                                            gh.data_ptr(), gxh.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), st))
+        _lib.check(lib.tmg_nhwc_to_nchw(gxh.data_ptr(), gx.data_ptr(), B, Cin, H, W, st))
+    return gx, gw, gb

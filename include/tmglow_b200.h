@@ -173,6 +173,15 @@ int tmg_conv3x3(int mode, const float* x_nhwc, int B, int H, int W, int Cin, con
                 const float* bias, int Cout, int relu_in, int pad_replicate, int act, float* out_nhwc,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of the same convolution (autograd of F.conv2d as used by every conv of the path; first building block of
+ * training through TMGlow.sample, nn/trainFlowParallel.py:259-277): data gradient gx [B,H,W,Cin] (gated by the input
+ * ReLU when relu_in), weight gradient gw (OIHW) and bias gradient gbias [Cout]; any of the three may be NULL.
+ * Exact fp32, deterministic (fixed-order reductions, no atomics). */
+size_t tmg_conv3x3_backward_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int tmg_conv3x3_backward(const float* x_nhwc, int B, int H, int W, int Cin, const float* w_oihw, int Cout,
+                         int relu_in, int pad_replicate, const float* gout_nhwc, float* gx_nhwc, float* gw_oihw,
+                         float* gbias, void* workspace, size_t workspace_bytes, void* stream);
+
 /* layout helpers for the LSTM states at the API boundary */
 int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
