@@ -173,4 +173,237 @@ int launch_dgrad_ring(const RingArgs& a, cudaStream_t st) {
   return TMG_OK;
 }
 
+// ------------------------------------------------------------------ pointwise step backward
+constexpr int kSbThreads = 128;
+
+template <int C>
+__global__ void __launch_bounds__(kSbThreads)
+step_bwd_kernel(StepBwdArgs a) {
+  __shared__ __align__(16) float s_w[C * C];
+  __shared__ float s_nw[C], s_nb[C];
+  __shared__ float s_red[kSbThreads / 32][2 * C + 1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * kSbThreads + tid;
+  for (int i = tid; i < C * C; i += kSbThreads) s_w[i] = a.wmat ? __ldg(a.wmat + i) : ((i / C) == (i % C) ? 1.f : 0.f);
+  for (int i = tid; i < C; i += kSbThreads) { s_nw[i] = a.nw ? __ldg(a.nw + i) : 1.f; s_nb[i] = a.nw ? __ldg(a.nb + i) : 0.f; }
+  __syncthreads();
+  const float gain = __ldg(a.gain), gld = __ldg(a.g_ld + b);
+  float acc_nb[C], acc_nw[C], acc_gain = 0.f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) { acc_nb[i] = 0.f; acc_nw[i] = 0.f; }
+  if (p < a.HW) {
+    const size_t pix = (size_t)b * a.HW + p;
+    float y[C], h[C], v[C], gu[C];
+    const float4* y4 = reinterpret_cast<const float4*>(a.y_in + pix * C);
+    const float4* h4 = reinterpret_cast<const float4*>(a.h + pix * C);
+    const float4* g4 = reinterpret_cast<const float4*>(a.g_out + pix * C);
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      float4 t = __ldg(y4 + i); y[4 * i] = t.x; y[4 * i + 1] = t.y; y[4 * i + 2] = t.z; y[4 * i + 3] = t.w;
+      t = __ldg(h4 + i); h[4 * i] = t.x; h[4 * i + 1] = t.y; h[4 * i + 2] = t.z; h[4 * i + 3] = t.w;
+      t = __ldg(g4 + i); gu[4 * i] = t.x; gu[4 * i + 1] = t.y; gu[4 * i + 2] = t.z; gu[4 * i + 3] = t.w;
+    }
+    float ea[C / 2], dadr[C / 2];
+#pragma unroll
+    for (int j = 0; j < C / 2; ++j) {
+      const float raw = h[2 * j + 1], den = 1.f + fabsf(raw);
+      const float la = 2.f * (raw / den);
+      ea[j] = expf(-la);
+      dadr[j] = 2.f / (den * den);                 // d(2*softsign)/d raw
+      v[j] = y[j];
+      v[C / 2 + j] = fmaf(y[C / 2 + j], ea[j], -h[2 * j]);
+    }
+    // u = W v, out = (u - nb)/nw; g_u = g_out / nw
+#pragma unroll
+    for (int c = 0; c < C; ++c) gu[c] = gu[c] / s_nw[c];
+    if (a.nw) {
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        float u = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) u = fmaf(s_w[c * C + k], v[k], u);
+        const float out = (u - s_nb[c]) / s_nw[c];
+        acc_nb[c] = -gu[c];
+        acc_nw[c] = -gu[c] * out;
+      }
+    }
+    float gv[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) gv[k] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const float g = gu[c];
+#pragma unroll
+      for (int k = 0; k < C; ++k) gv[k] = fmaf(s_w[c * C + k], g, gv[k]);
+    }
+    float4* gu4 = reinterpret_cast<float4*>(a.gu + pix * C);
+    float4* v4 = reinterpret_cast<float4*>(a.v + pix * C);
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      gu4[i] = make_float4(gu[4 * i], gu[4 * i + 1], gu[4 * i + 2], gu[4 * i + 3]);
+      v4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    float gy[C], gz[C];
+#pragma unroll
+    for (int j = 0; j < C / 2; ++j) {
+      const float g2 = gv[C / 2 + j];
+      gy[j] = gv[j];
+      gy[C / 2 + j] = g2 * ea[j];
+      const float g_shift = -g2;
+      const float g_a = fmaf(-g2 * y[C / 2 + j], ea[j], gld);
+      const float g_raw = g_a * dadr[j];
+      acc_gain += (g_shift * h[2 * j] + g_raw * h[2 * j + 1]) / gain;
+      gz[2 * j] = g_shift * gain;
+      gz[2 * j + 1] = g_raw * gain;
+    }
+    float4* gy4 = reinterpret_cast<float4*>(a.g_y + pix * C);
+    float4* gz4 = reinterpret_cast<float4*>(a.g_z + pix * C);
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      gy4[i] = make_float4(gy[4 * i], gy[4 * i + 1], gy[4 * i + 2], gy[4 * i + 3]);
+      gz4[i] = make_float4(gz[4 * i], gz[4 * i + 1], gz[4 * i + 2], gz[4 * i + 3]);
+    }
+  }
+  // CTA partial sums in a fixed order: warp shuffle tree, then the four warps in order
+#pragma unroll
+  for (int i = 0; i < 2 * C + 1; ++i) {
+    float x = i < C ? acc_nb[i < C ? i : 0] : (i < 2 * C ? acc_nw[i < 2 * C ? (i >= C ? i - C : 0) : 0] : acc_gain);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[wid][i] = x;
+  }
+  __syncthreads();
+  float* pp = a.part + ((size_t)b * gridDim.x + blockIdx.x) * (2 * C + 1);
+  for (int i = tid; i < 2 * C + 1; i += kSbThreads) pp[i] = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
+}
+
+int step_bwd_blocks(int B, int HW) { return B * cdiv(HW, kSbThreads); }
+
+int launch_step_bwd(const StepBwdArgs& a, cudaStream_t st) {
+  dim3 grid(cdiv(a.HW, kSbThreads), a.B);
+  switch (a.C) {
+#define TMG_CASE(CC) case CC: step_bwd_kernel<CC><<<grid, kSbThreads, 0, st>>>(a); break;
+    TMG_CASE(4) TMG_CASE(8) TMG_CASE(12) TMG_CASE(16) TMG_CASE(24) TMG_CASE(32) TMG_CASE(48)
+#undef TMG_CASE
+    default:
+      set_error("step backward: %d channels not supported", a.C);
+      return TMG_ERR_UNSUPPORTED;
+  }
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+// out[c] (+)= sum over rows (fixed order) of part[row*row_stride + col0 + c]
+__global__ void reduce_cols_kernel(const float* __restrict__ part, int nrows, int row_stride, int col0, int ncols,
+                                   float* __restrict__ out, int accum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int r = 0; r < nrows; ++r) s += (double)part[(size_t)r * row_stride + col0 + c];
+  out[c] = accum ? out[c] + (float)s : (float)s;
+}
+int launch_reduce_cols(const float* part, int nrows, int row_stride, int col0, int ncols, float* out, int accum, cudaStream_t st) {
+  reduce_cols_kernel<<<cdiv(ncols, 64), 64, 0, st>>>(part, nrows, row_stride, col0, ncols, out, accum);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+// ------------------------------------------------------------------ 1x1 weight gradient: gw[o][k] = sum_px gu[px][o] v[px][k]
+constexpr int kOwThreads = 256, kOwTile = 32;
+__global__ void __launch_bounds__(kOwThreads)
+outer_wgrad_kernel(const float* __restrict__ gu, const float* __restrict__ v, int64_t npix, int C, int nsplit, float* part) {
+  extern __shared__ float sm[];
+  float* g_s = sm;                 // [tile][C]
+  float* v_s = sm + kOwTile * C;
+  const int tid = threadIdx.x, split = blockIdx.x;
+  const int npairs = C * C;
+  float acc[9];                    // C <= 48: at most 9 (o,k) pairs per thread
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  const int64_t ntiles = (npix + kOwTile - 1) / kOwTile;
+  for (int64_t t = split; t < ntiles; t += nsplit) {
+    const int64_t p0 = t * kOwTile;
+    const int np = (int)min((int64_t)kOwTile, npix - p0);
+    __syncthreads();
+    for (int i = tid; i < np * C; i += kOwThreads) { g_s[i] = __ldg(gu + p0 * C + i); v_s[i] = __ldg(v + p0 * C + i); }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int pr = tid + i * kOwThreads;
+      if (pr < npairs) {
+        const int o = pr / C, k = pr - o * C;
+        float s = acc[i];
+        for (int q = 0; q < np; ++q) s = fmaf(g_s[q * C + o], v_s[q * C + k], s);
+        acc[i] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int pr = tid + i * kOwThreads;
+    if (pr < npairs) part[(size_t)split * npairs + pr] = acc[i];
+  }
+}
+static int outer_splits(int64_t npix) { return (int)std::max<int64_t>(1, std::min<int64_t>(296, (npix + kOwTile - 1) / kOwTile)); }
+size_t outer_wgrad_scratch_floats(int64_t npix, int C) { return (size_t)outer_splits(npix) * C * C + 64; }
+int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, float* gw, float* scratch, cudaStream_t st) {
+  if (C * C > 9 * kOwThreads) { set_error("1x1 weight gradient: C=%d not supported", C); return TMG_ERR_UNSUPPORTED; }
+  const int ns = outer_splits(npix);
+  outer_wgrad_kernel<<<ns, kOwThreads, 2 * kOwTile * C * sizeof(float), st>>>(gu, v, npix, C, ns, scratch);
+  TMG_LAUNCH_CHECK();
+  reduce_partials_kernel<<<cdiv(C * C, 256), 256, 0, st>>>(scratch, gw, C * C, ns, 0);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+// ------------------------------------------------------------------ LU parameterisation + log-det constants, backward
+__global__ void __launch_bounds__(256)
+lu_bwd_kernel(LuBwdArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C, tid = threadIdx.x;
+  float* L = sm; float* U = L + C * C; float* A = U + C * C;
+  __shared__ float s_gld;
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    L[i] = a.l[i] * a.lmask[i] + a.eye[i];
+    U[i] = a.u[i] * a.umask[i] + (r == c ? expf(a.log_s[r]) * a.sign_s[r] : 0.f) + 0.01f * a.eye[i];
+  }
+  if (tid == 0) { double s = 0.0; for (int b = 0; b < a.B; ++b) s += (double)a.g_ld[b]; s_gld = (float)s; }
+  __syncthreads();
+  // A = P^T dW
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    float s = 0.f;
+    for (int q = 0; q < C; ++q) s = fmaf(a.p[q * C + r], a.dW[q * C + c], s);
+    A[i] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    float dl = 0.f, du = 0.f;
+    for (int j = 0; j < C; ++j) dl = fmaf(A[r * C + j], U[c * C + j], dl);        // dL = A U^T
+    for (int q = 0; q < C; ++q) du = fmaf(L[q * C + r], A[q * C + c], du);        // dU = L^T A
+    a.g_l[i] += dl * a.lmask[i];
+    a.g_u[i] += du * a.umask[i];
+    if (r == c) a.g_log_s[r] += du * a.sign_s[r] * expf(a.log_s[r]) - a.hw * s_gld;
+  }
+  if (a.nw) for (int c = tid; c < C; c += blockDim.x) a.g_nw[c] += a.hw * s_gld / a.nw[c];
+}
+// g_scale += S_gain * d gain/d scale, gain = exp(clamp(scale, -4, ln 4))  (flowUtils.py:247)
+__global__ void scale_grad_kernel(const float* s_gain, const float* scale_param, float* g_scale) {
+  const float sp = *scale_param;
+  if (sp > -4.f && sp < kLog4) *g_scale += *s_gain * expf(sp);
+}
+int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st) {
+  scale_grad_kernel<<<1, 1, 0, st>>>(s_gain, scale_param, g_scale);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st) {
+  lu_bwd_kernel<<<1, 256, 3 * a.C * a.C * sizeof(float), st>>>(a);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
 }  // namespace tmg

@@ -353,6 +353,45 @@ struct RingArgs {
 };
 int launch_dgrad_ring(const RingArgs& a, cudaStream_t st);
 
+// Pointwise part of one REVERSE flow step (z -> y, the direction training runs: TMGlow.sample), backward:
+//   forward:  a = 2*softsign(h_odd), v = [y1, y2*exp(-a) - h_even], u = W v, out = (u - nb)/nw,
+//             h = (z + b3)*gain with z the raw Conv2dZeros output, ld += sum(a)
+struct StepBwdArgs {
+  const float* y_in;       // [B,HW,C] step input
+  const float* h;          // [B,HW,C] coupling-net output (after bias and gain)
+  const float* g_out;      // [B,HW,C] gradient w.r.t. the step output
+  const float* g_ld;       // [B] gradient w.r.t. the per-sample log-det
+  const float* wmat;       // [C][C] W (or null: no mix)
+  const float* nw;         // ActNorm weight / bias or null
+  const float* nb;
+  const float* gain;       // scalar exp(clamp(scale))
+  float* g_y;              // [B,HW,C] gradient w.r.t. y_in (direct part: the coupling-net part is added by the conv dgrads)
+  float* g_z;              // [B,HW,C] gradient w.r.t. the raw Conv2dZeros output
+  float* gu;               // [B,HW,C] gradient w.r.t. u   (1x1 weight gradient = sum gu (x) v)
+  float* v;                // [B,HW,C] mixed vector v
+  float* part;             // per-CTA partial sums [nblocks][2C+1]: -sum gu | -sum gu*out | sum g_h*h/gain
+  int B, HW, C;
+};
+int launch_step_bwd(const StepBwdArgs& a, cudaStream_t st);
+int step_bwd_blocks(int B, int HW);
+// sum over CTAs (fixed order) of column-partials: out[i] (+)= scale * sum_k part[k][stride] ...
+int launch_reduce_cols(const float* part, int nrows, int row_stride, int col0, int ncols, float* out, int accum, cudaStream_t st);
+// gw[o][k] (+)= sum_px gu[px][o] * v[px][k]   (C x C), deterministic
+int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, float* gw, float* scratch, cudaStream_t st);
+size_t outer_wgrad_scratch_floats(int64_t npix, int C);
+// Chain rule of W = P (l*lm + I)(u*um + diag(sign*exp(log_s)) + 0.01 I)  (glowConv.py:151-160) and of the log-det
+// constants: g_l, g_u, g_log_s (+=), g_norm_w += HW/w * sum_b g_ld
+struct LuBwdArgs {
+  const float* dW;         // [C][C]
+  const float *l, *u, *log_s, *p, *sign_s, *lmask, *umask, *eye;
+  float *g_l, *g_u, *g_log_s;
+  const float* nw; float* g_nw;      // ActNorm weight and its gradient (or null)
+  const float* g_ld; int B; float hw;
+  int C;
+};
+int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st);
+int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st);
+
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
                    JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9 };

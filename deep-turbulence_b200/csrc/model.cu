@@ -66,6 +66,9 @@ struct StepW {
   // fp16 fused step (flow_step_f16.cu)
   int64_t s2_wE = -1, s2_wZ = -1, s2_misc = -1;
   int s2_nch0 = 0, s2_nch1 = 0;
+  // parameter offsets needed by the backward pass
+  int64_t lu[8] = {-1, -1, -1, -1, -1, -1, -1, -1};     // l, u, log_s, p, sign_s, l_mask, u_mask, eye
+  int64_t zc_scale = -1;
 };
 
 struct DenseW { ConvW conv; int64_t bn_w, bn_b, bn_rm, bn_rv; int64_t scale, shift; int cin; };
@@ -317,6 +320,7 @@ static int build_model(tmg_model& m) {
       st.W = B.pack_alloc((int64_t)C * C);
       st.Wi = B.pack_alloc((int64_t)C * C);
       st.const_idx = m.n_steps++;
+      for (int q = 0; q < 8; ++q) st.lu[q] = j.src[q];
       j.dst[0] = st.W; j.dst[1] = st.Wi; j.dst[2] = -1;   // step_const offset patched below
       j.b = st.const_idx;
       m.jobs.push_back(j);
@@ -329,6 +333,7 @@ static int build_model(tmg_model& m) {
         st.d1 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.dense_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
         int64_t sc = B.add(sp + "coupling.out_conv.zero_conv.scale", {1, 1, 1, 1});
+        st.zc_scale = sc;
         st.zc = B.conv(sp + "coupling.out_conv.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
         B.coupling_jobs(st, cin_t, 0, C);
@@ -337,6 +342,7 @@ static int build_model(tmg_model& m) {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
         int64_t sc = B.add(sp + "coupling.coupling_nn.zero_conv.scale", {1, 1, 1, 1});
+        st.zc_scale = sc;
         st.zc = B.conv(sp + "coupling.coupling_nn.zero_conv.conv", C, cin_t + 2, true, true);
         st.zc_gain = B.gain(sc);
         B.coupling_jobs(st, C / 2, c.cond_features, C);
@@ -1377,6 +1383,148 @@ int tmg_flow_step(tmg_model* m, int level, int step, int reverse, int B, int Hl,
   a.n_levels = 1; a.step_begin[0] = st.const_idx; a.step_begin[1] = st.const_idx + 1; a.hw[0] = HW;
   a.out = logdet; a.B = B;
   return launch_logdet_reduce(a, c.st);
+}
+
+// ---- backward of one REVERSE flow step (plain / un-normed steps): gradients w.r.t. the step input, the
+// conditioning map and every parameter of the step (accumulated into a flat gradient buffer laid out like the
+// parameter buffer).  The forward is recomputed with the exact-fp32 kernels.
+struct BwdExtra { size_t go, gy, gz, gu, v, gcond, gd, part, dw, tmp, wt3, wt2, wt1, wscr, oscr, total; };
+
+static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) {
+  const int C = m.levels[level].C, cf = m.cfg.cond_features, cin_t = C / 2 + cf;
+  const size_t px = (size_t)B * Hl * Wl;
+  BwdExtra e{};
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n, 64); return o; };
+  e.go = take(px * C); e.gy = take(px * C); e.gz = take(px * C); e.gu = take(px * C); e.v = take(px * C);
+  e.gcond = take(px * cf); e.gd = take(px * 2);
+  e.part = take((size_t)step_bwd_blocks(B, Hl * Wl) * (2 * C + 1));
+  e.dw = take((size_t)C * C); e.tmp = take(16);
+  e.wt3 = take((size_t)9 * C * ((cin_t + 2 + 3) / 4 * 4) + 64);
+  e.wt2 = take((size_t)9 * 1 * ((cin_t + 1 + 3) / 4 * 4) + 64);
+  e.wt1 = take((size_t)9 * 1 * ((cin_t + 3) / 4 * 4) + 64);
+  size_t ws = wgrad_scratch_floats(C, cin_t + 2, B, Hl, Wl);
+  ws = std::max(ws, wgrad_scratch_floats(1, cin_t + 1, B, Hl, Wl));
+  e.wscr = take(ws);
+  e.oscr = take(outer_wgrad_scratch_floats((int64_t)px, C));
+  e.total = off;
+  return e;
+}
+
+size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl) {
+  Plan p;
+  if (!m || op_plan(m, level, B, Hl, Wl, p) != TMG_OK) return 0;
+  return p.total + bwd_extra(*m, level, B, Hl, Wl).total * sizeof(float) + 256;
+}
+
+int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int Wl, const float* x, const float* cond,
+                           const float* g_out, const float* g_logdet, float* g_x, float* g_cond, float* grads,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  Plan p;
+  TMG_TRY(op_plan(m, level, B, Hl, Wl, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !cond || !g_out || !g_logdet || !g_x || !g_cond || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
+  const LevelW& lv = m->levels[level];
+  if (step < 1 || step > (int)lv.steps.size()) { set_error("bad step %d", step); return TMG_ERR_BAD_SHAPE; }
+  const StepW& st = lv.steps[step - 1];
+  if (st.kind == STEP_LSTM) { set_error("backward of the LSTM step is not implemented yet"); return TMG_ERR_UNSUPPORTED; }
+  const BwdExtra e = bwd_extra(*m, level, B, Hl, Wl);
+  if (workspace_bytes < p.total + e.total * sizeof(float)) { set_error("workspace too small for the backward pass"); return TMG_ERR_WORKSPACE; }
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  float* ex = (float*)((char*)workspace + align_up(p.total, 256));
+  const int HW = Hl * Wl, C = lv.C, cf = m->cfg.cond_features, cin_t = C / 2 + cf;
+  float* Y = ws + p.scratch_in;
+  float* CN = ws + p.scratch_cond;
+  float* D = ws + p.d;
+  float* HR = ws + p.hr;
+  float *GO = ex + e.go, *GY = ex + e.gy, *GZ = ex + e.gz, *GU = ex + e.gu, *V = ex + e.v, *GC = ex + e.gcond, *GD = ex + e.gd;
+  PermArgs pa{};
+  pa.mode = PERM_NCHW_TO_NHWC; pa.B = B; pa.H = Hl; pa.W = Wl;
+  pa.src = x; pa.dst = Y; pa.C = C; pa.dst_cstride = C; TMG_TRY(launch_permute(pa, c.st));
+  pa.src = g_out; pa.dst = GO; TMG_TRY(launch_permute(pa, c.st));
+  pa.src = cond; pa.dst = CN; pa.C = cf; pa.dst_cstride = cf; TMG_TRY(launch_permute(pa, c.st));
+  // forward recompute with the exact-fp32 kernels: D (d1, d2) and HR (h)
+  const int prec = m->precision;
+  m->precision = TMG_PREC_FP32;
+  int rc = run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, nullptr, nullptr, nullptr, nullptr);
+  m->precision = prec;
+  TMG_TRY(rc);
+  const bool normed = st.kind != STEP_UNNORMED;
+  StepBwdArgs sa{};
+  sa.y_in = Y; sa.h = HR; sa.g_out = GO; sa.g_ld = g_logdet;
+  sa.wmat = c.Q() + st.W;
+  if (normed) { sa.nw = c.P() + st.norm_w; sa.nb = c.P() + st.norm_b; }
+  sa.gain = c.Q() + st.zc_gain;
+  sa.g_y = GY; sa.g_z = GZ; sa.gu = GU; sa.v = V; sa.part = ex + e.part;
+  sa.B = B; sa.HW = HW; sa.C = C;
+  TMG_TRY(launch_step_bwd(sa, c.st));
+  const int nblk = step_bwd_blocks(B, HW), pstride = 2 * C + 1;
+  if (normed) {
+    TMG_TRY(launch_reduce_cols(ex + e.part, nblk, pstride, 0, C, grads + st.norm_b, 1, c.st));
+    TMG_TRY(launch_reduce_cols(ex + e.part, nblk, pstride, C, C, grads + st.norm_w, 1, c.st));
+  }
+  TMG_TRY(launch_reduce_cols(ex + e.part, nblk, pstride, 2 * C, 1, ex + e.tmp, 0, c.st));
+  TMG_TRY(launch_scale_grad(ex + e.tmp, c.P() + st.zc_scale, grads + st.zc_scale, c.st));
+  // 1x1 convolution: dW, then the LU parameterisation and the log-det constants
+  TMG_TRY(launch_outer_wgrad(GU, V, (int64_t)B * HW, C, ex + e.dw, ex + e.oscr, c.st));
+  LuBwdArgs la{};
+  la.dW = ex + e.dw;
+  la.l = c.P() + st.lu[0]; la.u = c.P() + st.lu[1]; la.log_s = c.P() + st.lu[2]; la.p = c.P() + st.lu[3];
+  la.sign_s = c.P() + st.lu[4]; la.lmask = c.P() + st.lu[5]; la.umask = c.P() + st.lu[6]; la.eye = c.P() + st.lu[7];
+  la.g_l = grads + st.lu[0]; la.g_u = grads + st.lu[1]; la.g_log_s = grads + st.lu[2];
+  if (normed) { la.nw = c.P() + st.norm_w; la.g_nw = grads + st.norm_w; }
+  la.g_ld = g_logdet; la.B = B; la.hw = (float)HW; la.C = C;
+  TMG_TRY(launch_lu_bwd(la, c.st));
+  // coupling network: three convolutions, last to first
+  TMG_CUDA_OK(cudaMemsetAsync(GC, 0, (size_t)B * HW * cf * sizeof(float), c.st));
+  struct Dest { float* g; const float* fwd; int cstride, coff, nch; int accum; };
+  auto conv_bwd = [&](const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate, const float* g, int g_cs, int g_co,
+                      float* wt, const Dest* dests, int ndest) -> int {
+    WgradArgs wa{};
+    for (int i = 0; i < nsrc_fwd; ++i) wa.src[i] = fsrc[i];
+    wa.nsrc = nsrc_fwd; wa.cin = w.I;
+    wa.g = g; wa.g_cstride = g_cs; wa.g_coff = g_co; wa.cout = w.O;
+    wa.B = B; wa.H = Hl; wa.W = Wl; wa.pad_replicate = replicate ? 1 : 0;
+    wa.gw = grads + w.w_param; wa.gbias = w.b_param >= 0 ? grads + w.b_param : nullptr; wa.accum = 1; wa.scratch = ex + e.wscr;
+    TMG_TRY(launch_wgrad(wa, c.st));
+    TMG_TRY(launch_pack_dgrad(c.P() + w.w_param, wt, w.O, w.I, c.st));
+    const int Ip = (w.I + 3) / 4 * 4;
+    int c0 = 0;
+    for (int d = 0; d < ndest; ++d) {
+      ConvArgs a{};
+      a.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; a.nsrc = 1;
+      a.w = wt + c0; a.cin_w = w.O; a.cout_w = Ip; a.cout = dests[d].nch;
+      a.out = dests[d].g; a.out_cstride = dests[d].cstride; a.out_coff = dests[d].coff;
+      a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
+      a.mask = dests[d].fwd; a.accum = dests[d].accum;
+      TMG_TRY(launch_conv3x3(a, c.st));
+      if (replicate) {
+        RingArgs r{};
+        r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
+        r.w_oihw = c.P() + w.w_param; r.cin_total = w.I; r.c0 = c0; r.nch = dests[d].nch;
+        r.mask = dests[d].fwd; r.gx = dests[d].g; r.gx_cstride = dests[d].cstride; r.gx_coff = dests[d].coff;
+        r.B = B; r.H = Hl; r.W = Wl;
+        TMG_TRY(launch_dgrad_ring(r, c.st));
+      }
+      c0 += dests[d].nch;
+    }
+    return TMG_OK;
+  };
+  const ConvSrc f3[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 2, 1}};
+  const Dest d3[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 2, 0}};
+  TMG_TRY(conv_bwd(st.zc, 3, f3, true, GZ, C, 0, ex + e.wt3, d3, 3));
+  const ConvSrc f2[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 1, 1}};
+  const Dest d2[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 1, 1}};
+  TMG_TRY(conv_bwd(st.d2, 3, f2, false, GD, 2, 1, ex + e.wt2, d2, 3));
+  const Dest d1[2] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}};
+  TMG_TRY(conv_bwd(st.d1, 2, f3, false, GD, 2, 0, ex + e.wt1, d1, 2));
+  (void)cin_t;
+  PermArgs pb{};
+  pb.mode = PERM_NHWC_TO_NCHW; pb.B = B; pb.H = Hl; pb.W = Wl;
+  pb.src = GY; pb.dst = g_x; pb.C = C; pb.src_cstride = C; TMG_TRY(launch_permute(pb, c.st));
+  pb.src = GC; pb.dst = g_cond; pb.C = cf; pb.src_cstride = cf; TMG_TRY(launch_permute(pb, c.st));
+  return TMG_OK;
 }
 
 static int split_common(tmg_model* m, int level, int B, int Hl, int Wl, const float* zin, int cin_ch,

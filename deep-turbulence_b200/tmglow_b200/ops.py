@@ -166,3 +166,27 @@ def conv3x3_backward(x_nchw, weight, gout_nchw, relu_in=False, pad_replicate=Fal
                                             ws.data_ptr(), ws.numel(), st))
         _lib.check(lib.tmg_nhwc_to_nchw(gxh.data_ptr(), gx.data_ptr(), B, Cin, H, W, st))
     return gx, gw, gb
+
+
+def flow_step_backward(model, level, step, x, cond, g_out, g_logdet):
+    """Gradients of one reverse flow step (``flow_step(..., reverse=True)``): returns ``(g_x, g_cond, grads)`` where
+    ``grads`` maps the reference parameter names of the step to their gradients."""
+    _need_cuda(x)
+    device = x.device
+    lib, h = model._prepare(device)
+    x = x.detach().float().contiguous(); cond = cond.detach().float().contiguous()
+    g_out = g_out.detach().float().contiguous(); g_logdet = g_logdet.detach().float().contiguous()
+    B, C, Hl, Wl = x.shape
+    g_x = torch.empty_like(x)
+    g_cond = torch.empty_like(cond)
+    flat = torch.zeros(model._n_flat, dtype=torch.float32, device=device)
+    n = lib.tmg_flow_step_backward_workspace_bytes(h, level, B, Hl, Wl)
+    assert n > 0, lib.tmg_last_error().decode()
+    ws = torch.empty(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.tmg_flow_step_backward(h, level, step, B, Hl, Wl, x.data_ptr(), cond.data_ptr(), g_out.data_ptr(),
+                                              g_logdet.data_ptr(), g_x.data_ptr(), g_cond.data_ptr(), flat.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _stream(device)))
+    pre = "glow.flow_blocks.%d.revlayers.affine_layer%d." % (level, step)
+    grads = {name: flat[off:off + numel].view(shape).clone() for name, off, numel, shape in model._table if name.startswith(pre)}
+    return g_x, g_cond, grads

@@ -182,6 +182,17 @@ int tmg_conv3x3_backward(const float* x_nhwc, int B, int H, int W, int Cin, cons
                          int relu_in, int pad_replicate, const float* gout_nhwc, float* gx_nhwc, float* gw_oihw,
                          float* gbias, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of one REVERSE flow step (the direction training runs: TMGlow.sample -> loss.backward(),
+ * nn/trainFlowParallel.py:259-277), un-normed and plain steps (UnNormedAffineCouplingBlock.reverse /
+ * AffineCouplingBlock.reverse, flowLSTMBlock.py:71-86,132-146): given the gradients w.r.t. the step output
+ * g_out [B,C_l,Hl,Wl] (NCHW) and the per-sample log-det g_logdet [B], returns g_x, g_cond (NCHW) and ACCUMULATES the
+ * gradient of every parameter of the step into `grads`, a flat fp32 buffer laid out like the parameter buffer
+ * (tmg_model_param_offset).  The forward is recomputed with the exact-fp32 kernels. */
+size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl);
+int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int Wl, const float* x, const float* cond,
+                           const float* g_out, const float* g_logdet, float* g_x, float* g_cond, float* grads,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* layout helpers for the LSTM states at the API boundary */
 int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);

@@ -38,3 +38,46 @@ def test_conv3x3_backward(B, Cin, Cout, H, W, relu_in, pad_replicate):
     # deterministic: same call twice -> bit-identical
     gx2, gw2, gb2 = ops.conv3x3_backward(x.to(dev), w.to(dev), g.to(dev), relu_in, pad_replicate)
     assert torch.equal(gx, gx2) and torch.equal(gw, gw2) and torch.equal(gb, gb2)
+
+
+@pytest.mark.parametrize("step", [1, 2])
+def test_flow_step_backward_vs_oracle_autograd(step):
+    """Reverse flow step (un-normed step 1, plain steps 2-3 of block 0): gradients w.r.t. the input, the conditioning map
+    and every parameter of the step against torch autograd through the pinned oracle."""
+    import json
+    from conftest import load_golden
+    from oracle import tmglow_oracle as O
+    from tmglow_b200 import TMGlow, ops
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    m.load_state_dict(g["state_dict"])
+    dev = torch.device("cuda:0")
+    m = m.to(dev).eval()
+    rec = g["modules"]["steps"][step - 1]
+    x, cond = rec["x"], rec["cond"]
+    gen = torch.Generator().manual_seed(step)
+    g_out = torch.randn(x.shape, generator=gen)
+    g_ld = torch.randn(x.shape[0], generator=gen)
+    pre = "glow.flow_blocks.0.revlayers.affine_layer%d." % step
+    trainable = {n for n, _ in m.named_parameters()}          # buffers (p, sign_s, masks, eye, log_s_old) get no gradient
+    sd = {k: (v.clone().requires_grad_(True) if k in trainable and k.startswith(pre) else v.clone())
+          for k, v in g["state_dict"].items()}
+    xr = x.clone().requires_grad_(True); cr = cond.clone().requires_grad_(True)
+    kind = "unnormed" if step == 1 else "plain"
+    y, ld, _ = O.flow_step_rev(sd, pre, xr, cr, kind)
+    ((y * g_out).sum() + (ld * g_ld).sum()).backward()
+    gx, gc, grads = ops.flow_step_backward(m, 0, step, x.to(dev), cond.to(dev), g_out.to(dev), g_ld.to(dev))
+
+    def close(a, r, what):
+        err = (a.cpu() - r).abs().max().item()
+        assert err <= 2e-5 * max(r.abs().max().item(), 1.0), "%s: max abs err %.3e (ref max %.3e)" % (what, err, r.abs().max().item())
+    close(gx, xr.grad, "g_x"); close(gc, cr.grad, "g_cond")
+    checked = 0
+    for k, v in sd.items():
+        if k.startswith(pre) and v.requires_grad and v.grad is not None:
+            close(grads[k], v.grad, k)
+            checked += 1
+    assert checked >= 8, checked
