@@ -390,6 +390,32 @@ lu_bwd_kernel(LuBwdArgs a) {
   }
   if (a.nw) for (int c = tid; c < C; c += blockDim.x) a.g_nw[c] += a.hw * s_gld / a.nw[c];
 }
+__global__ void lstm_bwd_kernel(LstmBwdArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int64_t pix = i / a.R;
+  const int r = (int)(i - pix * a.R);
+  const float* g = a.gates + pix * 4 * a.R;
+  const float gi = 1.f / (1.f + expf(-g[r])), gf = 1.f / (1.f + expf(-g[a.R + r]));
+  const float go = 1.f / (1.f + expf(-g[2 * a.R + r])), gg = tanhf(g[3 * a.R + r]);
+  const float c = a.c_prev ? a.c_prev[i] : 0.f;
+  const float cn = gf * c + gi * gg;
+  const float tc = tanhf(cn);
+  const float gh = a.g_h[i];
+  const float gct = (a.g_c ? a.g_c[i] : 0.f) + gh * go * (1.f - tc * tc);
+  float* o = a.g_gates + pix * 4 * a.R;
+  o[r] = gct * gg * gi * (1.f - gi);
+  o[a.R + r] = gct * c * gf * (1.f - gf);
+  o[2 * a.R + r] = gh * tc * go * (1.f - go);
+  o[3 * a.R + r] = gct * gi * (1.f - gg * gg);
+  if (a.g_c_prev) a.g_c_prev[i] = gct * gf;
+}
+int launch_lstm_bwd(const LstmBwdArgs& a, cudaStream_t st) {
+  lstm_bwd_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
 // g_scale += S_gain * d gain/d scale, gain = exp(clamp(scale, -4, ln 4))  (flowUtils.py:247)
 __global__ void scale_grad_kernel(const float* s_gain, const float* scale_param, float* g_scale) {
   const float sp = *scale_param;

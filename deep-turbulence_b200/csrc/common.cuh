@@ -391,6 +391,14 @@ struct LuBwdArgs {
 };
 int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st);
 int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st);
+// ConvLSTM cell backward (convLSTM.py:76-83): gates = pre-activations [B,HW,4R] (i,f,o,g), returns g_gates and g_c_prev
+struct LstmBwdArgs {
+  const float* gates; const float* c_prev;      // c_prev may be null (zeros)
+  const float* g_h; const float* g_c;           // gradients w.r.t. h', c' (g_c may be null)
+  float* g_gates; float* g_c_prev;              // g_c_prev may be null
+  int64_t n; int R;
+};
+int launch_lstm_bwd(const LstmBwdArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,

@@ -1385,13 +1385,17 @@ int tmg_flow_step(tmg_model* m, int level, int step, int reverse, int B, int Hl,
   return launch_logdet_reduce(a, c.st);
 }
 
-// ---- backward of one REVERSE flow step (plain / un-normed steps): gradients w.r.t. the step input, the
-// conditioning map and every parameter of the step (accumulated into a flat gradient buffer laid out like the
-// parameter buffer).  The forward is recomputed with the exact-fp32 kernels.
-struct BwdExtra { size_t go, gy, gz, gu, v, gcond, gd, part, dw, tmp, wt3, wt2, wt1, wscr, oscr, total; };
+// ---- backward of one REVERSE flow step: gradients w.r.t. the step input, the conditioning map, the incoming LSTM
+// states and every parameter of the step (accumulated into a flat gradient buffer laid out like the parameter
+// buffer).  The forward is recomputed with the exact-fp32 kernels.
+struct BwdExtra {
+  size_t go, gy, gz, gu, v, gcond, gd, part, dw, tmp, wt, wscr, oscr;
+  size_t hn, cn, ghn, ggates, gu0;      // LSTM step
+  size_t total;
+};
 
 static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) {
-  const int C = m.levels[level].C, cf = m.cfg.cond_features, cin_t = C / 2 + cf;
+  const int C = m.levels[level].C, cf = m.cfg.cond_features, cin_t = C / 2 + cf, R = m.cfg.rec_features;
   const size_t px = (size_t)B * Hl * Wl;
   BwdExtra e{};
   size_t off = 0;
@@ -1400,59 +1404,58 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
   e.gcond = take(px * cf); e.gd = take(px * 2);
   e.part = take((size_t)step_bwd_blocks(B, Hl * Wl) * (2 * C + 1));
   e.dw = take((size_t)C * C); e.tmp = take(16);
-  e.wt3 = take((size_t)9 * C * ((cin_t + 2 + 3) / 4 * 4) + 64);
-  e.wt2 = take((size_t)9 * 1 * ((cin_t + 1 + 3) / 4 * 4) + 64);
-  e.wt1 = take((size_t)9 * 1 * ((cin_t + 3) / 4 * 4) + 64);
+  // transposed weights of the widest convolution (gate conv) and the largest weight-gradient scratch
+  size_t wt = (size_t)9 * std::max(C, 4 * R) * ((cin_t + R + 3) / 4 * 4) + 64;
+  e.wt = take(wt);
   size_t ws = wgrad_scratch_floats(C, cin_t + 2, B, Hl, Wl);
   ws = std::max(ws, wgrad_scratch_floats(1, cin_t + 1, B, Hl, Wl));
+  ws = std::max(ws, wgrad_scratch_floats(4 * R, cin_t + R, B, Hl, Wl));
+  ws = std::max(ws, wgrad_scratch_floats(cin_t, cin_t + R, B, Hl, Wl));
   e.wscr = take(ws);
   e.oscr = take(outer_wgrad_scratch_floats((int64_t)px, C));
+  e.hn = take(px * R); e.cn = take(px * R); e.ghn = take(px * R); e.ggates = take(px * 4 * R);
+  e.gu0 = take(px * ((cin_t + 3) / 4 * 4));
   e.total = off;
   return e;
 }
 
-size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl) {
-  Plan p;
-  if (!m || op_plan(m, level, B, Hl, Wl, p) != TMG_OK) return 0;
-  return p.total + bwd_extra(*m, level, B, Hl, Wl).total * sizeof(float) + 256;
-}
+struct StepBwdIO {
+  const float* Y;        // step input, NHWC [B,HW,C]
+  const float* COND;     // NHWC [B,HW,cond]
+  const float* GO;       // gradient w.r.t. the step output, NHWC
+  const float* g_ld;     // [B]
+  float* GY;             // out: gradient w.r.t. Y (written)
+  float* GC;             // gradient w.r.t. COND: ACCUMULATED (the caller zeroes it)
+  const float* h_prev; const float* c_prev;     // LSTM step: incoming states (null = zeros)
+  const float* g_hn; const float* g_cn;         // gradients w.r.t. the returned states (null = zero)
+  float* g_hprev; float* g_cprev;               // out (written when non-null)
+  float* grads;
+};
 
-int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int Wl, const float* x, const float* cond,
-                           const float* g_out, const float* g_logdet, float* g_x, float* g_cond, float* grads,
-                           void* workspace, size_t workspace_bytes, void* stream) {
-  Plan p;
-  TMG_TRY(op_plan(m, level, B, Hl, Wl, p));
-  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
-  if (!x || !cond || !g_out || !g_logdet || !g_x || !g_cond || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
-  const LevelW& lv = m->levels[level];
-  if (step < 1 || step > (int)lv.steps.size()) { set_error("bad step %d", step); return TMG_ERR_BAD_SHAPE; }
-  const StepW& st = lv.steps[step - 1];
-  if (st.kind == STEP_LSTM) { set_error("backward of the LSTM step is not implemented yet"); return TMG_ERR_UNSUPPORTED; }
-  const BwdExtra e = bwd_extra(*m, level, B, Hl, Wl);
-  if (workspace_bytes < p.total + e.total * sizeof(float)) { set_error("workspace too small for the backward pass"); return TMG_ERR_WORKSPACE; }
-  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int Wl, const StepBwdIO& io, float* ex,
+                         const BwdExtra& e) {
+  tmg_model* m = &c.m;
+  const Plan& p = c.p;
   float* ws = c.ws;
-  float* ex = (float*)((char*)workspace + align_up(p.total, 256));
-  const int HW = Hl * Wl, C = lv.C, cf = m->cfg.cond_features, cin_t = C / 2 + cf;
-  float* Y = ws + p.scratch_in;
-  float* CN = ws + p.scratch_cond;
+  const LevelW& lv = m->levels[level];
+  const int HW = Hl * Wl, C = lv.C, cf = m->cfg.cond_features, cin_t = C / 2 + cf, R = m->cfg.rec_features;
+  const int u0s = (cin_t + 3) / 4 * 4;
+  const float* Y = io.Y; const float* CN = io.COND;
   float* D = ws + p.d;
   float* HR = ws + p.hr;
-  float *GO = ex + e.go, *GY = ex + e.gy, *GZ = ex + e.gz, *GU = ex + e.gu, *V = ex + e.v, *GC = ex + e.gcond, *GD = ex + e.gd;
-  PermArgs pa{};
-  pa.mode = PERM_NCHW_TO_NHWC; pa.B = B; pa.H = Hl; pa.W = Wl;
-  pa.src = x; pa.dst = Y; pa.C = C; pa.dst_cstride = C; TMG_TRY(launch_permute(pa, c.st));
-  pa.src = g_out; pa.dst = GO; TMG_TRY(launch_permute(pa, c.st));
-  pa.src = cond; pa.dst = CN; pa.C = cf; pa.dst_cstride = cf; TMG_TRY(launch_permute(pa, c.st));
-  // forward recompute with the exact-fp32 kernels: D (d1, d2) and HR (h)
+  float *GY = io.GY, *GC = io.GC, *GZ = ex + e.gz, *GU = ex + e.gu, *V = ex + e.v, *GD = ex + e.gd;
+  float *HN = ex + e.hn, *CNW = ex + e.cn, *GHN = ex + e.ghn, *GG = ex + e.ggates, *GU0 = ex + e.gu0, *U0 = ws + p.u0;
+  float* grads = io.grads;
+  const bool lstm = st.kind == STEP_LSTM;
+  // forward recompute with the exact-fp32 kernels: D (d1, d2), HR (h) and, for the LSTM step, gates / h' / c' / u0
   const int prec = m->precision;
   m->precision = TMG_PREC_FP32;
-  int rc = run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, nullptr, nullptr, nullptr, nullptr);
+  int rc = run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, io.h_prev, io.c_prev, lstm ? HN : nullptr, lstm ? CNW : nullptr);
   m->precision = prec;
   TMG_TRY(rc);
   const bool normed = st.kind != STEP_UNNORMED;
   StepBwdArgs sa{};
-  sa.y_in = Y; sa.h = HR; sa.g_out = GO; sa.g_ld = g_logdet;
+  sa.y_in = Y; sa.h = HR; sa.g_out = io.GO; sa.g_ld = io.g_ld;
   sa.wmat = c.Q() + st.W;
   if (normed) { sa.nw = c.P() + st.norm_w; sa.nb = c.P() + st.norm_b; }
   sa.gain = c.Q() + st.zc_gain;
@@ -1474,13 +1477,12 @@ int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int
   la.sign_s = c.P() + st.lu[4]; la.lmask = c.P() + st.lu[5]; la.umask = c.P() + st.lu[6]; la.eye = c.P() + st.lu[7];
   la.g_l = grads + st.lu[0]; la.g_u = grads + st.lu[1]; la.g_log_s = grads + st.lu[2];
   if (normed) { la.nw = c.P() + st.norm_w; la.g_nw = grads + st.norm_w; }
-  la.g_ld = g_logdet; la.B = B; la.hw = (float)HW; la.C = C;
+  la.g_ld = io.g_ld; la.B = B; la.hw = (float)HW; la.C = C;
   TMG_TRY(launch_lu_bwd(la, c.st));
-  // coupling network: three convolutions, last to first
-  TMG_CUDA_OK(cudaMemsetAsync(GC, 0, (size_t)B * HW * cf * sizeof(float), c.st));
+
   struct Dest { float* g; const float* fwd; int cstride, coff, nch; int accum; };
   auto conv_bwd = [&](const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate, const float* g, int g_cs, int g_co,
-                      float* wt, const Dest* dests, int ndest) -> int {
+                      const Dest* dests, int ndest) -> int {
     WgradArgs wa{};
     for (int i = 0; i < nsrc_fwd; ++i) wa.src[i] = fsrc[i];
     wa.nsrc = nsrc_fwd; wa.cin = w.I;
@@ -1488,38 +1490,113 @@ int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int
     wa.B = B; wa.H = Hl; wa.W = Wl; wa.pad_replicate = replicate ? 1 : 0;
     wa.gw = grads + w.w_param; wa.gbias = w.b_param >= 0 ? grads + w.b_param : nullptr; wa.accum = 1; wa.scratch = ex + e.wscr;
     TMG_TRY(launch_wgrad(wa, c.st));
+    float* wt = ex + e.wt;
     TMG_TRY(launch_pack_dgrad(c.P() + w.w_param, wt, w.O, w.I, c.st));
     const int Ip = (w.I + 3) / 4 * 4;
     int c0 = 0;
     for (int d = 0; d < ndest; ++d) {
-      ConvArgs a{};
-      a.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; a.nsrc = 1;
-      a.w = wt + c0; a.cin_w = w.O; a.cout_w = Ip; a.cout = dests[d].nch;
-      a.out = dests[d].g; a.out_cstride = dests[d].cstride; a.out_coff = dests[d].coff;
-      a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
-      a.mask = dests[d].fwd; a.accum = dests[d].accum;
-      TMG_TRY(launch_conv3x3(a, c.st));
-      if (replicate) {
-        RingArgs r{};
-        r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
-        r.w_oihw = c.P() + w.w_param; r.cin_total = w.I; r.c0 = c0; r.nch = dests[d].nch;
-        r.mask = dests[d].fwd; r.gx = dests[d].g; r.gx_cstride = dests[d].cstride; r.gx_coff = dests[d].coff;
-        r.B = B; r.H = Hl; r.W = Wl;
-        TMG_TRY(launch_dgrad_ring(r, c.st));
+      if (dests[d].g) {
+        ConvArgs a{};
+        a.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; a.nsrc = 1;
+        a.w = wt + c0; a.cin_w = w.O; a.cout_w = Ip; a.cout = dests[d].nch;
+        a.out = dests[d].g; a.out_cstride = dests[d].cstride; a.out_coff = dests[d].coff;
+        a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
+        a.mask = dests[d].fwd; a.accum = dests[d].accum;
+        TMG_TRY(launch_conv3x3(a, c.st));
+        if (replicate) {
+          RingArgs r{};
+          r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
+          r.w_oihw = c.P() + w.w_param; r.cin_total = w.I; r.c0 = c0; r.nch = dests[d].nch;
+          r.mask = dests[d].fwd; r.gx = dests[d].g; r.gx_cstride = dests[d].cstride; r.gx_coff = dests[d].coff;
+          r.B = B; r.H = Hl; r.W = Wl;
+          TMG_TRY(launch_dgrad_ring(r, c.st));
+        }
       }
       c0 += dests[d].nch;
     }
     return TMG_OK;
   };
-  const ConvSrc f3[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 2, 1}};
-  const Dest d3[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 2, 0}};
-  TMG_TRY(conv_bwd(st.zc, 3, f3, true, GZ, C, 0, ex + e.wt3, d3, 3));
-  const ConvSrc f2[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 1, 1}};
-  const Dest d2[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 1, 1}};
-  TMG_TRY(conv_bwd(st.d2, 3, f2, false, GD, 2, 1, ex + e.wt2, d2, 3));
-  const Dest d1[2] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}};
-  TMG_TRY(conv_bwd(st.d1, 2, f3, false, GD, 2, 0, ex + e.wt1, d1, 2));
-  (void)cin_t;
+
+  if (!lstm) {
+    // coupling network on t = cat(y1, cond): three convolutions, last to first
+    const ConvSrc f3[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 2, 1}};
+    const Dest d3[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 2, 0}};
+    TMG_TRY(conv_bwd(st.zc, 3, f3, true, GZ, C, 0, d3, 3));
+    const ConvSrc f2[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 1, 1}};
+    const Dest d2[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 1, 1}};
+    TMG_TRY(conv_bwd(st.d2, 3, f2, false, GD, 2, 1, d2, 3));
+    const Dest d1[2] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}};
+    TMG_TRY(conv_bwd(st.d1, 2, f3, false, GD, 2, 0, d1, 2));
+    return TMG_OK;
+  }
+  // ---- LSTM step (flowAffine.py:161-236, convLSTM.py:54-152): coupling network on u0 = relu(LSTM_out_conv(cat(t, h')))
+  {
+    const ConvSrc f3[2] = {{U0, u0s, 0, cin_t, 1}, {D, 2, 0, 2, 1}};
+    const Dest d3[2] = {{GU0, U0, u0s, 0, cin_t, 0}, {GD, D, 2, 0, 2, 0}};
+    TMG_TRY(conv_bwd(st.zc, 2, f3, true, GZ, C, 0, d3, 2));
+    const ConvSrc f2[2] = {{U0, u0s, 0, cin_t, 1}, {D, 2, 0, 1, 1}};
+    const Dest d2[2] = {{GU0, U0, u0s, 0, cin_t, 1}, {GD, D, 2, 0, 1, 1}};
+    TMG_TRY(conv_bwd(st.d2, 2, f2, false, GD, 2, 1, d2, 2));
+    const Dest d1[1] = {{GU0, U0, u0s, 0, cin_t, 1}};
+    TMG_TRY(conv_bwd(st.d1, 1, f3, false, GD, 2, 0, d1, 1));
+  }
+  // GU0 is gated by u0 > 0, i.e. it is already the gradient w.r.t. the pre-ReLU output of LSTM_out_conv
+  if (io.g_hn) TMG_CUDA_OK(cudaMemcpyAsync(GHN, io.g_hn, (size_t)B * HW * R * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  else TMG_CUDA_OK(cudaMemsetAsync(GHN, 0, (size_t)B * HW * R * sizeof(float), c.st));
+  {
+    const ConvSrc fo[3] = {{Y, C, 0, C / 2, 0}, {CN, cf, 0, cf, 0}, {HN, R, 0, R, 0}};
+    const Dest dox[3] = {{GY, nullptr, C, 0, C / 2, 1}, {GC, nullptr, cf, 0, cf, 1}, {GHN, nullptr, R, 0, R, 1}};
+    TMG_TRY(conv_bwd(st.outc, 3, fo, false, GU0, u0s, 0, dox, 3));
+  }
+  LstmBwdArgs lb{};
+  lb.gates = ws + p.gates; lb.c_prev = io.c_prev; lb.g_h = GHN; lb.g_c = io.g_cn;
+  lb.g_gates = GG; lb.g_c_prev = io.g_cprev; lb.n = (int64_t)B * HW * R; lb.R = R;
+  TMG_TRY(launch_lstm_bwd(lb, c.st));
+  {
+    const ConvSrc fg[3] = {{Y, C, 0, C / 2, 0}, {CN, cf, 0, cf, 0}, {io.h_prev, R, 0, R, 0}};
+    const Dest dg[3] = {{GY, nullptr, C, 0, C / 2, 1}, {GC, nullptr, cf, 0, cf, 1}, {io.g_hprev, nullptr, R, 0, R, 0}};
+    TMG_TRY(conv_bwd(st.gate, 3, fg, false, GG, 4 * R, 0, dg, 3));
+  }
+  return TMG_OK;
+}
+
+size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl) {
+  Plan p;
+  if (!m || op_plan(m, level, B, Hl, Wl, p) != TMG_OK) return 0;
+  return p.total + bwd_extra(*m, level, B, Hl, Wl).total * sizeof(float) + 256;
+}
+
+int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int Wl, const float* x, const float* cond,
+                           const float* h_in, const float* c_in, const float* g_out, const float* g_logdet,
+                           const float* g_h_out, const float* g_c_out, float* g_x, float* g_cond, float* g_h_in,
+                           float* g_c_in, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan p;
+  TMG_TRY(op_plan(m, level, B, Hl, Wl, p));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !cond || !g_out || !g_logdet || !g_x || !g_cond || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
+  const LevelW& lv = m->levels[level];
+  if (step < 1 || step > (int)lv.steps.size()) { set_error("bad step %d", step); return TMG_ERR_BAD_SHAPE; }
+  const StepW& st = lv.steps[step - 1];
+  const BwdExtra e = bwd_extra(*m, level, B, Hl, Wl);
+  if (workspace_bytes < align_up(p.total, 256) + e.total * sizeof(float)) { set_error("workspace too small for the backward pass"); return TMG_ERR_WORKSPACE; }
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  float* ex = (float*)((char*)workspace + align_up(p.total, 256));
+  const int HW = Hl * Wl, C = lv.C, cf = m->cfg.cond_features;
+  float* Y = ws + p.scratch_in;
+  float* CN = ws + p.scratch_cond;
+  float *GO = ex + e.go, *GY = ex + e.gy, *GC = ex + e.gcond;
+  PermArgs pa{};
+  pa.mode = PERM_NCHW_TO_NHWC; pa.B = B; pa.H = Hl; pa.W = Wl;
+  pa.src = x; pa.dst = Y; pa.C = C; pa.dst_cstride = C; TMG_TRY(launch_permute(pa, c.st));
+  pa.src = g_out; pa.dst = GO; TMG_TRY(launch_permute(pa, c.st));
+  pa.src = cond; pa.dst = CN; pa.C = cf; pa.dst_cstride = cf; TMG_TRY(launch_permute(pa, c.st));
+  TMG_CUDA_OK(cudaMemsetAsync(GC, 0, (size_t)B * HW * cf * sizeof(float), c.st));
+  StepBwdIO io{};
+  io.Y = Y; io.COND = CN; io.GO = GO; io.g_ld = g_logdet; io.GY = GY; io.GC = GC;
+  io.h_prev = h_in; io.c_prev = c_in; io.g_hn = g_h_out; io.g_cn = g_c_out; io.g_hprev = g_h_in; io.g_cprev = g_c_in;
+  io.grads = grads;
+  TMG_TRY(step_backward(c, level, st, B, Hl, Wl, io, ex, e));
   PermArgs pb{};
   pb.mode = PERM_NHWC_TO_NCHW; pb.B = B; pb.H = Hl; pb.W = Wl;
   pb.src = GY; pb.dst = g_x; pb.C = C; pb.src_cstride = C; TMG_TRY(launch_permute(pb, c.st));

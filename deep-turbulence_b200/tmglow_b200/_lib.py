@@ -47,7 +47,7 @@ SIGNATURES = {
     "tmg_conv3x3_backward_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "tmg_conv3x3_backward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "tmg_flow_step_backward_workspace_bytes": (_SZ, [_P, _I, _I, _I, _I]),
-    "tmg_flow_step_backward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tmg_flow_step_backward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tmg_model_param_entries": (_I64, [_P]),
     "tmg_model_param_name": (C.c_char_p, [_P, _I64]),
     "tmg_model_param_offset": (_I64, [_P, _I64]),

@@ -168,9 +168,10 @@ def conv3x3_backward(x_nchw, weight, gout_nchw, relu_in=False, pad_replicate=Fal
     return gx, gw, gb
 
 
-def flow_step_backward(model, level, step, x, cond, g_out, g_logdet):
-    """Gradients of one reverse flow step (``flow_step(..., reverse=True)``): returns ``(g_x, g_cond, grads)`` where
-    ``grads`` maps the reference parameter names of the step to their gradients."""
+def flow_step_backward(model, level, step, x, cond, g_out, g_logdet, state=None, g_state=None):
+    """Gradients of one reverse flow step (``flow_step(..., reverse=True)``): returns ``(g_x, g_cond, grads, g_state_in)``
+    where ``grads`` maps the reference parameter names of the step to their gradients.  ``state`` / ``g_state`` are the
+    incoming LSTM states and the gradients w.r.t. the returned ones (LSTM step only, NCHW tensors)."""
     _need_cuda(x)
     device = x.device
     lib, h = model._prepare(device)
@@ -183,10 +184,17 @@ def flow_step_backward(model, level, step, x, cond, g_out, g_logdet):
     n = lib.tmg_flow_step_backward_workspace_bytes(h, level, B, Hl, Wl)
     assert n > 0, lib.tmg_last_error().decode()
     ws = torch.empty(n, dtype=torch.uint8, device=device)
+    R = model.rec_features
+    cl = lambda t: None if t is None else t.detach().float().to(device).contiguous(memory_format=torch.channels_last)
+    hs = [cl(t) for t in (state or (None, None))]
+    gs = [cl(t) for t in (g_state or (None, None))]
+    gin = [_empty_channels_last((B, R, Hl, Wl), device) for _ in range(2)] if (state is not None or g_state is not None) else [None, None]
+    ptr = lambda t: None if t is None else t.data_ptr()
     with torch.cuda.device(device):
-        _lib.check(lib.tmg_flow_step_backward(h, level, step, B, Hl, Wl, x.data_ptr(), cond.data_ptr(), g_out.data_ptr(),
-                                              g_logdet.data_ptr(), g_x.data_ptr(), g_cond.data_ptr(), flat.data_ptr(),
+        _lib.check(lib.tmg_flow_step_backward(h, level, step, B, Hl, Wl, x.data_ptr(), cond.data_ptr(), ptr(hs[0]), ptr(hs[1]),
+                                              g_out.data_ptr(), g_logdet.data_ptr(), ptr(gs[0]), ptr(gs[1]),
+                                              g_x.data_ptr(), g_cond.data_ptr(), ptr(gin[0]), ptr(gin[1]), flat.data_ptr(),
                                               ws.data_ptr(), ws.numel(), _stream(device)))
     pre = "glow.flow_blocks.%d.revlayers.affine_layer%d." % (level, step)
     grads = {name: flat[off:off + numel].view(shape).clone() for name, off, numel, shape in model._table if name.startswith(pre)}
-    return g_x, g_cond, grads
+    return g_x, g_cond, grads, gin

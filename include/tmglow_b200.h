@@ -183,15 +183,17 @@ int tmg_conv3x3_backward(const float* x_nhwc, int B, int H, int W, int Cin, cons
                          float* gbias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of one REVERSE flow step (the direction training runs: TMGlow.sample -> loss.backward(),
- * nn/trainFlowParallel.py:259-277), un-normed and plain steps (UnNormedAffineCouplingBlock.reverse /
- * AffineCouplingBlock.reverse, flowLSTMBlock.py:71-86,132-146): given the gradients w.r.t. the step output
- * g_out [B,C_l,Hl,Wl] (NCHW) and the per-sample log-det g_logdet [B], returns g_x, g_cond (NCHW) and ACCUMULATES the
- * gradient of every parameter of the step into `grads`, a flat fp32 buffer laid out like the parameter buffer
- * (tmg_model_param_offset).  The forward is recomputed with the exact-fp32 kernels. */
+ * nn/trainFlowParallel.py:259-277): UnNormedAffineCouplingBlock / AffineCouplingBlock / LSTMCouplingBlock .reverse
+ * (flowLSTMBlock.py:71-86,132-146,200-218).  Given the gradients w.r.t. the step output g_out [B,C_l,Hl,Wl] (NCHW),
+ * the per-sample log-det g_logdet [B] and, for the LSTM step, the returned states g_h_out / g_c_out (channels-last,
+ * may be NULL), returns g_x, g_cond (NCHW), g_h_in / g_c_in (channels-last, may be NULL) and ACCUMULATES the gradient
+ * of every parameter of the step into `grads`, a flat fp32 buffer laid out like the parameter buffer
+ * (tmg_model_param_offset).  The forward is recomputed with the exact-fp32 kernels; deterministic. */
 size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl);
 int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int Wl, const float* x, const float* cond,
-                           const float* g_out, const float* g_logdet, float* g_x, float* g_cond, float* grads,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           const float* h_in, const float* c_in, const float* g_out, const float* g_logdet,
+                           const float* g_h_out, const float* g_c_out, float* g_x, float* g_cond, float* g_h_in,
+                           float* g_c_in, float* grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* layout helpers for the LSTM states at the API boundary */
 int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);

@@ -40,7 +40,7 @@ def test_conv3x3_backward(B, Cin, Cout, H, W, relu_in, pad_replicate):
     assert torch.equal(gx, gx2) and torch.equal(gw, gw2) and torch.equal(gb, gb2)
 
 
-@pytest.mark.parametrize("step", [1, 2])
+@pytest.mark.parametrize("step", [1, 2, 3])
 def test_flow_step_backward_vs_oracle_autograd(step):
     """Reverse flow step (un-normed step 1, plain steps 2-3 of block 0): gradients w.r.t. the input, the conditioning map
     and every parameter of the step against torch autograd through the pinned oracle."""
@@ -66,15 +66,27 @@ def test_flow_step_backward_vs_oracle_autograd(step):
     sd = {k: (v.clone().requires_grad_(True) if k in trainable and k.startswith(pre) else v.clone())
           for k, v in g["state_dict"].items()}
     xr = x.clone().requires_grad_(True); cr = cond.clone().requires_grad_(True)
-    kind = "unnormed" if step == 1 else "plain"
-    y, ld, _ = O.flow_step_rev(sd, pre, xr, cr, kind)
-    ((y * g_out).sum() + (ld * g_ld).sum()).backward()
-    gx, gc, grads = ops.flow_step_backward(m, 0, step, x.to(dev), cond.to(dev), g_out.to(dev), g_ld.to(dev))
+    nsteps = cfg["glow_blocks"][0]
+    kind = "unnormed" if step == 1 else ("lstm" if step == nsteps else "plain")
+    state = g_state = None
+    if kind == "lstm":
+        R = cfg["rec_features"]
+        hs = [torch.randn(x.shape[0], R, x.shape[2], x.shape[3], generator=gen).requires_grad_(True) for _ in range(2)]
+        g_state = [torch.randn(x.shape[0], R, x.shape[2], x.shape[3], generator=gen) for _ in range(2)]
+        y, ld, (hn, cn) = O.flow_step_rev(sd, pre, xr, cr, kind, (hs[0], hs[1]), R)
+        ((y * g_out).sum() + (ld * g_ld).sum() + (hn * g_state[0]).sum() + (cn * g_state[1]).sum()).backward()
+        state = [t.detach() for t in hs]
+    else:
+        y, ld, _ = O.flow_step_rev(sd, pre, xr, cr, kind)
+        ((y * g_out).sum() + (ld * g_ld).sum()).backward()
+    gx, gc, grads, gin = ops.flow_step_backward(m, 0, step, x.to(dev), cond.to(dev), g_out.to(dev), g_ld.to(dev), state, g_state)
 
     def close(a, r, what):
         err = (a.cpu() - r).abs().max().item()
         assert err <= 2e-5 * max(r.abs().max().item(), 1.0), "%s: max abs err %.3e (ref max %.3e)" % (what, err, r.abs().max().item())
     close(gx, xr.grad, "g_x"); close(gc, cr.grad, "g_cond")
+    if kind == "lstm":
+        close(gin[0], hs[0].grad, "g_h_in"); close(gin[1], hs[1].grad, "g_c_in")
     checked = 0
     for k, v in sd.items():
         if k.startswith(pre) and v.requires_grad and v.grad is not None:
