@@ -416,6 +416,51 @@ int launch_lstm_bwd(const LstmBwdArgs& a, cudaStream_t st) {
   return TMG_OK;
 }
 
+__global__ void __launch_bounds__(128)
+gauss_bwd_kernel(GaussBwdArgs a) {
+  __shared__ float s_red[4];
+  const int b = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  float acc = 0.f;
+  if (p < a.HW) {
+    const size_t pix = (size_t)b * a.HW + p;
+    const float* pr = a.prm + pix * a.prm_cstride;
+    const float* gv = a.g_val + pix * a.gv_cstride + a.gv_coff;
+    float* gp = a.g_prm + pix * a.gp_cstride;
+    const float gain = a.gain ? __ldg(a.gain) : 1.f;
+    const float gld = a.g_ld ? __ldg(a.g_ld + b) : 0.f;
+    for (int j = 0; j < a.n; ++j) {
+      const float mu = pr[j], lsr = pr[a.n + j];
+      const float ls = fminf(fmaxf(lsr, -10.f), kLog5);
+      const float e = __ldg(a.eps + ((size_t)b * a.n + j) * a.HW + p);
+      const float g = gv[j];
+      float g_mu = g;
+      float g_ls = g * expf(ls) * e - gld;                  // d logp / d ls = -1 per element
+      if (!(lsr > -10.f && lsr < kLog5)) g_ls = 0.f;        // clamp_ (flowUtils.py:163)
+      if (a.hardtanh) {
+        if (!(mu > -2.f && mu < kLog5)) g_mu = 0.f;
+        if (!(lsr > -2.f && lsr < kLog5)) g_ls = 0.f;
+      }
+      acc += (g_mu * mu + g_ls * lsr) / gain;
+      gp[j] = g_mu * gain;
+      gp[a.n + j] = g_ls * gain;
+    }
+  }
+  if (a.part) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) a.part[(size_t)b * gridDim.x + blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+  }
+}
+int gauss_bwd_blocks(int B, int HW) { return B * cdiv(HW, 128); }
+int launch_gauss_bwd(const GaussBwdArgs& a, cudaStream_t st) {
+  dim3 grid(cdiv(a.HW, 128), a.B);
+  gauss_bwd_kernel<<<grid, 128, 0, st>>>(a);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
 // g_scale += S_gain * d gain/d scale, gain = exp(clamp(scale, -4, ln 4))  (flowUtils.py:247)
 __global__ void scale_grad_kernel(const float* s_gain, const float* scale_param, float* g_scale) {
   const float sp = *scale_param;

@@ -399,6 +399,23 @@ struct LstmBwdArgs {
   int64_t n; int R;
 };
 int launch_lstm_bwd(const LstmBwdArgs& a, cudaStream_t st);
+// Diagonal Gaussian, reverse direction (value = mean + exp(logsd)*eps [, logp = sum -0.5(log2pi + 2 logsd + eps^2)]):
+// gradient w.r.t. the prior parameters.  Split prior: prm = hardtanh((conv+b)*gain, -2, ln5) (flowUtils.py:270-274),
+// the result is the gradient w.r.t. the raw conv output (gain applied) and the gain partial sums; top prior
+// (tmGlow.py:460-463): prm = encoder output, clamp(-10, ln5) on the log-std half, no log-prob term.
+struct GaussBwdArgs {
+  const float* prm; int prm_cstride;     // NHWC: mean at j, log-std at n + j
+  const float* g_val; int gv_cstride, gv_coff;    // gradient w.r.t. the value (NHWC)
+  const float* eps;                       // NCHW [B,n,HW]
+  const float* g_ld;                      // [B] or null (no log-prob term)
+  const float* gain;                      // scalar or null
+  int hardtanh;                           // 1: prm went through hardtanh(-2, ln5)
+  float* g_prm; int gp_cstride;           // out: gradient w.r.t. the 2n prior channels (before gain when gain != null)
+  float* part;                            // per-CTA partial sums of g_prm * prm / gain (gain gradient) or null
+  int B, HW, n;
+};
+int launch_gauss_bwd(const GaussBwdArgs& a, cudaStream_t st);
+int gauss_bwd_blocks(int B, int HW);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,

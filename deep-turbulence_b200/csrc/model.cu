@@ -76,7 +76,7 @@ struct DenseW { ConvW conv; int64_t bn_w, bn_b, bn_rm, bn_rv; int64_t scale, shi
 struct LevelW {
   int C = 0;                      // flow channels at this level (after squeeze)
   std::vector<StepW> steps;
-  ConvW split; int64_t split_gain = -1;
+  ConvW split; int64_t split_gain = -1; int64_t split_scale = -1;
   // encoder side
   ConvW trans; bool has_trans = false;
   std::vector<DenseW> dense;
@@ -394,6 +394,7 @@ static int build_model(tmg_model& m) {
     }
     std::string pp = "glow.flow_blocks." + std::to_string(b) + ".split.latent_encoder.conv2d";
     int64_t sc = B.add(pp + ".scale", {1, 1, 1, 1});
+    lv.split_scale = sc;
     lv.split = B.conv(pp + ".conv", C, C / 2, true);
     B.conv_f16_job(lv.split, C / 2, 0, 0);
     lv.split_gain = B.gain(sc);
@@ -537,7 +538,7 @@ static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int ns
 }
 
 // ------------------------------------------------------------------ encoder
-static int run_encoder(Ctx& c, const float* x, bool bn_train) {
+static int run_encoder(Ctx& c, const float* x, bool bn_train, float bn_momentum = 0.1f) {
   const tmg_config& g = c.m.cfg;
   const Plan& p = c.p;
   float* ws = c.ws;
@@ -577,7 +578,7 @@ static int run_encoder(Ctx& c, const float* x, bool bn_train) {
         fa.w = c.P() + d.bn_w; fa.b = c.P() + d.bn_b;
         fa.run_mean = c.m.params + d.bn_rm; fa.run_var = c.m.params + d.bn_rv;
         fa.scale = ws + p.bn_scale; fa.shift = ws + p.bn_shift;
-        fa.n = d.cin; fa.N = sa.N; fa.eps = 1e-5f; fa.momentum = 0.1f;
+        fa.n = d.cin; fa.N = sa.N; fa.eps = 1e-5f; fa.momentum = bn_momentum;
         TMG_TRY(launch_bn_fold_train(fa, c.st));
         sc = ws + p.bn_scale; sh = ws + p.bn_shift;
       } else {
@@ -1080,10 +1081,46 @@ int tmg_encoder_forward(tmg_model* m, int B, int h, int w, const float* x, float
   return TMG_OK;
 }
 
+// Tape of the training forward: the input of every flow step (NHWC), levels 0..L-1, steps 0..n-1.
+static size_t tape_off(const tmg_model& m, const Plan& p, int l, int s) {
+  size_t off = 0;
+  for (int q = 0; q < l; ++q) off += (size_t)m.levels[q].steps.size() * p.B * p.Hl[q] * p.Wl[q] * m.levels[q].C;
+  return off + (size_t)s * p.B * p.Hl[l] * p.Wl[l] * m.levels[l].C;
+}
+static size_t tape_floats(const tmg_model& m, const Plan& p) { return tape_off(m, p, p.L, 0); }
+
+static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                            const float* const* c_in, const float* const* eps, float* y, float* log_det,
+                            float* const* h_out, float* const* c_out, void* workspace, size_t workspace_bytes,
+                            uint32_t flags, void* stream, float* tape);
+
 int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
                     const float* const* c_in, const float* const* eps, float* y, float* log_det,
                     float* const* h_out, float* const* c_out, void* workspace, size_t workspace_bytes,
                     uint32_t flags, void* stream) {
+  return reconstruct_impl(m, B, h, w, x, h_in, c_in, eps, y, log_det, h_out, c_out, workspace, workspace_bytes, flags, stream, nullptr);
+}
+
+size_t tmg_tape_bytes(const tmg_model* m, int B, int h, int w) {
+  if (!m) return 0;
+  Plan p;
+  if (make_plan(*m, B, h, w, p) != TMG_OK) return 0;
+  return tape_floats(*m, p) * sizeof(float);
+}
+
+int tmg_reconstruct_train(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                          const float* const* c_in, const float* const* eps, float* y, float* log_det,
+                          float* const* h_out, float* const* c_out, void* tape, size_t tape_bytes, void* workspace,
+                          size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!tape || tape_bytes < tmg_tape_bytes(m, B, h, w)) { set_error("tape missing or too small"); return TMG_ERR_WORKSPACE; }
+  if (flags & TMG_FLAG_SHARED_X) { set_error("TMG_FLAG_SHARED_X is an inference option"); return TMG_ERR_BAD_CONFIG; }
+  return reconstruct_impl(m, B, h, w, x, h_in, c_in, eps, y, log_det, h_out, c_out, workspace, workspace_bytes, flags, stream, (float*)tape);
+}
+
+static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                            const float* const* c_in, const float* const* eps, float* y, float* log_det,
+                            float* const* h_out, float* const* c_out, void* workspace, size_t workspace_bytes,
+                            uint32_t flags, void* stream, float* tape) {
   if (!m) { set_error("null model"); return TMG_ERR_NULL; }
   Plan p;
   const bool shared = (flags & TMG_FLAG_SHARED_X) != 0;
@@ -1128,6 +1165,7 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x, const flo
     // steps n..1 reversed (flowLSTMBlock.py:348-359)
     for (int s = (int)lv.steps.size() - 1; s >= 0; --s) {
       const StepW& st = lv.steps[s];
+      if (tape) TMG_CUDA_OK(cudaMemcpyAsync(tape + tape_off(*m, p, l, s), Y, (size_t)B * HW * lv.C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
       TMG_TRY(run_step(c, l, st, &st, true, B, Hl, Wl, Y, Y2, ws + p.cond[l], h_in ? h_in[l] : nullptr,
                        c_in ? c_in[l] : nullptr, h_out[l], c_out[l], ws + p.ldp + (size_t)(slot++) * p.ctas));
     }
@@ -1419,6 +1457,45 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
   return e;
 }
 
+// weight gradient (accumulated into the flat gradient buffer) + data gradient of one 3x3 convolution into up to three
+// destination slices (the sources of the virtual concatenation), with ReLU gating and replicate-padding border terms
+struct BwdDest { float* g; const float* fwd; int cstride, coff, nch; int accum; };
+static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate,
+                         const float* g, int g_cs, int g_co, const BwdDest* dests, int ndest, float* grads, float* wt,
+                         float* wscr) {
+  WgradArgs wa{};
+  for (int i = 0; i < nsrc_fwd; ++i) wa.src[i] = fsrc[i];
+  wa.nsrc = nsrc_fwd; wa.cin = w.I;
+  wa.g = g; wa.g_cstride = g_cs; wa.g_coff = g_co; wa.cout = w.O;
+  wa.B = B; wa.H = Hl; wa.W = Wl; wa.pad_replicate = replicate ? 1 : 0;
+  wa.gw = grads + w.w_param; wa.gbias = w.b_param >= 0 ? grads + w.b_param : nullptr; wa.accum = 1; wa.scratch = wscr;
+  TMG_TRY(launch_wgrad(wa, c.st));
+  TMG_TRY(launch_pack_dgrad(c.P() + w.w_param, wt, w.O, w.I, c.st));
+  const int Ip = (w.I + 3) / 4 * 4;
+  int c0 = 0;
+  for (int d = 0; d < ndest; ++d) {
+    if (dests[d].g) {
+      ConvArgs a{};
+      a.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; a.nsrc = 1;
+      a.w = wt + c0; a.cin_w = w.O; a.cout_w = Ip; a.cout = dests[d].nch;
+      a.out = dests[d].g; a.out_cstride = dests[d].cstride; a.out_coff = dests[d].coff;
+      a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
+      a.mask = dests[d].fwd; a.accum = dests[d].accum;
+      TMG_TRY(launch_conv3x3(a, c.st));
+      if (replicate) {
+        RingArgs r{};
+        r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
+        r.w_oihw = c.P() + w.w_param; r.cin_total = w.I; r.c0 = c0; r.nch = dests[d].nch;
+        r.mask = dests[d].fwd; r.gx = dests[d].g; r.gx_cstride = dests[d].cstride; r.gx_coff = dests[d].coff;
+        r.B = B; r.H = Hl; r.W = Wl;
+        TMG_TRY(launch_dgrad_ring(r, c.st));
+      }
+    }
+    c0 += dests[d].nch;
+  }
+  return TMG_OK;
+}
+
 struct StepBwdIO {
   const float* Y;        // step input, NHWC [B,HW,C]
   const float* COND;     // NHWC [B,HW,cond]
@@ -1480,42 +1557,11 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   la.g_ld = io.g_ld; la.B = B; la.hw = (float)HW; la.C = C;
   TMG_TRY(launch_lu_bwd(la, c.st));
 
-  struct Dest { float* g; const float* fwd; int cstride, coff, nch; int accum; };
   auto conv_bwd = [&](const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate, const float* g, int g_cs, int g_co,
-                      const Dest* dests, int ndest) -> int {
-    WgradArgs wa{};
-    for (int i = 0; i < nsrc_fwd; ++i) wa.src[i] = fsrc[i];
-    wa.nsrc = nsrc_fwd; wa.cin = w.I;
-    wa.g = g; wa.g_cstride = g_cs; wa.g_coff = g_co; wa.cout = w.O;
-    wa.B = B; wa.H = Hl; wa.W = Wl; wa.pad_replicate = replicate ? 1 : 0;
-    wa.gw = grads + w.w_param; wa.gbias = w.b_param >= 0 ? grads + w.b_param : nullptr; wa.accum = 1; wa.scratch = ex + e.wscr;
-    TMG_TRY(launch_wgrad(wa, c.st));
-    float* wt = ex + e.wt;
-    TMG_TRY(launch_pack_dgrad(c.P() + w.w_param, wt, w.O, w.I, c.st));
-    const int Ip = (w.I + 3) / 4 * 4;
-    int c0 = 0;
-    for (int d = 0; d < ndest; ++d) {
-      if (dests[d].g) {
-        ConvArgs a{};
-        a.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; a.nsrc = 1;
-        a.w = wt + c0; a.cin_w = w.O; a.cout_w = Ip; a.cout = dests[d].nch;
-        a.out = dests[d].g; a.out_cstride = dests[d].cstride; a.out_coff = dests[d].coff;
-        a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
-        a.mask = dests[d].fwd; a.accum = dests[d].accum;
-        TMG_TRY(launch_conv3x3(a, c.st));
-        if (replicate) {
-          RingArgs r{};
-          r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
-          r.w_oihw = c.P() + w.w_param; r.cin_total = w.I; r.c0 = c0; r.nch = dests[d].nch;
-          r.mask = dests[d].fwd; r.gx = dests[d].g; r.gx_cstride = dests[d].cstride; r.gx_coff = dests[d].coff;
-          r.B = B; r.H = Hl; r.W = Wl;
-          TMG_TRY(launch_dgrad_ring(r, c.st));
-        }
-      }
-      c0 += dests[d].nch;
-    }
-    return TMG_OK;
+                      const BwdDest* dests, int ndest) -> int {
+    return conv_backward(c, B, Hl, Wl, w, nsrc_fwd, fsrc, replicate, g, g_cs, g_co, dests, ndest, grads, ex + e.wt, ex + e.wscr);
   };
+  typedef BwdDest Dest;
 
   if (!lstm) {
     // coupling network on t = cat(y1, cond): three convolutions, last to first
@@ -1557,6 +1603,129 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
     const Dest dg[3] = {{GY, nullptr, C, 0, C / 2, 1}, {GC, nullptr, cf, 0, cf, 1}, {io.g_hprev, nullptr, R, 0, R, 0}};
     TMG_TRY(conv_bwd(st.gate, 3, fg, false, GG, 4 * R, 0, dg, 3));
   }
+  return TMG_OK;
+}
+
+// ---- backward of TMGlow.reconstruct / TMGlow.sample (tmGlow.py:417-467 + LSTMCFlowDecoder.reverse :269-303) given the
+// tape of the training forward.  Decoder (flow) parameters, LSTM state gradients and the gradient w.r.t. the
+// conditioning maps / top prior parameters; the encoder backward follows (run_encoder_backward).
+struct RbExtra { BwdExtra e; size_t ga, gb, gcond[TMG_MAX_LEVELS], gzout, gpart, total; };
+
+static RbExtra rb_extra(const tmg_model& m, const Plan& p) {
+  RbExtra r{};
+  r.e = bwd_extra(m, 0, p.B, p.Hl[0], p.Wl[0]);
+  for (int l = 1; l < p.L; ++l) {          // level 0 is the largest in pixels; wider levels need wider per-pixel rows
+    BwdExtra q = bwd_extra(m, l, p.B, p.Hl[l], p.Wl[l]);
+    r.e.total = std::max(r.e.total, q.total);
+  }
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n, 64); return o; };
+  size_t mx = 0, mxpix = 0;
+  for (int l = 0; l < p.L; ++l) { mx = std::max(mx, (size_t)p.B * p.Hl[l] * p.Wl[l] * m.levels[l].C); mxpix = std::max(mxpix, (size_t)p.B * p.Hl[l] * p.Wl[l]); }
+  r.ga = take(mx); r.gb = take(mx);
+  for (int l = 0; l < p.L; ++l) r.gcond[l] = take((size_t)p.B * p.Hl[l] * p.Wl[l] * m.cfg.cond_features);
+  r.gzout = take((size_t)p.B * p.Hl[p.L - 1] * p.Wl[p.L - 1] * 2 * m.Cz);
+  r.gpart = take((size_t)gauss_bwd_blocks(p.B, p.Hl[0] * p.Wl[0]) + 64);
+  r.total = off;
+  return r;
+}
+
+size_t tmg_reconstruct_backward_workspace_bytes(const tmg_model* m, int B, int h, int w) {
+  if (!m) return 0;
+  Plan p;
+  if (make_plan(*m, B, h, w, p) != TMG_OK) return 0;
+  const RbExtra r = rb_extra(*m, p);
+  return align_up(p.total, 256) + (r.e.total + r.total) * sizeof(float) + 512;
+}
+
+int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                             const float* const* c_in, const float* const* eps, const void* tape_v, const float* g_y,
+                             const float* g_log_det, const float* const* g_h_out, const float* const* g_c_out,
+                             float* const* g_h_in, float* const* g_c_in, float* grads, void* workspace,
+                             size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  Plan p;
+  TMG_TRY(make_plan(*m, B, h, w, p, false));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !eps || !tape_v || !g_y || !g_log_det || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (workspace_bytes < tmg_reconstruct_backward_workspace_bytes(m, B, h, w)) { set_error("workspace too small for the backward pass"); return TMG_ERR_WORKSPACE; }
+  const float* tape = (const float*)tape_v;
+  const int L = p.L;
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const RbExtra rx = rb_extra(*m, p);
+  float* ex = (float*)((char*)workspace + align_up(p.total, 256));      // per-step scratch (BwdExtra layout)
+  float* rb = ex + rx.e.total;                                           // chain buffers
+  // conditioning maps and top prior parameters: recompute the encoder (batch statistics, running stats untouched)
+  TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN, 0.f));
+  for (int l = 0; l < L; ++l)
+    TMG_CUDA_OK(cudaMemsetAsync(rb + rx.gcond[l], 0, (size_t)B * p.Hl[l] * p.Wl[l] * m->cfg.cond_features * sizeof(float), c.st));
+  float* Gc = rb + rx.ga;      // current gradient w.r.t. the flow state
+  float* Gn = rb + rx.gb;
+  {   // adjoint of the final CheckerSqueeze.reverse: g_y [B,out,H,W] -> [B,H/2,W/2,4*out]
+    PermArgs pa{};
+    pa.mode = PERM_SQUEEZE_NCHW_TO_NHWC; pa.src = g_y; pa.dst = Gc; pa.dst_cstride = m->levels[0].C; pa.dst_coff = 0;
+    pa.B = B; pa.C = m->cfg.out_features; pa.H = p.H; pa.W = p.W;
+    TMG_TRY(launch_permute(pa, c.st));
+  }
+  const int prec = m->precision;
+  for (int l = 0; l < L; ++l) {
+    const LevelW& lv = m->levels[l];
+    const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl, C = lv.C, n = (int)lv.steps.size();
+    const BwdExtra e = bwd_extra(*m, l, B, Hl, Wl);
+    for (int s = 0; s < n; ++s) {
+      const StepW& st = lv.steps[s];
+      StepBwdIO io{};
+      io.Y = tape + tape_off(*m, p, l, s); io.COND = ws + p.cond[l]; io.GO = Gc; io.g_ld = g_log_det;
+      io.GY = Gn; io.GC = rb + rx.gcond[l]; io.grads = grads;
+      if (st.kind == STEP_LSTM) {
+        io.h_prev = h_in ? h_in[l] : nullptr; io.c_prev = c_in ? c_in[l] : nullptr;
+        io.g_hn = g_h_out ? g_h_out[l] : nullptr; io.g_cn = g_c_out ? g_c_out[l] : nullptr;
+        io.g_hprev = (g_h_in && io.h_prev) ? g_h_in[l] : nullptr; io.g_cprev = (g_c_in && io.c_prev) ? g_c_in[l] : nullptr;
+      }
+      TMG_TRY(step_backward(c, l, st, B, Hl, Wl, io, ex, e));
+      float* t = Gc; Gc = Gn; Gn = t;
+    }
+    // Split.reverse backward (flowUtils.py:316-335): Gc = gradient w.r.t. cat(z1, z2)
+    const float* Ysplit = tape + tape_off(*m, p, l, n - 1);
+    m->precision = TMG_PREC_FP32;
+    int rc = run_split_prior(c, l, B, Hl, Wl, Ysplit);
+    m->precision = prec;
+    TMG_TRY(rc);
+    GaussBwdArgs ga{};
+    ga.prm = ws + p.hr; ga.prm_cstride = C;
+    ga.g_val = Gc; ga.gv_cstride = C; ga.gv_coff = C / 2;
+    ga.eps = eps[l]; ga.g_ld = g_log_det; ga.gain = c.Q() + lv.split_gain; ga.hardtanh = 1;
+    ga.g_prm = ex + e.gz; ga.gp_cstride = C; ga.part = rb + rx.gpart;
+    ga.B = B; ga.HW = HW; ga.n = C / 2;
+    TMG_TRY(launch_gauss_bwd(ga, c.st));
+    TMG_TRY(launch_reduce_cols(rb + rx.gpart, gauss_bwd_blocks(B, HW), 1, 0, 1, ex + e.tmp, 0, c.st));
+    TMG_TRY(launch_scale_grad(ex + e.tmp, c.P() + lv.split_scale, grads + lv.split_scale, c.st));
+    {
+      const ConvSrc fs[1] = {{Ysplit, C, 0, C / 2, 0}};
+      const BwdDest ds[1] = {{Gc, nullptr, C, 0, C / 2, 1}};
+      TMG_TRY(conv_backward(c, B, Hl, Wl, lv.split, 1, fs, true, ex + e.gz, C, 0, ds, 1, grads, ex + e.wt, ex + e.wscr));
+    }
+    if (l + 1 < L) {
+      // z1 of this level is the un-squeezed output of the next one: adjoint = squeeze of the first C/2 channels
+      PermArgs pa{};
+      pa.mode = PERM_SQUEEZE_NHWC_TO_NHWC; pa.src = Gc; pa.src_cstride = C; pa.src_coff = 0;
+      pa.dst = Gn; pa.dst_cstride = m->levels[l + 1].C; pa.dst_coff = 0;
+      pa.B = B; pa.C = C / 2; pa.H = Hl; pa.W = Wl;
+      TMG_TRY(launch_permute(pa, c.st));
+      float* t = Gc; Gc = Gn; Gn = t;
+    } else {
+      // top latent z = cmean + exp(clamp(clog_std)) * eps[L]: gradient w.r.t. the encoder output [2*Cz]
+      GaussBwdArgs gt{};
+      gt.prm = ws + p.zout; gt.prm_cstride = 2 * m->Cz;
+      gt.g_val = Gc; gt.gv_cstride = C; gt.gv_coff = 0;
+      gt.eps = eps[L]; gt.g_ld = nullptr; gt.gain = nullptr; gt.hardtanh = 0;
+      gt.g_prm = rb + rx.gzout; gt.gp_cstride = 2 * m->Cz; gt.part = nullptr;
+      gt.B = B; gt.HW = HW; gt.n = m->Cz;
+      TMG_TRY(launch_gauss_bwd(gt, c.st));
+    }
+  }
+  // zero states: the caller's state gradients stay untouched when no state was passed in
   return TMG_OK;
 }
 

@@ -410,6 +410,46 @@ class TMGlow(nn.Module):
             self._bump_bn_counters()
         return y, log_det, list(zip(ho, co))
 
+    # ------------------------------------------------------------------ training (reverse-KL training runs through sample())
+    def flat_parameters(self):
+        """The flat fp32 buffer that holds every parameter and buffer (the module's parameters are views of it).
+        ``reconstruct_train`` returns gradients w.r.t. it; an optimizer can be built directly on it."""
+        device = next(self.parameters()).device
+        self._sync_flat(device)
+        return self._flat
+
+    def reconstruct_train(self, x, h_in, eps):
+        """Differentiable ``reconstruct`` (and therefore ``sample``): the forward runs in the model's precision mode
+        and records the input of every flow step; ``backward`` (hand-written CUDA, exact fp32) returns the gradients
+        w.r.t. the incoming LSTM states and ACCUMULATES the parameter gradients into ``self.flat_grad`` (a flat
+        buffer laid out like ``flat_parameters()``; ``zero_flat_grad()`` clears it, ``scatter_flat_grad()`` exposes it
+        as ``p.grad`` of every parameter).  Round 1: gradients of the flow (decoder) parameters; the encoder's are the
+        next step."""
+        return _ReconstructFn.apply(self, x, eps, *([t for hc in (h_in or []) for t in hc]))
+
+    def sample_train(self, x, h_in=None):
+        B, (H, W) = x.shape[0], self._hf_size(x)
+        shapes = self.latent_shapes(B, H, W)
+        eps = [None] * len(shapes)
+        for i in [len(shapes) - 1] + list(range(len(shapes) - 2, -1, -1)):
+            eps[i] = torch.randn(shapes[i], dtype=torch.float32, device=x.device)
+        return self.reconstruct_train(x, h_in, eps)
+
+    def zero_flat_grad(self):
+        flat = self.flat_parameters()
+        if getattr(self, "flat_grad", None) is None or self.flat_grad.shape != flat.shape or self.flat_grad.device != flat.device:
+            self.flat_grad = torch.zeros_like(flat)
+        else:
+            self.flat_grad.zero_()
+        return self.flat_grad
+
+    def scatter_flat_grad(self):
+        """``p.grad`` of every parameter = its slice of ``flat_grad`` (views, no copies)."""
+        for i, (name, off, numel, shape) in enumerate(self._table):
+            mod, attr, is_param = self._leaves[i]
+            if is_param:
+                mod._parameters[attr].grad = self.flat_grad[off:off + numel].view(shape)
+
     def sample(self, x, h_in=None):
         """Conditional generation (reference nn/tmGlow.py:417-440).  The Gaussian noise is drawn with
         ``torch.randn`` in the order and shapes of the reference (top latent first, then the splits of
@@ -471,3 +511,72 @@ class TMGlow(nn.Module):
             _lib.check(lib.tmg_model_get_conv1x1(h, level, step, int(inverse), out.data_ptr(),
                                                  torch.cuda.current_stream(device).cuda_stream))
         return out
+
+
+class _ReconstructFn(torch.autograd.Function):
+    """autograd bridge of ``TMGlow.reconstruct``: tmg_reconstruct_train / tmg_reconstruct_backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, eps, *states):
+        device = x.device
+        lib, h = model._prepare(device)
+        L = len(model.glow_blocks)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            x = model._f32c(x, device)
+            B, H, W = x.shape[0], *model._hf_size(x)
+            shapes = model.latent_shapes(B, H, W)
+            eps_c = [model._f32c(e, device) for e in eps]
+            assert [tuple(e.shape) for e in eps_c] == [tuple(s) for s in shapes]
+            dims = model._state_dims(B, H, W)
+            h_in = [(states[2 * l], states[2 * l + 1]) for l in range(L)] if states else None
+            hp, cp, keep = model._states_in(lib, h_in, dims, device, st)
+            ho, co = model._states_out(dims, device)
+            y = torch.empty((B, model._cfg.out_features, H, W), dtype=torch.float32, device=device)
+            log_det = torch.empty(B, dtype=torch.float32, device=device)
+            ws = model._workspace(lib, h, B, x.shape[2], x.shape[3], device)
+            tape = torch.empty(lib.tmg_tape_bytes(h, B, x.shape[2], x.shape[3]), dtype=torch.uint8, device=device)
+            _lib.check(lib.tmg_reconstruct_train(
+                h, B, x.shape[2], x.shape[3], x.data_ptr(), hp, cp, _lib.ptr_array([t.data_ptr() for t in eps_c]),
+                y.data_ptr(), log_det.data_ptr(), _lib.ptr_array([t.data_ptr() for t in ho]),
+                _lib.ptr_array([t.data_ptr() for t in co]), tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(),
+                model._flags(), st))
+            model._bump_bn_counters()
+        ctx.model, ctx.x, ctx.eps, ctx.tape, ctx.keep, ctx.has_states = model, x, eps_c, tape, keep, bool(states)
+        ctx.state_ptrs = (hp, cp)
+        ctx.dims = dims
+        outs = [y, log_det]
+        for a, b in zip(ho, co):
+            outs += [a, b]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_y, g_ld, *g_states):
+        model, x = ctx.model, ctx.x
+        device = x.device
+        lib, h = model._prepare(device)
+        L = len(model.glow_blocks)
+        B = x.shape[0]
+        if getattr(model, "flat_grad", None) is None:
+            model.zero_flat_grad()
+        cl = lambda t, d: None if t is None else t.detach().float().contiguous(memory_format=torch.channels_last)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            g_y = torch.zeros_like(ctx.x.new_empty((B, model._cfg.out_features) + tuple(model._hf_size(x)))) if g_y is None else g_y.contiguous().float()
+            g_ld = torch.zeros(B, device=device) if g_ld is None else g_ld.contiguous().float()
+            gh = [cl(g_states[2 * l], None) for l in range(L)]
+            gc = [cl(g_states[2 * l + 1], None) for l in range(L)]
+            g_in = [(_empty_channels_last(d, device), _empty_channels_last(d, device)) for d in ctx.dims] if ctx.has_states else []
+            n = lib.tmg_reconstruct_backward_workspace_bytes(h, B, x.shape[2], x.shape[3])
+            ws = torch.empty(n, dtype=torch.uint8, device=device)
+            hp, cp = ctx.state_ptrs
+            pa = lambda ts: _lib.ptr_array([None if t is None else t.data_ptr() for t in ts])
+            _lib.check(lib.tmg_reconstruct_backward(
+                h, B, x.shape[2], x.shape[3], x.data_ptr(), hp, cp, _lib.ptr_array([t.data_ptr() for t in ctx.eps]),
+                ctx.tape.data_ptr(), g_y.data_ptr(), g_ld.data_ptr(), pa(gh), pa(gc),
+                pa([a for a, _ in g_in]) if g_in else None, pa([b for _, b in g_in]) if g_in else None,
+                model.flat_grad.data_ptr(), ws.data_ptr(), ws.numel(), model._flags(), st))
+        grads = [None, None, None]
+        for a, b in g_in:
+            grads += [a, b]
+        return tuple(grads)

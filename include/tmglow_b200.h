@@ -125,6 +125,29 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x,
                     float* y, float* log_det, float* const* h_out, float* const* c_out,
                     void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* Training forward: tmg_reconstruct that also records the input of every flow step into `tape`
+ * (tmg_tape_bytes) for tmg_reconstruct_backward.  Runs in the model's precision mode. */
+size_t tmg_tape_bytes(const tmg_model* m, int B, int h, int w);
+int tmg_reconstruct_train(tmg_model* m, int B, int h, int w, const float* x,
+                          const float* const* h_in, const float* const* c_in, const float* const* eps,
+                          float* y, float* log_det, float* const* h_out, float* const* c_out,
+                          void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes, uint32_t flags,
+                          void* stream);
+
+/* Backward of TMGlow.sample / reconstruct (what loss.backward() does through the reference's autograd graph,
+ * nn/trainFlowParallel.py:259-277): given g_y [B,out,H,W], g_log_det [B] and the gradients w.r.t. the returned LSTM
+ * states (channels-last, entries may be NULL), ACCUMULATES the gradient of every flow (decoder) parameter into `grads`
+ * (flat, laid out like the parameter buffer) and returns the gradients w.r.t. the incoming states g_h_in / g_c_in
+ * (written where a state was passed in).  The coupling networks are recomputed from the tape with the exact-fp32
+ * kernels; deterministic.  Encoder parameters: not yet (their gradient is left untouched). */
+size_t tmg_reconstruct_backward_workspace_bytes(const tmg_model* m, int B, int h, int w);
+int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x,
+                             const float* const* h_in, const float* const* c_in, const float* const* eps,
+                             const void* tape, const float* g_y, const float* g_log_det,
+                             const float* const* g_h_out, const float* const* g_c_out,
+                             float* const* g_h_in, float* const* g_c_in, float* grads,
+                             void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
 /* TMGlow.forward (nn/tmGlow.py:378-414) + LSTMCFlowDecoder.forward (:231-267).
  * Outputs: z [B,Cz,H_L,W_L] NCHW, logp [B] (= log prior + sum of log-dets), states, and when
  * eps_out != NULL the n_levels+1 noise tensors (return_eps=True). */

@@ -93,3 +93,63 @@ def test_flow_step_backward_vs_oracle_autograd(step):
             close(grads[k], v.grad, k)
             checked += 1
     assert checked >= 8, checked
+
+
+def test_reconstruct_backward_decoder_vs_oracle_autograd():
+    """Whole reverse pass (TMGlow.sample with explicit noise) with BPTT over two time steps: gradients of every flow
+    (decoder) parameter and of the initial LSTM states against torch autograd through the pinned oracle."""
+    import json
+    from conftest import load_golden
+    from oracle import tmglow_oracle as O
+    from tmglow_b200 import TMGlow
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    m.load_state_dict(g["state_dict"])
+    dev = torch.device("cuda:0")
+    m = m.to(dev).eval()
+    ocfg = O.OracleConfig.from_dict(cfg)
+    x = g["x"]
+    eps = g["rec2"]["eps"]
+    gen = torch.Generator().manual_seed(0)
+    trainable = {n for n, _ in m.named_parameters() if n.startswith("glow.")}
+    sd = {k: (v.clone().requires_grad_(True) if k in trainable else v.clone()) for k, v in g["state_dict"].items()}
+    h0 = [(h.clone().requires_grad_(True), c.clone().requires_grad_(True)) for h, c in g["h_in"]]
+    wy = [torch.randn(g["rec2"]["y"].shape, generator=gen) for _ in range(2)]
+    wl = [torch.randn(x.shape[0], generator=gen) * 0.01 for _ in range(2)]
+    # oracle: two chained time steps (same LF input and noise), loss = sum_t <y_t, wy_t> + <log_det_t, wl_t>
+    h = h0
+    loss = 0.0
+    for t in range(2):
+        y, ld, h = O.reconstruct(sd, ocfg, x, h, eps)
+        loss = loss + (y * wy[t]).sum() + (ld * wl[t]).sum()
+    loss.backward()
+    # CUDA
+    m.zero_flat_grad()
+    hd = [(a.detach().to(dev).requires_grad_(True), b.detach().to(dev).requires_grad_(True)) for a, b in g["h_in"]]
+    hh = hd
+    loss_d = 0.0
+    for t in range(2):
+        outs = m.reconstruct_train(x.to(dev), hh, [e.to(dev) for e in eps])
+        y, ld = outs[0], outs[1]
+        hh = [(outs[2 + 2 * l], outs[3 + 2 * l]) for l in range(len(hd))]
+        loss_d = loss_d + (y * wy[t].to(dev)).sum() + (ld * wl[t].to(dev)).sum()
+    assert abs(loss_d.item() - loss.item()) <= 1e-4 * max(1.0, abs(loss.item()))
+    loss_d.backward()
+    m.scatter_flat_grad()
+
+    def close(a, r, what, rel=5e-5):
+        err = (a.detach().cpu() - r).abs().max().item()
+        assert err <= rel * max(r.abs().max().item(), 1.0), "%s: max abs err %.3e (ref max %.3e)" % (what, err, r.abs().max().item())
+    for (a, b), (ar, br) in zip(hd, h0):
+        close(a.grad, ar.grad, "g_h0"); close(b.grad, br.grad, "g_c0")
+    params = dict(m.named_parameters())
+    checked = 0
+    for k in sorted(trainable):
+        if sd[k].grad is None:          # norm2.* of the LSTM step: declared, never used (flowLSTMBlock.py:170)
+            continue
+        close(params[k].grad, sd[k].grad, k)
+        checked += 1
+    assert checked >= 60, checked
