@@ -28,13 +28,14 @@ constexpr int kWgOB = 16, kWgCB = 8, kWgThreads = 128, kWgMaxPx = 512;
 __global__ void __launch_bounds__(kWgThreads)
 wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
   extern __shared__ __align__(16) float smem[];
-  const int tw = a.W + 2;
+  const int S = a.stride == 2 ? 2 : 1;
+  const int Hin = S == 2 ? a.Hin : a.H, Win = S == 2 ? a.Win : a.W;
+  const int tw = Win + 2;
   float* g_s = smem;                                   // [TR*W][16]
-  float* x_s = smem + (size_t)TR * a.W * kWgOB;        // [(TR+2)*(W+2)][8]
+  float* x_s = smem + (size_t)TR * a.W * kWgOB;        // [S*(TR-1)+3][Win+2][8]
   const int tid = threadIdx.x, o_l = tid & 15, c_l = tid >> 4;
   const int c0 = blockIdx.x * kWgCB, o0 = blockIdx.y * kWgOB, split = blockIdx.z;
   const int rtiles = (a.H + TR - 1) / TR, units = a.B * rtiles;
-  // source of this thread's staging channels is resolved per element (scalar path, like the forward kernel)
   float acc[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.f;
@@ -42,25 +43,28 @@ wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
   for (int u = split; u < units; u += nsplit) {
     const int b = u / rtiles, r0 = (u - b * rtiles) * TR;
     const int rows = min(TR, a.H - r0);
+    const int xrows = S * (rows - 1) + 3;
     __syncthreads();
     for (int i = tid; i < rows * a.W * kWgOB; i += kWgThreads) {
       const int o = i & 15, p = i >> 4;
       const int r = r0 + p / a.W, cc = p % a.W;
       g_s[i] = (o0 + o < a.cout) ? __ldg(a.g + ((size_t)(b * a.H + r) * a.W + cc) * a.g_cstride + a.g_coff + o0 + o) : 0.f;
     }
-    for (int i = tid; i < (rows + 2) * tw * kWgCB; i += kWgThreads) {
+    for (int i = tid; i < xrows * tw * kWgCB; i += kWgThreads) {
       const int c = i & 7, q = i >> 3;
-      int r = r0 - 1 + q / tw, cc = q % tw - 1;
-      bool inb = r >= 0 && r < a.H && cc >= 0 && cc < a.W;
-      if (a.pad_replicate) { r = min(max(r, 0), a.H - 1); cc = min(max(cc, 0), a.W - 1); inb = true; }
+      int r = S * r0 - 1 + q / tw, cc = q % tw - 1;
+      bool inb = r >= 0 && r < Hin && cc >= 0 && cc < Win;
+      if (a.pad_replicate) { r = min(max(r, 0), Hin - 1); cc = min(max(cc, 0), Win - 1); inb = true; }
       float v = 0.f;
       int ch = c0 + c;
+      const int chc = ch;
       if (inb && ch < a.cin) {
         const ConvSrc* s = &a.src[0];
         if (ch >= s->nch && a.nsrc > 1) { ch -= s->nch; s = &a.src[1];
           if (ch >= s->nch && a.nsrc > 2) { ch -= s->nch; s = &a.src[2]; } }
         if (ch < s->nch && s->p) {
-          v = __ldg(s->p + ((size_t)((s->bshared ? 0 : b) * a.H + r) * a.W + cc) * s->cstride + s->coff + ch);
+          v = __ldg(s->p + ((size_t)((s->bshared ? 0 : b) * Hin + r) * Win + cc) * s->cstride + s->coff + ch);
+          if (a.bn_scale) v = fmaf(v, __ldg(a.bn_scale + chc), __ldg(a.bn_shift + chc));
           if (s->relu) v = fmaxf(v, 0.f);
         }
       }
@@ -69,12 +73,12 @@ wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
     __syncthreads();
     for (int pr = 0; pr < rows; ++pr) {
       const float* gp = g_s + (size_t)pr * a.W * kWgOB + o_l;
-      const float* xp = x_s + (size_t)pr * tw * kWgCB + c_l;
+      const float* xp = x_s + (size_t)(S * pr) * tw * kWgCB + c_l;
       for (int pc = 0; pc < a.W; ++pc) {
         const float gv = gp[pc * kWgOB];
         accb += gv;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t] = fmaf(gv, xp[((t / 3) * tw + pc + t % 3) * kWgCB], acc[t]);
+        for (int t = 0; t < 9; ++t) acc[t] = fmaf(gv, xp[((t / 3) * tw + S * pc + t % 3) * kWgCB], acc[t]);
       }
     }
   }
@@ -111,7 +115,8 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   if (a.W > kWgMaxPx) { set_error("wgrad: width %d not supported", a.W); return TMG_ERR_UNSUPPORTED; }
   int TR, ns;
   wgrad_plan(a.cout, a.cin, a.B, a.H, a.W, TR, ns);
-  const size_t smem = ((size_t)TR * a.W * kWgOB + (size_t)(TR + 2) * (a.W + 2) * kWgCB) * sizeof(float);
+  const int S = a.stride == 2 ? 2 : 1, Win = S == 2 ? a.Win : a.W;
+  const size_t smem = ((size_t)TR * a.W * kWgOB + (size_t)(S * (TR - 1) + 3) * (Win + 2) * kWgCB) * sizeof(float);
   if (smem > 96 * 1024) { set_error("wgrad: tile needs %zu B of shared memory", smem); return TMG_ERR_UNSUPPORTED; }
   TMG_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   float* part = a.scratch;
@@ -473,6 +478,113 @@ int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_sc
 }
 int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st) {
   lu_bwd_kernel<<<1, 256, 3 * a.C * a.C * sizeof(float), st>>>(a);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+// ------------------------------------------------------------------ encoder adjoints
+__global__ void upsample_bwd_kernel(const float* __restrict__ gdst, float* __restrict__ gsrc, int B, int h, int w, int C, int f,
+                                    float sy, float sx, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C); int64_t t = i / C; const int x = (int)(t % w); t /= w; const int y = (int)(t % h); const int b = (int)(t / h);
+  const int H = h * f, W = w * f;
+  const int Y0 = max(0, (y - 1) * f - f), Y1 = min(H - 1, (y + 1) * f + f);
+  const int X0 = max(0, (x - 1) * f - f), X1 = min(W - 1, (x + 1) * f + f);
+  float sum = 0.f;
+  for (int Y = Y0; Y <= Y1; ++Y) {
+    const float fy = sy * Y; const int y0 = (int)fy; const int y1 = min(y0 + 1, h - 1); const float ly = fy - y0;
+    float wy = 0.f;
+    if (y0 == y) wy += 1.f - ly;
+    if (y1 == y) wy += ly;
+    if (wy == 0.f) continue;
+    for (int X = X0; X <= X1; ++X) {
+      const float fx = sx * X; const int x0 = (int)fx; const int x1 = min(x0 + 1, w - 1); const float lx = fx - x0;
+      float wx = 0.f;
+      if (x0 == x) wx += 1.f - lx;
+      if (x1 == x) wx += lx;
+      if (wx == 0.f) continue;
+      sum = fmaf(wy * wx, __ldg(gdst + (((size_t)b * H + Y) * W + X) * C + c), sum);
+    }
+  }
+  gsrc[i] = sum;
+}
+int launch_upsample_bwd(const float* gdst, float* gsrc, int B, int h, int w, int C, int f, cudaStream_t st) {
+  const int64_t total = (int64_t)B * h * w * C;
+  if (total == 0) return TMG_OK;
+  const int H = h * f, W = w * f;
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  upsample_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gdst, gsrc, B, h, w, C, f, sy, sx, total);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+__global__ void dgrad_s2_kernel(S2DgradArgs a, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % a.cin); int64_t t = i / a.cin; const int x = (int)(t % a.Win); t /= a.Win; const int y = (int)(t % a.Hin); const int b = (int)(t / a.Hin);
+  const size_t pix = ((size_t)b * a.Hin + y) * a.Win + x;
+  float* dst = a.gx + pix * a.gx_cstride + a.gx_coff + c;
+  float sum = 0.f;
+  if (!a.mask || __ldg(a.mask + pix * a.gx_cstride + a.gx_coff + c) > 0.f) {
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);       // = 2 * p
+      if ((yy & 1) || (xx & 1) || yy < 0 || xx < 0) continue;
+      const int py = yy >> 1, px = xx >> 1;
+      if (py >= a.Hout || px >= a.Wout) continue;
+      const float* gp = a.g + (((size_t)b * a.Hout + py) * a.Wout + px) * a.g_cstride + a.g_coff;
+      for (int o = 0; o < a.cout; ++o) sum = fmaf(__ldg(a.w_oihw + ((size_t)o * a.cin + c) * 9 + tap), __ldg(gp + o), sum);
+    }
+  }
+  *dst = a.accum ? *dst + sum : sum;
+}
+int launch_dgrad_s2(const S2DgradArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.B * a.Hin * a.Win * a.cin;
+  if (total == 0) return TMG_OK;
+  dgrad_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
+// per-channel sums S1 = sum g_m, S2 = sum g_m * xhat with g_m = ga gated by relu(bn(x)) > 0; one CTA per channel
+__global__ void __launch_bounds__(256)
+bn_bwd_sums_kernel(BnBwdArgs a) {
+  __shared__ double s_red[2][8];
+  const int c = blockIdx.x;
+  const float mean = a.mean[c], rstd = rsqrtf(a.var[c] + a.eps), gm = a.gamma[c], bt = a.beta[c];
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = threadIdx.x; i < a.N; i += 256) {
+    const float xh = (a.x[i * a.x_cstride + c] - mean) * rstd;
+    const float g = (fmaf(gm, xh, bt) > 0.f) ? a.ga[i * a.ga_cstride + c] : 0.f;
+    s1 += g; s2 += (double)g * xh;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = s1; s_red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < 8; ++k) { t1 += s_red[0][k]; t2 += s_red[1][k]; }
+    a.sums[c] = (float)t1; a.sums[a.n + c] = (float)t2;
+    a.g_beta[c] += (float)t1; a.g_gamma[c] += (float)t2;
+  }
+}
+__global__ void bn_bwd_apply_kernel(BnBwdArgs a, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % a.n); const int64_t px = i / a.n;
+  const float mean = a.mean[c], rstd = rsqrtf(a.var[c] + a.eps), gm = a.gamma[c], bt = a.beta[c];
+  const float xh = (a.x[px * a.x_cstride + c] - mean) * rstd;
+  float g = (fmaf(gm, xh, bt) > 0.f) ? a.ga[px * a.ga_cstride + c] : 0.f;
+  if (a.train) g = g - a.sums[c] / (float)a.N - xh * (a.sums[a.n + c] / (float)a.N);
+  a.gx[px * a.gx_cstride + c] += gm * rstd * g;
+}
+int launch_bn_relu_bwd(const BnBwdArgs& a, cudaStream_t st) {
+  if (a.n <= 0) return TMG_OK;
+  bn_bwd_sums_kernel<<<a.n, 256, 0, st>>>(a);
+  TMG_LAUNCH_CHECK();
+  const int64_t total = a.N * a.n;
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }

@@ -332,7 +332,11 @@ struct WgradArgs {
   int cin;                 // channels of the concatenation
   const float* g;          // output gradient [B,HW,g_cstride], channels [g_coff, g_coff + cout)
   int g_cstride, g_coff, cout;
-  int B, H, W;
+  int B, H, W;             // OUTPUT size of the convolution (= input size when stride is 1)
+  int stride;              // 0/1: stride 1, 2: stride 2 (input size Hin x Win)
+  int Hin, Win;
+  const float* bn_scale;   // optional per-(concatenated)-channel affine applied before the ReLU (folded BatchNorm)
+  const float* bn_shift;
   int pad_replicate;
   float* gw;               // OIHW [cout][cin][3][3], accumulated into (+=) when accum
   float* gbias;            // [cout] column sums of g (+= when accum) or null
@@ -415,6 +419,29 @@ struct GaussBwdArgs {
   int B, HW, n;
 };
 int launch_gauss_bwd(const GaussBwdArgs& a, cudaStream_t st);
+// adjoint of the bilinear upsampling (align_corners=True): gsrc[b,y,x,c] = sum of the dst gradients that read it
+int launch_upsample_bwd(const float* gdst, float* gsrc, int B, int h, int w, int C, int f, cudaStream_t st);
+// data gradient of a stride-2 3x3 convolution (pad 1): gx[b,q,c] (+)= sum_{tap,o} w[o][c][tap] g[b,(q-off)/2,o], gated by mask > 0
+struct S2DgradArgs {
+  const float* g; int g_cstride, g_coff, cout; int Hout, Wout;
+  const float* w_oihw; int cin;
+  const float* mask; float* gx; int gx_cstride, gx_coff; int accum;
+  int B, Hin, Win;
+};
+int launch_dgrad_s2(const S2DgradArgs& a, cudaStream_t st);
+// BatchNorm2d + ReLU backward (denseBlock.py:49-50): ga = gradient w.r.t. relu(bn(x)); batch statistics (train) or
+// running statistics (eval); accumulates g_x into gx and g_gamma / g_beta into the flat gradient buffer
+struct BnBwdArgs {
+  const float* x; int x_cstride;          // channels [0, n)
+  const float* ga; int ga_cstride;
+  const float* mean; const float* var;    // per channel (batch or running)
+  const float* gamma; const float* beta;
+  float* gx; int gx_cstride;              // +=
+  float* g_gamma; float* g_beta;          // +=
+  float* sums;                            // scratch [2n]
+  int n; int64_t N; float eps; int train;
+};
+int launch_bn_relu_bwd(const BnBwdArgs& a, cudaStream_t st);
 int gauss_bwd_blocks(int B, int HW);
 
 // ------------------------------------------------------------------ weight packing jobs

@@ -1609,7 +1609,8 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
 // ---- backward of TMGlow.reconstruct / TMGlow.sample (tmGlow.py:417-467 + LSTMCFlowDecoder.reverse :269-303) given the
 // tape of the training forward.  Decoder (flow) parameters, LSTM state gradients and the gradient w.r.t. the
 // conditioning maps / top prior parameters; the encoder backward follows (run_encoder_backward).
-struct RbExtra { BwdExtra e; size_t ga, gb, gcond[TMG_MAX_LEVELS], gzout, gpart, total; };
+struct RbExtra { BwdExtra e; size_t ga, gb, gcond[TMG_MAX_LEVELS], gzout, gpart;
+                 size_t gdb[TMG_MAX_LEVELS], gcc, gact, ge0, bnsums, encw, encwt; size_t total; };
 
 static RbExtra rb_extra(const tmg_model& m, const Plan& p) {
   RbExtra r{};
@@ -1626,8 +1627,131 @@ static RbExtra rb_extra(const tmg_model& m, const Plan& p) {
   for (int l = 0; l < p.L; ++l) r.gcond[l] = take((size_t)p.B * p.Hl[l] * p.Wl[l] * m.cfg.cond_features);
   r.gzout = take((size_t)p.B * p.Hl[p.L - 1] * p.Wl[p.L - 1] * 2 * m.Cz);
   r.gpart = take((size_t)gauss_bwd_blocks(p.B, p.Hl[0] * p.Wl[0]) + 64);
+  {   // encoder backward
+    const tmg_config& g = m.cfg;
+    size_t mxcc = 0, mxact = 0, encw = 0, encwt = 0;
+    int nfmax = 0;
+    auto need = [&](int O, int I, int H, int W) {
+      encw = std::max(encw, wgrad_scratch_floats(O, I, p.B, H, W));
+      encwt = std::max(encwt, (size_t)9 * O * ((I + 3) / 4 * 4) + 64);
+    };
+    for (int l = 0; l < p.L; ++l) {
+      const LevelW& lv = m.levels[l];
+      const size_t px = (size_t)p.B * p.eh[l] * p.ew[l];
+      r.gdb[l] = take(px * lv.nf_out);
+      mxcc = std::max(mxcc, px * std::max(g.cond_features, 2 * m.Cz));
+      mxact = std::max(mxact, px * lv.nf_out);
+      nfmax = std::max(nfmax, lv.nf_out);
+      need(g.cond_features, lv.nf_out, p.eh[l], p.ew[l]);
+      need(2 * m.Cz, lv.nf_out, p.eh[l], p.ew[l]);
+      need(g.growth_rate, lv.nf_out, p.eh[l], p.ew[l]);
+      need(lv.nf_in, l > 0 ? m.levels[l - 1].nf_out : g.init_features / 2, p.eh[l], p.ew[l]);
+    }
+    need(g.init_features / 2, g.in_features, p.h, p.w);
+    r.gcc = take(mxcc); r.gact = take(mxact);
+    r.ge0 = take((size_t)p.B * p.h * p.w * (g.init_features / 2));
+    r.bnsums = take((size_t)2 * nfmax + 64);
+    r.encw = take(encw); r.encwt = take(encwt);
+  }
   r.total = off;
   return r;
+}
+
+// Encoder.forward backward (nn/tmGlow.py:104-186, denseBlock.py:15-100, misc.py:34): from the gradients w.r.t. the
+// conditioning maps and the top prior parameters to every encoder parameter.  The activations are in the workspace
+// (run_encoder was just re-run); BatchNorm uses batch statistics (train) or the running ones (eval).
+static int run_encoder_backward(Ctx& c, bool bn_train, float* rb, const RbExtra& rx, float* grads) {
+  tmg_model& m = c.m;
+  const tmg_config& g = m.cfg;
+  const Plan& p = c.p;
+  float* ws = c.ws;
+  const int B = p.B, L = p.L, up = g.cglow_upscale;
+  float* wt = rb + rx.encwt;
+  float* wscr = rb + rx.encw;
+  float* GCC = rb + rx.gcc;
+  float* GA = rb + rx.gact;
+  for (int l = 0; l < L; ++l)
+    TMG_CUDA_OK(cudaMemsetAsync(rb + rx.gdb[l], 0, (size_t)B * p.eh[l] * p.ew[l] * m.levels[l].nf_out * sizeof(float), c.st));
+  for (int i = L - 1; i >= 0; --i) {
+    const LevelW& lv = m.levels[i];
+    const int eh = p.eh[i], ew = p.ew[i];
+    const int64_t N = (int64_t)B * eh * ew;
+    float* db = ws + p.db[i];
+    float* GDB = rb + rx.gdb[i];
+    const ConvSrc sdb{db, lv.nf_out, 0, lv.nf_out, 0};
+    const BwdDest ddb{GDB, nullptr, lv.nf_out, 0, lv.nf_out, 1};
+    if (i == L - 1) {
+      const float* gz = rb + rx.gzout;
+      if (up > 1) { TMG_TRY(launch_upsample_bwd(gz, GCC, B, eh, ew, 2 * m.Cz, up, c.st)); gz = GCC; }
+      TMG_TRY(conv_backward(c, B, eh, ew, m.out_conv, 1, &sdb, false, gz, 2 * m.Cz, 0, &ddb, 1, grads, wt, wscr));
+    }
+    {
+      const float* gc = rb + rx.gcond[i];
+      if (up > 1) { TMG_TRY(launch_upsample_bwd(gc, GCC, B, eh, ew, g.cond_features, up, c.st)); gc = GCC; }
+      TMG_TRY(conv_backward(c, B, eh, ew, lv.cond, 1, &sdb, false, gc, g.cond_features, 0, &ddb, 1, grads, wt, wscr));
+    }
+    for (int l = (int)lv.dense.size() - 1; l >= 0; --l) {
+      const DenseW& d = lv.dense[l];
+      const float *mean, *var, *sc, *sh;
+      if (bn_train) {
+        BnStatArgs sa{};
+        sa.x = db; sa.cstride = lv.nf_out; sa.c0 = 0; sa.n = d.cin; sa.N = N; sa.mean = ws + p.bn_mean; sa.var = ws + p.bn_var;
+        TMG_TRY(launch_bn_stats(sa, c.st));
+        BnFoldArgs fa{};
+        fa.mean = ws + p.bn_mean; fa.var = ws + p.bn_var; fa.w = c.P() + d.bn_w; fa.b = c.P() + d.bn_b;
+        fa.run_mean = m.params + d.bn_rm; fa.run_var = m.params + d.bn_rv;
+        fa.scale = ws + p.bn_scale; fa.shift = ws + p.bn_shift; fa.n = d.cin; fa.N = N; fa.eps = 1e-5f; fa.momentum = 0.f;
+        TMG_TRY(launch_bn_fold_train(fa, c.st));
+        mean = ws + p.bn_mean; var = ws + p.bn_var; sc = ws + p.bn_scale; sh = ws + p.bn_shift;
+      } else {
+        mean = c.P() + d.bn_rm; var = c.P() + d.bn_rv; sc = c.Q() + d.scale; sh = c.Q() + d.shift;
+      }
+      // conv: weight gradient on relu(bn(x)), data gradient w.r.t. relu(bn(x)) into GA
+      WgradArgs wa{};
+      wa.src[0] = ConvSrc{db, lv.nf_out, 0, d.cin, 1}; wa.nsrc = 1; wa.cin = d.cin;
+      wa.bn_scale = sc; wa.bn_shift = sh;
+      wa.g = GDB; wa.g_cstride = lv.nf_out; wa.g_coff = d.cin; wa.cout = d.conv.O;
+      wa.B = B; wa.H = eh; wa.W = ew; wa.gw = grads + d.conv.w_param; wa.accum = 1; wa.scratch = wscr;
+      TMG_TRY(launch_wgrad(wa, c.st));
+      TMG_TRY(launch_pack_dgrad(c.P() + d.conv.w_param, wt, d.conv.O, d.conv.I, c.st));
+      ConvArgs a{};
+      a.src[0] = ConvSrc{GDB, lv.nf_out, d.cin, d.conv.O, 0}; a.nsrc = 1;
+      a.w = wt; a.cin_w = d.conv.O; a.cout_w = (d.cin + 3) / 4 * 4; a.cout = d.cin;
+      a.out = GA; a.out_cstride = d.cin; a.out_coff = 0;
+      a.B = B; a.Hin = eh; a.Win = ew; a.Hout = eh; a.Wout = ew; a.stride = 1;
+      TMG_TRY(launch_conv3x3(a, c.st));
+      BnBwdArgs ba{};
+      ba.x = db; ba.x_cstride = lv.nf_out; ba.ga = GA; ba.ga_cstride = d.cin; ba.mean = mean; ba.var = var;
+      ba.gamma = c.P() + d.bn_w; ba.beta = c.P() + d.bn_b; ba.gx = GDB; ba.gx_cstride = lv.nf_out;
+      ba.g_gamma = grads + d.bn_w; ba.g_beta = grads + d.bn_b; ba.sums = rb + rx.bnsums;
+      ba.n = d.cin; ba.N = N; ba.eps = 1e-5f; ba.train = bn_train ? 1 : 0;
+      TMG_TRY(launch_bn_relu_bwd(ba, c.st));
+    }
+    // the stride-2 convolution that produced the first nf_in channels of this level
+    const ConvW& cw = i > 0 ? lv.trans : m.in_conv3;
+    const float* src = i > 0 ? ws + p.db[i - 1] : ws + p.e0;
+    const int sch = i > 0 ? m.levels[i - 1].nf_out : g.init_features / 2;
+    const int Hin = i > 0 ? p.eh[i - 1] : p.h, Win = i > 0 ? p.ew[i - 1] : p.w;
+    float* gsrc = i > 0 ? rb + rx.gdb[i - 1] : rb + rx.ge0;
+    WgradArgs wa{};
+    wa.src[0] = ConvSrc{src, sch, 0, sch, 1}; wa.nsrc = 1; wa.cin = sch;
+    wa.g = GDB; wa.g_cstride = lv.nf_out; wa.g_coff = 0; wa.cout = cw.O;
+    wa.B = B; wa.H = eh; wa.W = ew; wa.stride = 2; wa.Hin = Hin; wa.Win = Win;
+    wa.gw = grads + cw.w_param; wa.accum = 1; wa.scratch = wscr;
+    TMG_TRY(launch_wgrad(wa, c.st));
+    S2DgradArgs da{};
+    da.g = GDB; da.g_cstride = lv.nf_out; da.g_coff = 0; da.cout = cw.O; da.Hout = eh; da.Wout = ew;
+    da.w_oihw = c.P() + cw.w_param; da.cin = sch; da.mask = src; da.gx = gsrc; da.gx_cstride = sch; da.gx_coff = 0;
+    da.accum = i > 0 ? 1 : 0; da.B = B; da.Hin = Hin; da.Win = Win;
+    TMG_TRY(launch_dgrad_s2(da, c.st));
+  }
+  // In_conv (tmGlow.py:148): weight gradient only (the LF input needs no gradient)
+  WgradArgs wa{};
+  wa.src[0] = ConvSrc{ws + p.xn, g.in_features, 0, g.in_features, 0}; wa.nsrc = 1; wa.cin = g.in_features;
+  wa.g = rb + rx.ge0; wa.g_cstride = g.init_features / 2; wa.g_coff = 0; wa.cout = m.in_conv.O;
+  wa.B = B; wa.H = p.h; wa.W = p.w; wa.gw = grads + m.in_conv.w_param; wa.accum = 1; wa.scratch = wscr;
+  TMG_TRY(launch_wgrad(wa, c.st));
+  return TMG_OK;
 }
 
 size_t tmg_reconstruct_backward_workspace_bytes(const tmg_model* m, int B, int h, int w) {
@@ -1725,8 +1849,8 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
       TMG_TRY(launch_gauss_bwd(gt, c.st));
     }
   }
-  // zero states: the caller's state gradients stay untouched when no state was passed in
-  return TMG_OK;
+  // encoder parameters
+  return run_encoder_backward(c, (flags & TMG_FLAG_BN_TRAIN) != 0, rb, rx, grads);
 }
 
 size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl) {

@@ -95,9 +95,11 @@ def test_flow_step_backward_vs_oracle_autograd(step):
     assert checked >= 8, checked
 
 
-def test_reconstruct_backward_decoder_vs_oracle_autograd():
-    """Whole reverse pass (TMGlow.sample with explicit noise) with BPTT over two time steps: gradients of every flow
-    (decoder) parameter and of the initial LSTM states against torch autograd through the pinned oracle."""
+@pytest.mark.parametrize("train_bn", [False, True])
+def test_reconstruct_backward_vs_oracle_autograd(train_bn):
+    """Whole reverse pass (TMGlow.sample with explicit noise) with BPTT over two time steps: gradients of EVERY
+    parameter (encoder incl. BatchNorm in eval and train mode, flow steps, split priors) and of the initial LSTM
+    states against torch autograd through the pinned oracle."""
     import json
     from conftest import load_golden
     from oracle import tmglow_oracle as O
@@ -109,12 +111,13 @@ def test_reconstruct_backward_decoder_vs_oracle_autograd():
                init_features=cfg["init_features"], rec_features=cfg["rec_features"])
     m.load_state_dict(g["state_dict"])
     dev = torch.device("cuda:0")
-    m = m.to(dev).eval()
+    m = m.to(dev)
+    m.train(train_bn)
     ocfg = O.OracleConfig.from_dict(cfg)
     x = g["x"]
     eps = g["rec2"]["eps"]
     gen = torch.Generator().manual_seed(0)
-    trainable = {n for n, _ in m.named_parameters() if n.startswith("glow.")}
+    trainable = {n for n, _ in m.named_parameters()}
     sd = {k: (v.clone().requires_grad_(True) if k in trainable else v.clone()) for k, v in g["state_dict"].items()}
     h0 = [(h.clone().requires_grad_(True), c.clone().requires_grad_(True)) for h, c in g["h_in"]]
     wy = [torch.randn(g["rec2"]["y"].shape, generator=gen) for _ in range(2)]
@@ -123,7 +126,7 @@ def test_reconstruct_backward_decoder_vs_oracle_autograd():
     h = h0
     loss = 0.0
     for t in range(2):
-        y, ld, h = O.reconstruct(sd, ocfg, x, h, eps)
+        y, ld, h = O.reconstruct(sd, ocfg, x, h, eps, training=train_bn)
         loss = loss + (y * wy[t]).sum() + (ld * wl[t]).sum()
     loss.backward()
     # CUDA
