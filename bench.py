@@ -197,6 +197,82 @@ def workload_config(S, n, note=None):
     return c
 
 
+TRAIN_GEOM = dict(nic=3, h=16, w=16, noc=3, H=64, W=64)       # cylinder-array (x[B,3,16,16] -> y[B,3,64,64])
+TRAIN_KW = dict(cond_features=32, cglow_upscale=4, growth_rate=4, init_features=16, rec_features=64)
+
+
+def run_train(args, rank, world, local):
+    """BASELINE.json configs[2]: TM-Glow cylinder-array training, data-parallel, one NCCL all-reduce of the flat
+    gradient per optimizer step.  One "step" = one BPTT block of `tback` time steps at the global batch
+    (trainFlowParallel.py:241-303); strong scaling: the global batch is fixed, each rank takes global_batch / N."""
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    from tmglow_b200 import TMGlow, _lib, train as T
+    lib = _lib.load()
+    torch.manual_seed(12345); np.random.seed(12345)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TMGlow(TRAIN_GEOM["nic"], TRAIN_GEOM["noc"], [4, 4, 4], [16, 16, 16], **TRAIN_KW)
+    perturb_(m, 12346)
+    m = m.to(dev).train()
+    m.precision = args.precision
+    GB, tb = args.global_batch, args.tback
+    assert GB % world == 0
+    Bl = GB // world
+    g = torch.Generator().manual_seed(7 + rank)
+    x = torch.randn(Bl, tb, TRAIN_GEOM["nic"], TRAIN_GEOM["h"], TRAIN_GEOM["w"], generator=g).to(dev)
+    tgt = torch.randn(Bl, tb, TRAIN_GEOM["noc"], TRAIN_GEOM["H"], TRAIN_GEOM["W"], generator=g).to(dev)
+    h0 = m.initLSTMStates(torch.arange(Bl) + 1000 * rank, [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
+    opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1e-4, amsgrad=True)      # args.py:143-147
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    h = h0
+    for _ in range(max(args.warmup, 1)):
+        loss, norm, h = T.train_block(m, opt, x, tgt, h, max_norm=1.0)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    lib.tmg_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, norm, h = T.train_block(m, opt, x, tgt, h, max_norm=1.0)
+    e1.record()
+    barrier()
+    launches = lib.tmg_launch_count(0)
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop()
+    assert torch.isfinite(loss).all(), "non-finite loss"
+    if rank == 0:
+        line = {"metric": "train_steps_per_sec", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "forward " + DTYPES[args.precision] + "; backward f32 (CUDA cores)",
+                "data": "synthetic",
+                "config": {"workload": "TM-Glow cylinder-array training (BASELINE.json configs[2]): global batch %d, BPTT block of %d "
+                                       "time steps, x[B,T,3,16,16] -> y[B,T,3,64,64], default model, Adam-amsgrad, grad clip 1.0, "
+                                       "loss = beta*(MSE+RMS) + entropy (PDE stencil terms of TMGLowLoss not included)" % (GB, tb),
+                           "global_batch": GB, "tback": tb, "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world},
+                "clocks": clk, "gpu_launches": int(launches), "loss": float(loss), "grad_norm": norm,
+                "hf_snapshots_per_sec": GB * tb * args.steps / (ms * 1e-3)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +285,10 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: HF samples/s (configs[1], the default line); train: train steps/s (configs[2])")
+    ap.add_argument("--global-batch", type=int, default=64)
+    ap.add_argument("--tback", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -217,6 +297,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "train":
+        run_train(args, rank, world, local)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"

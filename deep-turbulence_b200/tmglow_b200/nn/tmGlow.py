@@ -418,6 +418,17 @@ class TMGlow(nn.Module):
         self._sync_flat(device)
         return self._flat
 
+    def flat_parameter_for_optimizer(self):
+        """An ``nn.Parameter`` aliasing the flat buffer (NOT registered on the module, so ``state_dict`` keeps the
+        reference layout): build the optimizer on ``[model.flat_parameter_for_optimizer()]``.  Buffers inside the flat
+        buffer (masks, running statistics) receive zero gradients, hence zero Adam updates; do not use weight decay."""
+        flat = self.flat_parameters()
+        fp = self.__dict__.get("_flat_param")
+        if fp is None or fp.data_ptr() != flat.data_ptr():
+            fp = torch.nn.Parameter(flat)
+            object.__setattr__(self, "_flat_param", fp)
+        return fp
+
     def reconstruct_train(self, x, h_in, eps):
         """Differentiable ``reconstruct`` (and therefore ``sample``): the forward runs in the model's precision mode
         and records the input of every flow step; ``backward`` (hand-written CUDA, exact fp32) returns the gradients
@@ -425,7 +436,9 @@ class TMGlow(nn.Module):
         buffer laid out like ``flat_parameters()``; ``zero_flat_grad()`` clears it, ``scatter_flat_grad()`` exposes it
         as ``p.grad`` of every parameter).  Round 1: gradients of the flow (decoder) parameters; the encoder's are the
         next step."""
-        return _ReconstructFn.apply(self, x, eps, *([t for hc in (h_in or []) for t in hc]))
+        # the flat parameter is passed so that the outputs carry a graph even without incoming states; its gradient
+        # is accumulated into ``flat_grad`` by the backward kernel (autograd gets None for it)
+        return _ReconstructFn.apply(self, x, eps, self.flat_parameter_for_optimizer(), *([t for hc in (h_in or []) for t in hc]))
 
     def sample_train(self, x, h_in=None):
         B, (H, W) = x.shape[0], self._hf_size(x)
@@ -517,7 +530,7 @@ class _ReconstructFn(torch.autograd.Function):
     """autograd bridge of ``TMGlow.reconstruct``: tmg_reconstruct_train / tmg_reconstruct_backward."""
 
     @staticmethod
-    def forward(ctx, model, x, eps, *states):
+    def forward(ctx, model, x, eps, flat_param, *states):
         device = x.device
         lib, h = model._prepare(device)
         L = len(model.glow_blocks)
@@ -576,7 +589,7 @@ class _ReconstructFn(torch.autograd.Function):
                 ctx.tape.data_ptr(), g_y.data_ptr(), g_ld.data_ptr(), pa(gh), pa(gc),
                 pa([a for a, _ in g_in]) if g_in else None, pa([b for _, b in g_in]) if g_in else None,
                 model.flat_grad.data_ptr(), ws.data_ptr(), ws.numel(), model._flags(), st))
-        grads = [None, None, None]
+        grads = [None, None, None, None]
         for a, b in g_in:
             grads += [a, b]
         return tuple(grads)

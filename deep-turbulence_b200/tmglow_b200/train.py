@@ -1,0 +1,70 @@
+"""Data-parallel training step on top of ``TMGlow.sample_train`` (hand-written CUDA forward + backward).
+
+Mirrors the inner loop of the reference trainer (``nn/trainFlowParallel.py:241-303``): reverse-KL training runs through
+``sample()`` -- back-propagation through time over a block of ``tback`` time steps with the ConvLSTM states carried
+from step to step --, the gradient norm is clipped, the optimizer steps once per block and the states are detached.
+The reference replicates the model with ``nn.DataParallel`` threads inside one process (``utils/parallel.py``); here
+every rank is one process with one GPU and the ONLY collective is one all-reduce of the flat gradient buffer per
+optimizer step (all parameters live in one flat buffer, so there is nothing to bucket).  Works on NCCL (GPU) and on
+gloo (the averaging / clipping logic is tested at world size 2 on CPU, tests/test_parallel_cpu.py).
+"""
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+
+def allreduce_mean_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place mean over the ranks of ``group`` (no-op without an initialised process group).  Equal shards:
+    mean over ranks of per-rank means == the reference's mean over GPUs (trainFlowParallel.py:285)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, group=group)
+        t.div_(dist.get_world_size(group))
+    return t
+
+
+def clip_flat_grad_(g: torch.Tensor, max_norm: float) -> float:
+    """``torch.nn.utils.clip_grad_norm_`` on the flat gradient (trainFlowParallel.py:290): returns the norm before."""
+    norm = float(g.norm())
+    if max_norm is not None and norm > max_norm:
+        g.mul_(max_norm / (norm + 1e-6))
+    return norm
+
+
+def reverse_kl_loss(y_pred: torch.Tensor, log_det: torch.Tensor, target: torch.Tensor, beta: float = 200.0) -> torch.Tensor:
+    """Data terms + entropy term of ``TMGLowLoss.forward`` (trainFlowParallel.py:121-153): beta * (MSE + RMS mismatch)
+    + log_det / (ln 2 * pixels).  The PDE-residual terms of the reference loss (3-channel Sobel stencils on the
+    prediction, pc/*.py) are the caller's and are not restated here.  y_pred, target: [B,T,C,H,W]; log_det: [B,T]."""
+    mse = torch.mean((y_pred - target) ** 2)
+    pred_rms = torch.sqrt(torch.mean((y_pred - y_pred.mean(dim=1, keepdim=True)) ** 2, dim=1) + 1e-12)
+    tgt_rms = torch.sqrt(torch.mean((target - target.mean(dim=1, keepdim=True)) ** 2, dim=1) + 1e-12)
+    rms = torch.mean((pred_rms - tgt_rms) ** 2)
+    n_out = y_pred.shape[-3] * y_pred.shape[-2] * y_pred.shape[-1]
+    neg_entropy = log_det.mean() / math.log(2.0) / n_out
+    return beta * (mse + rms) + neg_entropy
+
+
+def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h_in: Optional[list],
+                loss_fn: Callable = reverse_kl_loss, max_norm: Optional[float] = 1.0, group=None):
+    """One optimizer step on a BPTT block.  ``x_block [B,T,nic,h,w]``, ``target [B,T,noc,H,W]``, ``h_in`` list of
+    (h, c) or None; ``optimizer`` must have been built on ``[model.flat_parameter_for_optimizer()]``.
+    Returns ``(loss, grad_norm, h_out)`` with ``h_out`` detached (truncated BPTT, trainFlowParallel.py:296-300)."""
+    T = x_block.shape[1]
+    model.zero_flat_grad()
+    ys, lds = [], []
+    h = h_in
+    for t in range(T):
+        outs = model.sample_train(x_block[:, t], h)
+        ys.append(outs[0]); lds.append(outs[1])
+        h = [(outs[2 + 2 * l], outs[3 + 2 * l]) for l in range(len(model.glow_blocks))]
+    loss = loss_fn(torch.stack(ys, 1), torch.stack(lds, 1), target)
+    loss.backward()
+    g = model.flat_grad
+    allreduce_mean_(g, group)                       # the one collective of data-parallel training
+    norm = clip_flat_grad_(g, max_norm)
+    flat = model.flat_parameter_for_optimizer()
+    flat.grad = g
+    optimizer.step()
+    model.refresh_weights()                         # derived (packed) weights follow the new parameters
+    return loss.detach(), norm, [(a.detach(), b.detach()) for a, b in h]

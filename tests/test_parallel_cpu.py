@@ -107,3 +107,35 @@ def test_bench_sharding_is_weak_scaling():
     spec.loader.exec_module(bench)
     c = bench.workload_config(1024, 8)
     assert c["samples_per_gpu_per_step"] == 1024 and "x8" in c["parallelism"] and "no collective" in c["parallelism"]
+
+
+def _run_dp_rank(rank, world, port, out):
+    import torch.distributed as dist
+    from tmglow_b200 import train as T
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.randn(1000, generator=g)          # this rank's flat gradient
+    T.allreduce_mean_(grad)
+    norm = T.clip_flat_grad_(grad, 1.0)
+    if rank == 0:
+        torch.save({"grad": grad, "norm": norm}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_allreduce_and_clip_gloo(tmp_path):
+    """Data-parallel step logic: mean of the ranks' flat gradients (one all-reduce), then global-norm clipping --
+    identical on every rank, equal to the single-process computation on the concatenated batch of equal shards."""
+    from tmglow_b200 import train as T
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_run_dp_rank, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    gs = [torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(2)]
+    ref = (gs[0] + gs[1]) / 2
+    n = float(ref.norm())
+    assert abs(got["norm"] - n) < 1e-5
+    assert torch.allclose(got["grad"], ref * (1.0 / (n + 1e-6)), atol=1e-6)
+    assert abs(float(got["grad"].norm()) - 1.0) < 1e-4
+    # single process: no process group -> no-op
+    t = torch.ones(4)
+    assert torch.equal(T.allreduce_mean_(t.clone()), t)
