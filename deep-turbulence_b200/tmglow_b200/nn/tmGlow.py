@@ -337,9 +337,15 @@ class TMGlow(nn.Module):
             return self._f32c(x[:1], device), True
         return self._f32c(x, device), False
 
+    def train(self, mode=True):
+        # the eval-mode BatchNorm fold is derived from the running statistics, which train-mode calls update in place
+        # inside the library: re-derive when the mode changes (not on every train-mode call)
+        if mode != self.training:
+            self._refreshed_for = None
+        return super().train(mode)
+
     def _bump_bn_counters(self):
         if self.training:
-            self._refreshed_for = None      # the library updated the BatchNorm running statistics in place
             for name, b in self.named_buffers():
                 if name.endswith("num_batches_tracked"):
                     b += 1
