@@ -126,7 +126,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_samples_per_s(sd, cfg_dict, batch, min_seconds, max_calls=50):
+def cpu_port_samples_per_s(sd, cfg_dict, batch, min_seconds, max_calls=400):
     """The pinned oracle (CPU port of the reference path, torch CPU operators -- the same ATen
     kernels the reference runs) timed on the host cores."""
     from oracle import tmglow_oracle as O
@@ -201,18 +201,8 @@ TRAIN_GEOM = dict(nic=3, h=16, w=16, noc=3, H=64, W=64)       # cylinder-array (
 TRAIN_KW = dict(cond_features=32, cglow_upscale=4, growth_rate=4, init_features=16, rec_features=64)
 
 
-def run_train(args, rank, world, local):
-    """BASELINE.json configs[2]: TM-Glow cylinder-array training, data-parallel, one NCCL all-reduce of the flat
-    gradient per optimizer step.  One "step" = one BPTT block of `tback` time steps at the global batch
-    (trainFlowParallel.py:241-303); strong scaling: the global batch is fixed, each rank takes global_batch / N."""
-    assert torch.cuda.is_available()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+def measure_train(args, rank, world, dev, dist, steps, warmup):
+    """Times `steps` optimizer steps (after `warmup`) of data-parallel training; returns (ms, loss, norm, launches)."""
     from tmglow_b200 import TMGlow, _lib, train as T
     lib = _lib.load()
     torch.manual_seed(12345); np.random.seed(12345)
@@ -228,35 +218,49 @@ def run_train(args, rank, world, local):
     g = torch.Generator().manual_seed(7 + rank)
     x = torch.randn(Bl, tb, TRAIN_GEOM["nic"], TRAIN_GEOM["h"], TRAIN_GEOM["w"], generator=g).to(dev)
     tgt = torch.randn(Bl, tb, TRAIN_GEOM["noc"], TRAIN_GEOM["H"], TRAIN_GEOM["W"], generator=g).to(dev)
-    h0 = m.initLSTMStates(torch.arange(Bl) + 1000 * rank, [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
+    h = m.initLSTMStates(torch.arange(Bl) + 1000 * rank, [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
     opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1e-4, amsgrad=True)      # args.py:143-147
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    h = h0
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         loss, norm, h = T.train_block(m, opt, x, tgt, h, max_norm=1.0)
-    clocks = ClockSampler(local)
-    barrier()
-    clocks.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
     lib.tmg_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss, norm, h = T.train_block(m, opt, x, tgt, h, max_norm=1.0)
     e1.record()
-    barrier()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
     launches = lib.tmg_launch_count(0)
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clk = clocks.stop()
     assert torch.isfinite(loss).all(), "non-finite loss"
+    return ms, float(loss), norm, int(launches)
+
+
+def run_train(args, rank, world, local):
+    """BASELINE.json configs[2]: TM-Glow cylinder-array training, data-parallel, one NCCL all-reduce of the flat
+    gradient per optimizer step.  One "step" = one BPTT block of `tback` time steps at the global batch
+    (trainFlowParallel.py:241-303); strong scaling: the global batch is fixed, each rank takes global_batch / N."""
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, loss, norm, launches = measure_train(args, rank, world, dev, dist, args.steps, args.warmup)
+    clk = clocks.stop()
+    GB, tb = args.global_batch, args.tback
     if rank == 0:
         line = {"metric": "train_steps_per_sec", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -266,7 +270,7 @@ def run_train(args, rank, world, local):
                                        "time steps, x[B,T,3,16,16] -> y[B,T,3,64,64], default model, Adam-amsgrad, grad clip 1.0, "
                                        "loss = beta*(MSE+RMS) + entropy (PDE stencil terms of TMGLowLoss not included)" % (GB, tb),
                            "global_batch": GB, "tback": tb, "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world},
-                "clocks": clk, "gpu_launches": int(launches), "loss": float(loss), "grad_norm": norm,
+                "clocks": clk, "gpu_launches": int(launches), "loss": loss, "grad_norm": norm,
                 "hf_snapshots_per_sec": GB * tb * args.steps / (ms * 1e-3)}
         print(json.dumps(line))
     if dist is not None:
@@ -289,6 +293,7 @@ def main():
                     help="sample: HF samples/s (configs[1], the default line); train: train steps/s (configs[2])")
     ap.add_argument("--global-batch", type=int, default=64)
     ap.add_argument("--tback", type=int, default=10)
+    ap.add_argument("--no-train", action="store_true", help="skip the short training measurement of the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -470,13 +475,28 @@ def main():
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": "%d x oracle.sample() of %d HF samples (%.1f s) on %d host threads" % (ncalls, args.ref_batch, el, cores)}
 
+    # ---------------- the other half of BASELINE.json's metric: data-parallel train steps/s (configs[2]), short run
+    train = None
+    if not args.no_train:
+        del y, ld, h
+        model = None
+        torch.cuda.empty_cache()
+        try:
+            ms_t, loss_t, norm_t, _ = measure_train(args, rank, world, dev, dist, steps=2, warmup=1)
+            train = {"metric": "train_steps_per_sec", "value": 2 / (ms_t * 1e-3), "unit": "steps/s", "ms_per_step": ms_t / 2,
+                     "global_batch": args.global_batch, "tback": args.tback, "scaling": "strong",
+                     "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world,
+                     "workload": "TM-Glow cylinder-array training (configs[2]); see bench.py --workload train", "loss": loss_t}
+        except Exception as ex:        # the sampling line must not be lost to a training failure
+            train = {"error": repr(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": "hf_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": dict(workload_config(S, world), precision=args.precision),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "fast_mode": fast,
+            "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "fast_mode": fast, "train": train,
             "whole_path": {"alg_tflops": value * ALG_FLOP_PER_SAMPLE / 1e12 / world,
                            "alg_gbs": value * ALG_BYTES_PER_SAMPLE / 1e9 / world, "per": "GPU"},
             "kernel_classes": classes,

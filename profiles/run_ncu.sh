@@ -8,13 +8,13 @@ TAG=${1:-r01}
 PREC=${2:-f16x3}
 S=${3:-1024}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --samples $S --no-cpu-baseline --precision $PREC"
+CMD="python bench.py --steps 1 --warmup 3 --samples $S --no-cpu-baseline --no-train --precision $PREC"
 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-310} -c ${NCU_COUNT:-420} --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_launches.log 2>&1
 if [ -z "$NCU_LIST_ONLY" ]; then
   ncu --set full --clock-control none --import-source on -k regex:flow_step_f16_kernel -s 35 -c 1 \
       -o gpurun_out/${TAG}_step -f $CMD > gpurun_out/${TAG}_step.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:conv3x3_f16_kernel -s 7 -c 1 \
+  ncu --set full --clock-control none --import-source on -k regex:conv3x3_f16_kernel -s 11 -c 1 \
       -o gpurun_out/${TAG}_gate -f $CMD > gpurun_out/${TAG}_gate.log 2>&1
 fi
 ls -la gpurun_out
