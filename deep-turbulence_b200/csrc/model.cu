@@ -48,6 +48,7 @@ struct ConvW {
   int64_t w_pack = -1;    // tap-major in the packed buffer
   int64_t w_pack_tc = -1; // tcgen05 layout (hi/lo split) in the packed buffer, -1: CUDA-core path only
   int64_t w_pack_f16 = -1, inv_f16 = -1;   // fp16 hi/lo layout of conv3x3_f16.cu + inverse weight scale
+  int f16_nch[3] = {0, 0, 0};              // channel split of the sources the fp16 weights were packed for
   int O = 0, I = 0, OP = 0, NP = 0;
 };
 
@@ -166,6 +167,7 @@ struct Builder {
     const int nsrc = n2 > 0 ? 3 : (n1 > 0 ? 2 : 1);
     const int NP = tc_npad(c.O);
     c.NP = NP;
+    c.f16_nch[0] = n0; c.f16_nch[1] = n1; c.f16_nch[2] = n2;
     c.w_pack_f16 = pack_alloc((int64_t)convf16_packed_floats(nch, nsrc, NP));
     c.inv_f16 = pack_alloc(1);
     PackJob j{};
@@ -338,6 +340,7 @@ static int build_model(tmg_model& m) {
         st.zc_gain = B.gain(sc);
         B.coupling_jobs(st, cin_t, 0, C);
         B.step2_jobs(st, cin_t, 0, C);
+        B.conv_f16_job(st.d1, cin_t, 0, 0); B.conv_f16_job(st.d2, cin_t, 1, 0); B.conv_f16_job(st.zc, cin_t, 2, 0);
       } else {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
@@ -347,6 +350,8 @@ static int build_model(tmg_model& m) {
         st.zc_gain = B.gain(sc);
         B.coupling_jobs(st, C / 2, c.cond_features, C);
         B.step2_jobs(st, C / 2, c.cond_features, C);
+        B.conv_f16_job(st.d1, C / 2, c.cond_features, 0); B.conv_f16_job(st.d2, C / 2, c.cond_features, 1);
+        B.conv_f16_job(st.zc, C / 2, c.cond_features, 2);
       }
       lv.steps.push_back(st);
     }
@@ -499,6 +504,7 @@ struct Ctx {
   float* ws;
   cudaStream_t st;
   bool hoist_ready = false;     // the per-step conditioning tables dc_all / hc_all of this call are filled
+  bool unfused = false;         // backward recompute: every conv on its own (the intermediates are needed), no fused epilogues
   const float* P() const { return m.params; }
   const float* Q() const { return m.packed; }
 };
@@ -519,7 +525,23 @@ static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int ns
   a.Hout = stride == 1 ? Hin : (Hin + 1) / 2;
   a.Wout = stride == 1 ? Win : (Win + 1) / 2;
   a.pad_replicate = replicate ? 1 : 0;
-  if (c.m.precision != TMG_PREC_FP32 && w.w_pack_tc >= 0 && stride == 1 && !bn_scale && Win + 2 <= 512) {
+  if (c.unfused && prec_f16(c.m.precision) && w.w_pack_f16 >= 0 && stride == 1 && !bn_scale) {
+    bool match = true;
+    for (int i = 0; i < 3; ++i) match = match && (i < nsrc ? srcs[i].nch : 0) == w.f16_nch[i];
+    ConvF16Args t{};
+    for (int i = 0; i < nsrc; ++i) t.src[i] = srcs[i];
+    t.nsrc = nsrc;
+    t.wpk = c.Q() + w.w_pack_f16; t.inv_scale = c.Q() + w.inv_f16; t.npad = w.NP;
+    t.bias = a.bias; t.gain = a.gain; t.act = act;
+    t.out = out; t.out_cstride = out_cstride; t.out_coff = out_coff; t.cout = w.O;
+    t.B = B; t.H = Hin; t.W = Win; t.pad_replicate = a.pad_replicate; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+    if (match && convf16_supported(t)) {
+      const double M = (double)B * Hin * Win;
+      ProfScope ps(c.st, tag, 2.0 * M * w.O * 9.0 * w.I, 4.0 * ((double)B * Hin * Win * w.I + M * w.O));
+      return launch_conv3x3_f16(t, c.st);
+    }
+  }
+  if (c.m.precision != TMG_PREC_FP32 && w.w_pack_tc >= 0 && stride == 1 && !bn_scale && Win + 2 <= 512 && !c.unfused) {
     TcConvArgs t{};
     for (int i = 0; i < nsrc; ++i) t.src[i] = srcs[i];
     t.nsrc = nsrc; t.cin = w.I; t.wpk = c.Q() + w.w_pack_tc; t.npad = w.NP;
@@ -647,7 +669,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
     ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_in, R, 0, R, 0}};
     bool gate_done = false, out_done = false;
     const int u0s_f = (cin_t + 3) / 4 * 4;
-    if (prec_f16(c.m.precision) && s.gate.w_pack_f16 >= 0) {
+    if (prec_f16(c.m.precision) && s.gate.w_pack_f16 >= 0 && !c.unfused) {
       ConvF16Args t{};
       const int ns = h_in ? 3 : 2;
       for (int i = 0; i < 3; ++i) t.src[i] = gs[i];
@@ -682,7 +704,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
     }
     if (gate_done) {
       // fall through to the output conv below if it was not done
-    } else if (c.m.precision != TMG_PREC_FP32 && s.gate.w_pack_tc >= 0 && R % 16 == 0 && Wl + 2 <= 512) {
+    } else if (c.m.precision != TMG_PREC_FP32 && s.gate.w_pack_tc >= 0 && R % 16 == 0 && Wl + 2 <= 512 && !c.unfused) {
       // gate conv on tcgen05 with the ConvLSTM cell update fused into its epilogue (gates never touch HBM)
       TcConvArgs t{};
       const int ns = h_in ? 3 : 2;
@@ -1525,10 +1547,14 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   float* grads = io.grads;
   const bool lstm = st.kind == STEP_LSTM;
   // forward recompute with the exact-fp32 kernels: D (d1, d2), HR (h) and, for the LSTM step, gates / h' / c' / u0
+  // (f16x3 / f16 modes: every conv on its own through conv3x3_f16_kernel, fp32-grade in f16x3; else the fp32 kernels)
   const int prec = m->precision;
-  m->precision = TMG_PREC_FP32;
+  const bool was_unfused = c.unfused;
+  c.unfused = true;
+  if (!prec_f16(prec)) m->precision = TMG_PREC_FP32;
   int rc = run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, io.h_prev, io.c_prev, lstm ? HN : nullptr, lstm ? CNW : nullptr);
   m->precision = prec;
+  c.unfused = was_unfused;
   TMG_TRY(rc);
   const bool normed = st.kind != STEP_UNNORMED;
   StepBwdArgs sa{};

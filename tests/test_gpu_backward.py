@@ -97,8 +97,9 @@ def test_flow_step_backward_vs_oracle_autograd(step):
     assert checked >= 8, checked
 
 
+@pytest.mark.parametrize("precision,rel", [("fp32", 5e-5), ("f16x3", 2e-4)])
 @pytest.mark.parametrize("train_bn", [False, True])
-def test_reconstruct_backward_vs_oracle_autograd(train_bn):
+def test_reconstruct_backward_vs_oracle_autograd(train_bn, precision, rel):
     """Whole reverse pass (TMGlow.sample with explicit noise) with BPTT over two time steps: gradients of EVERY
     parameter (encoder incl. BatchNorm in eval and train mode, flow steps, split priors) and of the initial LSTM
     states against torch autograd through the pinned oracle."""
@@ -115,6 +116,7 @@ def test_reconstruct_backward_vs_oracle_autograd(train_bn):
     dev = torch.device("cuda:0")
     m = m.to(dev)
     m.train(train_bn)
+    m.precision = precision      # f16x3: tensor-core forward AND tensor-core recompute inside the backward (fp32-grade)
     ocfg = O.OracleConfig.from_dict(cfg)
     x = g["x"]
     eps = g["rec2"]["eps"]
@@ -145,7 +147,7 @@ def test_reconstruct_backward_vs_oracle_autograd(train_bn):
     loss_d.backward()
     m.scatter_flat_grad()
 
-    def close(a, r, what, rel=5e-5):
+    def close(a, r, what):
         err = (a.detach().cpu() - r).abs().max().item()
         assert err <= rel * max(r.abs().max().item(), 1.0), "%s: max abs err %.3e (ref max %.3e)" % (what, err, r.abs().max().item())
     for (a, b), (ar, br) in zip(hd, h0):
