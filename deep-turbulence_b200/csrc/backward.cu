@@ -23,7 +23,7 @@ int launch_pack_dgrad(const float* w_oihw, float* wt, int O, int I, cudaStream_t
 }
 
 // ------------------------------------------------------------------ weight gradient
-constexpr int kWgOB = 16, kWgCB = 8, kWgThreads = 128, kWgMaxPx = 512;
+constexpr int kWgOB = 32, kWgCB = 8, kWgThreads = 128, kWgMaxPx = 256;   // thread: 2 output channels x 1 input channel x 9 taps
 
 __global__ void __launch_bounds__(kWgThreads)
 wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
@@ -36,17 +36,18 @@ wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
   const int tid = threadIdx.x, o_l = tid & 15, c_l = tid >> 4;
   const int c0 = blockIdx.x * kWgCB, o0 = blockIdx.y * kWgOB, split = blockIdx.z;
   const int rtiles = (a.H + TR - 1) / TR, units = a.B * rtiles;
-  float acc[9];
+  float acc[9], acc2[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-  float accb = 0.f;
+  for (int t = 0; t < 9; ++t) { acc[t] = 0.f; acc2[t] = 0.f; }
+  float accb = 0.f, accb2 = 0.f;
+  const bool two = o0 + 16 < a.cout;                  // warp-uniform: this CTA has a second half of output channels
   for (int u = split; u < units; u += nsplit) {
     const int b = u / rtiles, r0 = (u - b * rtiles) * TR;
     const int rows = min(TR, a.H - r0);
     const int xrows = S * (rows - 1) + 3;
     __syncthreads();
     for (int i = tid; i < rows * a.W * kWgOB; i += kWgThreads) {
-      const int o = i & 15, p = i >> 4;
+      const int o = i & (kWgOB - 1), p = i / kWgOB;
       const int r = r0 + p / a.W, cc = p % a.W;
       g_s[i] = (o0 + o < a.cout) ? __ldg(a.g + ((size_t)(b * a.H + r) * a.W + cc) * a.g_cstride + a.g_coff + o0 + o) : 0.f;
     }
@@ -74,20 +75,43 @@ wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
     for (int pr = 0; pr < rows; ++pr) {
       const float* gp = g_s + (size_t)pr * a.W * kWgOB + o_l;
       const float* xp = x_s + (size_t)(S * pr) * tw * kWgCB + c_l;
-      for (int pc = 0; pc < a.W; ++pc) {
-        const float gv = gp[pc * kWgOB];
-        accb += gv;
+      if (two) {
+        for (int pc = 0; pc < a.W; ++pc) {
+          const float gv = gp[pc * kWgOB], gv2 = gp[pc * kWgOB + 16];
+          accb += gv; accb2 += gv2;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t] = fmaf(gv, xp[((t / 3) * tw + S * pc + t % 3) * kWgCB], acc[t]);
+          for (int t = 0; t < 9; ++t) {
+            const float xv = xp[((t / 3) * tw + S * pc + t % 3) * kWgCB];
+            acc[t] = fmaf(gv, xv, acc[t]);
+            acc2[t] = fmaf(gv2, xv, acc2[t]);
+          }
+        }
+      } else {
+        for (int pc = 0; pc < a.W; ++pc) {
+          const float gv = gp[pc * kWgOB];
+          accb += gv;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[t] = fmaf(gv, xp[((t / 3) * tw + S * pc + t % 3) * kWgCB], acc[t]);
+        }
       }
     }
   }
-  if (o0 + o_l < a.cout && c0 + c_l < a.cin) {
-    float* pp = part + (((size_t)split * a.cout + o0 + o_l) * a.cin + c0 + c_l) * 9;
+  if (c0 + c_l < a.cin) {
+    if (o0 + o_l < a.cout) {
+      float* pp = part + (((size_t)split * a.cout + o0 + o_l) * a.cin + c0 + c_l) * 9;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) pp[t] = acc[t];
+      for (int t = 0; t < 9; ++t) pp[t] = acc[t];
+    }
+    if (o0 + o_l + 16 < a.cout) {
+      float* pp = part + (((size_t)split * a.cout + o0 + o_l + 16) * a.cin + c0 + c_l) * 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) pp[t] = acc2[t];
+    }
   }
-  if (part_b && blockIdx.x == 0 && c_l == 0 && o0 + o_l < a.cout) part_b[(size_t)split * a.cout + o0 + o_l] = accb;
+  if (part_b && blockIdx.x == 0 && c_l == 0) {
+    if (o0 + o_l < a.cout) part_b[(size_t)split * a.cout + o0 + o_l] = accb;
+    if (o0 + o_l + 16 < a.cout) part_b[(size_t)split * a.cout + o0 + o_l + 16] = accb2;
+  }
 }
 
 // out[i] (+)= sum_s part[s][i], fixed order
