@@ -1,6 +1,7 @@
 // Shared declarations of libtmglow_b200 (sm_100a).  Internal layout: NHWC fp32 ("pixels x channels").
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -18,7 +19,7 @@ constexpr int kPixTile = 128;                    // pixels per CTA of the pointw
 constexpr int kMaxC = 64;                        // widest flow state the pointwise kernels take
 
 void set_error(const char* fmt, ...);
-extern thread_local int64_t g_launches;
+extern std::atomic<int64_t> g_launches;
 
 #define TMG_CUDA_OK(expr)                                                              \
   do {                                                                                 \
@@ -133,6 +134,14 @@ __host__ __device__ inline size_t tc_packed_floats(int cin, int npad) {
 }
 inline int tc_npad(int cout) { return (cout + 15) / 16 * 16; }
 
+// one destination of a routed (data-gradient) epilogue: columns [base, base + nch) -> p[pixel * cstride + coff + (n - base)]
+struct ConvDst {
+  float* p;
+  const float* mask;       // same layout as p: result kept where mask > 0 (ReLU of the forward input), or null
+  int cstride, coff, nch;
+  int accum;               // 1: p += result
+};
+
 // fp16-operand persistent conv (conv3x3_f16.cu): stride 1, sources start on 8-channel plane boundaries
 struct ConvF16Args {
   ConvSrc src[3];
@@ -152,8 +161,15 @@ struct ConvF16Args {
   const float* c_prev;
   float* h_out;
   float* c_out;
+  // backward use (data gradient = this kernel on transposed / tap-flipped weights, JOB_CONV_F16_T):
+  const float* in_scale;   // device [2]: power-of-two scale applied to the source while staging (gradients are far below
+                           // the fp16 normal range) and its inverse, applied in the epilogue; null = none
+  int ndst;                // > 0: the output columns are routed to up to 3 destinations (the sources of the forward
+  ConvDst dst[3];          // conv), each optionally gated by the sign of the forward input and accumulated
 };
 int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st);
+// scale[0] = 2^k with max|g| * 2^k in [2^10, 2^11) (1 when g == 0), scale[1] = 2^-k; scratch: 1024 floats
+int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, float* scratch, cudaStream_t st);
 bool convf16_supported(const ConvF16Args& a);
 int convf16_ksteps(const int* nch, int nsrc);
 size_t convf16_packed_floats(const int* nch, int nsrc, int npad);
@@ -446,7 +462,7 @@ int gauss_bwd_blocks(int B, int HW);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
-                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9 };
+                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n

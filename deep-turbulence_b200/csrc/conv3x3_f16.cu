@@ -118,7 +118,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     // =========================================================== epilogue (256 threads)
     const int el = tid & 127, half = tid >> 7;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const float inv = a.inv_scale ? __ldg(a.inv_scale) : 1.f;
+    const float inv = (a.inv_scale ? __ldg(a.inv_scale) : 1.f) * (a.in_scale ? __ldg(a.in_scale + 1) : 1.f);
     const float gain = a.gain ? __ldg(a.gain) : 1.f;
     const bool vec_ok = (a.out_cstride & 3) == 0 && (a.out_coff & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
     CvTileIt it;
@@ -172,6 +172,30 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
               for (int e = 0; e < 4; ++e) {
                 co[e] = make_float4(cn[4 * e], cn[4 * e + 1], cn[4 * e + 2], cn[4 * e + 3]);
                 ho[e] = make_float4(hn[4 * e], hn[4 * e + 1], hn[4 * e + 2], hn[4 * e + 3]);
+              }
+            }
+          }
+        } else if (a.ndst > 0) {
+          // data gradient: column n is input channel n of the forward conv, routed to the tensor that channel came from
+          const int nb1 = a.dst[0].nch, nb2 = nb1 + (a.ndst > 1 ? a.dst[1].nch : 0), nb3 = nb2 + (a.ndst > 2 ? a.dst[2].nch : 0);
+          for (int n0 = half * 16; n0 < NP; n0 += 32) {
+            if (n0 >= nb3) break;
+            float v[16];
+            tmem_ld16(trow + n0, v);
+            if (valid) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int n = n0 + e;
+                if (n < nb3) {
+                  const int d = n < nb1 ? 0 : (n < nb2 ? 1 : 2);
+                  const ConvDst& ds = a.dst[d];
+                  if (ds.p) {
+                    const size_t o = pix * ds.cstride + ds.coff + (n - (d == 0 ? 0 : (d == 1 ? nb1 : nb2)));
+                    float t = v[e] * inv;
+                    if (ds.mask && !(__ldg(ds.mask + o) > 0.f)) t = 0.f;
+                    ds.p[o] = ds.accum ? ds.p[o] + t : t;
+                  }
+                }
               }
             }
           }
@@ -269,6 +293,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     CvTileIt it;
     it.init(blockIdx.x, tiles_img);
     int ja = 0;
+    const float isc = a.in_scale ? __ldg(a.in_scale) : 1.f;
     for (int k = 0; k < nmy; ++k) {
       int r0, c0;
       it.origin(g, r0, c0);
@@ -326,7 +351,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
             uint32_t ph[4], pl[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float y0 = fminf(v[q][2 * e], 60000.f), y1 = fminf(v[q][2 * e + 1], 60000.f);
+              float y0 = fminf(v[q][2 * e] * isc, 60000.f), y1 = fminf(v[q][2 * e + 1] * isc, 60000.f);
               y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
               const __half2 h2 = __floats2half2_rn(y0, y1);
               const float2 hf = __half22float2(h2);
@@ -348,6 +373,47 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
   tc_fence_before();
   __syncthreads();
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------ power-of-two scale of a gradient tensor
+__global__ void __launch_bounds__(256)
+absmax_part_kernel(const float* __restrict__ g, int64_t npix, int cstride, int coff, int nch, float* __restrict__ part) {
+  float m = 0.f;
+  const int64_t total = npix * nch;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t p = i / nch; const int c = (int)(i - p * nch);
+    m = fmaxf(m, fabsf(__ldg(g + p * cstride + coff + c)));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s[w]);
+    part[blockIdx.x] = m;
+  }
+}
+__global__ void absmax_final_kernel(const float* __restrict__ part, int n, float* __restrict__ scale) {
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) m = fmaxf(m, part[i]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) {
+    int ex = 0;
+    float sc = 1.f;
+    if (m > 0.f && m < 3.0e38f) { frexpf(m, &ex); sc = ldexpf(1.f, min(max(11 - ex, -100), 100)); }
+    scale[0] = sc; scale[1] = 1.f / sc;
+  }
+}
+int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, float* scratch, cudaStream_t st) {
+  const int64_t total = npix * nch;
+  const int nb = (int)std::min<int64_t>(592, std::max<int64_t>(1, (total + 2047) / 2048));
+  absmax_part_kernel<<<nb, 256, 0, st>>>(g, npix, cstride, coff, nch, scratch);
+  TMG_LAUNCH_CHECK();
+  absmax_final_kernel<<<1, 32, 0, st>>>(scratch, nb, scale);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
 }
 
 // ------------------------------------------------------------------ host side

@@ -12,7 +12,7 @@
 
 namespace tmg {
 
-thread_local int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};   // process-wide: the backward runs on autograd's thread
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -49,6 +49,8 @@ struct ConvW {
   int64_t w_pack_tc = -1; // tcgen05 layout (hi/lo split) in the packed buffer, -1: CUDA-core path only
   int64_t w_pack_f16 = -1, inv_f16 = -1;   // fp16 hi/lo layout of conv3x3_f16.cu + inverse weight scale
   int f16_nch[3] = {0, 0, 0};              // channel split of the sources the fp16 weights were packed for
+  int64_t w_pack_f16t = -1, inv_f16t = -1; // transposed / tap-flipped fp16 weights (data gradient, JOB_CONV_F16_T)
+  int NPt = 0;                             // their MMA N (padded I)
   int O = 0, I = 0, OP = 0, NP = 0;
 };
 
@@ -174,6 +176,19 @@ struct Builder {
     j.type = JOB_CONV_F16; j.a = c.O; j.b = c.I; j.opad = NP; j.nch0 = n0; j.nch1 = n1; j.nd = n2;
     for (auto& s : j.src) s = -1;
     j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16; j.dst[1] = c.inv_f16;
+    m.jobs.push_back(j);
+  }
+  void conv_f16t_job(ConvW& c) {             // data-gradient weights: K = O, N = I
+    const int NP = tc_npad(c.I);
+    if (NP > 256) return;
+    const int nch[1] = {c.O};
+    c.NPt = NP;
+    c.w_pack_f16t = pack_alloc((int64_t)convf16_packed_floats(nch, 1, NP));
+    c.inv_f16t = pack_alloc(1);
+    PackJob j{};
+    j.type = JOB_CONV_F16_T; j.a = c.O; j.b = c.I; j.opad = NP;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16t; j.dst[1] = c.inv_f16t;
     m.jobs.push_back(j);
   }
   void coupling_jobs(StepW& st, int nch0, int nch1, int C) {
@@ -341,6 +356,7 @@ static int build_model(tmg_model& m) {
         B.coupling_jobs(st, cin_t, 0, C);
         B.step2_jobs(st, cin_t, 0, C);
         B.conv_f16_job(st.d1, cin_t, 0, 0); B.conv_f16_job(st.d2, cin_t, 1, 0); B.conv_f16_job(st.zc, cin_t, 2, 0);
+        B.conv_f16t_job(st.gate); B.conv_f16t_job(st.outc);
       } else {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
@@ -353,6 +369,7 @@ static int build_model(tmg_model& m) {
         B.conv_f16_job(st.d1, C / 2, c.cond_features, 0); B.conv_f16_job(st.d2, C / 2, c.cond_features, 1);
         B.conv_f16_job(st.zc, C / 2, c.cond_features, 2);
       }
+      B.conv_f16t_job(st.d1); B.conv_f16t_job(st.d2); B.conv_f16t_job(st.zc);
       lv.steps.push_back(st);
     }
     // hoisted conditioning tables: one weight slice per plain step, concatenated along Cout
@@ -402,6 +419,7 @@ static int build_model(tmg_model& m) {
     lv.split_scale = sc;
     lv.split = B.conv(pp + ".conv", C, C / 2, true);
     B.conv_f16_job(lv.split, C / 2, 0, 0);
+    B.conv_f16t_job(lv.split);
     lv.split_gain = B.gain(sc);
     C = C / 2;
   }
@@ -987,8 +1005,7 @@ int tmg_profile_query(int tag, double* ms, int64_t* launches, double* flops, dou
 }
 
 int64_t tmg_launch_count(int reset) {
-  int64_t v = tmg::g_launches;
-  if (reset) tmg::g_launches = 0;
+  int64_t v = reset ? tmg::g_launches.exchange(0) : tmg::g_launches.load();
   return v;
 }
 
@@ -1449,7 +1466,7 @@ int tmg_flow_step(tmg_model* m, int level, int step, int reverse, int B, int Hl,
 // states and every parameter of the step (accumulated into a flat gradient buffer laid out like the parameter
 // buffer).  The forward is recomputed with the exact-fp32 kernels.
 struct BwdExtra {
-  size_t go, gy, gz, gu, v, gcond, gd, part, dw, tmp, wt, wscr, oscr;
+  size_t go, gy, gz, gu, v, gcond, gd, part, dw, tmp, wt, wscr, oscr, gscale;
   size_t hn, cn, ghn, ggates, gu0;      // LSTM step
   size_t total;
 };
@@ -1473,6 +1490,7 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
   ws = std::max(ws, wgrad_scratch_floats(cin_t, cin_t + R, B, Hl, Wl));
   e.wscr = take(ws);
   e.oscr = take(outer_wgrad_scratch_floats((int64_t)px, C));
+  e.gscale = take(1024 + 64);           // [0..1] power-of-two scale of a gradient tensor and its inverse, [64..] block maxima
   e.hn = take(px * R); e.cn = take(px * R); e.ghn = take(px * R); e.ggates = take(px * 4 * R);
   e.gu0 = take(px * ((cin_t + 3) / 4 * 4));
   e.total = off;
@@ -1484,7 +1502,7 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
 struct BwdDest { float* g; const float* fwd; int cstride, coff, nch; int accum; };
 static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate,
                          const float* g, int g_cs, int g_co, const BwdDest* dests, int ndest, float* grads, float* wt,
-                         float* wscr) {
+                         float* wscr, float* gscale = nullptr) {
   WgradArgs wa{};
   for (int i = 0; i < nsrc_fwd; ++i) wa.src[i] = fsrc[i];
   wa.nsrc = nsrc_fwd; wa.cin = w.I;
@@ -1492,7 +1510,28 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
   wa.B = B; wa.H = Hl; wa.W = Wl; wa.pad_replicate = replicate ? 1 : 0;
   wa.gw = grads + w.w_param; wa.gbias = w.b_param >= 0 ? grads + w.b_param : nullptr; wa.accum = 1; wa.scratch = wscr;
   TMG_TRY(launch_wgrad(wa, c.st));
-  TMG_TRY(launch_pack_dgrad(c.P() + w.w_param, wt, w.O, w.I, c.st));
+  // data gradient on tensor cores (f16 modes): ONE launch of the fp16 hi/lo conv kernel on the transposed, tap-flipped
+  // weights with the output gradient scaled into the fp16 range; its epilogue routes the columns to the destinations
+  bool dgrad_tc = false;
+  if (gscale && prec_f16(c.m.precision) && w.w_pack_f16t >= 0 && ndest <= 3) {
+    ConvF16Args t{};
+    t.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; t.nsrc = 1;
+    t.wpk = c.Q() + w.w_pack_f16t; t.inv_scale = c.Q() + w.inv_f16t; t.npad = w.NPt; t.cout = w.I;
+    t.B = B; t.H = Hl; t.W = Wl; t.pad_replicate = 0; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+    t.in_scale = gscale;
+    t.ndst = ndest;
+    int tot = 0;
+    for (int d = 0; d < ndest; ++d) {
+      t.dst[d] = ConvDst{dests[d].g, dests[d].fwd, dests[d].cstride, dests[d].coff, dests[d].nch, dests[d].accum};
+      tot += dests[d].nch;
+    }
+    if (tot == w.I && convf16_supported(t)) {
+      TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st));
+      TMG_TRY(launch_conv3x3_f16(t, c.st));
+      dgrad_tc = true;
+    }
+  }
+  if (!dgrad_tc) TMG_TRY(launch_pack_dgrad(c.P() + w.w_param, wt, w.O, w.I, c.st));
   const int Ip = (w.I + 3) / 4 * 4;
   int c0 = 0;
   for (int d = 0; d < ndest; ++d) {
@@ -1503,7 +1542,7 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
       a.out = dests[d].g; a.out_cstride = dests[d].cstride; a.out_coff = dests[d].coff;
       a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
       a.mask = dests[d].fwd; a.accum = dests[d].accum;
-      TMG_TRY(launch_conv3x3(a, c.st));
+      if (!dgrad_tc) TMG_TRY(launch_conv3x3(a, c.st));
       if (replicate) {
         RingArgs r{};
         r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
@@ -1585,7 +1624,8 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
 
   auto conv_bwd = [&](const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate, const float* g, int g_cs, int g_co,
                       const BwdDest* dests, int ndest) -> int {
-    return conv_backward(c, B, Hl, Wl, w, nsrc_fwd, fsrc, replicate, g, g_cs, g_co, dests, ndest, grads, ex + e.wt, ex + e.wscr);
+    return conv_backward(c, B, Hl, Wl, w, nsrc_fwd, fsrc, replicate, g, g_cs, g_co, dests, ndest, grads, ex + e.wt, ex + e.wscr,
+                         ex + e.gscale);
   };
   typedef BwdDest Dest;
 
@@ -1854,7 +1894,7 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
     {
       const ConvSrc fs[1] = {{Ysplit, C, 0, C / 2, 0}};
       const BwdDest ds[1] = {{Gc, nullptr, C, 0, C / 2, 1}};
-      TMG_TRY(conv_backward(c, B, Hl, Wl, lv.split, 1, fs, true, ex + e.gz, C, 0, ds, 1, grads, ex + e.wt, ex + e.wscr));
+      TMG_TRY(conv_backward(c, B, Hl, Wl, lv.split, 1, fs, true, ex + e.gz, C, 0, ds, 1, grads, ex + e.wt, ex + e.wscr, ex + e.gscale));
     }
     if (l + 1 < L) {
       // z1 of this level is the un-squeezed output of the next one: adjoint = squeeze of the first C/2 channels

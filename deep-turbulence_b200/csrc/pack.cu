@@ -210,6 +210,37 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
     }
     if (tid == 0) Q[j.dst[1]] = 1.f / sc;
+  } else if (j.type == JOB_CONV_F16_T) {
+    // Data-gradient weights for conv3x3_f16.cu: the gradient w.r.t. the input of a 3x3 convolution is the convolution
+    // of the output gradient with the transposed, tap-flipped kernel: K = forward output channel o (one source of O
+    // channels), N = forward input channel c (npad >= I), tap t' holds w[o][c][8 - t'].  Same power-of-two scaling.
+    const int O = j.a, I = j.b, NP = j.opad;
+    const int KS = ((O + 7) / 8 + 1) / 2;
+    const float* w = P + j.src[0];
+    float m = 0.f;
+    for (int i = tid; i < O * I * 9; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) sm[tid >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm[q]);
+    int ex = 0;
+    if (m > 0.f && m < 3.0e38f) frexpf(m, &ex);
+    const float sc = m > 0.f ? ldexpf(1.f, min(max(11 - ex, -20), 40)) : 1.f;
+    __half* d = reinterpret_cast<__half*>(Q + j.dst[0]);
+    const size_t total = (size_t)KS * 9 * 2 * 2 * NP * 8;
+    for (size_t i = tid; i < total; i += blockDim.x) {
+      const int e = (int)(i & 7); size_t t = i >> 3; const int n = (int)(t % NP); t /= NP;
+      const int lp = (int)(t & 1); t >>= 1; const int hl = (int)(t & 1); t >>= 1;
+      const int tap = (int)(t % 9); const int ks = (int)(t / 9);
+      const int o = (2 * ks + lp) * 8 + e;
+      float v = 0.f;
+      if (o < O && n < I) v = w[((size_t)o * I + n) * 9 + (8 - tap)] * sc;
+      const __half hi = __float2half_rn(v);
+      d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    if (tid == 0) Q[j.dst[1]] = 1.f / sc;
   } else if (j.type == JOB_GAIN) {
     if (tid == 0) Q[j.dst[0]] = expf(fminf(fmaxf(P[j.src[0]], -4.f), kLog4));
   } else if (j.type == JOB_BN) {

@@ -69,6 +69,9 @@ SIGNATURES = {
     "tmg_flow_step": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tmg_split_forward": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "tmg_split_reverse": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tmg_tmglow_loss_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "tmg_tmglow_loss": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P,
+                             _P, _SZ, _P]),
     "tmg_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "tmg_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "tmg_launch_count": (_I64, [_I]),

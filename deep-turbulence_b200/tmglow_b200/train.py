@@ -33,9 +33,9 @@ def clip_flat_grad_(g: torch.Tensor, max_norm: float) -> float:
 
 
 def reverse_kl_loss(y_pred: torch.Tensor, log_det: torch.Tensor, target: torch.Tensor, beta: float = 200.0) -> torch.Tensor:
-    """Data terms + entropy term of ``TMGLowLoss.forward`` (trainFlowParallel.py:121-153): beta * (MSE + RMS mismatch)
-    + log_det / (ln 2 * pixels).  The PDE-residual terms of the reference loss (3-channel Sobel stencils on the
-    prediction, pc/*.py) are the caller's and are not restated here.  y_pred, target: [B,T,C,H,W]; log_det: [B,T]."""
+    """Data terms + entropy term only (torch ops; kept for tests of the BPTT chain).  The full reference loss with the
+    PDE-residual terms is ``tmglow_b200.loss.TMGLowLoss`` (one fused CUDA kernel) -- pass it to ``train_block`` as
+    ``criterion``.  y_pred, target: [B,T,C,H,W]; log_det: [B,T]."""
     mse = torch.mean((y_pred - target) ** 2)
     pred_rms = torch.sqrt(torch.mean((y_pred - y_pred.mean(dim=1, keepdim=True)) ** 2, dim=1) + 1e-12)
     tgt_rms = torch.sqrt(torch.mean((target - target.mean(dim=1, keepdim=True)) ** 2, dim=1) + 1e-12)
@@ -46,9 +46,13 @@ def reverse_kl_loss(y_pred: torch.Tensor, log_det: torch.Tensor, target: torch.T
 
 
 def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h_in: Optional[list],
-                loss_fn: Callable = reverse_kl_loss, max_norm: Optional[float] = 1.0, group=None):
-    """One optimizer step on a BPTT block.  ``x_block [B,T,nic,h,w]``, ``target [B,T,noc,H,W]``, ``h_in`` list of
-    (h, c) or None; ``optimizer`` must have been built on ``[model.flat_parameter_for_optimizer()]``.
+                loss_fn: Callable = reverse_kl_loss, max_norm: Optional[float] = 1.0, group=None,
+                criterion=None, target_mean: Optional[torch.Tensor] = None, target_rms: Optional[torch.Tensor] = None):
+    """One optimizer step on a BPTT block (trainFlowParallel.py:248-293).  ``x_block [B,T,nic,h,w]``, ``target
+    [B,T,noc,H,W]``, ``h_in`` list of (h, c) or None; ``optimizer`` must have been built on
+    ``[model.flat_parameter_for_optimizer()]``.  With ``criterion`` (a ``TMGLowLoss``) the loss is the reference's
+    ``criterion(yPred, logp, target, target_mean, target_rms)`` with the statistics of the full series
+    (``loss.target_statistics``); otherwise ``loss_fn(yPred, logp, target)``.
     Returns ``(loss, grad_norm, h_out)`` with ``h_out`` detached (truncated BPTT, trainFlowParallel.py:296-300)."""
     T = x_block.shape[1]
     model.zero_flat_grad()
@@ -58,7 +62,10 @@ def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h
         outs = model.sample_train(x_block[:, t], h)
         ys.append(outs[0]); lds.append(outs[1])
         h = [(outs[2 + 2 * l], outs[3 + 2 * l]) for l in range(len(model.glow_blocks))]
-    loss = loss_fn(torch.stack(ys, 1), torch.stack(lds, 1), target)
+    if criterion is not None:
+        loss = criterion(torch.stack(ys, 1), torch.stack(lds, 1), target, target_mean, target_rms)
+    else:
+        loss = loss_fn(torch.stack(ys, 1), torch.stack(lds, 1), target)
     loss.backward()
     g = model.flat_grad
     allreduce_mean_(g, group)                       # the one collective of data-parallel training
@@ -68,3 +75,32 @@ def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h
     optimizer.step()
     model.refresh_weights()                         # derived (packed) weights follow the new parameters
     return loss.detach(), norm, [(a.detach(), b.detach()) for a, b in h]
+
+
+def mix_states(h_out: list, h_key: list) -> list:
+    """trainFlowParallel.py:296-300: after each optimizer step the carried LSTM states are averaged with the initial
+    ("key") states of the series: ``0.5*a_out.detach() + 0.5*a_key``."""
+    return [(0.5 * a.detach() + 0.5 * ak, 0.5 * c.detach() + 0.5 * ck) for (a, c), (ak, ck) in zip(h_out, h_key)]
+
+
+def train_series(model, optimizer, criterion, input0: torch.Tensor, target0: torch.Tensor, lstm_seeds: torch.Tensor,
+                 tback: int = 10, max_norm: Optional[float] = 1.0, group=None):
+    """One mini-batch of ``TrainFlow.trainParallel`` (trainFlowParallel.py:225-303): a time series ``input0
+    [B,Tmax,nic,h,w]`` / ``target0 [B,Tmax,noc,H,W]`` is cut into ``Tmax // tback`` BPTT blocks, one optimizer step
+    each; LSTM states start from ``initLSTMStates(lstm_seeds)`` and are mixed with them between blocks.  Returns the
+    summed loss (``total_loss``) and the final states."""
+    dev = model.flat_parameter_for_optimizer().device
+    a_key = [(a.to(dev), c.to(dev)) for a, c in model.initLSTMStates(lstm_seeds, [target0.size(-2), target0.size(-1)])]
+    a0 = a_key
+    target0 = target0.to(dev)
+    from .loss import target_statistics
+    t_mean, t_rms = target_statistics(target0)
+    total = torch.zeros((), device=dev)
+    for i in range(target0.size(1) // tback):
+        xb = input0[:, i * tback:(i + 1) * tback].to(dev, non_blocking=True)
+        tb = target0[:, i * tback:(i + 1) * tback]
+        loss, _, a_out = train_block(model, optimizer, xb, tb, a0, max_norm=max_norm, group=group, criterion=criterion,
+                                     target_mean=t_mean, target_rms=t_rms)
+        a0 = mix_states(a_out, a_key)
+        total = total + loss
+    return total, a0

@@ -218,6 +218,20 @@ int tmg_flow_step_backward(tmg_model* m, int level, int step, int B, int Hl, int
                            const float* g_h_out, const float* g_c_out, float* g_x, float* g_cond, float* g_h_in,
                            float* g_c_in, float* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* TMGLowLoss.forward (nn/trainFlowParallel.py:121-153) with calcVPres / calcVDiv (:155-177), the residuals of
+ * PhysConstrainedLES (pc/physicsConstrained.py:43-94) and the 3x3 filters of pc/grad1Filter.py, pc/grad2Filter.py, FUSED
+ * WITH ITS BACKWARD: loss = beta*(vPres + vDiv + vL1 + vRMS) + mean(logp)/(ln2 * 3HW).
+ *   y_pred, target [B,T,3,H,W] (channels u, v, p); logp: n_logp floats (only the mean is used; the reference passes [B,T]);
+ *   target_rms [B,3,H,W]; out_mu, out_std [3] (model.out_mu / out_std, trainFlowParallel.py:119-120); dx, dy, beta =
+ *   args.dx, args.dy, args.beta.
+ * Outputs (device): loss [1]; terms [5] = vPres, vDiv, vL1, vRMS, neg_entropy (may be NULL); g_y = d loss / d y_pred
+ * [B,T,3,H,W] and g_logp [n_logp] (each may be NULL).  Deterministic; H, W >= 3. */
+size_t tmg_tmglow_loss_workspace_bytes(int B, int T, int H, int W);
+int tmg_tmglow_loss(const float* y_pred, const float* logp, const float* target, const float* target_rms,
+                    const float* out_mu, const float* out_std, int B, int T, int H, int W, int n_logp, double dx, double dy,
+                    double beta, float* loss, float* terms, float* g_y, float* g_logp, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* layout helpers for the LSTM states at the API boundary */
 int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
@@ -232,7 +246,7 @@ int         tmg_profile_classes(void);
 const char* tmg_profile_class_name(int tag);
 int         tmg_profile_query(int tag, double* ms, int64_t* launches, double* flops, double* bytes);
 
-/* number of kernels this library launched on the calling thread since the last reset
+/* number of kernels this library launched (process-wide, all threads) since the last reset
  * (bench.py's "gpu_launches") */
 int64_t tmg_launch_count(int reset);
 

@@ -110,3 +110,36 @@ def test_init_lstm_states_matches_reference():
     mine = O.init_lstm_states(cfg, torch.arange(B) + 7, list(g["y"].shape[2:]))
     for (h, c), (hr, cr) in zip(mine, g["h_in"]):
         assert torch.equal(h, hr) and torch.equal(c, cr)
+
+
+# ---------------------------------------------------------------- training loss (tests/golden/make_golden_loss.py)
+LOSS_CASES = ["loss_cyl_rand", "loss_cyl_smooth", "loss_step_aniso"]
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_loss_oracle_matches_reference(name):
+    """oracle/tmglow_loss_oracle.py reproduces TMGLowLoss (value, terms, residual fields, autograd gradients)."""
+    from oracle import tmglow_loss_oracle as L
+    g = load_golden(name)
+    dx, dy, beta = float(g["dx"]), float(g["dy"]), float(g["beta"])
+    y = g["y_pred"].clone().requires_grad_(True)
+    lp = g["logp"].clone().requires_grad_(True)
+    loss, terms = L.tmglow_loss(y, lp, g["target"], g["target_rms"], g["out_mu"], g["out_std"], dx, dy, beta, return_terms=True)
+    loss.backward()
+    _close(loss.detach(), g["loss"]); _close(terms, g["terms"])
+    _close(y.grad, g["g_y"]); _close(lp.grad, g["g_logp"])
+    flat = g["y_pred"].view(-1, *g["y_pred"].shape[2:])
+    y_hat = g["out_std"].view(1, 3, 1, 1) * flat + g["out_mu"].view(1, 3, 1, 1)
+    _close(L.pressure_poisson(y_hat[:, :2], y_hat[:, 2:], dx, dy), g["p_star"])
+    _close(L.divergence(y_hat[:, :2], dx, dy), g["u_star"])
+    # the cases cover both clamp branches
+    if name == "loss_cyl_rand":
+        assert 0.05 < float(g["clamped_frac"][0]) < 0.95
+
+
+def test_target_statistics_matches_reference_expression():
+    from oracle import tmglow_loss_oracle as L
+    t = torch.randn(2, 6, 3, 4, 5, generator=torch.Generator().manual_seed(3))
+    mean, rms = L.target_statistics(t)
+    assert torch.equal(mean, torch.mean(t, axis=1))
+    assert torch.equal(rms, torch.sqrt(torch.mean((t - mean.unsqueeze(1)) ** 2, dim=1)))
