@@ -164,8 +164,13 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // (sample, border pixel, channel) sums its ring positions in a fixed order (no atomics).
 __global__ void dgrad_ring_kernel(RingArgs a, int nborder) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.B * nborder * a.nch) return;
-  const int c = i % a.nch; int t = i / a.nch; const int k = t % nborder, b = t / nborder;
+  if (i >= a.B * nborder * a.cin_total) return;
+  const int c = i % a.cin_total; int t = i / a.cin_total; const int k = t % nborder, b = t / nborder;
+  // destination of concatenated input channel c
+  int d = 0, cl = c;
+  while (d < a.ndst - 1 && cl >= a.dst[d].nch) { cl -= a.dst[d].nch; ++d; }
+  const ConvDst& ds = a.dst[d];
+  if (ds.p == nullptr || cl >= ds.nch) return;
   // border pixel k: top row, bottom row, then the left / right columns without the corners
   int y, x;
   if (k < a.W) { y = 0; x = k; }
@@ -173,6 +178,9 @@ __global__ void dgrad_ring_kernel(RingArgs a, int nborder) {
   else { const int r = k - 2 * a.W; y = 1 + (r >> 1); x = (r & 1) ? a.W - 1 : 0; }
   if (a.H == 1 && k >= a.W) return;                       // single row: the top row already covers it
   if (a.W == 1 && k >= 2 * a.W && ((k - 2 * a.W) & 1)) return;
+  const size_t pix = (size_t)(b * a.H + y) * a.W + x;
+  const size_t o_dst = pix * ds.cstride + ds.coff + cl;
+  if (ds.mask && !(__ldg(ds.mask + o_dst) > 0.f)) return;
   float sum = 0.f;
   // ring positions (yr, xr) outside the image with clamp(yr, xr) == (y, x)
   for (int dy = -1; dy <= 1; ++dy) {
@@ -185,17 +193,15 @@ __global__ void dgrad_ring_kernel(RingArgs a, int nborder) {
         const int py = yr - (tap / 3 - 1), px = xr - (tap % 3 - 1);
         if (py < 0 || py >= a.H || px < 0 || px >= a.W) continue;
         const float* gp = a.g + ((size_t)(b * a.H + py) * a.W + px) * a.g_cstride + a.g_coff;
-        for (int o = 0; o < a.cout; ++o) sum = fmaf(__ldg(a.w_oihw + ((size_t)o * a.cin_total + a.c0 + c) * 9 + tap), __ldg(gp + o), sum);
+        for (int o = 0; o < a.cout; ++o) sum = fmaf(__ldg(a.w_oihw + ((size_t)o * a.cin_total + c) * 9 + tap), __ldg(gp + o), sum);
       }
     }
   }
-  const size_t pix = (size_t)(b * a.H + y) * a.W + x;
-  if (a.mask && !(__ldg(a.mask + pix * a.gx_cstride + a.gx_coff + c) > 0.f)) return;
-  a.gx[pix * a.gx_cstride + a.gx_coff + c] += sum;
+  ds.p[o_dst] += sum;
 }
 int launch_dgrad_ring(const RingArgs& a, cudaStream_t st) {
   const int nborder = 2 * a.W + 2 * std::max(a.H - 2, 0);
-  const int n = a.B * nborder * a.nch;
+  const int n = a.B * nborder * a.cin_total;
   if (n <= 0) return TMG_OK;
   dgrad_ring_kernel<<<cdiv(n, 128), 128, 0, st>>>(a, nborder);
   TMG_LAUNCH_CHECK();
@@ -324,16 +330,52 @@ int launch_step_bwd(const StepBwdArgs& a, cudaStream_t st) {
 }
 
 // out[c] (+)= sum over rows (fixed order) of part[row*row_stride + col0 + c]
-__global__ void reduce_cols_kernel(const float* __restrict__ part, int nrows, int row_stride, int col0, int ncols,
-                                   float* __restrict__ out, int accum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
+// out[c] (+)= sum over rows of part[r][col0 + c]: one block per column, rows strided over the threads, fixed-order tree
+__device__ __forceinline__ double block_col_sum(const float* __restrict__ part, int nrows, int row_stride, int col) {
+  __shared__ double sm[128];
   double s = 0.0;
-  for (int r = 0; r < nrows; ++r) s += (double)part[(size_t)r * row_stride + col0 + c];
-  out[c] = accum ? out[c] + (float)s : (float)s;
+  for (int r = threadIdx.x; r < nrows; r += 128) s += (double)part[(size_t)r * row_stride + col];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  return sm[0];
+}
+__global__ void __launch_bounds__(128)
+reduce_cols_kernel(const float* __restrict__ part, int nrows, int row_stride, int col0, int ncols,
+                   float* __restrict__ out, int accum) {
+  const int c = blockIdx.x;
+  const double s = block_col_sum(part, nrows, row_stride, col0 + c);
+  if (threadIdx.x == 0) out[c] = accum ? out[c] + (float)s : (float)s;
 }
 int launch_reduce_cols(const float* part, int nrows, int row_stride, int col0, int ncols, float* out, int accum, cudaStream_t st) {
-  reduce_cols_kernel<<<cdiv(ncols, 64), 64, 0, st>>>(part, nrows, row_stride, col0, ncols, out, accum);
+  if (ncols <= 0) return TMG_OK;
+  reduce_cols_kernel<<<ncols, 128, 0, st>>>(part, nrows, row_stride, col0, ncols, out, accum);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+// The per-CTA partial sums of step_bwd_kernel [nrows][2C+1] -> ActNorm bias / weight gradients (columns [0,C), [C,2C),
+// accumulated, skipped when null) and the Conv2dZeros log-scale gradient (column 2C: d/dscale of exp(clamp(scale,-4,ln4)),
+// flowUtils.py:247), in ONE launch.
+__global__ void __launch_bounds__(128)
+step_param_grads_kernel(const float* __restrict__ part, int nrows, int C, float* __restrict__ g_nb, float* __restrict__ g_nw,
+                        const float* __restrict__ scale_param, float* __restrict__ g_scale) {
+  const int c = blockIdx.x;
+  if (c < 2 * C && g_nb == nullptr) return;
+  const double s = block_col_sum(part, nrows, 2 * C + 1, c);
+  if (threadIdx.x != 0) return;
+  if (c < C) g_nb[c] += (float)s;
+  else if (c < 2 * C) g_nw[c - C] += (float)s;
+  else {
+    const float sp = *scale_param;
+    if (sp > -4.f && sp < kLog4) *g_scale += (float)s * expf(sp);
+  }
+}
+int launch_step_param_grads(const float* part, int nrows, int C, float* g_nb, float* g_nw, const float* scale_param, float* g_scale,
+                            cudaStream_t st) {
+  step_param_grads_kernel<<<2 * C + 1, 128, 0, st>>>(part, nrows, C, g_nb, g_nw, scale_param, g_scale);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }
@@ -398,7 +440,13 @@ lu_bwd_kernel(LuBwdArgs a) {
     L[i] = a.l[i] * a.lmask[i] + a.eye[i];
     U[i] = a.u[i] * a.umask[i] + (r == c ? expf(a.log_s[r]) * a.sign_s[r] : 0.f) + 0.01f * a.eye[i];
   }
-  if (tid == 0) { double s = 0.0; for (int b = 0; b < a.B; ++b) s += (double)a.g_ld[b]; s_gld = (float)s; }
+  if (tid < 32) {      // sum of the per-sample log-det gradients: one warp, fixed order
+    double s = 0.0;
+    for (int b = tid; b < a.B; b += 32) s += (double)a.g_ld[b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (tid == 0) s_gld = (float)s;
+  }
   __syncthreads();
   // A = P^T dW
   for (int i = tid; i < C * C; i += blockDim.x) {

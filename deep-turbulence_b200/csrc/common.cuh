@@ -361,14 +361,18 @@ struct WgradArgs {
 };
 size_t wgrad_scratch_floats(int cout, int cin, int B, int H, int W);
 int launch_wgrad(const WgradArgs& a, cudaStream_t st);
+// tensor-core weight gradient (wgrad_f16.cu): stride 1, no folded BatchNorm; gscale = launch_absmax_scale of a.g;
+// a.scratch >= wgrad_f16_scratch_floats
+bool wgrad_f16_supported(const WgradArgs& a);
+size_t wgrad_f16_scratch_floats(int cout, const int* nch, int nsrc, int B, int H, int W);
+int launch_wgrad_f16(const WgradArgs& a, const float* gscale, cudaStream_t st);
 // tap-major transposed + flipped weights for the data gradient: wt[tap][o][c (padded to 4)] = w[o][c][8 - tap]
 int launch_pack_dgrad(const float* w_oihw, float* wt, int O, int I, cudaStream_t st);
 // replicate padding: adds the gradient of the out-of-image ring to the clamped border pixels
 struct RingArgs {
   const float* g; int g_cstride, g_coff, cout;
-  const float* w_oihw; int cin_total, c0, nch;      // weight rows [c0, c0+nch) of the concatenation
-  const float* mask;                                  // forward input of this source (ReLU gate) or null
-  float* gx; int gx_cstride, gx_coff;
+  const float* w_oihw; int cin_total;                 // all input channels of the concatenation, routed to dst[]
+  int ndst; ConvDst dst[3];                           // mask = forward input of the source (ReLU gate) or null; p += ring
   int B, H, W;
 };
 int launch_dgrad_ring(const RingArgs& a, cudaStream_t st);
@@ -410,6 +414,8 @@ struct LuBwdArgs {
   int C;
 };
 int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st);
+int launch_step_param_grads(const float* part, int nrows, int C, float* g_nb, float* g_nw, const float* scale_param, float* g_scale,
+                            cudaStream_t st);
 int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st);
 // ConvLSTM cell backward (convLSTM.py:76-83): gates = pre-activations [B,HW,4R] (i,f,o,g), returns g_gates and g_c_prev
 struct LstmBwdArgs {

@@ -1404,13 +1404,36 @@ int tmg_conv3x3_backward(const float* x, int B, int H, int W, int Cin, const flo
     if (pad_replicate) {
       RingArgs r{};
       r.g = gout; r.g_cstride = Cout; r.g_coff = 0; r.cout = Cout;
-      r.w_oihw = w_oihw; r.cin_total = Cin; r.c0 = 0; r.nch = Cin;
-      r.mask = relu_in ? x : nullptr;
-      r.gx = gx; r.gx_cstride = Cin; r.gx_coff = 0; r.B = B; r.H = H; r.W = W;
+      r.w_oihw = w_oihw; r.cin_total = Cin;
+      r.ndst = 1; r.dst[0] = ConvDst{gx, relu_in ? x : nullptr, Cin, 0, Cin, 1};
+      r.B = B; r.H = H; r.W = W;
       TMG_TRY(launch_dgrad_ring(r, st));
     }
   }
   return TMG_OK;
+}
+
+// Weight / bias gradient of the same convolution through the tensor-core kernel (wgrad_f16.cu, fp16 hi/lo split): what the
+// training path runs in the f16x3 mode.  workspace: tmg_conv3x3_wgrad_tc_workspace_bytes.
+size_t tmg_conv3x3_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+  const int nch[1] = {Cin};
+  return (wgrad_f16_scratch_floats(Cout, nch, 1, B, H, W) + 2048) * sizeof(float);
+}
+int tmg_conv3x3_wgrad_tc(const float* x, int B, int H, int W, int Cin, int Cout, int relu_in, int pad_replicate,
+                         const float* gout, float* gw, float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !gout || !gw || !workspace) { set_error("null pointer"); return TMG_ERR_NULL; }
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) { set_error("bad shape"); return TMG_ERR_BAD_SHAPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* wsf = (float*)workspace;
+  WgradArgs wa{};
+  wa.src[0] = ConvSrc{x, Cin, 0, Cin, relu_in}; wa.nsrc = 1; wa.cin = Cin;
+  wa.g = gout; wa.g_cstride = Cout; wa.g_coff = 0; wa.cout = Cout;
+  wa.B = B; wa.H = H; wa.W = W; wa.pad_replicate = pad_replicate;
+  wa.gw = gw; wa.gbias = gbias; wa.accum = 0; wa.scratch = wsf + 2048;
+  if (!wgrad_f16_supported(wa)) { set_error("tensor-core weight gradient: unsupported shape Cin=%d Cout=%d", Cin, Cout); return TMG_ERR_UNSUPPORTED; }
+  if (workspace_bytes < tmg_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout)) { set_error("workspace too small"); return TMG_ERR_WORKSPACE; }
+  TMG_TRY(launch_absmax_scale(gout, (int64_t)B * H * W, Cout, 0, Cout, wsf, wsf + 64, st));
+  return launch_wgrad_f16(wa, wsf, st);
 }
 
 // Plan for the single-operator entry points: the workspace is sized by tmg_workspace_bytes of
@@ -1488,6 +1511,17 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
   ws = std::max(ws, wgrad_scratch_floats(1, cin_t + 1, B, Hl, Wl));
   ws = std::max(ws, wgrad_scratch_floats(4 * R, cin_t + R, B, Hl, Wl));
   ws = std::max(ws, wgrad_scratch_floats(cin_t, cin_t + R, B, Hl, Wl));
+  {   // tensor-core weight gradients (f16 modes)
+    const int n_zc[3] = {C / 2, cf, 2}, n_zl[2] = {cin_t, 2}, n_g[3] = {C / 2, cf, R}, n_d2[3] = {C / 2, cf, 1}, n_d2l[2] = {cin_t, 1};
+    ws = std::max(ws, wgrad_f16_scratch_floats(C, n_zc, 3, B, Hl, Wl));
+    ws = std::max(ws, wgrad_f16_scratch_floats(C, n_zl, 2, B, Hl, Wl));
+    ws = std::max(ws, wgrad_f16_scratch_floats(4 * R, n_g, 3, B, Hl, Wl));
+    ws = std::max(ws, wgrad_f16_scratch_floats(cin_t, n_g, 3, B, Hl, Wl));
+    ws = std::max(ws, wgrad_f16_scratch_floats(1, n_d2, 3, B, Hl, Wl));
+    ws = std::max(ws, wgrad_f16_scratch_floats(1, n_d2l, 2, B, Hl, Wl));
+    const int n_sp[1] = {C / 2};
+    ws = std::max(ws, wgrad_f16_scratch_floats(C, n_sp, 1, B, Hl, Wl));
+  }
   e.wscr = take(ws);
   e.oscr = take(outer_wgrad_scratch_floats((int64_t)px, C));
   e.gscale = take(1024 + 64);           // [0..1] power-of-two scale of a gradient tensor and its inverse, [64..] block maxima
@@ -1509,11 +1543,18 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
   wa.g = g; wa.g_cstride = g_cs; wa.g_coff = g_co; wa.cout = w.O;
   wa.B = B; wa.H = Hl; wa.W = Wl; wa.pad_replicate = replicate ? 1 : 0;
   wa.gw = grads + w.w_param; wa.gbias = w.b_param >= 0 ? grads + w.b_param : nullptr; wa.accum = 1; wa.scratch = wscr;
-  TMG_TRY(launch_wgrad(wa, c.st));
+  // f16 modes: weight gradient (pixels as the GEMM K dimension, MN-major operands) and data gradient on tensor cores;
+  // the output gradient is scaled into the fp16 range by a power of two measured once per convolution
+  const bool tc_bwd = gscale && prec_f16(c.m.precision);
+  if (tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st));
+  static const bool wg_off = [] { const char* e = getenv("TMG_WGRAD_FFMA"); return e && e[0] == '1'; }();
+  if (tc_bwd && !wg_off && wgrad_f16_supported(wa)) TMG_TRY(launch_wgrad_f16(wa, gscale, c.st));
+  else TMG_TRY(launch_wgrad(wa, c.st));
   // data gradient on tensor cores (f16 modes): ONE launch of the fp16 hi/lo conv kernel on the transposed, tap-flipped
   // weights with the output gradient scaled into the fp16 range; its epilogue routes the columns to the destinations
   bool dgrad_tc = false;
   if (gscale && prec_f16(c.m.precision) && w.w_pack_f16t >= 0 && ndest <= 3) {
+    if (!tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st));
     ConvF16Args t{};
     t.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; t.nsrc = 1;
     t.wpk = c.Q() + w.w_pack_f16t; t.inv_scale = c.Q() + w.inv_f16t; t.npad = w.NPt; t.cout = w.I;
@@ -1526,7 +1567,6 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
       tot += dests[d].nch;
     }
     if (tot == w.I && convf16_supported(t)) {
-      TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st));
       TMG_TRY(launch_conv3x3_f16(t, c.st));
       dgrad_tc = true;
     }
@@ -1543,16 +1583,21 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
       a.B = B; a.Hin = Hl; a.Win = Wl; a.Hout = Hl; a.Wout = Wl; a.stride = 1;
       a.mask = dests[d].fwd; a.accum = dests[d].accum;
       if (!dgrad_tc) TMG_TRY(launch_conv3x3(a, c.st));
-      if (replicate) {
-        RingArgs r{};
-        r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
-        r.w_oihw = c.P() + w.w_param; r.cin_total = w.I; r.c0 = c0; r.nch = dests[d].nch;
-        r.mask = dests[d].fwd; r.gx = dests[d].g; r.gx_cstride = dests[d].cstride; r.gx_coff = dests[d].coff;
-        r.B = B; r.H = Hl; r.W = Wl;
-        TMG_TRY(launch_dgrad_ring(r, c.st));
-      }
     }
     c0 += dests[d].nch;
+  }
+  if (replicate && ndest <= 3 && c0 == w.I) {     // border terms of replicate padding, all destinations in one launch
+    RingArgs r{};
+    r.g = g; r.g_cstride = g_cs; r.g_coff = g_co; r.cout = w.O;
+    r.w_oihw = c.P() + w.w_param; r.cin_total = w.I;
+    r.ndst = ndest;
+    for (int d = 0; d < ndest; ++d)
+      r.dst[d] = ConvDst{dests[d].g, dests[d].fwd, dests[d].cstride, dests[d].coff, dests[d].nch, 1};
+    r.B = B; r.H = Hl; r.W = Wl;
+    TMG_TRY(launch_dgrad_ring(r, c.st));
+  } else if (replicate) {
+    set_error("conv_backward: replicate-padding destinations do not cover the input channels");
+    return TMG_ERR_UNSUPPORTED;
   }
   return TMG_OK;
 }
@@ -1605,12 +1650,9 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   sa.B = B; sa.HW = HW; sa.C = C;
   TMG_TRY(launch_step_bwd(sa, c.st));
   const int nblk = step_bwd_blocks(B, HW), pstride = 2 * C + 1;
-  if (normed) {
-    TMG_TRY(launch_reduce_cols(ex + e.part, nblk, pstride, 0, C, grads + st.norm_b, 1, c.st));
-    TMG_TRY(launch_reduce_cols(ex + e.part, nblk, pstride, C, C, grads + st.norm_w, 1, c.st));
-  }
-  TMG_TRY(launch_reduce_cols(ex + e.part, nblk, pstride, 2 * C, 1, ex + e.tmp, 0, c.st));
-  TMG_TRY(launch_scale_grad(ex + e.tmp, c.P() + st.zc_scale, grads + st.zc_scale, c.st));
+  (void)pstride;
+  TMG_TRY(launch_step_param_grads(ex + e.part, nblk, C, normed ? grads + st.norm_b : nullptr, normed ? grads + st.norm_w : nullptr,
+                                  c.P() + st.zc_scale, grads + st.zc_scale, c.st));
   // 1x1 convolution: dW, then the LU parameterisation and the log-det constants
   TMG_TRY(launch_outer_wgrad(GU, V, (int64_t)B * HW, C, ex + e.dw, ex + e.oscr, c.st));
   LuBwdArgs la{};

@@ -46,6 +46,8 @@ SIGNATURES = {
     "tmg_conv3x3": (_I, [_I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "tmg_conv3x3_backward_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "tmg_conv3x3_backward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tmg_conv3x3_wgrad_tc_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "tmg_conv3x3_wgrad_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "tmg_flow_step_backward_workspace_bytes": (_SZ, [_P, _I, _I, _I, _I]),
     "tmg_flow_step_backward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "tmg_model_param_entries": (_I64, [_P]),

@@ -198,3 +198,27 @@ def flow_step_backward(model, level, step, x, cond, g_out, g_logdet, state=None,
     pre = "glow.flow_blocks.%d.revlayers.affine_layer%d." % (level, step)
     grads = {name: flat[off:off + numel].view(shape).clone() for name, off, numel, shape in model._table if name.startswith(pre)}
     return g_x, g_cond, grads, gin
+
+
+def conv3x3_wgrad_tc(x_nchw, gout_nchw, relu_in=False, pad_replicate=False):
+    """Weight and bias gradient of ``F.conv2d(pad(relu?(x)), w, b)`` through the tensor-core weight-gradient kernel
+    (``csrc/wgrad_f16.cu``): returns ``(gw [Cout,Cin,3,3], gbias [Cout])``."""
+    _need_cuda(x_nchw)
+    device = x_nchw.device
+    lib = _lib.load()
+    x = x_nchw.detach().float().contiguous()
+    g = gout_nchw.detach().float().contiguous()
+    B, Cin, H, W = x.shape
+    Cout = g.shape[1]
+    xh = torch.empty((B, H, W, Cin), dtype=torch.float32, device=device)
+    gh = torch.empty((B, H, W, Cout), dtype=torch.float32, device=device)
+    gw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=device)
+    gb = torch.empty(Cout, dtype=torch.float32, device=device)
+    ws = torch.empty(lib.tmg_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        st = _stream(device)
+        _lib.check(lib.tmg_nchw_to_nhwc(x.data_ptr(), xh.data_ptr(), B, Cin, H, W, st))
+        _lib.check(lib.tmg_nchw_to_nhwc(g.data_ptr(), gh.data_ptr(), B, Cout, H, W, st))
+        _lib.check(lib.tmg_conv3x3_wgrad_tc(xh.data_ptr(), B, H, W, Cin, Cout, int(relu_in), int(pad_replicate), gh.data_ptr(),
+                                            gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    return gw, gb

@@ -205,6 +205,14 @@ int tmg_conv3x3_backward(const float* x_nhwc, int B, int H, int W, int Cin, cons
                          int relu_in, int pad_replicate, const float* gout_nhwc, float* gx_nhwc, float* gw_oihw,
                          float* gbias, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight and bias gradient of the same convolution on the tensor cores (tcgen05 GEMM per filter tap with the pixels as the
+ * contraction dimension, fp16 hi/lo operand split, fp32 accumulate): the kernel the training path uses in the f16x3 mode.
+ * fp32-grade (hi*hi + lo*hi + hi*lo), deterministic.  gbias may be NULL. */
+size_t tmg_conv3x3_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int tmg_conv3x3_wgrad_tc(const float* x_nhwc, int B, int H, int W, int Cin, int Cout, int relu_in, int pad_replicate,
+                         const float* gout_nhwc, float* gw_oihw, float* gbias, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* Backward of one REVERSE flow step (the direction training runs: TMGlow.sample -> loss.backward(),
  * nn/trainFlowParallel.py:259-277): UnNormedAffineCouplingBlock / AffineCouplingBlock / LSTMCouplingBlock .reverse
  * (flowLSTMBlock.py:71-86,132-146,200-218).  Given the gradients w.r.t. the step output g_out [B,C_l,Hl,Wl] (NCHW),

@@ -42,6 +42,30 @@ def test_conv3x3_backward(B, Cin, Cout, H, W, relu_in, pad_replicate):
     assert torch.equal(gx, gx2) and torch.equal(gw, gw2) and torch.equal(gb, gb2)
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 38, 1, 32, 64), (3, 40, 12, 16, 32), (2, 102, 256, 8, 16), (1, 6, 12, 5, 7),
+                                            (2, 120, 56, 8, 16), (1, 3, 5, 1, 9), (2, 4, 3, 6, 1), (2, 58, 48, 17, 33),
+                                            (4, 102, 256, 32, 32)])
+@pytest.mark.parametrize("relu_in,pad_replicate", [(False, False), (True, False), (True, True)])
+def test_conv3x3_wgrad_tensor_core(B, Cin, Cout, H, W, relu_in, pad_replicate):
+    """Weight / bias gradient through the tcgen05 kernel (pixels as the GEMM K dimension, MN-major fp16 hi/lo operands,
+    csrc/wgrad_f16.cu) against torch autograd: fp32-grade (same 2e-5 tolerance as the exact-fp32 kernel), with gradient
+    magnitudes far below the fp16 range (scaled by 1e-5: the power-of-two rescaling is exercised), deterministic."""
+    from tmglow_b200 import ops
+    gen = torch.Generator().manual_seed(B * 1000 + Cin * 10 + Cout)
+    x = torch.randn(B, Cin, H, W, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) * 0.1
+    b = torch.randn(Cout, generator=gen)
+    g = torch.randn(B, Cout, H, W, generator=gen) * 1e-5
+    _, gw_r, gb_r = _ref(x, w, b, g, relu_in, pad_replicate)
+    dev = torch.device("cuda:0")
+    gw, gb = ops.conv3x3_wgrad_tc(x.to(dev), g.to(dev), relu_in, pad_replicate)
+    for name, a, r in (("gw", gw, gw_r), ("gb", gb, gb_r)):
+        err = (a.cpu() - r).abs().max().item()
+        assert err <= 2e-5 * r.abs().max().item(), "%s: max abs err %.3e (ref max %.3e)" % (name, err, r.abs().max().item())
+    gw2, gb2 = ops.conv3x3_wgrad_tc(x.to(dev), g.to(dev), relu_in, pad_replicate)
+    assert torch.equal(gw, gw2) and torch.equal(gb, gb2)
+
+
 @pytest.mark.parametrize("step", [1, 2, 3])
 def test_flow_step_backward_vs_oracle_autograd(step):
     """Reverse flow step (un-normed step 1, plain steps 2-3 of block 0): gradients w.r.t. the input, the conditioning map
