@@ -228,6 +228,8 @@ struct Step2Args {
   int B, H, W;
   int x3;                  // 1: hi/lo operand split (fp32-grade), 0: single-pass fp16
   long long* prof;         // developer profiling (TMG_STEP2_PROF=1): per-CTA cycle counters per role, else null
+  float* d_emit;           // training forward: relu(d1), relu(d2) [B,HW,2] and ...
+  float* h_emit;           // ... h [B,HW,C] written for the backward pass (both or neither)
 };
 int launch_step2(const Step2Args& a, cudaStream_t st);
 bool step2_supported(const Step2Args& a);

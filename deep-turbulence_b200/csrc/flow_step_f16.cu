@@ -111,7 +111,10 @@ struct TileIt {
 // NG epilogue groups of 256 threads (8 warps); warps 8*NG .. 8*NG+2 issue the MMAs (E, Z of M tile 0, Z of M tile 1:
 // three issuers on three schedulers -- a lone issuing warp that shares its scheduler with busy epilogue warps runs
 // at ~100 cycles per MMA instead of 40, tools/ubench_mma.cu); the next 4 warps are producers.
-template <int C, bool X3, int NG>
+// EMIT (training forward): the coupling-network intermediates relu(d1), relu(d2) and h = Conv2dZeros output (after bias and
+// gain) are also written to HBM (a.d_emit [B,HW,2], a.h_emit [B,HW,C]): the backward pass reads them from the tape
+// instead of recomputing three convolutions per step.  A separate instantiation: the inference kernels are unchanged.
+template <int C, bool X3, int NG, bool EMIT>
 __global__ void __launch_bounds__(NG * 256 + 96 + (NG == 2 ? 192 : 128), 1)
 flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   constexpr int NP = (C + 15) / 16 * 16;
@@ -291,6 +294,12 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
             else { sa += e[t]; da = fmaf(s_w2d[t], D1[pc + off], da); }
           }
           const float d1 = D1[pc], d2 = fmaxf(fmaf(sa + sb, inv2, da + db), 0.f);
+          if constexpr (EMIT) {
+            const int rr = pd[j] / kRP, rc = pd[j] - rr * kRP;
+            const int ir = r0 - 3 + rr, ic = c0 - 3 + rc;
+            if (rr >= 3 && rr <= 18 && rc >= 3 && rc <= 18 && ir < a.H && ic < a.W)      // tile interior, inside the image
+              *reinterpret_cast<float2*>(a.d_emit + ((size_t)it.b * HW + (size_t)ir * a.W + ic) * 2) = make_float2(d1, d2);
+          }
           __half h1, l1, h2, l2;
           split_h(d1, h1, l1); split_h(d2, h2, l2);
           *reinterpret_cast<uint32_t*>(dslot + (size_t)pd[j] * 16) = pack_h2(h1, h2);
@@ -348,6 +357,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
               for (int e = 0; e < 4; e += 2) {
                 const float shift = (hv[e] + s_b3[n0 + q + e]) * gain;            // h[:, 0::2]
                 const float raw = (hv[e + 1] + s_b3[n0 + q + e + 1]) * gain;      // h[:, 1::2]
+                if constexpr (EMIT) *reinterpret_cast<float2*>(a.h_emit + pix * C + n0 + q + e) = make_float2(shift, raw);
                 const float la = 2.f * __fdividef(raw, 1.f + fabsf(raw));      // 2*softsign; rcp.approx, 2 ulp
                 ldsum += la;
                 const int j = C / 2 + (n0 + q + e) / 2;
@@ -753,11 +763,13 @@ int launch_step2(const Step2Args& a_in, cudaStream_t st) {
     set_error("fused fp16 flow step: unsupported shape (C=%d, %dx%d)", a.C, a.H, a.W);
     return TMG_ERR_UNSUPPORTED;
   }
-#define TMG_S2(CC, XX, GG)                                                                                                       \
-  {                                                                                                                              \
-    TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-    flow_step_f16_kernel<CC, XX, GG><<<grid, GG * 256 + 96 + (GG == 2 ? 192 : 128), g.total, st>>>(a, g);                                               \
+  const bool emit = a.d_emit != nullptr && a.h_emit != nullptr;
+#define TMG_S2E(CC, XX, GG, EE)                                                                                                      \
+  {                                                                                                                                  \
+    TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX, GG, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    flow_step_f16_kernel<CC, XX, GG, EE><<<grid, GG * 256 + 96 + (GG == 2 ? 192 : 128), g.total, st>>>(a, g);                        \
   }
+#define TMG_S2(CC, XX, GG) { if (emit) TMG_S2E(CC, XX, GG, true) else TMG_S2E(CC, XX, GG, false) }
 #define TMG_S2N(CC)                                                                              \
   case CC:                                                                                       \
     if (g.ngroups == 2) { if (a.x3) TMG_S2(CC, true, 2) else TMG_S2(CC, false, 2) }              \
@@ -773,6 +785,7 @@ int launch_step2(const Step2Args& a_in, cudaStream_t st) {
 #undef TMG_S2W
 #undef TMG_S2N
 #undef TMG_S2
+#undef TMG_S2E
   TMG_LAUNCH_CHECK();
   if (a.prof) {      // developer profiling: average cycles per role and phase over the CTAs of this launch
     --prof_left;

@@ -118,6 +118,10 @@ struct tmg_model {
   float* params = nullptr;          // borrowed flat parameter buffer
   bool ready = false;
   int precision = TMG_PREC_FP32;    // which kernels run the heavy 3x3 convolutions
+  // training tape bookkeeping: which (level, step) of the last training forward recorded its coupling-network
+  // intermediates, and the configuration it ran under (a backward under another configuration is refused)
+  std::vector<std::vector<char>> tape_emit;
+  int tape_sig[4] = {0, 0, 0, -1};  // B, h, w, precision
 };
 
 namespace tmg {
@@ -523,6 +527,9 @@ struct Ctx {
   cudaStream_t st;
   bool hoist_ready = false;     // the per-step conditioning tables dc_all / hc_all of this call are filled
   bool unfused = false;         // backward recompute: every conv on its own (the intermediates are needed), no fused epilogues
+  float* emit_d = nullptr;      // training forward: where the fused step kernel records relu(d1), relu(d2) ...
+  float* emit_h = nullptr;      // ... and the coupling-network output h of the current step (tape)
+  bool emitted = false;         // set by run_step when the launch recorded them
   const float* P() const { return m.params; }
   const float* Q() const { return m.packed; }
 };
@@ -821,6 +828,7 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
     a.reverse = reverse ? 1 : 0;
     a.ld_part = ld_slot; a.ld_stride = c.p.nslots * c.p.ctas;
     a.B = B; a.H = Hl; a.W = Wl; a.x3 = prec_split(c.m.precision) ? 1 : 0;
+    if (st.kind != STEP_LSTM && c.emit_d && c.emit_h) { a.d_emit = c.emit_d; a.h_emit = c.emit_h; }
     if (step2_supported(a)) {
       if (st.kind == STEP_LSTM) TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, cond, h_in, c_in, h_out, c_out, true));
       const double px = (double)B * HW;
@@ -828,7 +836,7 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
       ProfScope ps(c.st, PROF_STEP_FUSED, 2.0 * px * 9.0 * (cin_t + (cin_t + 1) + (double)C * (cin_t + 2)) + 2.0 * px * C * C,
                    4.0 * px * (2.0 * C + cf));
       int rc = launch_step2(a, c.st);
-      if (rc == TMG_OK) { float* t = Y; Y = Y2; Y2 = t; }
+      if (rc == TMG_OK) { float* t = Y; Y = Y2; Y2 = t; c.emitted = a.d_emit != nullptr; }
       return rc;
     }
   }
@@ -1120,11 +1128,18 @@ int tmg_encoder_forward(tmg_model* m, int B, int h, int w, const float* x, float
   return TMG_OK;
 }
 
-// Tape of the training forward: the input of every flow step (NHWC), levels 0..L-1, steps 0..n-1.
+// Tape of the training forward, levels 0..L-1, steps 0..n-1, per step (NHWC): the step input Y [px,C], then the
+// coupling-network intermediates the fused step kernel records: relu(d1), relu(d2) [px,2] and h [px,C].
 static size_t tape_off(const tmg_model& m, const Plan& p, int l, int s) {
   size_t off = 0;
-  for (int q = 0; q < l; ++q) off += (size_t)m.levels[q].steps.size() * p.B * p.Hl[q] * p.Wl[q] * m.levels[q].C;
-  return off + (size_t)s * p.B * p.Hl[l] * p.Wl[l] * m.levels[l].C;
+  for (int q = 0; q < l; ++q) off += (size_t)m.levels[q].steps.size() * p.B * p.Hl[q] * p.Wl[q] * (2 * m.levels[q].C + 2);
+  return off + (size_t)s * p.B * p.Hl[l] * p.Wl[l] * (2 * m.levels[l].C + 2);
+}
+static size_t tape_off_d(const tmg_model& m, const Plan& p, int l, int s) {
+  return tape_off(m, p, l, s) + (size_t)p.B * p.Hl[l] * p.Wl[l] * m.levels[l].C;
+}
+static size_t tape_off_h(const tmg_model& m, const Plan& p, int l, int s) {
+  return tape_off_d(m, p, l, s) + (size_t)p.B * p.Hl[l] * p.Wl[l] * 2;
 }
 static size_t tape_floats(const tmg_model& m, const Plan& p) { return tape_off(m, p, p.L, 0); }
 
@@ -1175,6 +1190,11 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
   if (prec_f16(m->precision)) TMG_TRY(run_hoist(c));
+  if (tape) {
+    m->tape_emit.resize(L);
+    for (int l = 0; l < L; ++l) m->tape_emit[l].assign(m->levels[l].steps.size(), 0);
+    m->tape_sig[0] = B; m->tape_sig[1] = h; m->tape_sig[2] = w; m->tape_sig[3] = m->precision;
+  }
 
   // top latent: z = cmean + exp(clamp(clog_std)) * eps[L]   (tmGlow.py:460-463); no log-prob term
   {
@@ -1204,9 +1224,16 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
     // steps n..1 reversed (flowLSTMBlock.py:348-359)
     for (int s = (int)lv.steps.size() - 1; s >= 0; --s) {
       const StepW& st = lv.steps[s];
-      if (tape) TMG_CUDA_OK(cudaMemcpyAsync(tape + tape_off(*m, p, l, s), Y, (size_t)B * HW * lv.C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+      if (tape) {
+        TMG_CUDA_OK(cudaMemcpyAsync(tape + tape_off(*m, p, l, s), Y, (size_t)B * HW * lv.C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+        c.emit_d = tape + tape_off_d(*m, p, l, s); c.emit_h = tape + tape_off_h(*m, p, l, s); c.emitted = false;
+      }
       TMG_TRY(run_step(c, l, st, &st, true, B, Hl, Wl, Y, Y2, ws + p.cond[l], h_in ? h_in[l] : nullptr,
                        c_in ? c_in[l] : nullptr, h_out[l], c_out[l], ws + p.ldp + (size_t)(slot++) * p.ctas));
+      if (tape) {
+        m->tape_emit[l][s] = c.emitted ? 1 : 0;
+        c.emit_d = c.emit_h = nullptr;
+      }
     }
     // CheckerSqueeze.reverse (flowUtils.py:124-145)
     PermArgs pa{};
@@ -1613,6 +1640,8 @@ struct StepBwdIO {
   const float* g_hn; const float* g_cn;         // gradients w.r.t. the returned states (null = zero)
   float* g_hprev; float* g_cprev;               // out (written when non-null)
   float* grads;
+  const float* D_tape = nullptr;    // relu(d1), relu(d2) and h recorded by the training forward (plain steps), else null:
+  const float* HR_tape = nullptr;   // the coupling network is then recomputed from Y
 };
 
 static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int Wl, const StepBwdIO& io, float* ex,
@@ -1624,19 +1653,20 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   const int HW = Hl * Wl, C = lv.C, cf = m->cfg.cond_features, cin_t = C / 2 + cf, R = m->cfg.rec_features;
   const int u0s = (cin_t + 3) / 4 * 4;
   const float* Y = io.Y; const float* CN = io.COND;
-  float* D = ws + p.d;
-  float* HR = ws + p.hr;
+  const bool lstm = st.kind == STEP_LSTM;
+  const bool taped = !lstm && io.D_tape && io.HR_tape;
+  const float* D = taped ? io.D_tape : ws + p.d;
+  const float* HR = taped ? io.HR_tape : ws + p.hr;
   float *GY = io.GY, *GC = io.GC, *GZ = ex + e.gz, *GU = ex + e.gu, *V = ex + e.v, *GD = ex + e.gd;
   float *HN = ex + e.hn, *CNW = ex + e.cn, *GHN = ex + e.ghn, *GG = ex + e.ggates, *GU0 = ex + e.gu0, *U0 = ws + p.u0;
   float* grads = io.grads;
-  const bool lstm = st.kind == STEP_LSTM;
   // forward recompute with the exact-fp32 kernels: D (d1, d2), HR (h) and, for the LSTM step, gates / h' / c' / u0
   // (f16x3 / f16 modes: every conv on its own through conv3x3_f16_kernel, fp32-grade in f16x3; else the fp32 kernels)
   const int prec = m->precision;
   const bool was_unfused = c.unfused;
   c.unfused = true;
   if (!prec_f16(prec)) m->precision = TMG_PREC_FP32;
-  int rc = run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, io.h_prev, io.c_prev, lstm ? HN : nullptr, lstm ? CNW : nullptr);
+  int rc = taped ? TMG_OK : run_coupling_nn(c, level, st, B, Hl, Wl, Y, CN, io.h_prev, io.c_prev, lstm ? HN : nullptr, lstm ? CNW : nullptr);
   m->precision = prec;
   c.unfused = was_unfused;
   TMG_TRY(rc);
@@ -1882,6 +1912,10 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
   if (!x || !eps || !tape_v || !g_y || !g_log_det || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
   if (workspace_bytes < tmg_reconstruct_backward_workspace_bytes(m, B, h, w)) { set_error("workspace too small for the backward pass"); return TMG_ERR_WORKSPACE; }
   const float* tape = (const float*)tape_v;
+  // the recorded coupling-network intermediates are used only when this backward runs under the configuration the tape
+  // was recorded with; otherwise every step recomputes them from its taped input
+  const bool tape_ok = (int)m->tape_emit.size() == m->cfg.n_levels && m->tape_sig[0] == B && m->tape_sig[1] == h &&
+                       m->tape_sig[2] == w && m->tape_sig[3] == m->precision;
   const int L = p.L;
   Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
   float* ws = c.ws;
@@ -1909,6 +1943,7 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
       const StepW& st = lv.steps[s];
       StepBwdIO io{};
       io.Y = tape + tape_off(*m, p, l, s); io.COND = ws + p.cond[l]; io.GO = Gc; io.g_ld = g_log_det;
+      if (tape_ok && m->tape_emit[l][s]) { io.D_tape = tape + tape_off_d(*m, p, l, s); io.HR_tape = tape + tape_off_h(*m, p, l, s); }
       io.GY = Gn; io.GC = rb + rx.gcond[l]; io.grads = grads;
       if (st.kind == STEP_LSTM) {
         io.h_prev = h_in ? h_in[l] : nullptr; io.c_prev = c_in ? c_in[l] : nullptr;
