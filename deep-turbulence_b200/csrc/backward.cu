@@ -361,8 +361,19 @@ int launch_reduce_cols(const float* part, int nrows, int row_stride, int col0, i
 // flowUtils.py:247), in ONE launch.
 __global__ void __launch_bounds__(128)
 step_param_grads_kernel(const float* __restrict__ part, int nrows, int C, float* __restrict__ g_nb, float* __restrict__ g_nw,
-                        const float* __restrict__ scale_param, float* __restrict__ g_scale) {
+                        const float* __restrict__ scale_param, float* __restrict__ g_scale, const float* __restrict__ g_ld, int B,
+                        float hw, float* __restrict__ gld_stash) {
   const int c = blockIdx.x;
+  if (c == 2 * C + 1) {       // deferred LU backward: hw * sum_b g_ld[b] accumulated over the time steps of the block
+    if (threadIdx.x < 32) {
+      double s = 0.0;
+      for (int b = threadIdx.x; b < B; b += 32) s += (double)g_ld[b];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) *gld_stash += hw * (float)s;
+    }
+    return;
+  }
   if (c < 2 * C && g_nb == nullptr) return;
   const double s = block_col_sum(part, nrows, 2 * C + 1, c);
   if (threadIdx.x != 0) return;
@@ -374,8 +385,9 @@ step_param_grads_kernel(const float* __restrict__ part, int nrows, int C, float*
   }
 }
 int launch_step_param_grads(const float* part, int nrows, int C, float* g_nb, float* g_nw, const float* scale_param, float* g_scale,
-                            cudaStream_t st) {
-  step_param_grads_kernel<<<2 * C + 1, 128, 0, st>>>(part, nrows, C, g_nb, g_nw, scale_param, g_scale);
+                            const float* g_ld, int B, float hw, float* gld_stash, cudaStream_t st) {
+  step_param_grads_kernel<<<2 * C + 1 + (gld_stash ? 1 : 0), 128, 0, st>>>(part, nrows, C, g_nb, g_nw, scale_param, g_scale, g_ld, B,
+                                                                           hw, gld_stash);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }
@@ -418,12 +430,12 @@ outer_wgrad_kernel(const float* __restrict__ gu, const float* __restrict__ v, in
 }
 static int outer_splits(int64_t npix) { return (int)std::max<int64_t>(1, std::min<int64_t>(296, (npix + kOwTile - 1) / kOwTile)); }
 size_t outer_wgrad_scratch_floats(int64_t npix, int C) { return (size_t)outer_splits(npix) * C * C + 64; }
-int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, float* gw, float* scratch, cudaStream_t st) {
+int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, float* gw, float* scratch, cudaStream_t st, int accum) {
   if (C * C > 9 * kOwThreads) { set_error("1x1 weight gradient: C=%d not supported", C); return TMG_ERR_UNSUPPORTED; }
   const int ns = outer_splits(npix);
   outer_wgrad_kernel<<<ns, kOwThreads, 2 * kOwTile * C * sizeof(float), st>>>(gu, v, npix, C, ns, scratch);
   TMG_LAUNCH_CHECK();
-  reduce_partials_kernel<<<cdiv(C * C, 256), 256, 0, st>>>(scratch, gw, C * C, ns, 0);
+  reduce_partials_kernel<<<cdiv(C * C, 256), 256, 0, st>>>(scratch, gw, C * C, ns, accum);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }
@@ -545,6 +557,56 @@ __global__ void scale_grad_kernel(const float* s_gain, const float* scale_param,
 }
 int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st) {
   scale_grad_kernel<<<1, 1, 0, st>>>(s_gain, scale_param, g_scale);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+// Deferred form, once per optimizer step for ALL flow steps (one CTA each): the gradients of l, u, log_s (and the ActNorm
+// log-det term) are linear in dW and in hw * sum(g_ld), which the per-time-step backward accumulates in the gradient slots
+// of the (non-trainable) buffers `p` and `sign_s`; this kernel consumes and clears those slots.
+__global__ void __launch_bounds__(256)
+lu_bwd_batched_kernel(const LuTabEntry* __restrict__ tab, const float* __restrict__ P, float* __restrict__ G) {
+  extern __shared__ float sm[];
+  const LuTabEntry e = tab[blockIdx.x];
+  const int C = e.C, tid = threadIdx.x;
+  float* L = sm; float* U = L + C * C; float* A = U + C * C; float* DW = A + C * C;
+  const float* l = P + e.off[0]; const float* u = P + e.off[1]; const float* log_s = P + e.off[2]; const float* pm = P + e.off[3];
+  const float* sign_s = P + e.off[4]; const float* lmask = P + e.off[5]; const float* umask = P + e.off[6]; const float* eye = P + e.off[7];
+  float* dWs = G + e.off[3];
+  __shared__ float s_hg;
+  if (tid == 0) s_hg = G[e.off[4]];
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    L[i] = l[i] * lmask[i] + eye[i];
+    U[i] = u[i] * umask[i] + (r == c ? expf(log_s[r]) * sign_s[r] : 0.f) + 0.01f * eye[i];
+    DW[i] = dWs[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < C * C; i += blockDim.x) dWs[i] = 0.f;           // the stash slots go back to zero gradients
+  if (tid == 0) G[e.off[4]] = 0.f;
+  for (int i = tid; i < C * C; i += blockDim.x) {                       // A = P^T dW
+    const int r = i / C, c = i % C;
+    float s = 0.f;
+    for (int q = 0; q < C; ++q) s = fmaf(pm[q * C + r], DW[q * C + c], s);
+    A[i] = s;
+  }
+  __syncthreads();
+  const float hg = s_hg;
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    float dl = 0.f, du = 0.f;
+    for (int j = 0; j < C; ++j) dl = fmaf(A[r * C + j], U[c * C + j], dl);        // dL = A U^T
+    for (int q = 0; q < C; ++q) du = fmaf(L[q * C + r], A[q * C + c], du);        // dU = L^T A
+    G[e.off[0] + i] += dl * lmask[i];
+    G[e.off[1] + i] += du * umask[i];
+    if (r == c) G[e.off[2] + r] += du * sign_s[r] * expf(log_s[r]) - hg;
+  }
+  if (e.norm_w >= 0) for (int c = tid; c < C; c += blockDim.x) G[e.norm_w + c] += hg / P[e.norm_w + c];
+}
+int launch_lu_bwd_batched(const LuTabEntry* tab_dev, int n, int cmax, const float* params, float* grads, cudaStream_t st) {
+  if (n <= 0) return TMG_OK;
+  const size_t smem = (size_t)4 * cmax * cmax * sizeof(float);
+  TMG_CUDA_OK(cudaFuncSetAttribute(lu_bwd_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lu_bwd_batched_kernel<<<n, 256, smem, st>>>(tab_dev, params, grads);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }

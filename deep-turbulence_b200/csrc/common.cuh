@@ -403,7 +403,7 @@ int step_bwd_blocks(int B, int HW);
 // sum over CTAs (fixed order) of column-partials: out[i] (+)= scale * sum_k part[k][stride] ...
 int launch_reduce_cols(const float* part, int nrows, int row_stride, int col0, int ncols, float* out, int accum, cudaStream_t st);
 // gw[o][k] (+)= sum_px gu[px][o] * v[px][k]   (C x C), deterministic
-int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, float* gw, float* scratch, cudaStream_t st);
+int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, float* gw, float* scratch, cudaStream_t st, int accum = 0);
 size_t outer_wgrad_scratch_floats(int64_t npix, int C);
 // Chain rule of W = P (l*lm + I)(u*um + diag(sign*exp(log_s)) + 0.01 I)  (glowConv.py:151-160) and of the log-det
 // constants: g_l, g_u, g_log_s (+=), g_norm_w += HW/w * sum_b g_ld
@@ -416,8 +416,12 @@ struct LuBwdArgs {
   int C;
 };
 int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st);
+// deferred LU backward (once per optimizer step): per flow step the offsets (floats, same in the parameter and gradient
+// buffers) of l, u, log_s, p, sign_s, l_mask, u_mask, eye and of the ActNorm weight (-1: none)
+struct LuTabEntry { int C; int64_t off[8]; int64_t norm_w; };
+int launch_lu_bwd_batched(const LuTabEntry* tab_dev, int n, int cmax, const float* params, float* grads, cudaStream_t st);
 int launch_step_param_grads(const float* part, int nrows, int C, float* g_nb, float* g_nw, const float* scale_param, float* g_scale,
-                            cudaStream_t st);
+                            const float* g_ld, int B, float hw, float* gld_stash, cudaStream_t st);
 int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st);
 // ConvLSTM cell backward (convLSTM.py:76-83): gates = pre-activations [B,HW,4R] (i,f,o,g), returns g_gates and g_c_prev
 struct LstmBwdArgs {

@@ -176,24 +176,48 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
             }
           }
         } else if (a.ndst > 0) {
-          // data gradient: column n is input channel n of the forward conv, routed to the tensor that channel came from
-          const int nb1 = a.dst[0].nch, nb2 = nb1 + (a.ndst > 1 ? a.dst[1].nch : 0), nb3 = nb2 + (a.ndst > 2 ? a.dst[2].nch : 0);
+          // data gradient: the columns are the input channels of the forward conv, each forward source padded to a
+          // multiple of 4 columns; groups of 4 columns are routed to the tensor their channels came from (16-byte
+          // accesses when the destination allows), gated by the ReLU of the forward input, optionally accumulated
+          const int pb1 = (a.dst[0].nch + 3) & ~3, pb2 = pb1 + (a.ndst > 1 ? (a.dst[1].nch + 3) & ~3 : 0);
+          const int pb3 = pb2 + (a.ndst > 2 ? (a.dst[2].nch + 3) & ~3 : 0);
           for (int n0 = half * 16; n0 < NP; n0 += 32) {
-            if (n0 >= nb3) break;
+            if (n0 >= pb3) break;
             float v[16];
             tmem_ld16(trow + n0, v);
             if (valid) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int n = n0 + e;
-                if (n < nb3) {
-                  const int d = n < nb1 ? 0 : (n < nb2 ? 1 : 2);
-                  const ConvDst& ds = a.dst[d];
-                  if (ds.p) {
-                    const size_t o = pix * ds.cstride + ds.coff + (n - (d == 0 ? 0 : (d == 1 ? nb1 : nb2)));
-                    float t = v[e] * inv;
-                    if (ds.mask && !(__ldg(ds.mask + o) > 0.f)) t = 0.f;
-                    ds.p[o] = ds.accum ? ds.p[o] + t : t;
+              for (int q = 0; q < 16; q += 4) {
+                const int n = n0 + q;
+                if (n >= pb3) break;
+                const int d = n < pb1 ? 0 : (n < pb2 ? 1 : 2);
+                const ConvDst& ds = a.dst[d];
+                const int ch = n - (d == 0 ? 0 : (d == 1 ? pb1 : pb2));
+                const int nv = min(4, ds.nch - ch);
+                if (ds.p == nullptr || nv <= 0) continue;
+                const size_t o = pix * ds.cstride + ds.coff + ch;
+                float t[4] = {v[q] * inv, v[q + 1] * inv, v[q + 2] * inv, v[q + 3] * inv};
+                const bool vec = nv == 4 && ((ds.cstride | ds.coff) & 3) == 0 && (reinterpret_cast<uintptr_t>(ds.p) & 15) == 0 &&
+                                 (ds.mask == nullptr || (reinterpret_cast<uintptr_t>(ds.mask) & 15) == 0);
+                if (vec) {
+                  if (ds.mask) {
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(ds.mask + o));
+                    if (!(m4.x > 0.f)) t[0] = 0.f;
+                    if (!(m4.y > 0.f)) t[1] = 0.f;
+                    if (!(m4.z > 0.f)) t[2] = 0.f;
+                    if (!(m4.w > 0.f)) t[3] = 0.f;
+                  }
+                  float4* op = reinterpret_cast<float4*>(ds.p + o);
+                  if (ds.accum) { const float4 p4 = *op; t[0] += p4.x; t[1] += p4.y; t[2] += p4.z; t[3] += p4.w; }
+                  *op = make_float4(t[0], t[1], t[2], t[3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    if (e < nv) {
+                      float x = t[e];
+                      if (ds.mask && !(__ldg(ds.mask + o + e) > 0.f)) x = 0.f;
+                      ds.p[o + e] = ds.accum ? ds.p[o + e] + x : x;
+                    }
                   }
                 }
               }

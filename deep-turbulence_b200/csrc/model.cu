@@ -120,6 +120,8 @@ struct tmg_model {
   int precision = TMG_PREC_FP32;    // which kernels run the heavy 3x3 convolutions
   // training tape bookkeeping: which (level, step) of the last training forward recorded its coupling-network
   // intermediates, and the configuration it ran under (a backward under another configuration is refused)
+  std::vector<LuTabEntry> lu_tab;   // deferred LU backward: one entry per flow step
+  LuTabEntry* lu_tab_dev = nullptr;
   std::vector<std::vector<char>> tape_emit;
   int tape_sig[4] = {0, 0, 0, -1};  // B, h, w, precision
 };
@@ -182,8 +184,9 @@ struct Builder {
     j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16; j.dst[1] = c.inv_f16;
     m.jobs.push_back(j);
   }
-  void conv_f16t_job(ConvW& c) {             // data-gradient weights: K = O, N = I
-    const int NP = tc_npad(c.I);
+  void conv_f16t_job(ConvW& c) {             // data-gradient weights: K = O, N = I (each forward source padded to 4 columns)
+    if (c.f16_nch[0] + c.f16_nch[1] + c.f16_nch[2] != c.I) return;
+    const int NP = tc_npad((c.f16_nch[0] + 3) / 4 * 4 + (c.f16_nch[1] + 3) / 4 * 4 + (c.f16_nch[2] + 3) / 4 * 4);
     if (NP > 256) return;
     const int nch[1] = {c.O};
     c.NPt = NP;
@@ -191,6 +194,7 @@ struct Builder {
     c.inv_f16t = pack_alloc(1);
     PackJob j{};
     j.type = JOB_CONV_F16_T; j.a = c.O; j.b = c.I; j.opad = NP;
+    j.nch0 = c.f16_nch[0]; j.nch1 = c.f16_nch[1]; j.nd = c.f16_nch[2];
     for (auto& s : j.src) s = -1;
     j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16t; j.dst[1] = c.inv_f16t;
     m.jobs.push_back(j);
@@ -1031,6 +1035,7 @@ void tmg_model_destroy(tmg_model* m) {
   if (!m) return;
   if (m->jobs_dev) cudaFree(m->jobs_dev);
   if (m->jobs2_dev) cudaFree(m->jobs2_dev);
+  if (m->lu_tab_dev) cudaFree(m->lu_tab_dev);
   if (m->packed) cudaFree(m->packed);
   delete m;
 }
@@ -1071,6 +1076,19 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
     TMG_CUDA_OK(cudaMemset(m->packed, 0, (size_t)m->n_packed * sizeof(float)));
     TMG_CUDA_OK(cudaMalloc(&m->jobs_dev, m->jobs.size() * sizeof(PackJob)));
     TMG_CUDA_OK(cudaMemcpy(m->jobs_dev, m->jobs.data(), m->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    {
+      m->lu_tab.clear();
+      for (const LevelW& lv : m->levels)
+        for (const StepW& sw : lv.steps) {
+          LuTabEntry t{};
+          t.C = lv.C;
+          for (int q = 0; q < 8; ++q) t.off[q] = sw.lu[q];
+          t.norm_w = sw.kind != STEP_UNNORMED ? sw.norm_w : -1;
+          m->lu_tab.push_back(t);
+        }
+      TMG_CUDA_OK(cudaMalloc(&m->lu_tab_dev, m->lu_tab.size() * sizeof(LuTabEntry)));
+      TMG_CUDA_OK(cudaMemcpy(m->lu_tab_dev, m->lu_tab.data(), m->lu_tab.size() * sizeof(LuTabEntry), cudaMemcpyHostToDevice));
+    }
     if (!m->jobs2.empty()) {
       TMG_CUDA_OK(cudaMalloc(&m->jobs2_dev, m->jobs2.size() * sizeof(PackJob)));
       TMG_CUDA_OK(cudaMemcpy(m->jobs2_dev, m->jobs2.data(), m->jobs2.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
@@ -1589,11 +1607,15 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
     t.in_scale = gscale;
     t.ndst = ndest;
     int tot = 0;
-    for (int d = 0; d < ndest; ++d) {
-      t.dst[d] = ConvDst{dests[d].g, dests[d].fwd, dests[d].cstride, dests[d].coff, dests[d].nch, dests[d].accum};
-      tot += dests[d].nch;
+    bool split_ok = true;          // the destinations are the forward sources the transposed weights were packed for
+    for (int d = 0; d < 3; ++d) {
+      if (d < ndest) {
+        t.dst[d] = ConvDst{dests[d].g, dests[d].fwd, dests[d].cstride, dests[d].coff, dests[d].nch, dests[d].accum};
+        tot += dests[d].nch;
+      }
+      split_ok = split_ok && (d < ndest ? dests[d].nch : 0) == w.f16_nch[d];
     }
-    if (tot == w.I && convf16_supported(t)) {
+    if (tot == w.I && split_ok && convf16_supported(t)) {
       TMG_TRY(launch_conv3x3_f16(t, c.st));
       dgrad_tc = true;
     }
@@ -1640,6 +1662,7 @@ struct StepBwdIO {
   const float* g_hn; const float* g_cn;         // gradients w.r.t. the returned states (null = zero)
   float* g_hprev; float* g_cprev;               // out (written when non-null)
   float* grads;
+  bool defer_lu = false;            // accumulate dW and hw*sum(g_ld) into the stash slots; tmg_backward_finalize finishes
   const float* D_tape = nullptr;    // relu(d1), relu(d2) and h recorded by the training forward (plain steps), else null:
   const float* HR_tape = nullptr;   // the coupling network is then recomputed from Y
 };
@@ -1682,8 +1705,14 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   const int nblk = step_bwd_blocks(B, HW), pstride = 2 * C + 1;
   (void)pstride;
   TMG_TRY(launch_step_param_grads(ex + e.part, nblk, C, normed ? grads + st.norm_b : nullptr, normed ? grads + st.norm_w : nullptr,
-                                  c.P() + st.zc_scale, grads + st.zc_scale, c.st));
+                                  c.P() + st.zc_scale, grads + st.zc_scale, io.g_ld, B, (float)HW,
+                                  io.defer_lu ? grads + st.lu[4] : nullptr, c.st));
   // 1x1 convolution: dW, then the LU parameterisation and the log-det constants
+  if (io.defer_lu) {
+    // linear in dW and in hw * sum(g_ld): accumulated over the time steps of a BPTT block in the gradient slots of the
+    // buffers `p` / `sign_s` and turned into the gradients of l, u, log_s, norm.weight once (tmg_backward_finalize)
+    TMG_TRY(launch_outer_wgrad(GU, V, (int64_t)B * HW, C, grads + st.lu[3], ex + e.oscr, c.st, 1));
+  } else {
   TMG_TRY(launch_outer_wgrad(GU, V, (int64_t)B * HW, C, ex + e.dw, ex + e.oscr, c.st));
   LuBwdArgs la{};
   la.dW = ex + e.dw;
@@ -1693,6 +1722,7 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   if (normed) { la.nw = c.P() + st.norm_w; la.g_nw = grads + st.norm_w; }
   la.g_ld = io.g_ld; la.B = B; la.hw = (float)HW; la.C = C;
   TMG_TRY(launch_lu_bwd(la, c.st));
+  }
 
   auto conv_bwd = [&](const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate, const float* g, int g_cs, int g_co,
                       const BwdDest* dests, int ndest) -> int {
@@ -1945,6 +1975,7 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
       io.Y = tape + tape_off(*m, p, l, s); io.COND = ws + p.cond[l]; io.GO = Gc; io.g_ld = g_log_det;
       if (tape_ok && m->tape_emit[l][s]) { io.D_tape = tape + tape_off_d(*m, p, l, s); io.HR_tape = tape + tape_off_h(*m, p, l, s); }
       io.GY = Gn; io.GC = rb + rx.gcond[l]; io.grads = grads;
+      io.defer_lu = true;
       if (st.kind == STEP_LSTM) {
         io.h_prev = h_in ? h_in[l] : nullptr; io.c_prev = c_in ? c_in[l] : nullptr;
         io.g_hn = g_h_out ? g_h_out[l] : nullptr; io.g_cn = g_c_out ? g_c_out[l] : nullptr;
@@ -1994,6 +2025,14 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
   }
   // encoder parameters
   return run_encoder_backward(c, (flags & TMG_FLAG_BN_TRAIN) != 0, rb, rx, grads);
+}
+
+// Finishes the parameter gradients tmg_reconstruct_backward defers: the LU-parameterised 1x1 convolutions
+// (glowConv.py:151-174: l, u, log_s) and the log-det terms of log_s / ActNorm weights, for all flow steps in one launch.
+int tmg_backward_finalize(tmg_model* m, float* grads, void* stream) {
+  if (!m || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (!m->ready || !m->lu_tab_dev) { set_error("tmg_model_refresh() has not been called"); return TMG_ERR_NOT_READY; }
+  return launch_lu_bwd_batched(m->lu_tab_dev, (int)m->lu_tab.size(), m->cmax, m->params, grads, (cudaStream_t)stream);
 }
 
 size_t tmg_flow_step_backward_workspace_bytes(tmg_model* m, int level, int B, int Hl, int Wl) {

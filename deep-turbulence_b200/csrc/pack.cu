@@ -213,7 +213,8 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
   } else if (j.type == JOB_CONV_F16_T) {
     // Data-gradient weights for conv3x3_f16.cu: the gradient w.r.t. the input of a 3x3 convolution is the convolution
     // of the output gradient with the transposed, tap-flipped kernel: K = forward output channel o (one source of O
-    // channels), N = forward input channel c (npad >= I), tap t' holds w[o][c][8 - t'].  Same power-of-two scaling.
+    // channels), N = forward input channel c (sources padded to 4 columns each), tap t' holds w[o][c][8 - t'].  Same
+    // power-of-two scaling.
     const int O = j.a, I = j.b, NP = j.opad;
     const int KS = ((O + 7) / 8 + 1) / 2;
     const float* w = P + j.src[0];
@@ -235,8 +236,15 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       const int lp = (int)(t & 1); t >>= 1; const int hl = (int)(t & 1); t >>= 1;
       const int tap = (int)(t % 9); const int ks = (int)(t / 9);
       const int o = (2 * ks + lp) * 8 + e;
+      // column n -> forward input channel c: the channels of each forward source start on a 4-column boundary, so the
+      // routed epilogue can use 16-byte accesses per destination
+      const int pb1 = (j.nch0 + 3) / 4 * 4, pb2 = pb1 + (j.nch1 + 3) / 4 * 4;
+      int c = -1;
+      if (n < pb1) { if (n < j.nch0) c = n; }
+      else if (n < pb2) { if (n - pb1 < j.nch1) c = j.nch0 + (n - pb1); }
+      else if (n - pb2 < j.nd) c = j.nch0 + j.nch1 + (n - pb2);
       float v = 0.f;
-      if (o < O && n < I) v = w[((size_t)o * I + n) * 9 + (8 - tap)] * sc;
+      if (o < O && c >= 0 && c < I) v = w[((size_t)o * I + c) * 9 + (8 - tap)] * sc;
       const __half hi = __float2half_rn(v);
       d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
     }

@@ -462,8 +462,23 @@ class TMGlow(nn.Module):
             self.flat_grad.zero_()
         return self.flat_grad
 
+    def finalize_flat_grad(self):
+        """Finish the gradients the per-time-step backward leaves in accumulated form (LU-parameterised 1x1 convolutions
+        and their log-det terms: linear in quantities summed over the time steps of a BPTT block, so they are turned into
+        the gradients of ``l, u, log_s`` and the ActNorm weights once, for all flow steps in one launch).  Call after the
+        last ``backward()`` of an optimizer step and before reading ``flat_grad`` (``scatter_flat_grad`` and
+        ``train.train_block`` do).  Idempotent: the accumulation slots are cleared."""
+        g = getattr(self, "flat_grad", None)
+        if g is None or g.device.type != "cuda":
+            return g
+        lib, h = self._prepare(g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(lib.tmg_backward_finalize(h, g.data_ptr(), torch.cuda.current_stream(g.device).cuda_stream))
+        return g
+
     def scatter_flat_grad(self):
         """``p.grad`` of every parameter = its slice of ``flat_grad`` (views, no copies)."""
+        self.finalize_flat_grad()
         for i, (name, off, numel, shape) in enumerate(self._table):
             mod, attr, is_param = self._leaves[i]
             if is_param:

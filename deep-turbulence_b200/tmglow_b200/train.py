@@ -68,6 +68,8 @@ def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h
         loss = loss_fn(torch.stack(ys, 1), torch.stack(lds, 1), target)
     loss.backward()
     g = model.flat_grad
+    if hasattr(model, "finalize_flat_grad"):
+        model.finalize_flat_grad()                  # deferred LU-parameter gradients, once per optimizer step
     allreduce_mean_(g, group)                       # the one collective of data-parallel training
     norm = clip_flat_grad_(g, max_norm)
     flat = model.flat_parameter_for_optimizer()

@@ -148,6 +148,13 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x,
                              float* const* g_h_in, float* const* g_c_in, float* grads,
                              void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* tmg_reconstruct_backward leaves the gradients of the LU-parameterised 1x1 convolutions (l, u, log_s, glowConv.py:151-174)
+ * and the log-det terms of log_s / ActNorm weights in an accumulated, linear form (dW in the gradient slot of the buffer
+ * `p`, H_l*W_l*sum(g_log_det) in the slot of `sign_s`): call this ONCE after the last backward call of an optimizer step
+ * (before reading `grads`) to turn them into the parameter gradients for all flow steps in one launch; the slots are
+ * cleared.  tmg_flow_step_backward is not deferred. */
+int tmg_backward_finalize(tmg_model* m, float* grads, void* stream);
+
 /* TMGlow.forward (nn/tmGlow.py:378-414) + LSTMCFlowDecoder.forward (:231-267).
  * Outputs: z [B,Cz,H_L,W_L] NCHW, logp [B] (= log prior + sum of log-dets), states, and when
  * eps_out != NULL the n_levels+1 noise tensors (return_eps=True). */
