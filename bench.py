@@ -201,8 +201,75 @@ TRAIN_GEOM = dict(nic=3, h=16, w=16, noc=3, H=64, W=64)       # cylinder-array (
 TRAIN_KW = dict(cond_features=32, cglow_upscale=4, growth_rate=4, init_features=16, rec_features=64)
 
 
-def measure_train(args, rank, world, dev, dist, steps, warmup):
-    """Times `steps` optimizer steps (after `warmup`) of data-parallel training; returns (ms, loss, norm, launches)."""
+def cpu_port_train_steps(batch, tback, steps, warmup=0):
+    """One optimizer step of the reference training objective on the host cores through the pinned oracle port: BPTT block
+    of `tback` sample() calls under autograd (training-mode BatchNorm), TMGLowLoss, clip, Adam-amsgrad -- the arithmetic
+    of trainFlowParallel.py:248-293 at a bounded batch.  Returns (seconds per step, threads, loss)."""
+    from oracle import tmglow_oracle as O
+    from oracle import tmglow_loss_oracle as OL
+    from tmglow_b200 import TMGlow
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(12345); np.random.seed(12345)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TMGlow(TRAIN_GEOM["nic"], TRAIN_GEOM["noc"], [4, 4, 4], [16, 16, 16], **TRAIN_KW)
+    perturb_(m, 12346)
+    cfg = O.OracleConfig.from_dict(m._cfg_dict)
+    trainable = {n for n, _ in m.named_parameters()}
+    sd = {k: (v.detach().clone().requires_grad_(True) if k in trainable else v.detach().clone()) for k, v in m.state_dict().items()}
+    params = [v for k, v in sd.items() if k in trainable]
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-8, amsgrad=True)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, tback, TRAIN_GEOM["nic"], TRAIN_GEOM["h"], TRAIN_GEOM["w"], generator=g)
+    tgt = torch.randn(batch, tback, TRAIN_GEOM["noc"], TRAIN_GEOM["H"], TRAIN_GEOM["W"], generator=g)
+    _, t_rms = OL.target_statistics(tgt)
+    mu, sdv = torch.zeros(3), torch.ones(3)
+    h_key = O.init_lstm_states(cfg, torch.arange(batch), [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
+    h = h_key
+    el, loss = 0.0, None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        ys, lds = [], []
+        for t in range(tback):
+            eps = O.draw_eps(cfg, batch, TRAIN_GEOM["H"], TRAIN_GEOM["W"], g)
+            y, ld, h = O.reconstruct(sd, cfg, x[:, t], h, eps, training=True)
+            ys.append(y); lds.append(ld)
+        loss = OL.tmglow_loss(torch.stack(ys, 1), torch.stack(lds, 1), tgt, t_rms, mu, sdv, 5.0 / 64, 5.0 / 64, 200.0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p_ for p_ in params if p_.grad is not None], 1.0)
+        opt.step()
+        h = [(0.5 * a.detach() + 0.5 * ak, 0.5 * c.detach() + 0.5 * ck) for (a, c), (ak, ck) in zip(h, h_key)]
+        if it >= warmup:
+            el += time.perf_counter() - t0
+    return el / steps, threads, float(loss)
+
+
+def run_reference_train(args, rank, world):
+    """--impl reference --workload train: the reference's training step on the host cores (oracle port), bounded batch."""
+    if rank != 0:
+        return
+    Bc = args.ref_train_batch
+    sec, threads, loss = cpu_port_train_steps(Bc, args.tback, max(args.steps, 1), warmup=min(args.warmup, 1))
+    val = 1.0 / sec
+    line = {"impl": "reference", "metric": "train_steps_per_sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TM-Glow cylinder-array training (BASELINE.json configs[2]) on the CPU: bounded sample, batch %d "
+                                   "(the GPU arm's step is global batch %d), BPTT block of %d time steps, reference TMGLowLoss, "
+                                   "clip 1.0, Adam-amsgrad" % (Bc, args.global_batch, args.tback),
+                       "global_batch": Bc, "tback": args.tback, "parallelism": "cpu"},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port",
+                             "sample": "%d optimizer step(s) at batch %d x %d time steps through the oracle port (autograd)" % (max(args.steps, 1), Bc, args.tback)},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "hf_snapshots_per_sec": Bc * args.tback / sec, "gpu_launches": 0, "loss": loss}
+    print(json.dumps(line))
+
+
+def measure_train(args, rank, world, dev, dist, steps, warmup, e2e_steps=0):
+    """Times `steps` optimizer steps (after `warmup`) of data-parallel training with device-resident inputs and, when
+    e2e_steps > 0, the same step fed from pinned host memory; returns a dict (ms, launches, loss, norm, e2e_*)."""
     from tmglow_b200 import TMGlow, _lib, train as T
     lib = _lib.load()
     torch.manual_seed(12345); np.random.seed(12345)
@@ -220,41 +287,66 @@ def measure_train(args, rank, world, dev, dist, steps, warmup):
     tgt = torch.randn(Bl, tb, TRAIN_GEOM["noc"], TRAIN_GEOM["H"], TRAIN_GEOM["W"], generator=g).to(dev)
     h = m.initLSTMStates(torch.arange(Bl) + 1000 * rank, [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
     h_key = h
-    # main.py:78 (Adam, weight_decay 1e-8, amsgrad); lr below the reference's 1e-3 start because the synthetic targets
-    # are white noise -- the arithmetic per step is identical
-    opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1e-4, weight_decay=1e-8, amsgrad=True)
+    # main.py:78 (Adam, amsgrad, weight_decay 1e-8 -- applied by train_block on the trainable entries only); lr below the
+    # reference's 1e-3 start because the synthetic targets are white noise -- the arithmetic per step is identical
+    opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1e-4, amsgrad=True)
     # the reference loss: TMGLowLoss(beta=200, dx=dy=5/64) with the PDE-residual terms (args.py:61-63), one fused kernel
     import types
     from tmglow_b200.loss import TMGLowLoss, target_statistics
     crit = TMGLowLoss(types.SimpleNamespace(beta=200.0, dx=5.0 / 64, dy=5.0 / 64), m).to(dev)
     t_mean, t_rms = target_statistics(tgt)
 
-    def block(h):
-        loss, norm, h_out = T.train_block(m, opt, x, tgt, h, max_norm=1.0, criterion=crit, target_mean=t_mean, target_rms=t_rms)
+    def block(h, xb, tb_, tm, tr):
+        loss, norm, h_out = T.train_block(m, opt, xb, tb_, h, max_norm=1.0, criterion=crit, target_mean=tm, target_rms=tr,
+                                          weight_decay=1e-8)
         return loss, norm, T.mix_states(h_out, h_key)          # trainFlowParallel.py:296-300
 
+    def timed(fn, n):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.tmg_launch_count(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches = lib.tmg_launch_count(0)
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, int(launches)
+
+    state = {"h": h, "loss": None, "norm": None}
+
+    def resident():
+        state["loss"], state["norm"], state["h"] = block(state["h"], x, tgt, t_mean, t_rms)
+
     for _ in range(max(warmup, 1)):
-        loss, norm, h = block(h)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    lib.tmg_launch_count(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss, norm, h = block(h)
-    e1.record()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches = lib.tmg_launch_count(0)
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    assert torch.isfinite(loss).all(), "non-finite loss"
-    return ms, float(loss), norm, int(launches)
+        resident()
+    ms, launches = timed(resident, steps)
+    out = {"ms": ms, "launches": launches}
+    if e2e_steps > 0:
+        # end to end: every step copies its inputs (LF block + HF targets) from pinned host memory, recomputes the target
+        # statistics and reads the loss back
+        xh, th = x.cpu().pin_memory(), tgt.cpu().pin_memory()
+
+        def e2e():
+            xb, tb_ = xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)
+            tm, tr = target_statistics(tb_)
+            state["loss"], state["norm"], state["h"] = block(state["h"], xb, tb_, tm, tr)
+            state["loss_host"] = float(state["loss"])
+        e2e()
+        ms_e, _ = timed(e2e, e2e_steps)
+        out.update({"e2e_ms": ms_e, "e2e_steps": e2e_steps, "h2d_bytes": xh.numel() * 4 + th.numel() * 4, "d2h_bytes": 4})
+    assert torch.isfinite(state["loss"]).all(), "non-finite loss"
+    out.update({"loss": float(state["loss"]), "norm": state["norm"]})
+    return out
 
 
 def run_train(args, rank, world, local):
@@ -271,20 +363,33 @@ def run_train(args, rank, world, local):
         dist.init_process_group("nccl", device_id=dev)
     clocks = ClockSampler(local)
     clocks.start()
-    ms, loss, norm, launches = measure_train(args, rank, world, dev, dist, args.steps, args.warmup)
+    r = measure_train(args, rank, world, dev, dist, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)))
     clk = clocks.stop()
+    ms, loss, norm, launches = r["ms"], r["loss"], r["norm"], r["launches"]
     GB, tb = args.global_batch, args.tback
     if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, threads, _ = cpu_port_train_steps(args.ref_train_batch, tb, 1)
+            cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": threads, "kind": "port",
+                   "sample": "1 optimizer step at batch %d x %d time steps through the oracle port with autograd (%.1f s): "
+                             "%.2f HF snapshots/s vs %.0f here" % (args.ref_train_batch, tb, sec, args.ref_train_batch * tb / sec,
+                                                                  GB * tb * args.steps / (ms * 1e-3)),
+                   "hf_snapshots_per_sec": args.ref_train_batch * tb / sec}
         line = {"metric": "train_steps_per_sec", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "forward " + DTYPES[args.precision] + "; backward f32 (CUDA cores)",
+                "scaling": "strong", "vs_baseline": None, "dtype": DTYPES[args.precision] + " in the forward AND the backward (weight / data gradients on tcgen05)",
                 "data": "synthetic",
                 "config": {"workload": "TM-Glow cylinder-array training (BASELINE.json configs[2]): global batch %d, BPTT block of %d "
-                                       "time steps, x[B,T,3,16,16] -> y[B,T,3,64,64], default model, Adam-amsgrad, grad clip 1.0, "
+                                       "time steps, x[B,T,3,16,16] -> y[B,T,3,64,64], default model, Adam-amsgrad (weight decay 1e-8), grad clip 1.0, "
                                        "loss = the reference's TMGLowLoss (beta=200: pressure-Poisson + divergence residuals, MSE, RMS, entropy; fused "
                                        "CUDA kernel), LSTM states mixed with the initial states after each step" % (GB, tb),
-                           "global_batch": GB, "tback": tb, "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world},
+                           "global_batch": GB, "tback": tb, "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world,
+                           "l2_policy": "per-step working set (tape + activations, > 3 GB) exceeds the 126 MB L2; no explicit flush"},
                 "clocks": clk, "gpu_launches": int(launches), "loss": loss, "grad_norm": norm,
+                "e2e": {"value": r["e2e_steps"] / (r["e2e_ms"] * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": r["h2d_bytes"],
+                        "d2h_bytes_per_step": r["d2h_bytes"]},
+                "cpu_baseline": cpu,
                 "hf_snapshots_per_sec": GB * tb * args.steps / (ms * 1e-3)}
         print(json.dumps(line))
     if dist is not None:
@@ -307,6 +412,7 @@ def main():
                     help="sample: HF samples/s (configs[1], the default line); train: train steps/s (configs[2])")
     ap.add_argument("--global-batch", type=int, default=64)
     ap.add_argument("--tback", type=int, default=10)
+    ap.add_argument("--ref-train-batch", type=int, default=4, help="batch of the CPU training baseline (bounded sample)")
     ap.add_argument("--no-train", action="store_true", help="skip the short training measurement of the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -315,7 +421,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "train":
+            run_reference_train(args, rank, world)
+        else:
+            run_reference(args, rank, world)
         return
     if args.workload == "train":
         run_train(args, rank, world, local)
@@ -496,7 +605,8 @@ def main():
         model = None
         torch.cuda.empty_cache()
         try:
-            ms_t, loss_t, norm_t, _ = measure_train(args, rank, world, dev, dist, steps=2, warmup=1)
+            r_t = measure_train(args, rank, world, dev, dist, steps=2, warmup=1)
+            ms_t, loss_t, norm_t = r_t["ms"], r_t["loss"], r_t["norm"]
             train = {"metric": "train_steps_per_sec", "value": 2 / (ms_t * 1e-3), "unit": "steps/s", "ms_per_step": ms_t / 2,
                      "global_batch": args.global_batch, "tback": args.tback, "scaling": "strong",
                      "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world,

@@ -462,6 +462,19 @@ class TMGlow(nn.Module):
             self.flat_grad.zero_()
         return self.flat_grad
 
+    def trainable_mask(self):
+        """Flat 0/1 tensor laid out like ``flat_parameters()``: 1 on the entries that are ``nn.Parameter``s (the reference's
+        ``model.parameters()``), 0 on buffers (masks, permutations, running statistics).  Used for weight decay."""
+        flat = self.flat_parameters()
+        mk = self.__dict__.get("_train_mask")
+        if mk is None or mk.shape != flat.shape or mk.device != flat.device:
+            mk = torch.zeros_like(flat)
+            for i, (name, off, numel, shape) in enumerate(self._table):
+                if self._leaves[i][2]:
+                    mk[off:off + numel] = 1.0
+            object.__setattr__(self, "_train_mask", mk)
+        return mk
+
     def finalize_flat_grad(self):
         """Finish the gradients the per-time-step backward leaves in accumulated form (LU-parameterised 1x1 convolutions
         and their log-det terms: linear in quantities summed over the time steps of a BPTT block, so they are turned into

@@ -47,7 +47,8 @@ def reverse_kl_loss(y_pred: torch.Tensor, log_det: torch.Tensor, target: torch.T
 
 def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h_in: Optional[list],
                 loss_fn: Callable = reverse_kl_loss, max_norm: Optional[float] = 1.0, group=None,
-                criterion=None, target_mean: Optional[torch.Tensor] = None, target_rms: Optional[torch.Tensor] = None):
+                criterion=None, target_mean: Optional[torch.Tensor] = None, target_rms: Optional[torch.Tensor] = None,
+                weight_decay: float = 0.0):
     """One optimizer step on a BPTT block (trainFlowParallel.py:248-293).  ``x_block [B,T,nic,h,w]``, ``target
     [B,T,noc,H,W]``, ``h_in`` list of (h, c) or None; ``optimizer`` must have been built on
     ``[model.flat_parameter_for_optimizer()]``.  With ``criterion`` (a ``TMGLowLoss``) the loss is the reference's
@@ -73,6 +74,11 @@ def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h
     allreduce_mean_(g, group)                       # the one collective of data-parallel training
     norm = clip_flat_grad_(g, max_norm)
     flat = model.flat_parameter_for_optimizer()
+    if weight_decay:
+        # torch.optim.Adam(weight_decay=wd) adds wd * p to the (clipped) gradient inside step() (main.py:78: 1e-8); done
+        # here on the trainable entries only -- the flat buffer also holds masks / permutations / running statistics,
+        # which must see a zero gradient (build the optimizer WITHOUT weight_decay)
+        g.addcmul_(flat.detach(), model.trainable_mask(), value=weight_decay)
     flat.grad = g
     optimizer.step()
     model.refresh_weights()                         # derived (packed) weights follow the new parameters

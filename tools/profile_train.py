@@ -22,7 +22,8 @@ torch.cuda.set_device(0)
 from torch.profiler import profile, ProfilerActivity
 bench.measure_train(args, 0, 1, dev, None, steps=1, warmup=2)          # warm everything (allocator, derived weights)
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    ms, loss, norm, launches = bench.measure_train(args, 0, 1, dev, None, steps=1, warmup=1)
+    r = bench.measure_train(args, 0, 1, dev, None, steps=1, warmup=1)
+    ms = r["ms"]
     torch.cuda.synchronize()
 agg = collections.OrderedDict()
 for ev in prof.events():
