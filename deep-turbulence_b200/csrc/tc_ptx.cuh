@@ -35,6 +35,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   long long t0 = 0;
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef TMG_MBAR_SLEEP
+    __nanosleep(TMG_MBAR_SLEEP);      // back off: a spinning warp takes issue slots from the working warps of its scheduler
+#endif
     if ((++polls & 4095u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;

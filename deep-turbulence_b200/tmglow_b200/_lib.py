@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtmglow_b200.so")
+LIB_PATH = os.environ.get("TMGLOW_B200_LIB") or os.path.join(_HERE, "lib", "libtmglow_b200.so")   # override: A/B-testing builds
 
 TMG_MAX_LEVELS = 6
 TMG_FLAG_BN_TRAIN = 1
