@@ -125,8 +125,9 @@ int tmg_reconstruct(tmg_model* m, int B, int h, int w, const float* x,
                     float* y, float* log_det, float* const* h_out, float* const* c_out,
                     void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
-/* Training forward: tmg_reconstruct that also records the input of every flow step into `tape`
- * (tmg_tape_bytes) for tmg_reconstruct_backward.  Runs in the model's precision mode. */
+/* Training forward: tmg_reconstruct that also records, per flow step, the step input and (fused fp16 step kernel) the
+ * coupling-network intermediates relu(d1), relu(d2), h into `tape` (tmg_tape_bytes) for tmg_reconstruct_backward.  Runs in
+ * the model's precision mode. */
 size_t tmg_tape_bytes(const tmg_model* m, int B, int h, int w);
 int tmg_reconstruct_train(tmg_model* m, int B, int h, int w, const float* x,
                           const float* const* h_in, const float* const* c_in, const float* const* eps,
@@ -138,8 +139,10 @@ int tmg_reconstruct_train(tmg_model* m, int B, int h, int w, const float* x,
  * nn/trainFlowParallel.py:259-277): given g_y [B,out,H,W], g_log_det [B] and the gradients w.r.t. the returned LSTM
  * states (channels-last, entries may be NULL), ACCUMULATES the gradient of every flow (decoder) parameter into `grads`
  * (flat, laid out like the parameter buffer) and returns the gradients w.r.t. the incoming states g_h_in / g_c_in
- * (written where a state was passed in).  The coupling networks are recomputed from the tape with the exact-fp32
- * kernels; deterministic.  Encoder parameters: not yet (their gradient is left untouched). */
+ * (written where a state was passed in).  Coupling-network intermediates come from the tape (LSTM steps: recomputed);
+ * in the f16 modes the weight and data gradients of the flow convolutions run on tcgen05 (fp16 hi/lo split, fp32-grade),
+ * in the fp32 mode on the exact-fp32 CUDA-core kernels; the encoder adjoints are exact fp32.  Deterministic.  The gradients
+ * of the LU-parameterised 1x1 convolutions are left in accumulated form: call tmg_backward_finalize once per optimizer step. */
 size_t tmg_reconstruct_backward_workspace_bytes(const tmg_model* m, int B, int h, int w);
 int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x,
                              const float* const* h_in, const float* const* c_in, const float* const* eps,
