@@ -142,7 +142,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   const int S = a.stride == 2 ? 2 : 1, Win = S == 2 ? a.Win : a.W;
   const size_t smem = ((size_t)TR * a.W * kWgOB + (size_t)(S * (TR - 1) + 3) * (Win + 2) * kWgCB) * sizeof(float);
   if (smem > 96 * 1024) { set_error("wgrad: tile needs %zu B of shared memory", smem); return TMG_ERR_UNSUPPORTED; }
-  TMG_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  TMG_SMEM_ATTR(wgrad_kernel, 96 * 1024);
   float* part = a.scratch;
   float* part_b = a.gbias ? a.scratch + (size_t)ns * a.cout * a.cin * 9 : nullptr;
   dim3 grid(cdiv(a.cin, kWgCB), cdiv(a.cout, kWgOB), ns);
@@ -605,7 +605,7 @@ lu_bwd_batched_kernel(const LuTabEntry* __restrict__ tab, const float* __restric
 int launch_lu_bwd_batched(const LuTabEntry* tab_dev, int n, int cmax, const float* params, float* grads, cudaStream_t st) {
   if (n <= 0) return TMG_OK;
   const size_t smem = (size_t)4 * cmax * cmax * sizeof(float);
-  TMG_CUDA_OK(cudaFuncSetAttribute(lu_bwd_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMG_SMEM_ATTR(lu_bwd_batched_kernel, (int)smem);
   lu_bwd_batched_kernel<<<n, 256, smem, st>>>(tab_dev, params, grads);
   TMG_LAUNCH_CHECK();
   return TMG_OK;

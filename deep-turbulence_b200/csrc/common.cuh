@@ -70,6 +70,11 @@ struct ProfScope {
 };
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch: the call costs
+// about as much CPU time as the launch itself, and a training step is ~15 000 launches
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes);
+template <class K> inline cudaError_t ensure_dyn_smem_k(K kernel, int bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes); }
+#define TMG_SMEM_ATTR(...) TMG_CUDA_OK(tmg::ensure_dyn_smem_k(__VA_ARGS__))     // variadic: template commas in the kernel name
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------ generic 3x3 convolution
@@ -169,7 +174,11 @@ struct ConvF16Args {
 };
 int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st);
 // scale[0] = 2^k with max|g| * 2^k in [2^10, 2^11) (1 when g == 0), scale[1] = 2^-k; scratch: 1024 floats
-int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, float* scratch, cudaStream_t st);
+int launch_absmax_colsum(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, unsigned* sync, float* part,
+                         float* gbias, int accum, cudaStream_t st);
+// sync: two zero-initialised device words owned by the caller (self-resetting) -> one launch; null -> two launches via scratch
+int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, float* scratch, cudaStream_t st,
+                        unsigned* sync = nullptr);
 bool convf16_supported(const ConvF16Args& a);
 int convf16_ksteps(const int* nch, int nsrc);
 size_t convf16_packed_floats(const int* nch, int nsrc, int npad);
@@ -368,6 +377,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st);
 bool wgrad_f16_supported(const WgradArgs& a);
 size_t wgrad_f16_scratch_floats(int cout, const int* nch, int nsrc, int B, int H, int W);
 int launch_wgrad_f16(const WgradArgs& a, const float* gscale, cudaStream_t st);
+float* wgrad_f16_bias_partials(const WgradArgs& a);
 // tap-major transposed + flipped weights for the data gradient: wt[tap][o][c (padded to 4)] = w[o][c][8 - tap]
 int launch_pack_dgrad(const float* w_oihw, float* wt, int O, int I, cudaStream_t st);
 // replicate padding: adds the gradient of the out-of-image ring to the clamped border pixels

@@ -430,9 +430,104 @@ __global__ void absmax_final_kernel(const float* __restrict__ part, int n, float
     scale[0] = sc; scale[1] = 1.f / sc;
   }
 }
-int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, float* scratch, cudaStream_t st) {
+// single-launch form: block maxima meet in an atomicMax (max is order-independent, so still deterministic); the last block
+// to arrive derives the scale and resets the two words of `sync` (zero-initialised, library-owned) for the next use
+__global__ void __launch_bounds__(256)
+absmax_scale_kernel(const float* __restrict__ g, int64_t npix, int cstride, int coff, int nch, float* __restrict__ scale,
+                    unsigned* __restrict__ sync) {
+  float m = 0.f;
+  const int64_t total = npix * nch;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t p = i / nch; const int c = (int)(i - p * nch);
+    m = fmaxf(m, fabsf(__ldg(g + p * cstride + coff + c)));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s[w]);
+    if (!(m == m) || m > 3.0e38f) m = 3.0e38f;                       // NaN / inf gradients: keep the bit pattern ordered
+    atomicMax(sync, __float_as_uint(m));                             // non-negative floats order like their bit patterns
+    __threadfence();
+    if (atomicAdd(sync + 1, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const float mx = __uint_as_float(atomicExch(sync, 0u));
+      sync[1] = 0u;
+      int ex = 0;
+      float sc = 1.f;
+      if (mx > 0.f && mx < 3.0e38f) { frexpf(mx, &ex); sc = ldexpf(1.f, min(max(11 - ex, -100), 100)); }
+      scale[0] = sc; scale[1] = 1.f / sc;
+    }
+  }
+}
+// absmax scale AND column sums of g (the bias gradient of the convolution g belongs to) in one launch: threads are laid
+// out by column; per-block column sums go to part[block][nch], and the last block to arrive adds them up in block order
+// (fixed order: deterministic) into gbias.
+__global__ void __launch_bounds__(256)
+absmax_colsum_kernel(const float* __restrict__ g, int64_t npix, int cstride, int coff, int nch, int cw, float* __restrict__ scale,
+                     unsigned* __restrict__ sync, float* __restrict__ part, float* __restrict__ gbias, int accum) {
+  __shared__ float s_sum[256], s_max[256];
+  __shared__ unsigned s_last;
+  const int c = threadIdx.x % cw, rowi = threadIdx.x / cw, rows = 256 / cw;
+  float m = 0.f, acc = 0.f;
+  if (c < nch)
+    for (int64_t p = (int64_t)blockIdx.x * rows + rowi; p < npix; p += (int64_t)gridDim.x * rows) {
+      const float v = __ldg(g + p * cstride + coff + c);
+      acc += v; m = fmaxf(m, fabsf(v));
+    }
+  s_sum[threadIdx.x] = acc; s_max[threadIdx.x] = m;
+  __syncthreads();
+  if (rowi == 0 && c < nch) {
+    for (int r = 1; r < rows; ++r) acc += s_sum[r * cw + c];
+    part[(size_t)blockIdx.x * nch + c] = acc;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 256; ++i) m = fmaxf(m, s_max[i]);
+    if (!(m == m) || m > 3.0e38f) m = 3.0e38f;
+    atomicMax(sync, __float_as_uint(m));
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(sync + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int cc = threadIdx.x; cc < nch; cc += 256) {
+    float sum = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(part + (size_t)b * nch + cc);
+    gbias[cc] = accum ? gbias[cc] + sum : sum;
+  }
+  if (threadIdx.x == 0) {
+    const float mx = __uint_as_float(atomicExch(sync, 0u));
+    sync[1] = 0u;
+    int ex = 0;
+    float sc = 1.f;
+    if (mx > 0.f && mx < 3.0e38f) { frexpf(mx, &ex); sc = ldexpf(1.f, min(max(11 - ex, -100), 100)); }
+    scale[0] = sc; scale[1] = 1.f / sc;
+  }
+}
+// part: >= 148 * nch floats
+int launch_absmax_colsum(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, unsigned* sync, float* part,
+                         float* gbias, int accum, cudaStream_t st) {
+  if (nch > 256) { set_error("absmax_colsum: %d channels", nch); return TMG_ERR_UNSUPPORTED; }
+  int cw = 1;
+  while (cw < nch) cw <<= 1;
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(148, npix / 64));
+  absmax_colsum_kernel<<<nb, 256, 0, st>>>(g, npix, cstride, coff, nch, cw, scale, sync, part, gbias, accum);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, float* scratch, cudaStream_t st,
+                        unsigned* sync) {
   const int64_t total = npix * nch;
   const int nb = (int)std::min<int64_t>(592, std::max<int64_t>(1, (total + 2047) / 2048));
+  if (sync) {
+    absmax_scale_kernel<<<nb, 256, 0, st>>>(g, npix, cstride, coff, nch, scale, sync);
+    TMG_LAUNCH_CHECK();
+    return TMG_OK;
+  }
   absmax_part_kernel<<<nb, 256, 0, st>>>(g, npix, cstride, coff, nch, scratch);
   TMG_LAUNCH_CHECK();
   absmax_final_kernel<<<1, 32, 0, st>>>(scratch, nb, scale);
@@ -514,7 +609,7 @@ int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st) {
   }
 #define TMG_CV(XX, PW)                                                                                                      \
   {                                                                                                                         \
-    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_f16_kernel<XX, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    TMG_SMEM_ATTR(conv3x3_f16_kernel<XX, PW>, 227 * 1024); \
     conv3x3_f16_kernel<XX, PW><<<grid, (11 + PW) * 32, g.total, st>>>(a, g);                                                \
   }
   const bool wide = a.npad > 96 || a.lstm_R > 0;

@@ -159,7 +159,7 @@ static int launch_t(const ConvArgs& a, cudaStream_t st) {
   }
   static bool attr_set = false;      // per instantiation
   if (!attr_set) {
-    TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<NB, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TMG_SMEM_ATTR(conv3x3_kernel<NB, PX>, 200 * 1024);
     attr_set = true;
   }
   dim3 grid(cdiv(HWo, T), a.B, cdiv(a.cout, NB));

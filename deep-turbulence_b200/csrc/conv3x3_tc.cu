@@ -252,7 +252,7 @@ int launch_conv3x3_tc(const TcConvArgs& a, cudaStream_t st) {
   if (smem > 220 * 1024) { set_error("tc conv: width %d / N %d needs %zu B of shared memory", a.W, a.npad, smem); return TMG_ERR_UNSUPPORTED; }
   int cols = 32;
   while (cols < a.npad) cols *= 2;
-  TMG_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  TMG_SMEM_ATTR(conv3x3_tc_kernel, 220 * 1024);
   dim3 grid(cdiv(a.H * P, 128), a.B);
   conv3x3_tc_kernel<<<grid, kTcThreads, smem, st>>>(a, npos_pad, nstage, tps, cols);
   TMG_LAUNCH_CHECK();

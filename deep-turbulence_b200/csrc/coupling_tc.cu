@@ -448,7 +448,7 @@ int launch_coupling_tc(const CouplingArgs& a, cudaStream_t st) {
   switch (a.C) {
 #define TMG_CASE(CC)                                                                                                   \
   case CC:                                                                                                             \
-    TMG_CUDA_OK(cudaFuncSetAttribute(coupling_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    TMG_SMEM_ATTR(coupling_tc_kernel<CC>, 227 * 1024); \
     coupling_tc_kernel<CC><<<grid, 192, g.total, st>>>(a, g);                                                          \
     break;
     TMG_CASE(4) TMG_CASE(8) TMG_CASE(12) TMG_CASE(16) TMG_CASE(24) TMG_CASE(32) TMG_CASE(48) TMG_CASE(64)

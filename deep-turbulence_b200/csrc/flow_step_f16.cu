@@ -766,7 +766,7 @@ int launch_step2(const Step2Args& a_in, cudaStream_t st) {
   const bool emit = a.d_emit != nullptr && a.h_emit != nullptr;
 #define TMG_S2E(CC, XX, GG, EE)                                                                                                      \
   {                                                                                                                                  \
-    TMG_CUDA_OK(cudaFuncSetAttribute(flow_step_f16_kernel<CC, XX, GG, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    TMG_SMEM_ATTR(flow_step_f16_kernel<CC, XX, GG, EE>, 227 * 1024); \
     flow_step_f16_kernel<CC, XX, GG, EE><<<grid, GG * 256 + 96 + (GG == 2 ? 192 : 128), g.total, st>>>(a, g);                        \
   }
 #define TMG_S2(CC, XX, GG) { if (emit) TMG_S2E(CC, XX, GG, true) else TMG_S2E(CC, XX, GG, false) }

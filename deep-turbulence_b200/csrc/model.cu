@@ -5,6 +5,8 @@
 //   LSTMCFlowDecoder           nn/tmGlow.py:231-303
 //   TMGlow.forward/reconstruct nn/tmGlow.py:378-467
 // with every torch.cat / chunk / relu / pad tensor of the reference folded into the kernels.
+#include <mutex>
+#include <unordered_map>
 #include <cstdarg>
 #include <mutex>
 
@@ -12,7 +14,21 @@
 
 namespace tmg {
 
-std::atomic<int64_t> g_launches{0};   // process-wide: the backward runs on autograd's thread
+std::atomic<int64_t> g_launches{0};
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, std::vector<int>> done;     // kernel -> largest size set per device
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  std::vector<int>& v = done[kernel];
+  if ((int)v.size() <= dev) v.resize(dev + 1, -1);
+  if (v[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) v[dev] = bytes;
+  return e;
+}   // process-wide: the backward runs on autograd's thread
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -122,6 +138,7 @@ struct tmg_model {
   // intermediates, and the configuration it ran under (a backward under another configuration is refused)
   std::vector<LuTabEntry> lu_tab;   // deferred LU backward: one entry per flow step
   LuTabEntry* lu_tab_dev = nullptr;
+  unsigned* sync_dev = nullptr;     // zero-initialised, self-resetting words for single-launch reductions (absmax)
   std::vector<std::vector<char>> tape_emit;
   int tape_sig[4] = {0, 0, 0, -1};  // B, h, w, precision
 };
@@ -1036,6 +1053,7 @@ void tmg_model_destroy(tmg_model* m) {
   if (m->jobs_dev) cudaFree(m->jobs_dev);
   if (m->jobs2_dev) cudaFree(m->jobs2_dev);
   if (m->lu_tab_dev) cudaFree(m->lu_tab_dev);
+  if (m->sync_dev) cudaFree(m->sync_dev);
   if (m->packed) cudaFree(m->packed);
   delete m;
 }
@@ -1086,6 +1104,8 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
           t.norm_w = sw.kind != STEP_UNNORMED ? sw.norm_w : -1;
           m->lu_tab.push_back(t);
         }
+      TMG_CUDA_OK(cudaMalloc(&m->sync_dev, 64 * sizeof(unsigned)));
+      TMG_CUDA_OK(cudaMemset(m->sync_dev, 0, 64 * sizeof(unsigned)));
       TMG_CUDA_OK(cudaMalloc(&m->lu_tab_dev, m->lu_tab.size() * sizeof(LuTabEntry)));
       TMG_CUDA_OK(cudaMemcpy(m->lu_tab_dev, m->lu_tab.data(), m->lu_tab.size() * sizeof(LuTabEntry), cudaMemcpyHostToDevice));
     }
@@ -1591,15 +1611,24 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
   // f16 modes: weight gradient (pixels as the GEMM K dimension, MN-major operands) and data gradient on tensor cores;
   // the output gradient is scaled into the fp16 range by a power of two measured once per convolution
   const bool tc_bwd = gscale && prec_f16(c.m.precision);
-  if (tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st));
   static const bool wg_off = [] { const char* e = getenv("TMG_WGRAD_FFMA"); return e && e[0] == '1'; }();
-  if (tc_bwd && !wg_off && wgrad_f16_supported(wa)) TMG_TRY(launch_wgrad_f16(wa, gscale, c.st));
+  const bool wg_tc = tc_bwd && !wg_off && wgrad_f16_supported(wa);
+  if (wg_tc && wa.gbias && w.O <= 256) {
+    // the scale of g and the bias gradient (column sums of g) in one pass over g; the column-sum partials live at the
+    // tail of the weight-gradient scratch (wgrad_f16_scratch_floats reserves them)
+    float* pb = wgrad_f16_bias_partials(wa);
+    TMG_TRY(launch_absmax_colsum(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, c.m.sync_dev, pb, wa.gbias, 1, c.st));
+    wa.gbias = nullptr;
+  } else if (tc_bwd) {
+    TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st, c.m.sync_dev));
+  }
+  if (wg_tc) TMG_TRY(launch_wgrad_f16(wa, gscale, c.st));
   else TMG_TRY(launch_wgrad(wa, c.st));
   // data gradient on tensor cores (f16 modes): ONE launch of the fp16 hi/lo conv kernel on the transposed, tap-flipped
   // weights with the output gradient scaled into the fp16 range; its epilogue routes the columns to the destinations
   bool dgrad_tc = false;
   if (gscale && prec_f16(c.m.precision) && w.w_pack_f16t >= 0 && ndest <= 3) {
-    if (!tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st));
+    if (!tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st, c.m.sync_dev));
     ConvF16Args t{};
     t.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; t.nsrc = 1;
     t.wpk = c.Q() + w.w_pack_f16t; t.inv_scale = c.Q() + w.inv_f16t; t.npad = w.NPt; t.cout = w.I;

@@ -332,7 +332,7 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
 int launch_pack(const PackJob* jobs_dev, int njobs, const float* params, float* packed, int cmax,
                 cudaStream_t st) {
   size_t smem = (size_t)4 * cmax * cmax * sizeof(float);
-  TMG_CUDA_OK(cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMG_SMEM_ATTR(pack_kernel, (int)smem);
   pack_kernel<<<njobs, 256, smem, st>>>(jobs_dev, params, packed, cmax);
   TMG_LAUNCH_CHECK();
   return TMG_OK;

@@ -347,7 +347,13 @@ size_t wgrad_f16_scratch_floats(int cout, const int* nch, int nsrc, int B, int H
   for (int i = 0; i < nsrc && i < 3; ++i) a.src[i].nch = nch[i];
   WgF16Geom g{};
   if (!wf_geom(a, g)) return 0;
-  return (size_t)g.nsplit * 9 * 8 * g.NPl * g.Mrows + (size_t)wf_sm_count() * cout + 64;
+  return (size_t)g.nsplit * 9 * 8 * g.NPl * g.Mrows + (size_t)std::max(wf_sm_count(), 148) * cout + 64;
+}
+// where the bias column-sum partials ([blocks <= 148][cout]) live inside a.scratch
+float* wgrad_f16_bias_partials(const WgradArgs& a) {
+  WgF16Geom g{};
+  if (!wf_geom(a, g)) return nullptr;
+  return a.scratch + (size_t)g.nsplit * 9 * 8 * g.NPl * g.Mrows;
 }
 
 // a.scratch: wgrad_f16_scratch_floats; gscale: [2] from launch_absmax_scale on a.g
@@ -355,7 +361,7 @@ int launch_wgrad_f16(const WgradArgs& a, const float* gscale, cudaStream_t st) {
   WgF16Geom g{};
   if (!wf_geom(a, g)) { set_error("tensor-core weight gradient: unsupported shape"); return TMG_ERR_UNSUPPORTED; }
   float* part = a.scratch;
-  TMG_CUDA_OK(cudaFuncSetAttribute(wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  TMG_SMEM_ATTR(wgrad_f16_kernel, 220 * 1024);
   const int grid = g.mtiles * g.ntg * g.nsplit;
   wgrad_f16_kernel<<<grid, kWfThreads, g.total, st>>>(a, g, gscale, part);
   TMG_LAUNCH_CHECK();
