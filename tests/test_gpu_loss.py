@@ -136,7 +136,7 @@ def test_loss_module_interface_and_determinism():
         l3 = crit(y, lp, tgt, tgt.mean(1), rms)
     assert torch.equal(l3, l1)
     t = crit.last_terms
-    assert math.isclose(float(l1), 200.0 * float(t[:4].sum()) + float(t[4]), rel_tol=1e-6)
+    assert math.isclose(float(l1.detach()), 200.0 * float(t[:4].sum()) + float(t[4]), rel_tol=1e-6)
 
 
 def test_loss_errors():
@@ -210,3 +210,47 @@ def test_training_objective_gradients_vs_oracle_autograd():
         assert err <= 5e-4 * max(r.abs().max().item(), 1e-3), "%s: %.3e vs max %.3e" % (k, err, r.abs().max().item())
         checked += 1
     assert checked >= 60, checked
+
+
+def test_train_series_reference_minibatch():
+    """tmglow_b200.train.train_series = one mini-batch of TrainFlow.trainParallel (trainFlowParallel.py:225-303) on the
+    CUDA path with the fused TMGLowLoss: Tmax // tback optimizer steps, finite loss, trainable parameters move, the
+    non-trainable entries of the flat buffer (permutations, masks) stay bit-identical under weight decay, the deferred
+    LU-gradient stash is cleared, BatchNorm running statistics are updated (train mode)."""
+    import json
+    import types
+    from tmglow_b200 import TMGlow, train as T
+    from tmglow_b200.loss import TMGLowLoss
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    m.load_state_dict(g["state_dict"])
+    dev = _dev()
+    m = m.to(dev).train()
+    m.precision = "f16x3"
+    norm = types.SimpleNamespace(out_mu=torch.tensor([0.1, -0.2, 0.05]), out_std=torch.tensor([0.9, 1.1, 0.7]))
+    crit = TMGLowLoss(types.SimpleNamespace(beta=200.0, dx=5.0 / 64, dy=5.0 / 64), norm).to(dev)
+    gen = torch.Generator().manual_seed(9)
+    B, Tmax = 2, 4
+    x0 = torch.randn(B, Tmax, *g["x"].shape[1:], generator=gen)
+    t0 = 0.3 * torch.randn(B, Tmax, *g["rec2"]["y"].shape[1:], generator=gen)
+    opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1e-3, amsgrad=True)
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    torch.manual_seed(5)
+    total, states = T.train_series(m, opt, crit, x0, t0, torch.arange(B), tback=2, max_norm=1.0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(total) and len(states) == len(cfg["glow_blocks"])
+    sd1 = m.state_dict()
+    moved = [k for k in sd0 if k.endswith("conv.l") and not torch.equal(sd0[k], sd1[k])]
+    assert len(moved) >= 4, "LU parameters did not move (deferred LU backward not finalised?)"
+    for k in sd0:
+        if k.endswith((".p", ".sign_s", ".l_mask", ".u_mask", ".eye")):
+            assert torch.equal(sd0[k], sd1[k]), k
+    assert any(k.endswith("running_mean") and not torch.equal(sd0[k], sd1[k]) for k in sd0)
+    # the stash slots (gradient slots of p / sign_s) are back to zero after finalize
+    table = {name: (off, numel) for name, off, numel, shape in m._table}
+    for name, (off, numel) in table.items():
+        if name.endswith(("conv.p", "conv.sign_s")):
+            assert float(m.flat_grad[off:off + numel].abs().max()) == 0.0, name

@@ -139,3 +139,82 @@ def test_dp_gradient_allreduce_and_clip_gloo(tmp_path):
     # single process: no process group -> no-op
     t = torch.ones(4)
     assert torch.equal(T.allreduce_mean_(t.clone()), t)
+
+
+class _ToyModel:
+    """CPU stand-in with the host-side surface train_block / train_series use (the CUDA model has no CPU path): a flat
+    parameter buffer whose first 4 entries are trainable and last 2 are 'buffers', sample_train = a differentiable toy."""
+    glow_blocks = [1]
+
+    def __init__(self):
+        self._flat = torch.nn.Parameter(torch.tensor([0.5, -0.25, 1.0, 2.0, 7.0, 9.0]))
+        self.flat_grad = torch.zeros(6)
+        self.finalized = 0
+        self.refreshed = 0
+
+    def flat_parameter_for_optimizer(self):
+        return self._flat
+
+    def trainable_mask(self):
+        return torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0, 0.0])
+
+    def zero_flat_grad(self):
+        self.flat_grad.zero_()
+
+    def finalize_flat_grad(self):
+        self.finalized += 1
+
+    def refresh_weights(self):
+        self.refreshed += 1
+
+    def initLSTMStates(self, seeds, dims):
+        return [(torch.ones(len(seeds), 1, 1, 1), 2 * torch.ones(len(seeds), 1, 1, 1))]
+
+    def sample_train(self, x, h):
+        w = self._flat[:4].detach()
+        hh, cc = h[0]
+        y = x * w[0] + hh * w[1]
+        self.flat_grad[:4] += torch.tensor([1.0, 2.0, 3.0, 4.0])       # what the CUDA backward would accumulate
+        return y.requires_grad_(True), y.flatten(1).sum(1), hh + 1.0, cc * 0.5
+
+
+def test_train_block_host_logic_weight_decay_and_finalize():
+    """train_block: finalize before the all-reduce, clip, then the reference's Adam weight decay (main.py:78) added to the
+    TRAINABLE entries only (buffers inside the flat parameter buffer keep a zero gradient), optimizer step, refresh."""
+    from tmglow_b200 import train as T
+    m = _ToyModel()
+    opt = torch.optim.SGD([m.flat_parameter_for_optimizer()], lr=0.1)
+    x = torch.ones(2, 3, 1, 1, 1)
+    before = m._flat.detach().clone()
+    loss, norm, h = T.train_block(m, opt, x, torch.zeros(2, 3, 1, 1, 1), m.initLSTMStates(torch.arange(2), None),
+                                  loss_fn=lambda y, ld, t: (y ** 2).mean() + 0 * ld.sum(), max_norm=1.0, weight_decay=0.5)
+    assert m.finalized == 1 and m.refreshed == 1
+    g = torch.tensor([3.0, 6.0, 9.0, 12.0, 0.0, 0.0])                   # three time steps of the toy gradient
+    assert abs(norm - float(g.norm())) < 1e-5
+    expect = g / (float(g.norm()) + 1e-6) + 0.5 * before * m.trainable_mask()
+    assert torch.allclose(m._flat.detach(), before - 0.1 * expect, atol=1e-6)
+    assert torch.equal(m._flat.detach()[4:], before[4:])                # buffers untouched
+    assert not h[0][0].requires_grad
+
+
+def test_train_series_blocks_and_state_mixing():
+    """train_series = one mini-batch of TrainFlow.trainParallel (trainFlowParallel.py:225-303): Tmax // tback optimizer
+    steps, states mixed 50/50 with the initial states after each block, losses summed."""
+    from tmglow_b200 import train as T
+    m = _ToyModel()
+    opt = torch.optim.SGD([m.flat_parameter_for_optimizer()], lr=0.0)
+    calls = []
+
+    def crit(y, lp, tgt, tm, tr):
+        calls.append((tuple(y.shape), tuple(tm.shape), tuple(tr.shape)))
+        return (y ** 2).mean()
+    x0 = torch.ones(2, 6, 1, 1, 1)
+    tot, a = T.train_series(m, opt, crit, x0, torch.zeros(2, 6, 1, 1, 1), torch.arange(2), tback=3, max_norm=None)
+    assert len(calls) == 2 and calls[0] == ((2, 3, 1, 1, 1), (2, 1, 1, 1), (2, 1, 1, 1))
+    assert m.refreshed == 2
+    # h: 1 -> +3 -> mix with 1 -> (4+1)/2 = 2.5 -> +3 -> (5.5+1)/2 = 3.25 ; c: 2 -> /8 -> (0.25+2)/2 = 1.125 -> /8 -> mix
+    assert torch.allclose(a[0][0], torch.full((2, 1, 1, 1), 3.25))
+    assert torch.allclose(a[0][1], torch.full((2, 1, 1, 1), (1.125 / 8 + 2) / 2))
+    assert tot.ndim == 0 and float(tot) > 0
+    ms = T.mix_states([(torch.ones(1), torch.zeros(1))], [(3 * torch.ones(1), 2 * torch.ones(1))])
+    assert float(ms[0][0]) == 2.0 and float(ms[0][1]) == 1.0
