@@ -5,6 +5,7 @@
 //   LSTMCFlowDecoder           nn/tmGlow.py:231-303
 //   TMGlow.forward/reconstruct nn/tmGlow.py:378-467
 // with every torch.cat / chunk / relu / pad tensor of the reference folded into the kernels.
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <cstdarg>
@@ -139,6 +140,13 @@ struct tmg_model {
   std::vector<LuTabEntry> lu_tab;   // deferred LU backward: one entry per flow step
   LuTabEntry* lu_tab_dev = nullptr;
   unsigned* sync_dev = nullptr;     // zero-initialised, self-resetting words for single-launch reductions (absmax)
+  // CUDA graphs of the per-time-step backward (~1 400 launches each): keyed by every pointer / shape the launch sequence
+  // depends on; a key is run eagerly the first time it is seen, captured the second time, replayed from then on
+  struct BwdGraph { int seen = 0; cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
+  std::map<std::vector<uint64_t>, BwdGraph> bwd_graphs;
+  int n_graphs = 0;
+  cudaStream_t gstream = nullptr;   // capture / replay stream (stream capture is not allowed on the legacy default stream)
+  cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   std::vector<std::vector<char>> tape_emit;
   int tape_sig[4] = {0, 0, 0, -1};  // B, h, w, precision
 };
@@ -1054,6 +1062,10 @@ void tmg_model_destroy(tmg_model* m) {
   if (m->jobs2_dev) cudaFree(m->jobs2_dev);
   if (m->lu_tab_dev) cudaFree(m->lu_tab_dev);
   if (m->sync_dev) cudaFree(m->sync_dev);
+  for (auto& kv : m->bwd_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (m->gstream) cudaStreamDestroy(m->gstream);
+  if (m->gev_in) cudaEventDestroy(m->gev_in);
+  if (m->gev_out) cudaEventDestroy(m->gev_out);
   if (m->packed) cudaFree(m->packed);
   delete m;
 }
@@ -1959,11 +1971,11 @@ size_t tmg_reconstruct_backward_workspace_bytes(const tmg_model* m, int B, int h
   return align_up(p.total, 256) + (r.e.total + r.total) * sizeof(float) + 512;
 }
 
-int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
-                             const float* const* c_in, const float* const* eps, const void* tape_v, const float* g_y,
-                             const float* g_log_det, const float* const* g_h_out, const float* const* g_c_out,
-                             float* const* g_h_in, float* const* g_c_in, float* grads, void* workspace,
-                             size_t workspace_bytes, uint32_t flags, void* stream) {
+static int reconstruct_backward_impl(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                                     const float* const* c_in, const float* const* eps, const void* tape_v, const float* g_y,
+                                     const float* g_log_det, const float* const* g_h_out, const float* const* g_c_out,
+                                     float* const* g_h_in, float* const* g_c_in, float* grads, void* workspace,
+                                     size_t workspace_bytes, uint32_t flags, void* stream) {
   if (!m) { set_error("null model"); return TMG_ERR_NULL; }
   Plan p;
   TMG_TRY(make_plan(*m, B, h, w, p, false));
@@ -2054,6 +2066,83 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
   }
   // encoder parameters
   return run_encoder_backward(c, (flags & TMG_FLAG_BN_TRAIN) != 0, rb, rx, grads);
+}
+
+int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, const float* const* h_in,
+                             const float* const* c_in, const float* const* eps, const void* tape_v, const float* g_y,
+                             const float* g_log_det, const float* const* g_h_out, const float* const* g_c_out,
+                             float* const* g_h_in, float* const* g_c_in, float* grads, void* workspace,
+                             size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  auto eager = [&](void* s_) {
+    return reconstruct_backward_impl(m, B, h, w, x, h_in, c_in, eps, tape_v, g_y, g_log_det, g_h_out, g_c_out, g_h_in, g_c_in,
+                                     grads, workspace, workspace_bytes, flags, s_);
+  };
+  static const bool no_graph = [] { const char* e = getenv("TMG_NO_GRAPH"); return e && e[0] == '1'; }();
+  if (no_graph || !m->ready) return eager(stream);
+  // the launch sequence is a pure function of these values: same key -> same ~1 400 launches, replayed as one graph
+  const int L = m->cfg.n_levels;
+  std::vector<uint64_t> key;
+  key.reserve(16 + 8 * L);
+  auto put = [&](const void* p_) { key.push_back((uint64_t)(uintptr_t)p_); };
+  key.push_back(((uint64_t)B << 40) ^ ((uint64_t)h << 20) ^ (uint64_t)w);
+  key.push_back(((uint64_t)flags << 8) ^ (uint64_t)m->precision);
+  key.push_back((uint64_t)workspace_bytes);
+  put(m->params); put(m->packed); put(x); put(tape_v); put(g_y); put(g_log_det); put(grads); put(workspace);
+  for (int l = 0; l <= L; ++l) put(eps ? eps[l] : nullptr);
+  for (int l = 0; l < L; ++l) {
+    put(h_in ? h_in[l] : nullptr); put(c_in ? c_in[l] : nullptr);
+    put(g_h_out ? g_h_out[l] : nullptr); put(g_c_out ? g_c_out[l] : nullptr);
+    put(g_h_in ? g_h_in[l] : nullptr); put(g_c_in ? g_c_in[l] : nullptr);
+  }
+  {   // which steps read their intermediates from the tape (host-side state of the last training forward)
+    uint64_t hsh = 1469598103934665603ull;
+    for (int q = 0; q < 4; ++q) hsh = (hsh ^ (uint64_t)(uint32_t)m->tape_sig[q]) * 1099511628211ull;
+    for (const auto& v : m->tape_emit) for (char ch : v) hsh = (hsh ^ (uint64_t)(unsigned char)ch) * 1099511628211ull;
+    key.push_back(hsh);
+  }
+  tmg_model::BwdGraph& g = m->bwd_graphs[key];
+  cudaStream_t st = (cudaStream_t)stream;
+  auto replay = [&]() -> int {
+    TMG_CUDA_OK(cudaEventRecord(m->gev_in, st));
+    TMG_CUDA_OK(cudaStreamWaitEvent(m->gstream, m->gev_in, 0));
+    TMG_CUDA_OK(cudaGraphLaunch(g.exec, m->gstream));
+    TMG_CUDA_OK(cudaEventRecord(m->gev_out, m->gstream));
+    TMG_CUDA_OK(cudaStreamWaitEvent(st, m->gev_out, 0));
+    tmg::g_launches += g.kernels;             // the kernels the graph launches (tmg_launch_count reports kernels)
+    return TMG_OK;
+  };
+  if (g.exec) return replay();
+  if (g.seen++ == 0 || g.seen < 0 || m->n_graphs >= 64) return eager(stream);      // first sight (or capture gave up): eager
+  if (!m->gstream) {
+    TMG_CUDA_OK(cudaStreamCreateWithFlags(&m->gstream, cudaStreamNonBlocking));
+    TMG_CUDA_OK(cudaEventCreateWithFlags(&m->gev_in, cudaEventDisableTiming));
+    TMG_CUDA_OK(cudaEventCreateWithFlags(&m->gev_out, cudaEventDisableTiming));
+  }
+  if (cudaStreamBeginCapture(m->gstream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    g.seen = -1000000;
+    return eager(stream);
+  }
+  const int64_t launches_before = tmg::g_launches.load();
+  const int rc = eager((void*)m->gstream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(m->gstream, &graph);
+  g.kernels = tmg::g_launches.load() - launches_before;
+  tmg::g_launches.store(launches_before);          // nothing ran yet: the replay adds them
+  if (rc != TMG_OK || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g.seen = -1000000;
+    return rc != TMG_OK ? rc : eager(stream);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || !exec) { cudaGetLastError(); g.seen = -1000000; return eager(stream); }
+  g.exec = exec;
+  ++m->n_graphs;
+  return replay();
 }
 
 // Finishes the parameter gradients tmg_reconstruct_backward defers: the LU-parameterised 1x1 convolutions
