@@ -2101,6 +2101,10 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
     for (const auto& v : m->tape_emit) for (char ch : v) hsh = (hsh ^ (uint64_t)(unsigned char)ch) * 1099511628211ull;
     key.push_back(hsh);
   }
+  if (m->bwd_graphs.size() > 1024) {       // keys that never repeated (unstable buffer addresses): forget them
+    for (auto it = m->bwd_graphs.begin(); it != m->bwd_graphs.end();)
+      it = it->second.exec ? std::next(it) : m->bwd_graphs.erase(it);
+  }
   tmg_model::BwdGraph& g = m->bwd_graphs[key];
   cudaStream_t st = (cudaStream_t)stream;
   auto replay = [&]() -> int {
