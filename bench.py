@@ -345,7 +345,9 @@ def measure_train(args, rank, world, dev, dist, steps, warmup, e2e_steps=0):
         ms_e, _ = timed(e2e, e2e_steps)
         out.update({"e2e_ms": ms_e, "e2e_steps": e2e_steps, "h2d_bytes": xh.numel() * 4 + th.numel() * 4, "d2h_bytes": 4})
     assert torch.isfinite(state["loss"]).all(), "non-finite loss"
-    out.update({"loss": float(state["loss"]), "norm": state["norm"]})
+    gs = m.backward_graph_stats()
+    out.update({"loss": float(state["loss"]), "norm": state["norm"],
+                "backward_graphs": {"captured": gs[0], "replays": gs[1], "eager_calls": gs[2]}})
     return out
 
 
@@ -389,7 +391,7 @@ def run_train(args, rank, world, local):
                 "clocks": clk, "gpu_launches": int(launches), "loss": loss, "grad_norm": norm,
                 "e2e": {"value": r["e2e_steps"] / (r["e2e_ms"] * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": r["h2d_bytes"],
                         "d2h_bytes_per_step": r["d2h_bytes"]},
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "backward_graphs": r["backward_graphs"],
                 "hf_snapshots_per_sec": GB * tb * args.steps / (ms * 1e-3)}
         print(json.dumps(line))
     if dist is not None:

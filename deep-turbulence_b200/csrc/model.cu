@@ -145,6 +145,7 @@ struct tmg_model {
   struct BwdGraph { int seen = 0; cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
   std::map<std::vector<uint64_t>, BwdGraph> bwd_graphs;
   int n_graphs = 0;
+  int64_t n_replays = 0, n_eager = 0;
   cudaStream_t gstream = nullptr;   // capture / replay stream (stream capture is not allowed on the legacy default stream)
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   std::vector<std::vector<char>> tape_emit;
@@ -2078,8 +2079,12 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
     return reconstruct_backward_impl(m, B, h, w, x, h_in, c_in, eps, tape_v, g_y, g_log_det, g_h_out, g_c_out, g_h_in, g_c_in,
                                      grads, workspace, workspace_bytes, flags, s_);
   };
-  static const bool no_graph = [] { const char* e = getenv("TMG_NO_GRAPH"); return e && e[0] == '1'; }();
-  if (no_graph || !m->ready) return eager(stream);
+  // Opt-in (TMG_BWD_GRAPH=1): replay pays only when the caller's buffers keep their addresses from one optimizer step to
+  // the next; torch's caching allocator moves the per-call tensors (tape, noise, gradients) often enough that captures
+  // (~100 ms each) keep recurring in a short run -- measured: 193 -> 180 ms per step when the addresses repeat, slower
+  // when they do not.
+  static const bool use_graph = [] { const char* e = getenv("TMG_BWD_GRAPH"); return e && e[0] == '1'; }();
+  if (!use_graph || !m->ready) { ++m->n_eager; return eager(stream); }
   // the launch sequence is a pure function of these values: same key -> same ~1 400 launches, replayed as one graph
   const int L = m->cfg.n_levels;
   std::vector<uint64_t> key;
@@ -2114,10 +2119,11 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
     TMG_CUDA_OK(cudaEventRecord(m->gev_out, m->gstream));
     TMG_CUDA_OK(cudaStreamWaitEvent(st, m->gev_out, 0));
     tmg::g_launches += g.kernels;             // the kernels the graph launches (tmg_launch_count reports kernels)
+    ++m->n_replays;
     return TMG_OK;
   };
   if (g.exec) return replay();
-  if (g.seen++ == 0 || g.seen < 0 || m->n_graphs >= 64) return eager(stream);      // first sight (or capture gave up): eager
+  if (g.seen++ == 0 || g.seen < 0 || m->n_graphs >= 64) { ++m->n_eager; return eager(stream); }      // first sight (or capture gave up): eager
   if (!m->gstream) {
     TMG_CUDA_OK(cudaStreamCreateWithFlags(&m->gstream, cudaStreamNonBlocking));
     TMG_CUDA_OK(cudaEventCreateWithFlags(&m->gev_in, cudaEventDisableTiming));
@@ -2147,6 +2153,15 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
   g.exec = exec;
   ++m->n_graphs;
   return replay();
+}
+
+// how the backward calls of this model ran so far: captured graphs, graph replays, eager launch sequences
+int tmg_backward_graph_stats(const tmg_model* m, int64_t* graphs, int64_t* replays, int64_t* eager) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (graphs) *graphs = m->n_graphs;
+  if (replays) *replays = m->n_replays;
+  if (eager) *eager = m->n_eager;
+  return TMG_OK;
 }
 
 // Finishes the parameter gradients tmg_reconstruct_backward defers: the LU-parameterised 1x1 convolutions

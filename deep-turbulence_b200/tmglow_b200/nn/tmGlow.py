@@ -266,6 +266,20 @@ class TMGlow(nn.Module):
             self._ws[key] = ws
         return ws
 
+    def _scratch(self, name, shape, dtype, device):
+        """Persistent scratch tensors of the training backward (workspace, contiguous copies of the incoming gradients):
+        used only inside one stream-ordered backward call, so one buffer per name is enough -- and stable addresses
+        let the library replay its CUDA graph of the call instead of re-launching ~1 400 kernels."""
+        pool = self.__dict__.setdefault("_scratch_pool", {})
+        key = (name, tuple(shape), dtype, device)
+        t = pool.get(key)
+        if t is None:
+            for k in [k for k in pool if k[0] == name]:
+                del pool[k]
+            t = torch.empty(shape, dtype=dtype, device=device)
+            pool[key] = t
+        return t
+
     # ------------------------------------------------------------------ shapes
     def _hf_size(self, x):
         up = self._cfg.cglow_upscale
@@ -489,6 +503,15 @@ class TMGlow(nn.Module):
             _lib.check(lib.tmg_backward_finalize(h, g.data_ptr(), torch.cuda.current_stream(g.device).cuda_stream))
         return g
 
+    def backward_graph_stats(self):
+        """(graphs captured, graph replays, eager runs) of the per-time-step CUDA backward on the current device."""
+        import ctypes as C
+        device = next(self.parameters()).device
+        lib, h = self._prepare(device)
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.tmg_backward_graph_stats(h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def scatter_flat_grad(self):
         """``p.grad`` of every parameter = its slice of ``flat_grad`` (views, no copies)."""
         self.finalize_flat_grad()
@@ -609,13 +632,22 @@ class _ReconstructFn(torch.autograd.Function):
         cl = lambda t, d: None if t is None else t.detach().float().contiguous(memory_format=torch.channels_last)
         with torch.cuda.device(device):
             st = torch.cuda.current_stream(device).cuda_stream
-            g_y = torch.zeros_like(ctx.x.new_empty((B, model._cfg.out_features) + tuple(model._hf_size(x)))) if g_y is None else g_y.contiguous().float()
-            g_ld = torch.zeros(B, device=device) if g_ld is None else g_ld.contiguous().float()
+            gy_buf = model._scratch("g_y", (B, model._cfg.out_features) + tuple(model._hf_size(x)), torch.float32, device)
+            gld_buf = model._scratch("g_ld", (B,), torch.float32, device)
+            if g_y is None:
+                gy_buf.zero_()
+            else:
+                gy_buf.copy_(g_y)
+            if g_ld is None:
+                gld_buf.zero_()
+            else:
+                gld_buf.copy_(g_ld)
+            g_y, g_ld = gy_buf, gld_buf
             gh = [cl(g_states[2 * l], None) for l in range(L)]
             gc = [cl(g_states[2 * l + 1], None) for l in range(L)]
             g_in = [(_empty_channels_last(d, device), _empty_channels_last(d, device)) for d in ctx.dims] if ctx.has_states else []
             n = lib.tmg_reconstruct_backward_workspace_bytes(h, B, x.shape[2], x.shape[3])
-            ws = torch.empty(n, dtype=torch.uint8, device=device)
+            ws = model._scratch("bwd_ws", (n,), torch.uint8, device)
             hp, cp = ctx.state_ptrs
             pa = lambda ts: _lib.ptr_array([None if t is None else t.data_ptr() for t in ts])
             _lib.check(lib.tmg_reconstruct_backward(

@@ -158,6 +158,12 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x,
  * cleared.  tmg_flow_step_backward is not deferred. */
 int tmg_backward_finalize(tmg_model* m, float* grads, void* stream);
 
+/* With TMG_BWD_GRAPH=1 in the environment tmg_reconstruct_backward replays a CUDA graph of its ~1 400 launches when it is
+ * called again with the same buffers (same pointers, shapes, precision): a key is run eagerly the first time it is seen,
+ * captured the second time and replayed from then on.  Off by default: it pays only for callers with stable buffer
+ * addresses.  Counters for measurement: graphs held, replays, eager runs. */
+int tmg_backward_graph_stats(const tmg_model* m, int64_t* graphs, int64_t* replays, int64_t* eager);
+
 /* TMGlow.forward (nn/tmGlow.py:378-414) + LSTMCFlowDecoder.forward (:231-267).
  * Outputs: z [B,Cz,H_L,W_L] NCHW, logp [B] (= log prior + sum of log-dets), states, and when
  * eps_out != NULL the n_levels+1 noise tensors (return_eps=True). */
