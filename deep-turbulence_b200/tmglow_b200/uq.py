@@ -107,3 +107,52 @@ def sample_sequence(model, x_seq: torch.Tensor, samples: int, *, base_seed: int 
         raise ValueError("rank %d of %d has no samples: use samples >= world" % (rank, world))
     mean, var, ntot = combine_moments(s1, s2, S, group)
     return mean.float(), var.float(), ntot, (torch.stack(kept, 1) if keep_samples else None)
+
+
+@torch.no_grad()
+def model_pred(model, input_seq: torch.Tensor, samples: int, tmax: int, *, stride: int = 1, state_mix_every: int = 20,
+               seeds: Optional[torch.Tensor] = None, unnormalise: bool = True,
+               sampler: Optional[Callable] = None, init_states: Optional[Callable] = None):
+    """The prediction loops of the reference, ``modelPred`` (``utils/utils.py:151-235``, state mixing every 20 steps) and
+    the body of ``TrainFlow.test`` (``nn/trainFlowParallel.py:345-367``, every 10 steps), for a mini-batch of ``B`` test
+    cases ``input_seq [B, T, nic, h, w]``: ``samples`` stochastic predictions of ``tmax`` time steps each.  The reference
+    runs ``samples x tmax`` calls of ``model.sample`` on batch ``B``; here the sample loop is folded into the batch
+    (one call per time step on batch ``samples * B``, sample-major), each (sample, case) pair with its own seeded LSTM
+    state.  ``seeds [samples, B]`` (default: drawn like the reference, ``LongTensor.random_(0, 1e8)``).
+    Returns ``yPred [samples, B, tmax // stride, C, H, W]`` (un-normalised with ``model.out_mu / out_std`` when set)."""
+    sampler = sampler or model.sample
+    init_states = init_states or model.initLSTMStates
+    B = input_seq.shape[0]
+    dev = input_seq.device
+    if seeds is None:
+        seeds = torch.LongTensor(samples, B).random_(0, int(1e8))
+    assert tuple(seeds.shape) == (samples, B)
+    up = getattr(getattr(model, "_cfg", None), "cglow_upscale", None)
+    H, W = (input_seq.shape[-2] * up, input_seq.shape[-1] * up) if up else (None, None)
+    key = init_states(seeds.reshape(-1), [H, W])
+    h = key
+    out_mu = out_std = None
+    if unnormalise and getattr(model, "out_mu", None) is not None:
+        out_mu = model.out_mu.to(dev).view(1, -1, 1, 1)
+        out_std = model.out_std.to(dev).view(1, -1, 1, 1)
+        if float(out_std.abs().sum()) == 0.0:
+            out_mu = out_std = None
+    frames = []
+    for t in range(tmax):
+        x = input_seq[:, t].unsqueeze(0).expand(samples, *input_seq[:, t].shape).reshape(samples * B, *input_seq.shape[2:])
+        y, _, h = sampler(x, h)
+        if t % stride == 0:
+            frames.append(y if out_mu is None else out_std * y + out_mu)
+        if state_mix_every and t % state_mix_every == 0:
+            h = mix_states(h, key)
+    yp = torch.stack(frames, 1)                                   # [samples*B, T', C, H, W]
+    return yp.reshape(samples, B, *yp.shape[1:])
+
+
+@torch.no_grad()
+def test_error(model, input_seq: torch.Tensor, target_seq: torch.Tensor, samples: int, tmax: int = 40, **kw):
+    """The summand of ``TrainFlow.test`` (``nn/trainFlowParallel.py:374``) for one mini-batch: squared error between the mean
+    over the samples and the (un-normalised) target over time steps ``1..tmax``, summed.  The reference divides the total by
+    ``ntest * tmax * H * W`` (``:377``).  ``target_seq [B, >= tmax + 1, C, H, W]`` already un-normalised."""
+    yp = model_pred(model, input_seq, samples, tmax + 1, state_mix_every=kw.pop("state_mix_every", 10), **kw)
+    return torch.pow(yp[:, :, 1:tmax + 1].mean(0) - target_seq[:, 1:tmax + 1], 2).sum()

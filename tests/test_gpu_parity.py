@@ -473,3 +473,34 @@ def test_other_baseline_configs(geom):
     torch.manual_seed(3)
     yb, ldb, _ = m.sample(x1.expand(S, -1, -1, -1).contiguous(), hs)
     assert (ya - yb).abs().max().item() < 2e-4 and ((lda - ldb).abs() <= 1e-5 * ldb.abs() + 1e-3).all()
+
+
+def test_model_pred_driver_and_normalisation_buffers():
+    """uq.model_pred (the reference's modelPred / test loops folded into the batch) on the CUDA model, with the
+    normalisation buffers assigned as plain tensors the way the reference's data loader does (dataLoader.py:159-164)."""
+    from tmglow_b200 import uq
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = _model(cfg, g["state_dict"])
+    dev = _dev()
+    m.out_mu = torch.tensor([0.5, -1.0, 2.0]).to(dev)
+    m.out_std = torch.tensor([2.0, 3.0, 0.5]).to(dev)
+    m.precision = "f16x3"
+    gen = torch.Generator().manual_seed(3)
+    Bc, T, S = 2, 3, 3
+    inp = torch.randn(Bc, T, *g["x"].shape[1:], generator=gen).to(dev)
+    seeds = torch.arange(S * Bc).reshape(S, Bc)
+    torch.manual_seed(11)
+    yp = uq.model_pred(m, inp, S, T, state_mix_every=2, seeds=seeds)
+    H, W = g["rec2"]["y"].shape[-2:]
+    assert tuple(yp.shape) == (S, Bc, T, 3, H, W) and torch.isfinite(yp).all()
+    # the same folded batch by hand, normalised output
+    torch.manual_seed(11)
+    key = m.initLSTMStates(seeds.reshape(-1), [H, W])
+    x0 = inp[:, 0].unsqueeze(0).expand(S, -1, -1, -1, -1).reshape(S * Bc, *inp.shape[2:])
+    y0, _, _ = m.sample(x0, key)
+    ref = m.out_std.view(1, 3, 1, 1) * y0 + m.out_mu.view(1, 3, 1, 1)
+    assert torch.allclose(yp[:, :, 0].reshape(S * Bc, 3, H, W), ref, atol=1e-5)
+    assert torch.equal(m.state_dict()["out_std"].cpu(), torch.tensor([2.0, 3.0, 0.5]))      # the buffers are part of the checkpoint
+    err = uq.test_error(m, inp, torch.zeros(Bc, T, 3, H, W, device=dev), S, tmax=T - 1, seeds=seeds)
+    assert torch.isfinite(err) and err.ndim == 0

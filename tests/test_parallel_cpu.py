@@ -218,3 +218,31 @@ def test_train_series_blocks_and_state_mixing():
     assert tot.ndim == 0 and float(tot) > 0
     ms = T.mix_states([(torch.ones(1), torch.zeros(1))], [(3 * torch.ones(1), 2 * torch.ones(1))])
     assert float(ms[0][0]) == 2.0 and float(ms[0][1]) == 1.0
+
+
+def test_model_pred_matches_reference_loops():
+    """uq.model_pred folds the reference's sample loop (utils.py:197-222 / trainFlowParallel.py:345-367) into the batch:
+    same predictions as the loop over samples with the same seeds, state mixing at the same time steps."""
+    from tmglow_b200 import uq
+    g = torch.Generator().manual_seed(2)
+    Bc, T, S = 3, 7, 4
+    inp = torch.randn(Bc, T, 4, 2, 2, generator=g)
+    seeds = torch.arange(S * Bc).reshape(S, Bc) + 50
+    model = type("M", (), {"out_mu": None})()
+    got = uq.model_pred(model, inp, S, T, stride=2, state_mix_every=3, seeds=seeds, sampler=_sampler, init_states=_init_states)
+    assert got.shape[:3] == (S, Bc, (T + 1) // 2)
+    for i in range(S):                                       # the reference's loops, literally
+        hkey = _init_states(seeds[i], None)
+        h0 = hkey
+        k = 0
+        for t in range(T):
+            y, _, h0 = _sampler(inp[:, t], h0)
+            if t % 2 == 0:
+                assert torch.allclose(got[i, :, k], y, atol=1e-6), (i, t)
+                k += 1
+            if t % 3 == 0:
+                h0 = [(0.5 * a + 0.5 * ak, 0.5 * c + 0.5 * ck) for (a, c), (ak, ck) in zip(h0, hkey)]
+    tgt = torch.randn(Bc, T, *got.shape[3:], generator=g)
+    err = uq.test_error(model, inp, tgt, S, tmax=T - 1, seeds=seeds, sampler=_sampler, init_states=_init_states)
+    full = uq.model_pred(model, inp, S, T, state_mix_every=10, seeds=seeds, sampler=_sampler, init_states=_init_states)
+    assert torch.allclose(err, ((full[:, :, 1:].mean(0) - tgt[:, 1:]) ** 2).sum())
