@@ -272,9 +272,36 @@ unsqueeze_nchw_kernel(PermArgs a, int64_t npix) {
   }
 }
 
+// CheckerSqueeze.reverse between two flow levels (NHWC -> NHWC, into the first C channels of the wider state): one thread
+// per SOURCE pixel reads its 4C contiguous channels and writes the four destination pixels (C contiguous floats each) with
+// 8-byte accesses -- the generic kernel above spends its time on 64-bit index arithmetic per element.
+__global__ void __launch_bounds__(256)
+unsqueeze_nhwc_kernel(PermArgs a, int64_t npix2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix2) return;
+  const int H2 = a.H / 2, W2 = a.W / 2, C = a.C;
+  const int x = (int)(i % W2); const int64_t t = i / W2; const int y = (int)(t % H2); const int b = (int)(t / H2);
+  const float2* s2 = reinterpret_cast<const float2*>(a.src + i * a.src_cstride + a.src_coff);
+  const int h = C >> 1;                                   // float2 per channel group
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dr = (k == 1 || k == 2), dc = (k >= 2);    // (0,0),(1,0),(1,1),(0,1)   flowUtils.py:117-120
+    float2* d2 = reinterpret_cast<float2*>(a.dst + (((int64_t)b * a.H + 2 * y + dr) * a.W + 2 * x + dc) * a.dst_cstride + a.dst_coff);
+    for (int q = 0; q < h; ++q) d2[q] = __ldg(s2 + k * h + q);
+  }
+}
+
 int launch_permute(const PermArgs& a, cudaStream_t st) {
   int64_t total = (int64_t)a.B * a.C * a.H * a.W;
   if (total == 0) return TMG_OK;
+  if (a.mode == PERM_UNSQUEEZE_NHWC_TO_NHWC && (a.C & 1) == 0 && (a.src_cstride & 1) == 0 && (a.src_coff & 1) == 0 &&
+      (a.dst_cstride & 1) == 0 && (a.dst_coff & 1) == 0 && (a.H & 1) == 0 && (a.W & 1) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.src) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.dst) & 7) == 0) {
+    const int64_t npix2 = total / (4 * a.C);
+    unsqueeze_nhwc_kernel<<<(unsigned)((npix2 + 255) / 256), 256, 0, st>>>(a, npix2);
+    TMG_LAUNCH_CHECK();
+    return TMG_OK;
+  }
   if (a.mode == PERM_UNSQUEEZE_NHWC_TO_NCHW && a.src_cstride % 4 == 0 && a.src_coff % 4 == 0 && a.W % 2 == 0 &&
       (reinterpret_cast<uintptr_t>(a.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dst) & 7) == 0 &&
       (a.C == 3 || a.C == 1 || a.C == 2 || a.C == 4)) {
