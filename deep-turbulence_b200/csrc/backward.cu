@@ -208,6 +208,67 @@ int launch_dgrad_ring(const RingArgs& a, cudaStream_t st) {
   return TMG_OK;
 }
 
+// ------------------------------------------------------------------ data gradient of a Cout = 1 convolution (dense layers)
+// gx[p][c] = sum_tap g[p - off(tap)] * w[0][c][tap]: nine FMAs per element -- a streaming kernel, exact fp32; on the tensor
+// cores this is a K = 1 GEMM padded to 16 and costs a full pipeline trip.  Zero padding only (denseBlock.py:136).  The
+// channels are routed to up to three destinations (the sources of the forward concatenation), gated by the ReLU of the
+// forward input, optionally accumulated.
+struct DgradC1Args {
+  const float* g; int g_cstride, g_coff;
+  const float* w;                  // OIHW with O = 1: [cin][9]
+  int cin;
+  int ndst; ConvDst dst[3];
+  int B, H, W;
+};
+__global__ void __launch_bounds__(256)
+dgrad_cout1_kernel(DgradC1Args a, int npix) {
+  // a thread owns one pixel and every eighth channel: the nine taps of g are loaded once, the weights come from shared
+  // memory, consecutive lanes write consecutive channels
+  __shared__ float s_w[9 * 256];
+  for (int i = threadIdx.x; i < a.cin * 9; i += 256) s_w[i] = __ldg(a.w + i);
+  __syncthreads();
+  const int pix = blockIdx.x * 32 + (threadIdx.x >> 3), l = threadIdx.x & 7;
+  if (pix >= npix) return;
+  const int x = pix % a.W; const int t = pix / a.W; const int y = t % a.H; const int b = t / a.H;
+  float gt[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    // forward: out[q] += w[tap] * in[q + off(tap)]  =>  gx[p] += w[tap] * g[p - off(tap)]
+    const int py = y - (tap / 3 - 1), px = x - (tap % 3 - 1);
+    gt[tap] = (py >= 0 && py < a.H && px >= 0 && px < a.W)
+                  ? __ldg(a.g + ((size_t)(b * a.H + py) * a.W + px) * a.g_cstride + a.g_coff) : 0.f;
+  }
+  const int nb1 = a.dst[0].nch, nb2 = nb1 + (a.ndst > 1 ? a.dst[1].nch : 0);
+  for (int c = l; c < a.cin; c += 8) {
+    const int d = c < nb1 ? 0 : (c < nb2 || a.ndst < 3 ? 1 : 2);
+    const ConvDst& ds = a.dst[d];
+    const int cl = c - (d == 0 ? 0 : (d == 1 ? nb1 : nb2));
+    if (ds.p == nullptr || cl >= ds.nch) continue;
+    const size_t o = (size_t)pix * ds.cstride + ds.coff + cl;
+    float acc = 0.f;
+    if (!ds.mask || __ldg(ds.mask + o) > 0.f) {
+      const float* wc = s_w + c * 9;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) acc = fmaf(wc[tap], gt[tap], acc);
+    }
+    ds.p[o] = ds.accum ? ds.p[o] + acc : acc;
+  }
+}
+int launch_dgrad_cout1(const float* g, int g_cstride, int g_coff, const float* w_oihw, int cin, const ConvDst* dst, int ndst,
+                       int B, int H, int W, cudaStream_t st) {
+  DgradC1Args a{};
+  a.g = g; a.g_cstride = g_cstride; a.g_coff = g_coff; a.w = w_oihw; a.cin = cin;
+  a.ndst = ndst;
+  for (int d = 0; d < ndst && d < 3; ++d) a.dst[d] = dst[d];
+  a.B = B; a.H = H; a.W = W;
+  const int64_t npix = (int64_t)B * H * W;
+  if (npix <= 0 || cin <= 0) return TMG_OK;
+  if (cin > 256 || npix > 0x7fffffff) { set_error("dgrad_cout1: %d input channels / %lld pixels", cin, (long long)npix); return TMG_ERR_UNSUPPORTED; }
+  dgrad_cout1_kernel<<<(unsigned)((npix + 31) / 32), 256, 0, st>>>(a, (int)npix);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
 // ------------------------------------------------------------------ pointwise step backward
 constexpr int kSbThreads = 128;
 

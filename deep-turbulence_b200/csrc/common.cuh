@@ -388,6 +388,9 @@ struct RingArgs {
   int B, H, W;
 };
 int launch_dgrad_ring(const RingArgs& a, cudaStream_t st);
+// exact-fp32 data gradient of a Cout = 1, zero-padded 3x3 convolution, routed to the forward sources (ReLU mask, accumulate)
+int launch_dgrad_cout1(const float* g, int g_cstride, int g_coff, const float* w_oihw, int cin, const ConvDst* dst, int ndst,
+                       int B, int H, int W, cudaStream_t st);
 
 // Pointwise part of one REVERSE flow step (z -> y, the direction training runs: TMGlow.sample), backward:
 //   forward:  a = 2*softsign(h_odd), v = [y1, y2*exp(-a) - h_even], u = W v, out = (u - nb)/nw,

@@ -1640,6 +1640,19 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
   // data gradient on tensor cores (f16 modes): ONE launch of the fp16 hi/lo conv kernel on the transposed, tap-flipped
   // weights with the output gradient scaled into the fp16 range; its epilogue routes the columns to the destinations
   bool dgrad_tc = false;
+  if (gscale && w.O == 1 && !replicate && ndest <= 3) {
+    // dense layers (Cout = 1): nine FMAs per element, exact fp32 streaming kernel instead of a K = 1 GEMM
+    ConvDst cd[3];
+    int tot = 0;
+    for (int d = 0; d < ndest; ++d) {
+      cd[d] = ConvDst{dests[d].g, dests[d].fwd, dests[d].cstride, dests[d].coff, dests[d].nch, dests[d].accum};
+      tot += dests[d].nch;
+    }
+    if (tot == w.I) {
+      TMG_TRY(launch_dgrad_cout1(g, g_cs, g_co, c.P() + w.w_param, w.I, cd, ndest, B, Hl, Wl, c.st));
+      return TMG_OK;
+    }
+  }
   if (gscale && prec_f16(c.m.precision) && w.w_pack_f16t >= 0 && ndest <= 3) {
     if (!tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st, c.m.sync_dev));
     ConvF16Args t{};
