@@ -269,6 +269,91 @@ int launch_dgrad_cout1(const float* g, int g_cstride, int g_coff, const float* w
   return TMG_OK;
 }
 
+// ------------------------------------------------------------------ weight gradient of a Cout = 1 convolution (dense layers)
+// dW[c][tap] = sum_q relu?(x[q][c]) * g[q - off(tap)]: each input element is loaded once and meets the nine output-gradient
+// values around it (g has ONE channel: the loads are warp-uniform).  Exact fp32; a block sums a pixel range in a fixed
+// order, reduce_partials_kernel adds the blocks in order (deterministic).  Zero padding, no bias (denseBlock.py:136).
+constexpr int kWc1Lanes = 4, kWc1CW = 64, kWc1Rows = 8;      // 256 threads = 4 pixel lanes x 64 channel slots; 8 rows per block
+__global__ void __launch_bounds__(kWc1Lanes * kWc1CW)
+wgrad_cout1_kernel(WgradArgs a, int chunks, float* __restrict__ part) {
+  extern __shared__ float s_g[];                       // [(rows + 2)][W + 2] output gradient of this row chunk, zero halo
+  __shared__ float s_acc[kWc1Lanes][kWc1CW][9];
+  const int c = threadIdx.x % kWc1CW, lane = threadIdx.x / kWc1CW;
+  const int b = blockIdx.x / chunks, r0 = (blockIdx.x - b * chunks) * kWc1Rows;
+  const int rows = min(kWc1Rows, a.H - r0), gw = a.W + 2;
+  for (int i = threadIdx.x; i < (rows + 2) * gw; i += kWc1Lanes * kWc1CW) {
+    const int ry = i / gw, rx = i - ry * gw;
+    const int y = r0 - 1 + ry, x = rx - 1;
+    s_g[i] = (y >= 0 && y < a.H && x >= 0 && x < a.W) ? __ldg(a.g + ((size_t)(b * a.H + y) * a.W + x) * a.g_cstride + a.g_coff) : 0.f;
+  }
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  // source of concatenated channel c
+  const float* sp = nullptr; int scs = 0, srelu = 0;
+  if (c < a.cin) {
+    int cc = c, si = 0;
+    while (si < a.nsrc - 1 && cc >= a.src[si].nch) { cc -= a.src[si].nch; ++si; }
+    if (cc < a.src[si].nch && a.src[si].p) {
+      sp = a.src[si].p + a.src[si].coff + cc + (size_t)(a.src[si].bshared ? 0 : b) * a.H * a.W * a.src[si].cstride;
+      scs = a.src[si].cstride; srelu = a.src[si].relu;
+    }
+  }
+  __syncthreads();
+  if (sp) {
+    for (int q = lane; q < rows * a.W; q += kWc1Lanes) {
+      const int ly = q / a.W, lx = q - ly * a.W;
+      float xv = __ldg(sp + (size_t)((r0 + ly) * a.W + lx) * scs);
+      if (srelu) xv = fmaxf(xv, 0.f);
+      // forward: out[p] += w[tap] * in[p + off(tap)]  =>  dW[tap] += g[p] * in[q], p = q - off(tap)
+      const float* gp = s_g + (ly + 1) * gw + (lx + 1);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) acc[tap] = fmaf(xv, gp[-(tap / 3 - 1) * gw - (tap % 3 - 1)], acc[tap]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) s_acc[lane][c][t] = acc[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.cin * 9; i += kWc1Lanes * kWc1CW) {
+    const int cc = i / 9, t = i - cc * 9;
+    part[(size_t)blockIdx.x * a.cin * 9 + i] = (s_acc[0][cc][t] + s_acc[1][cc][t]) + (s_acc[2][cc][t] + s_acc[3][cc][t]);
+  }
+}
+// out[i] (+)= sum over shares of part[s][i]: 32 outputs per block, 8 threads per output walk the shares 8 apart, then a
+// fixed-order sum of the 8 partials (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_par_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int nsplit, int accum) {
+  __shared__ float sm[8][32];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + x;
+  float s = 0.f;
+  if (i < n) for (int k = y; k < nsplit; k += 8) s += part[(size_t)k * n + i];
+  sm[y][x] = s;
+  __syncthreads();
+  if (y == 0 && i < n) {
+    float t = sm[0][x];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += sm[q][x];
+    out[i] = accum ? out[i] + t : t;
+  }
+}
+bool wgrad_cout1_supported(const WgradArgs& a) {
+  return a.cout == 1 && a.cin <= kWc1CW && a.stride != 2 && !a.bn_scale && !a.pad_replicate && !a.gbias &&
+         (size_t)(kWc1Rows + 2) * (a.W + 2) * sizeof(float) <= 32 * 1024 && (int64_t)a.B * a.H * a.W < 0x7fffffff;
+}
+size_t wgrad_cout1_scratch_floats(int cin, int B, int H, int W) { (void)W; return (size_t)B * cdiv(H, kWc1Rows) * cin * 9 + 64; }
+int launch_wgrad_cout1(const WgradArgs& a, cudaStream_t st) {
+  if (a.B <= 0 || a.H <= 0 || a.W <= 0) return TMG_OK;
+  const int chunks = cdiv(a.H, kWc1Rows), nb = a.B * chunks;
+  const size_t smem = (size_t)(kWc1Rows + 2) * (a.W + 2) * sizeof(float);
+  wgrad_cout1_kernel<<<nb, kWc1Lanes * kWc1CW, smem, st>>>(a, chunks, a.scratch);
+  TMG_LAUNCH_CHECK();
+  const int n = a.cin * 9;
+  reduce_partials_par_kernel<<<cdiv(n, 32), 256, 0, st>>>(a.scratch, a.gw, n, nb, a.accum);
+  TMG_LAUNCH_CHECK();
+  return TMG_OK;
+}
+
 // ------------------------------------------------------------------ pointwise step backward
 constexpr int kSbThreads = 128;
 

@@ -372,6 +372,10 @@ struct WgradArgs {
 };
 size_t wgrad_scratch_floats(int cout, int cin, int B, int H, int W);
 int launch_wgrad(const WgradArgs& a, cudaStream_t st);
+// exact-fp32 streaming weight gradient of a Cout = 1, zero-padded, bias-free convolution (dense layers)
+bool wgrad_cout1_supported(const WgradArgs& a);
+size_t wgrad_cout1_scratch_floats(int cin, int B, int H, int W);
+int launch_wgrad_cout1(const WgradArgs& a, cudaStream_t st);
 // tensor-core weight gradient (wgrad_f16.cu): stride 1, no folded BatchNorm; gscale = launch_absmax_scale of a.g;
 // a.scratch >= wgrad_f16_scratch_floats
 bool wgrad_f16_supported(const WgradArgs& a);

@@ -1597,6 +1597,7 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
     ws = std::max(ws, wgrad_f16_scratch_floats(cin_t, n_g, 3, B, Hl, Wl));
     ws = std::max(ws, wgrad_f16_scratch_floats(1, n_d2, 3, B, Hl, Wl));
     ws = std::max(ws, wgrad_f16_scratch_floats(1, n_d2l, 2, B, Hl, Wl));
+    ws = std::max(ws, wgrad_cout1_scratch_floats(cin_t + 1, B, Hl, Wl));
     const int n_sp[1] = {C / 2};
     ws = std::max(ws, wgrad_f16_scratch_floats(C, n_sp, 1, B, Hl, Wl));
   }
@@ -1625,6 +1626,20 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
   // the output gradient is scaled into the fp16 range by a power of two measured once per convolution
   const bool tc_bwd = gscale && prec_f16(c.m.precision);
   static const bool wg_off = [] { const char* e = getenv("TMG_WGRAD_FFMA"); return e && e[0] == '1'; }();
+  if (gscale && ndest <= 3 && wgrad_cout1_supported(wa)) {
+    // dense layers (Cout = 1): both adjoints are streaming kernels in exact fp32 -- on the tensor cores they are an
+    // M = 1 / K = 1 GEMM padded to a full tile, i.e. pure pipeline latency; no gradient scaling needed either
+    ConvDst cd[3];
+    int tot = 0;
+    for (int d = 0; d < ndest; ++d) {
+      cd[d] = ConvDst{dests[d].g, dests[d].fwd, dests[d].cstride, dests[d].coff, dests[d].nch, dests[d].accum};
+      tot += dests[d].nch;
+    }
+    if (tot == w.I) {
+      TMG_TRY(launch_wgrad_cout1(wa, c.st));
+      return launch_dgrad_cout1(g, g_cs, g_co, c.P() + w.w_param, w.I, cd, ndest, B, Hl, Wl, c.st);
+    }
+  }
   const bool wg_tc = tc_bwd && !wg_off && wgrad_f16_supported(wa);
   if (wg_tc && wa.gbias && w.O <= 256) {
     // the scale of g and the bias gradient (column sums of g) in one pass over g; the column-sum partials live at the
