@@ -115,6 +115,7 @@ wgrad_kernel(WgradArgs a, int TR, int nsplit, float* part, float* part_b) {
 }
 
 // out[i] (+)= sum_s part[s][i], fixed order
+__global__ void reduce_partials_par_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int nsplit, int accum);
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int nsplit, int accum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -149,7 +150,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   wgrad_kernel<<<grid, kWgThreads, smem, st>>>(a, TR, ns, part, part_b);
   TMG_LAUNCH_CHECK();
   const int n = a.cout * a.cin * 9;
-  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, st>>>(part, a.gw, n, ns, a.accum);
+  reduce_partials_par_kernel<<<cdiv(n, 32), 256, 0, st>>>(part, a.gw, n, ns, a.accum);
   TMG_LAUNCH_CHECK();
   if (a.gbias) {
     reduce_partials_kernel<<<cdiv(a.cout, 256), 256, 0, st>>>(part_b, a.gbias, a.cout, ns, a.accum);
@@ -401,9 +402,16 @@ step_bwd_kernel(StepBwdArgs a) {
     if (a.nw) {
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
-        float u = 0.f;
+        // four independent partial sums and 16-byte weight loads: this loop is a chain of dependent FMAs otherwise
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+        const float4* w4 = reinterpret_cast<const float4*>(s_w + c * C);
 #pragma unroll
-        for (int k = 0; k < C; ++k) u = fmaf(s_w[c * C + k], v[k], u);
+        for (int k = 0; k < C / 4; ++k) {
+          const float4 w = w4[k];
+          u0 = fmaf(w.x, v[4 * k], u0); u1 = fmaf(w.y, v[4 * k + 1], u1);
+          u2 = fmaf(w.z, v[4 * k + 2], u2); u3 = fmaf(w.w, v[4 * k + 3], u3);
+        }
+        const float u = (u0 + u1) + (u2 + u3);
         const float out = (u - s_nb[c]) / s_nw[c];
         acc_nb[c] = -gu[c];
         acc_nw[c] = -gu[c] * out;
@@ -415,8 +423,13 @@ step_bwd_kernel(StepBwdArgs a) {
 #pragma unroll 1
     for (int c = 0; c < C; ++c) {
       const float g = gu[c];
+      const float4* w4 = reinterpret_cast<const float4*>(s_w + c * C);
 #pragma unroll
-      for (int k = 0; k < C; ++k) gv[k] = fmaf(s_w[c * C + k], g, gv[k]);
+      for (int k = 0; k < C / 4; ++k) {
+        const float4 w = w4[k];
+        gv[4 * k] = fmaf(w.x, g, gv[4 * k]); gv[4 * k + 1] = fmaf(w.y, g, gv[4 * k + 1]);
+        gv[4 * k + 2] = fmaf(w.z, g, gv[4 * k + 2]); gv[4 * k + 3] = fmaf(w.w, g, gv[4 * k + 3]);
+      }
     }
     float4* gu4 = reinterpret_cast<float4*>(a.gu + pix * C);
     float4* v4 = reinterpret_cast<float4*>(a.v + pix * C);
@@ -581,7 +594,7 @@ int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, flo
   const int ns = outer_splits(npix);
   outer_wgrad_kernel<<<ns, kOwThreads, 2 * kOwTile * C * sizeof(float), st>>>(gu, v, npix, C, ns, scratch);
   TMG_LAUNCH_CHECK();
-  reduce_partials_kernel<<<cdiv(C * C, 256), 256, 0, st>>>(scratch, gw, C * C, ns, accum);
+  reduce_partials_par_kernel<<<cdiv(C * C, 32), 256, 0, st>>>(scratch, gw, C * C, ns, accum);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }

@@ -471,12 +471,18 @@ absmax_colsum_kernel(const float* __restrict__ g, int64_t npix, int cstride, int
   __shared__ float s_sum[256], s_max[256];
   __shared__ unsigned s_last;
   const int c = threadIdx.x % cw, rowi = threadIdx.x / cw, rows = 256 / cw;
-  float m = 0.f, acc = 0.f;
-  if (c < nch)
-    for (int64_t p = (int64_t)blockIdx.x * rows + rowi; p < npix; p += (int64_t)gridDim.x * rows) {
-      const float v = __ldg(g + p * cstride + coff + c);
-      acc += v; m = fmaxf(m, fabsf(v));
+  float m = 0.f, acc0 = 0.f, acc1 = 0.f;
+  if (c < nch) {
+    // two independent chains per thread: the loads of consecutive iterations overlap
+    const int64_t step = (int64_t)gridDim.x * rows;
+    int64_t p = (int64_t)blockIdx.x * rows + rowi;
+    for (; p + step < npix; p += 2 * step) {
+      const float v0 = __ldg(g + p * cstride + coff + c), v1 = __ldg(g + (p + step) * cstride + coff + c);
+      acc0 += v0; acc1 += v1; m = fmaxf(m, fmaxf(fabsf(v0), fabsf(v1)));
     }
+    if (p < npix) { const float v = __ldg(g + p * cstride + coff + c); acc0 += v; m = fmaxf(m, fabsf(v)); }
+  }
+  float acc = acc0 + acc1;
   s_sum[threadIdx.x] = acc; s_max[threadIdx.x] = m;
   __syncthreads();
   if (rowi == 0 && c < nch) {
@@ -494,10 +500,15 @@ absmax_colsum_kernel(const float* __restrict__ g, int64_t npix, int cstride, int
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int cc = threadIdx.x; cc < nch; cc += 256) {
-    float sum = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(part + (size_t)b * nch + cc);
-    gbias[cc] = accum ? gbias[cc] + sum : sum;
+  // last block: every column is summed over the blocks by `rows` threads (block b = rowi, rowi + rows, ...), then the
+  // row partials in order -- a fixed order, whichever block happens to be last
+  float sum = 0.f;
+  if (c < nch) for (unsigned b = rowi; b < gridDim.x; b += rows) sum += __ldcg(part + (size_t)b * nch + c);
+  s_sum[threadIdx.x] = sum;
+  __syncthreads();
+  if (rowi == 0 && c < nch) {
+    for (int r = 1; r < rows; ++r) sum += s_sum[r * cw + c];
+    gbias[c] = accum ? gbias[c] + sum : sum;
   }
   if (threadIdx.x == 0) {
     const float mx = __uint_as_float(atomicExch(sync, 0u));
@@ -508,13 +519,13 @@ absmax_colsum_kernel(const float* __restrict__ g, int64_t npix, int cstride, int
     scale[0] = sc; scale[1] = 1.f / sc;
   }
 }
-// part: >= 148 * nch floats
+// part: >= 444 * nch floats
 int launch_absmax_colsum(const float* g, int64_t npix, int cstride, int coff, int nch, float* scale, unsigned* sync, float* part,
                          float* gbias, int accum, cudaStream_t st) {
   if (nch > 256) { set_error("absmax_colsum: %d channels", nch); return TMG_ERR_UNSUPPORTED; }
   int cw = 1;
   while (cw < nch) cw <<= 1;
-  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(148, npix / 64));
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(444, npix / 64));
   absmax_colsum_kernel<<<nb, 256, 0, st>>>(g, npix, cstride, coff, nch, cw, scale, sync, part, gbias, accum);
   TMG_LAUNCH_CHECK();
   return TMG_OK;

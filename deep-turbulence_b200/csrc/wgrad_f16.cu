@@ -347,9 +347,9 @@ size_t wgrad_f16_scratch_floats(int cout, const int* nch, int nsrc, int B, int H
   for (int i = 0; i < nsrc && i < 3; ++i) a.src[i].nch = nch[i];
   WgF16Geom g{};
   if (!wf_geom(a, g)) return 0;
-  return (size_t)g.nsplit * 9 * 8 * g.NPl * g.Mrows + (size_t)std::max(wf_sm_count(), 148) * cout + 64;
+  return (size_t)g.nsplit * 9 * 8 * g.NPl * g.Mrows + (size_t)std::max(wf_sm_count(), 444) * cout + 64;
 }
-// where the bias column-sum partials ([blocks <= 148][cout]) live inside a.scratch
+// where the bias column-sum partials ([blocks <= 444][cout]) live inside a.scratch
 float* wgrad_f16_bias_partials(const WgradArgs& a) {
   WgF16Geom g{};
   if (!wf_geom(a, g)) return nullptr;
