@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kSbThreads)
 step_bwd_kernel(StepBwdArgs a) {
   __shared__ __align__(16) float s_w[C * C];
   __shared__ float s_nw[C], s_nb[C];
-  __shared__ float s_red[kSbThreads / 32][2 * C + 1];
+  __shared__ float s_red[kSbThreads / 32][3 * C + 2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int b = blockIdx.y;
   const int p = blockIdx.x * kSbThreads + tid;
@@ -372,8 +372,9 @@ step_bwd_kernel(StepBwdArgs a) {
   __syncthreads();
   const float gain = __ldg(a.gain), gld = __ldg(a.g_ld + b);
   float acc_nb[C], acc_nw[C], acc_gain = 0.f;
+  float gz[C];                  // gradient w.r.t. the raw Conv2dZeros output: its column sums are the bias gradient
 #pragma unroll
-  for (int i = 0; i < C; ++i) { acc_nb[i] = 0.f; acc_nw[i] = 0.f; }
+  for (int i = 0; i < C; ++i) { acc_nb[i] = 0.f; acc_nw[i] = 0.f; gz[i] = 0.f; }
   if (p < a.HW) {
     const size_t pix = (size_t)b * a.HW + p;
     float y[C], h[C], v[C], gu[C];
@@ -438,7 +439,7 @@ step_bwd_kernel(StepBwdArgs a) {
       gu4[i] = make_float4(gu[4 * i], gu[4 * i + 1], gu[4 * i + 2], gu[4 * i + 3]);
       v4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
-    float gy[C], gz[C];
+    float gy[C];
 #pragma unroll
     for (int j = 0; j < C / 2; ++j) {
       const float g2 = gv[C / 2 + j];
@@ -467,9 +468,24 @@ step_bwd_kernel(StepBwdArgs a) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if (lane == 0) s_red[wid][i] = x;
   }
+  // columns [2C+1, 3C+1): sum of gz (bias gradient of the Conv2dZeros conv); column 3C+1: max |gz| (the power-of-two scale
+  // the tensor-core weight / data gradients stage gz with) -- saves a separate pass over gz
+  float gmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    float x = gz[i];
+    gmax = fmaxf(gmax, fabsf(x));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[wid][2 * C + 1 + i] = x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  if (lane == 0) s_red[wid][3 * C + 1] = gmax;
   __syncthreads();
-  float* pp = a.part + ((size_t)b * gridDim.x + blockIdx.x) * (2 * C + 1);
-  for (int i = tid; i < 2 * C + 1; i += kSbThreads) pp[i] = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
+  float* pp = a.part + ((size_t)b * gridDim.x + blockIdx.x) * (3 * C + 2);
+  for (int i = tid; i < 3 * C + 1; i += kSbThreads) pp[i] = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
+  if (tid == 0) pp[3 * C + 1] = fmaxf(fmaxf(s_red[0][3 * C + 1], s_red[1][3 * C + 1]), fmaxf(s_red[2][3 * C + 1], s_red[3][3 * C + 1]));
 }
 
 int step_bwd_blocks(int B, int HW) { return B * cdiv(HW, kSbThreads); }
@@ -521,10 +537,10 @@ int launch_reduce_cols(const float* part, int nrows, int row_stride, int col0, i
 __global__ void __launch_bounds__(128)
 step_param_grads_kernel(const float* __restrict__ part, int nrows, int C, float* __restrict__ g_nb, float* __restrict__ g_nw,
                         const float* __restrict__ scale_param, float* __restrict__ g_scale, const float* __restrict__ g_ld, int B,
-                        float hw, float* __restrict__ gld_stash) {
-  const int c = blockIdx.x;
-  if (c == 2 * C + 1) {       // deferred LU backward: hw * sum_b g_ld[b] accumulated over the time steps of the block
-    if (threadIdx.x < 32) {
+                        float hw, float* __restrict__ gld_stash, float* __restrict__ g_bias, float* __restrict__ gz_scale) {
+  const int c = blockIdx.x, stride = 3 * C + 2;
+  if (c == 3 * C + 2) {       // deferred LU backward: hw * sum_b g_ld[b] accumulated over the time steps of the block
+    if (gld_stash && threadIdx.x < 32) {
       double s = 0.0;
       for (int b = threadIdx.x; b < B; b += 32) s += (double)g_ld[b];
 #pragma unroll
@@ -533,20 +549,41 @@ step_param_grads_kernel(const float* __restrict__ part, int nrows, int C, float*
     }
     return;
   }
+  if (c == 3 * C + 1) {       // max |gz| over the CTAs -> power-of-two scale (same rule as launch_absmax_scale)
+    if (!gz_scale) return;
+    __shared__ float sm[128];
+    float m = 0.f;
+    for (int r = threadIdx.x; r < nrows; r += 128) m = fmaxf(m, part[(size_t)r * stride + c]);
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 64; o; o >>= 1) {
+      if ((int)threadIdx.x < o) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const float mx = sm[0];
+      int ex = 0;
+      float sc = 1.f;
+      if (mx > 0.f && mx < 3.0e38f) { frexpf(mx, &ex); sc = ldexpf(1.f, min(max(11 - ex, -100), 100)); }
+      gz_scale[0] = sc; gz_scale[1] = 1.f / sc;
+    }
+    return;
+  }
   if (c < 2 * C && g_nb == nullptr) return;
-  const double s = block_col_sum(part, nrows, 2 * C + 1, c);
+  if (c > 2 * C && g_bias == nullptr) return;
+  const double s = block_col_sum(part, nrows, stride, c);
   if (threadIdx.x != 0) return;
   if (c < C) g_nb[c] += (float)s;
   else if (c < 2 * C) g_nw[c - C] += (float)s;
-  else {
+  else if (c == 2 * C) {
     const float sp = *scale_param;
     if (sp > -4.f && sp < kLog4) *g_scale += (float)s * expf(sp);
-  }
+  } else g_bias[c - 2 * C - 1] += (float)s;
 }
 int launch_step_param_grads(const float* part, int nrows, int C, float* g_nb, float* g_nw, const float* scale_param, float* g_scale,
-                            const float* g_ld, int B, float hw, float* gld_stash, cudaStream_t st) {
-  step_param_grads_kernel<<<2 * C + 1 + (gld_stash ? 1 : 0), 128, 0, st>>>(part, nrows, C, g_nb, g_nw, scale_param, g_scale, g_ld, B,
-                                                                           hw, gld_stash);
+                            const float* g_ld, int B, float hw, float* gld_stash, float* g_bias, float* gz_scale, cudaStream_t st) {
+  step_param_grads_kernel<<<3 * C + 3, 128, 0, st>>>(part, nrows, C, g_nb, g_nw, scale_param, g_scale, g_ld, B, hw, gld_stash,
+                                                     g_bias, gz_scale);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }

@@ -412,7 +412,7 @@ struct StepBwdArgs {
   float* g_z;              // [B,HW,C] gradient w.r.t. the raw Conv2dZeros output
   float* gu;               // [B,HW,C] gradient w.r.t. u   (1x1 weight gradient = sum gu (x) v)
   float* v;                // [B,HW,C] mixed vector v
-  float* part;             // per-CTA partial sums [nblocks][2C+1]: -sum gu | -sum gu*out | sum g_h*h/gain
+  float* part;             // per-CTA partial sums [nblocks][3C+2]: -sum gu | -sum gu*out | sum g_h*h/gain | sum gz | max|gz|
   int B, HW, C;
 };
 int launch_step_bwd(const StepBwdArgs& a, cudaStream_t st);
@@ -437,8 +437,10 @@ int launch_lu_bwd(const LuBwdArgs& a, cudaStream_t st);
 // buffers) of l, u, log_s, p, sign_s, l_mask, u_mask, eye and of the ActNorm weight (-1: none)
 struct LuTabEntry { int C; int64_t off[8]; int64_t norm_w; };
 int launch_lu_bwd_batched(const LuTabEntry* tab_dev, int n, int cmax, const float* params, float* grads, cudaStream_t st);
+// g_bias: bias gradient of the Conv2dZeros conv (column sums of gz, accumulated) or null; gz_scale: [2] power-of-two scale
+// of gz and its inverse (or null)
 int launch_step_param_grads(const float* part, int nrows, int C, float* g_nb, float* g_nw, const float* scale_param, float* g_scale,
-                            const float* g_ld, int B, float hw, float* gld_stash, cudaStream_t st);
+                            const float* g_ld, int B, float hw, float* gld_stash, float* g_bias, float* gz_scale, cudaStream_t st);
 int launch_scale_grad(const float* s_gain, const float* scale_param, float* g_scale, cudaStream_t st);
 // ConvLSTM cell backward (convLSTM.py:76-83): gates = pre-activations [B,HW,4R] (i,f,o,g), returns g_gates and g_c_prev
 struct LstmBwdArgs {

@@ -1580,7 +1580,7 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
   auto take = [&](size_t n) { size_t o = off; off += align_up(n, 64); return o; };
   e.go = take(px * C); e.gy = take(px * C); e.gz = take(px * C); e.gu = take(px * C); e.v = take(px * C);
   e.gcond = take(px * cf); e.gd = take(px * 2);
-  e.part = take((size_t)step_bwd_blocks(B, Hl * Wl) * (2 * C + 1));
+  e.part = take((size_t)step_bwd_blocks(B, Hl * Wl) * (3 * C + 2));
   e.dw = take((size_t)C * C); e.tmp = take(16);
   // transposed weights of the widest convolution (gate conv) and the largest weight-gradient scratch
   size_t wt = (size_t)9 * std::max(C, 4 * R) * ((cin_t + R + 3) / 4 * 4) + 64;
@@ -1615,7 +1615,7 @@ static BwdExtra bwd_extra(const tmg_model& m, int level, int B, int Hl, int Wl) 
 struct BwdDest { float* g; const float* fwd; int cstride, coff, nch; int accum; };
 static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate,
                          const float* g, int g_cs, int g_co, const BwdDest* dests, int ndest, float* grads, float* wt,
-                         float* wscr, float* gscale = nullptr) {
+                         float* wscr, float* gscale = nullptr, bool pre_scaled = false) {
   WgradArgs wa{};
   for (int i = 0; i < nsrc_fwd; ++i) wa.src[i] = fsrc[i];
   wa.nsrc = nsrc_fwd; wa.cin = w.I;
@@ -1641,7 +1641,9 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
     }
   }
   const bool wg_tc = tc_bwd && !wg_off && wgrad_f16_supported(wa);
-  if (wg_tc && wa.gbias && w.O <= 256) {
+  if (pre_scaled) {
+    wa.gbias = nullptr;          // the caller's reduction already produced the bias gradient and filled gscale
+  } else if (wg_tc && wa.gbias && w.O <= 256) {
     // the scale of g and the bias gradient (column sums of g) in one pass over g; the column-sum partials live at the
     // tail of the weight-gradient scratch (wgrad_f16_scratch_floats reserves them)
     float* pb = wgrad_f16_bias_partials(wa);
@@ -1669,7 +1671,7 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
     }
   }
   if (gscale && prec_f16(c.m.precision) && w.w_pack_f16t >= 0 && ndest <= 3) {
-    if (!tc_bwd) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st, c.m.sync_dev));
+    if (!tc_bwd && !pre_scaled) TMG_TRY(launch_absmax_scale(g, (int64_t)B * Hl * Wl, g_cs, g_co, w.O, gscale, gscale + 64, c.st, c.m.sync_dev));
     ConvF16Args t{};
     t.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; t.nsrc = 1;
     t.wpk = c.Q() + w.w_pack_f16t; t.inv_scale = c.Q() + w.inv_f16t; t.npad = w.NPt; t.cout = w.I;
@@ -1772,11 +1774,14 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   sa.g_y = GY; sa.g_z = GZ; sa.gu = GU; sa.v = V; sa.part = ex + e.part;
   sa.B = B; sa.HW = HW; sa.C = C;
   TMG_TRY(launch_step_bwd(sa, c.st));
-  const int nblk = step_bwd_blocks(B, HW), pstride = 2 * C + 1;
+  const int nblk = step_bwd_blocks(B, HW), pstride = 3 * C + 2;
+  // f16 modes: the bias gradient of the Conv2dZeros conv and the scale of its output gradient come out of this reduction
+  const bool pre = prec_f16(m->precision) && st.zc.b_param >= 0;
   (void)pstride;
   TMG_TRY(launch_step_param_grads(ex + e.part, nblk, C, normed ? grads + st.norm_b : nullptr, normed ? grads + st.norm_w : nullptr,
                                   c.P() + st.zc_scale, grads + st.zc_scale, io.g_ld, B, (float)HW,
-                                  io.defer_lu ? grads + st.lu[4] : nullptr, c.st));
+                                  io.defer_lu ? grads + st.lu[4] : nullptr, pre ? grads + st.zc.b_param : nullptr,
+                                  pre ? ex + e.gscale : nullptr, c.st));
   // 1x1 convolution: dW, then the LU parameterisation and the log-det constants
   if (io.defer_lu) {
     // linear in dW and in hw * sum(g_ld): accumulated over the time steps of a BPTT block in the gradient slots of the
@@ -1795,9 +1800,9 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   }
 
   auto conv_bwd = [&](const ConvW& w, int nsrc_fwd, const ConvSrc* fsrc, bool replicate, const float* g, int g_cs, int g_co,
-                      const BwdDest* dests, int ndest) -> int {
+                      const BwdDest* dests, int ndest, bool pre_scaled = false) -> int {
     return conv_backward(c, B, Hl, Wl, w, nsrc_fwd, fsrc, replicate, g, g_cs, g_co, dests, ndest, grads, ex + e.wt, ex + e.wscr,
-                         ex + e.gscale);
+                         ex + e.gscale, pre_scaled);
   };
   typedef BwdDest Dest;
 
@@ -1805,7 +1810,7 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
     // coupling network on t = cat(y1, cond): three convolutions, last to first
     const ConvSrc f3[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 2, 1}};
     const Dest d3[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 2, 0}};
-    TMG_TRY(conv_bwd(st.zc, 3, f3, true, GZ, C, 0, d3, 3));
+    TMG_TRY(conv_bwd(st.zc, 3, f3, true, GZ, C, 0, d3, 3, pre));
     const ConvSrc f2[3] = {{Y, C, 0, C / 2, 1}, {CN, cf, 0, cf, 1}, {D, 2, 0, 1, 1}};
     const Dest d2[3] = {{GY, Y, C, 0, C / 2, 1}, {GC, CN, cf, 0, cf, 1}, {GD, D, 2, 0, 1, 1}};
     TMG_TRY(conv_bwd(st.d2, 3, f2, false, GD, 2, 1, d2, 3));
@@ -1817,7 +1822,7 @@ static int step_backward(Ctx& c, int level, const StepW& st, int B, int Hl, int 
   {
     const ConvSrc f3[2] = {{U0, u0s, 0, cin_t, 1}, {D, 2, 0, 2, 1}};
     const Dest d3[2] = {{GU0, U0, u0s, 0, cin_t, 0}, {GD, D, 2, 0, 2, 0}};
-    TMG_TRY(conv_bwd(st.zc, 2, f3, true, GZ, C, 0, d3, 2));
+    TMG_TRY(conv_bwd(st.zc, 2, f3, true, GZ, C, 0, d3, 2, pre));
     const ConvSrc f2[2] = {{U0, u0s, 0, cin_t, 1}, {D, 2, 0, 1, 1}};
     const Dest d2[2] = {{GU0, U0, u0s, 0, cin_t, 1}, {GD, D, 2, 0, 1, 1}};
     TMG_TRY(conv_bwd(st.d2, 2, f2, false, GD, 2, 1, d2, 2));
