@@ -126,6 +126,21 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class stdout_to_stderr:
+    """File-descriptor level redirect: stdout must carry exactly one JSON line, native libraries (NCCL) write there too."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def cpu_port_samples_per_s(sd, cfg_dict, batch, min_seconds, max_calls=400):
     """The pinned oracle (CPU port of the reference path, torch CPU operators -- the same ATen
     kernels the reference runs) timed on the host cores."""
@@ -362,7 +377,9 @@ def run_train(args, rank, world, local):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():        # NCCL prints its version banner on stdout while the communicator comes up
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
     r = measure_train(args, rank, world, dev, dist, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)))
@@ -439,7 +456,9 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():        # NCCL prints its version banner on stdout while the communicator comes up
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
 
     from tmglow_b200 import _lib
     lib = _lib.load()
