@@ -603,7 +603,9 @@ def main():
                         "peak_source": pk["source"], "share_of_step": top["share"],
                         "avg_launch_ms": top["ms_per_step"] / top["launches_per_step"],
                         "note": "algorithmic bytes = 4*px*(2C+cond) per step (SURVEY 8d, un-hoisted definition); with one LF "
-                                "input shared by all samples the conditioning map is served from L2 / hoisted tables"}
+                                "input shared by all samples the conditioning map is served from L2 / hoisted tables; traffic = ncu dram bytes of ONE "
+                                "level-0 launch (the largest of the three levels; its algorithmic bytes are 1.88 GB), achieved / avg_launch_ms "
+                                "average over the 48 launches of a step"}
             gate = [c for c in classes if c["class"] == "conv_lstm_gates"]
             if gate:
                 x3 = args.precision in ("f16x3", "tf32x3")
