@@ -183,18 +183,25 @@ __global__ void dgrad_ring_kernel(RingArgs a, int nborder) {
   const size_t o_dst = pix * ds.cstride + ds.coff + cl;
   if (ds.mask && !(__ldg(ds.mask + o_dst) > 0.f)) return;
   float sum = 0.f;
-  // ring positions (yr, xr) outside the image with clamp(yr, xr) == (y, x)
-  for (int dy = -1; dy <= 1; ++dy) {
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int yr = y + dy, xr = x + dx;
-      if (yr >= 0 && yr < a.H && xr >= 0 && xr < a.W) continue;                 // inside: covered by the main pass
-      if (min(max(yr, 0), a.H - 1) != y || min(max(xr, 0), a.W - 1) != x) continue;
-      // gxp[yr,xr][c] = sum_tap sum_o w[o][c][tap] * g[(yr,xr) - off(tap)][o]
-      for (int tap = 0; tap < 9; ++tap) {
-        const int py = yr - (tap / 3 - 1), px = xr - (tap % 3 - 1);
-        if (py < 0 || py >= a.H || px < 0 || px >= a.W) continue;
-        const float* gp = a.g + ((size_t)(b * a.H + py) * a.W + px) * a.g_cstride + a.g_coff;
-        for (int o = 0; o < a.cout; ++o) sum = fmaf(__ldg(a.w_oihw + ((size_t)o * a.cin_total + c) * 9 + tap), __ldg(gp + o), sum);
+  // ring positions (yr, xr) outside the image with clamp(yr, xr) == (y, x): rows {y, -1 if y == 0, H if y == H-1} x columns
+  // likewise, minus (y, x) itself -- enumerated directly (at most 8, typically 1 or 3), and for each only the output pixels
+  // p = (yr, xr) - off(tap) that lie inside the image (the first version walked 9 x 9 candidates with bounds checks: 2 000
+  // warp instructions at 14 active lanes, ncu r01h_ring)
+  int yc[3], xc[3], ny = 0, nx = 0;
+  yc[ny++] = y; if (y == 0) yc[ny++] = -1; if (y == a.H - 1) yc[ny++] = a.H;
+  xc[nx++] = x; if (x == 0) xc[nx++] = -1; if (x == a.W - 1) xc[nx++] = a.W;
+  for (int iy = 0; iy < ny; ++iy) {
+    for (int ix = 0; ix < nx; ++ix) {
+      if (iy == 0 && ix == 0) continue;                                        // (y, x) itself: covered by the main pass
+      const int yr = yc[iy], xr = xc[ix];
+      // gxp[yr,xr][c] = sum_tap sum_o w[o][c][tap] * g[(yr,xr) - off(tap)][o],  tap = (yr - py + 1, xr - px + 1)
+      for (int py = max(0, yr - 1); py <= min(a.H - 1, yr + 1); ++py) {
+        for (int px = max(0, xr - 1); px <= min(a.W - 1, xr + 1); ++px) {
+          const int tap = (yr - py + 1) * 3 + (xr - px + 1);
+          const float* gp = a.g + ((size_t)(b * a.H + py) * a.W + px) * a.g_cstride + a.g_coff;
+          const float* wp = a.w_oihw + (size_t)c * 9 + tap;
+          for (int o = 0; o < a.cout; ++o) sum = fmaf(__ldg(wp + (size_t)o * a.cin_total * 9), __ldg(gp + o), sum);
+        }
       }
     }
   }
