@@ -281,7 +281,7 @@ int launch_dgrad_cout1(const float* g, int g_cstride, int g_coff, const float* w
 // dW[c][tap] = sum_q relu?(x[q][c]) * g[q - off(tap)]: each input element is loaded once and meets the nine output-gradient
 // values around it (g has ONE channel: the loads are warp-uniform).  Exact fp32; a block sums a pixel range in a fixed
 // order, reduce_partials_kernel adds the blocks in order (deterministic).  Zero padding, no bias (denseBlock.py:136).
-constexpr int kWc1Lanes = 4, kWc1CW = 64, kWc1Rows = 8;      // 256 threads = 4 pixel lanes x 64 channel slots; 8 rows per block
+constexpr int kWc1Lanes = 4, kWc1CW = 64, kWc1Rows = 4;      // 256 threads = 4 pixel lanes x 64 channel slots; 4 rows per block (measured: 8 -> 14.9 us, 4 -> 10.3 us, 2 -> 9.8 us per launch but a costlier reduce)
 __global__ void __launch_bounds__(kWc1Lanes * kWc1CW)
 wgrad_cout1_kernel(WgradArgs a, int chunks, float* __restrict__ part) {
   extern __shared__ float s_g[];                       // [(rows + 2)][W + 2] output gradient of this row chunk, zero halo
