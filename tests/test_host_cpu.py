@@ -98,3 +98,33 @@ def test_no_cpu_fallback_and_bad_config():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "tmglow_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def _run_bench(args):
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py")] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one JSON line: %r" % lines
+    return json.loads(lines[0])
+
+
+def test_bench_reference_arm_contract_sampling():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys."""
+    d = _run_bench(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-batch", "2"])
+    assert d["impl"] == "reference" and d["metric"] == "hf_samples_per_sec" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+def test_bench_reference_arm_contract_training():
+    d = _run_bench(["--impl", "reference", "--workload", "train", "--steps", "1", "--warmup", "0", "--ref-train-batch", "1",
+                    "--tback", "2"])
+    assert d["impl"] == "reference" and d["metric"] == "train_steps_per_sec" and d["unit"] == "steps/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
+    assert d["config"]["tback"] == 2 and d["config"]["global_batch"] == 1 and d["hf_snapshots_per_sec"] > 0
