@@ -128,3 +128,23 @@ def test_bench_reference_arm_contract_training():
     assert d["impl"] == "reference" and d["metric"] == "train_steps_per_sec" and d["unit"] == "steps/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
     assert d["config"]["tback"] == 2 and d["config"]["global_batch"] == 1 and d["hf_snapshots_per_sec"] > 0
+
+
+def test_trainable_mask_and_scratch_pool_cpu():
+    """Host-side helpers of the training path: the trainable mask marks exactly the nn.Parameters inside the flat buffer
+    (what the reference's model.parameters() yields); the scratch pool hands back the same storage for the same request."""
+    from tmglow_b200 import TMGlow
+    m = TMGlow(4, 3, [2, 2], [3, 3], cond_features=8, cglow_upscale=2, growth_rate=4, init_features=8, rec_features=8)
+    mask = m.trainable_mask()
+    flat = m.flat_parameters()
+    assert mask.shape == flat.shape and set(mask.unique().tolist()) <= {0.0, 1.0}
+    assert int(mask.sum()) == sum(p.numel() for p in m.parameters()) == m._num_parameters()
+    table = {name: (off, numel) for name, off, numel, shape in m._table}
+    pnames = {n for n, _ in m.named_parameters()}
+    for name, (off, numel) in table.items():
+        assert float(mask[off:off + numel].min()) == float(mask[off:off + numel].max()) == (1.0 if name in pnames else 0.0), name
+    a = m._scratch("g_y", (2, 3, 4, 4), torch.float32, torch.device("cpu"))
+    b = m._scratch("g_y", (2, 3, 4, 4), torch.float32, torch.device("cpu"))
+    c = m._scratch("g_y", (3, 3, 4, 4), torch.float32, torch.device("cpu"))
+    assert a.data_ptr() == b.data_ptr() and c.shape[0] == 3
+    assert len([k for k in m._scratch_pool if k[0] == "g_y"]) == 1        # one buffer per name is kept alive
