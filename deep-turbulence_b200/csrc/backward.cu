@@ -150,7 +150,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   wgrad_kernel<<<grid, kWgThreads, smem, st>>>(a, TR, ns, part, part_b);
   TMG_LAUNCH_CHECK();
   const int n = a.cout * a.cin * 9;
-  reduce_partials_par_kernel<<<cdiv(n, 32), 256, 0, st>>>(part, a.gw, n, ns, a.accum);
+  reduce_partials_par_kernel<<<cdiv(n, 16), 256, 0, st>>>(part, a.gw, n, ns, a.accum);
   TMG_LAUNCH_CHECK();
   if (a.gbias) {
     reduce_partials_kernel<<<cdiv(a.cout, 256), 256, 0, st>>>(part_b, a.gbias, a.cout, ns, a.accum);
@@ -331,17 +331,22 @@ wgrad_cout1_kernel(WgradArgs a, int chunks, float* __restrict__ part) {
 // fixed-order sum of the 8 partials (deterministic)
 __global__ void __launch_bounds__(256)
 reduce_partials_par_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int nsplit, int accum) {
-  __shared__ float sm[8][32];
-  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + x;
-  float s = 0.f;
-  if (i < n) for (int k = y; k < nsplit; k += 8) s += part[(size_t)k * n + i];
-  sm[y][x] = s;
+  // 16 outputs x 16 share-lanes per block, two independent chains per thread
+  __shared__ float sm[16][16];
+  const int x = threadIdx.x & 15, y = threadIdx.x >> 4;
+  const int i = blockIdx.x * 16 + x;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < n) {
+    int k = y;
+    for (; k + 16 < nsplit; k += 32) { s0 += part[(size_t)k * n + i]; s1 += part[(size_t)(k + 16) * n + i]; }
+    if (k < nsplit) s0 += part[(size_t)k * n + i];
+  }
+  sm[y][x] = s0 + s1;
   __syncthreads();
   if (y == 0 && i < n) {
     float t = sm[0][x];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) t += sm[q][x];
+    for (int q = 1; q < 16; ++q) t += sm[q][x];
     out[i] = accum ? out[i] + t : t;
   }
 }
@@ -357,7 +362,7 @@ int launch_wgrad_cout1(const WgradArgs& a, cudaStream_t st) {
   wgrad_cout1_kernel<<<nb, kWc1Lanes * kWc1CW, smem, st>>>(a, chunks, a.scratch);
   TMG_LAUNCH_CHECK();
   const int n = a.cin * 9;
-  reduce_partials_par_kernel<<<cdiv(n, 32), 256, 0, st>>>(a.scratch, a.gw, n, nb, a.accum);
+  reduce_partials_par_kernel<<<cdiv(n, 16), 256, 0, st>>>(a.scratch, a.gw, n, nb, a.accum);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }
@@ -638,7 +643,7 @@ int launch_outer_wgrad(const float* gu, const float* v, int64_t npix, int C, flo
   const int ns = outer_splits(npix);
   outer_wgrad_kernel<<<ns, kOwThreads, 2 * kOwTile * C * sizeof(float), st>>>(gu, v, npix, C, ns, scratch);
   TMG_LAUNCH_CHECK();
-  reduce_partials_par_kernel<<<cdiv(C * C, 32), 256, 0, st>>>(scratch, gw, C * C, ns, accum);
+  reduce_partials_par_kernel<<<cdiv(C * C, 16), 256, 0, st>>>(scratch, gw, C * C, ns, accum);
   TMG_LAUNCH_CHECK();
   return TMG_OK;
 }
