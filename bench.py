@@ -141,60 +141,123 @@ class stdout_to_stderr:
         return False
 
 
-def cpu_port_samples_per_s(sd, cfg_dict, batch, min_seconds, max_calls=400):
-    """The pinned oracle (CPU port of the reference path, torch CPU operators -- the same ATen
-    kernels the reference runs) timed on the host cores."""
-    from oracle import tmglow_oracle as O
-    cfg = O.OracleConfig.from_dict(cfg_dict)
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=g).expand(batch, -1, -1, -1).contiguous()
-    h = O.init_lstm_states(cfg, torch.arange(batch), [GEOM["H"], GEOM["W"]])
-    with torch.no_grad():
-        for _ in range(2):
-            y, ld, h = O.sample(sd, cfg, x, h, g)
-        n, t0 = 0, time.perf_counter()
-        while True:
-            y, ld, h = O.sample(sd, cfg, x, h, g)
-            n += 1
-            el = time.perf_counter() - t0
-            if el >= min_seconds or n >= max_calls:
-                break
-    return batch * n / el, threads, n, el
+def reference_model(geom, kw, train=False):
+    """The UNMODIFIED reference ``TMGlow`` (oracle/_ref, made by oracle/make_ref.py) on the CPU with the reference's own
+    initialisation under the bench seeds plus the same well-conditioned perturbation as the GPU arm.  Returns
+    ``(model, "reference")`` or ``(None, why)`` when no copy of the reference is available.  Nothing of tmglow_b200 is
+    imported on this path."""
+    try:
+        from oracle import ref_loader
+        ns = ref_loader.load(trainer=train)
+        if train:
+            ref_loader.grad_shim()
+    except ImportError as ex:
+        return None, str(ex)
+    import contextlib
+    import io
+    torch.manual_seed(12345); np.random.seed(12345)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ns.TMGlow(geom["nic"], geom["noc"], [4, 4, 4], [16, 16, 16], **kw)
+    perturb_(m, 12346)
+    m.train() if train else m.eval()
+    m._ref_ns = ns
+    return m, "reference"
+
+
+class _CpuSampler:
+    """sample() of the path on the host cores: the real reference when oracle/_ref exists (kind "reference"), else the
+    pinned oracle port (kind "port"; it runs the same ATen CPU operators in the same order)."""
+
+    def __init__(self):
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.ref, why = reference_model(GEOM, MODEL_KW)
+        self.kind = "reference" if self.ref is not None else "port"
+        if self.ref is None:
+            from oracle import tmglow_oracle as O
+            m = build_model()            # only for its random-init state_dict; never moved to a GPU, no kernel runs
+            self.O, self.sd, self.cfg = O, {k: v.detach().clone() for k, v in m.state_dict().items()}, O.OracleConfig.from_dict(m._cfg_dict)
+            self.why = why
+        self.gen = torch.Generator().manual_seed(1)
+
+    def states(self, batch):
+        if self.ref is not None:
+            return self.ref.initLSTMStates(torch.arange(batch), [GEOM["H"], GEOM["W"]])
+        return self.O.init_lstm_states(self.cfg, torch.arange(batch), [GEOM["H"], GEOM["W"]])
+
+    def x(self, batch):
+        return torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=self.gen).expand(batch, -1, -1, -1).contiguous()
+
+    def sample(self, x, h):
+        with torch.no_grad():
+            if self.ref is not None:
+                return self.ref.sample(x, h)
+            return self.O.sample(self.sd, self.cfg, x, h, self.gen)
+
+    def rate(self, batch, calls, warm=1):
+        x, h = self.x(batch), self.states(batch)
+        for _ in range(warm):
+            y, ld, h = self.sample(x, h)
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            y, ld, h = self.sample(x, h)
+        return batch * calls / (time.perf_counter() - t0)
+
+    def best_batch(self, candidates=(16, 64, 256)):
+        """samples/s grows with the batch until the cores saturate: a short sweep, stated in the report."""
+        sweep = {}
+        for b in candidates:
+            sweep[b] = self.rate(b, 1)
+        best = max(sweep, key=sweep.get)
+        return best, sweep
+
+
+def cpu_samples_per_s(min_seconds, max_calls=400):
+    """cpu_baseline leg: the path on the host cores at the batch where samples/s saturates, for about `min_seconds`."""
+    s = _CpuSampler()
+    batch, sweep = s.best_batch()
+    x, h = s.x(batch), s.states(batch)
+    y, ld, h = s.sample(x, h)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        y, ld, h = s.sample(x, h)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or n >= max_calls:
+            break
+    return batch * n / el, s, batch, n, el, sweep
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is
-    Python (no compilable sources), /root/reference does not exist on the GPU box, so this arm
-    times the pinned oracle port (kind = "port") on all host cores; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores; rank 0 only.  The REAL
+    ``TMGlow.sample`` (oracle/_ref: an unmodified copy of the reference package, kind "reference"); only when that copy is
+    missing, the pinned oracle port (kind "port").  Each step is a bounded sample of the GPU arm's step (S = 4096 samples of
+    one LF input): `batch` samples, with `batch` taken where samples/s saturates on this host (sweep in the line)."""
     if rank != 0:
         return
-    m = build_model()
-    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    B = args.ref_batch
-    from oracle import tmglow_oracle as O
-    cfg = O.OracleConfig.from_dict(m._cfg_dict)
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, GEOM["nic"], GEOM["h"], GEOM["w"], generator=g).expand(B, -1, -1, -1).contiguous()
-    h = O.init_lstm_states(cfg, torch.arange(B), [GEOM["H"], GEOM["W"]])
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            y, ld, h = O.sample(sd, cfg, x, h, g)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            y, ld, h = O.sample(sd, cfg, x, h, g)
-        el = time.perf_counter() - t0
+    s = _CpuSampler()
+    if args.ref_batch > 0:
+        B, sweep = args.ref_batch, None
+    else:
+        B, sweep = s.best_batch()
+    x, h = s.x(B), s.states(B)
+    for _ in range(args.warmup):
+        y, ld, h = s.sample(x, h)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        y, ld, h = s.sample(x, h)
+    el = time.perf_counter() - t0
     val = B * args.steps / el
     line = {
         "impl": "reference", "metric": "hf_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(B, args.gpus, note="CPU: %d samples per step (bounded sample of the workload)" % B),
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps x %d HF samples, oracle.sample() on %d host threads" % (args.steps, B, threads)},
+        "config": dict(workload_config(args.samples, args.gpus), precision="fp32 (reference, CPU)"),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": s.threads, "kind": s.kind,
+                         "sample": "%d steps x %d of the %d HF samples of a step through %s on %d host threads%s" % (
+                             args.steps, B, args.samples,
+                             "the unmodified reference TMGlow.sample (oracle/_ref)" if s.kind == "reference" else "oracle.sample()",
+                             s.threads, "; samples/s by batch: %s" % {k: round(v, 1) for k, v in sweep.items()} if sweep else "")},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -217,14 +280,47 @@ TRAIN_KW = dict(cond_features=32, cglow_upscale=4, growth_rate=4, init_features=
 
 
 def cpu_port_train_steps(batch, tback, steps, warmup=0):
-    """One optimizer step of the reference training objective on the host cores through the pinned oracle port: BPTT block
-    of `tback` sample() calls under autograd (training-mode BatchNorm), TMGLowLoss, clip, Adam-amsgrad -- the arithmetic
-    of trainFlowParallel.py:248-293 at a bounded batch.  Returns (seconds per step, threads, loss)."""
+    """One optimizer step of the reference training objective on the host cores: BPTT block of `tback` sample() calls under
+    autograd (training-mode BatchNorm), TMGLowLoss, clip, Adam-amsgrad -- the arithmetic of trainFlowParallel.py:248-300 at
+    a bounded batch.  Runs the UNMODIFIED reference classes (oracle/_ref: ``TMGlow.sample``, ``TMGLowLoss``; the only
+    accommodation is the out-of-place clamp of SURVEY 8c so that autograd accepts ``GaussianDiag``) -- kind "reference";
+    only when that copy is missing, the pinned oracle ports (kind "port").
+    Returns (seconds per step, threads, loss, kind)."""
+    import types
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    ref, _ = reference_model(TRAIN_GEOM, TRAIN_KW, train=True)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, tback, TRAIN_GEOM["nic"], TRAIN_GEOM["h"], TRAIN_GEOM["w"], generator=g)
+    tgt = torch.randn(batch, tback, TRAIN_GEOM["noc"], TRAIN_GEOM["H"], TRAIN_GEOM["W"], generator=g)
+    t_mean = tgt.mean(1)
+    t_rms = torch.sqrt(torch.mean((tgt - t_mean.unsqueeze(1)) ** 2, dim=1))          # trainFlowParallel.py:237-238
+    if ref is not None:
+        ref.out_mu, ref.out_std = torch.zeros(3), torch.ones(3)
+        crit = ref._ref_ns.TMGLowLoss(types.SimpleNamespace(beta=200.0, dx=5.0 / 64, dy=5.0 / 64), types.SimpleNamespace(module=ref))
+        params = list(ref.parameters())
+        opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-8, amsgrad=True)       # main.py:78
+        h_key = ref.initLSTMStates(torch.arange(batch), [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
+        h = h_key
+        el, loss = 0.0, None
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            ys, lds = [], []
+            for t in range(tback):
+                y, ld, h = ref.sample(x[:, t], h)
+                ys.append(y); lds.append(ld)
+            loss = crit(torch.stack(ys, 1), torch.stack(lds, 1), tgt, t_mean, t_rms)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            opt.zero_grad()
+            h = [(0.5 * a.detach() + 0.5 * ak, 0.5 * c.detach() + 0.5 * ck) for (a, c), (ak, ck) in zip(h, h_key)]
+            if it >= warmup:
+                el += time.perf_counter() - t0
+        return el / steps, threads, float(loss.detach()), "reference"
     from oracle import tmglow_oracle as O
     from oracle import tmglow_loss_oracle as OL
     from tmglow_b200 import TMGlow
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     torch.manual_seed(12345); np.random.seed(12345)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -235,10 +331,6 @@ def cpu_port_train_steps(batch, tback, steps, warmup=0):
     sd = {k: (v.detach().clone().requires_grad_(True) if k in trainable else v.detach().clone()) for k, v in m.state_dict().items()}
     params = [v for k, v in sd.items() if k in trainable]
     opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-8, amsgrad=True)
-    g = torch.Generator().manual_seed(7)
-    x = torch.randn(batch, tback, TRAIN_GEOM["nic"], TRAIN_GEOM["h"], TRAIN_GEOM["w"], generator=g)
-    tgt = torch.randn(batch, tback, TRAIN_GEOM["noc"], TRAIN_GEOM["H"], TRAIN_GEOM["W"], generator=g)
-    _, t_rms = OL.target_statistics(tgt)
     mu, sdv = torch.zeros(3), torch.ones(3)
     h_key = O.init_lstm_states(cfg, torch.arange(batch), [TRAIN_GEOM["H"], TRAIN_GEOM["W"]])
     h = h_key
@@ -258,7 +350,7 @@ def cpu_port_train_steps(batch, tback, steps, warmup=0):
         h = [(0.5 * a.detach() + 0.5 * ak, 0.5 * c.detach() + 0.5 * ck) for (a, c), (ak, ck) in zip(h, h_key)]
         if it >= warmup:
             el += time.perf_counter() - t0
-    return el / steps, threads, float(loss)
+    return el / steps, threads, float(loss.detach()), "port"
 
 
 def run_reference_train(args, rank, world):
@@ -266,7 +358,7 @@ def run_reference_train(args, rank, world):
     if rank != 0:
         return
     Bc = args.ref_train_batch
-    sec, threads, loss = cpu_port_train_steps(Bc, args.tback, max(args.steps, 1), warmup=min(args.warmup, 1))
+    sec, threads, loss, kind = cpu_port_train_steps(Bc, args.tback, max(args.steps, 1), warmup=min(args.warmup, 1))
     val = 1.0 / sec
     line = {"impl": "reference", "metric": "train_steps_per_sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong",
@@ -275,8 +367,10 @@ def run_reference_train(args, rank, world):
                                    "(the GPU arm's step is global batch %d), BPTT block of %d time steps, reference TMGLowLoss, "
                                    "clip 1.0, Adam-amsgrad" % (Bc, args.global_batch, args.tback),
                        "global_batch": Bc, "tback": args.tback, "parallelism": "cpu"},
-            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port",
-                             "sample": "%d optimizer step(s) at batch %d x %d time steps through the oracle port (autograd)" % (max(args.steps, 1), Bc, args.tback)},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": kind,
+                             "sample": "%d optimizer step(s) at batch %d x %d time steps through %s (autograd)" % (
+                                 max(args.steps, 1), Bc, args.tback,
+                                 "the unmodified reference TMGlow.sample + TMGLowLoss (oracle/_ref)" if kind == "reference" else "the oracle port")},
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "hf_snapshots_per_sec": Bc * args.tback / sec, "gpu_launches": 0, "loss": loss}
     print(json.dumps(line))
@@ -389,9 +483,9 @@ def run_train(args, rank, world, local):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sec, threads, _ = cpu_port_train_steps(args.ref_train_batch, tb, 1)
-            cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": threads, "kind": "port",
-                   "sample": "1 optimizer step at batch %d x %d time steps through the oracle port with autograd (%.1f s): "
+            sec, threads, _, kind = cpu_port_train_steps(args.ref_train_batch, tb, 1)
+            cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": threads, "kind": kind,
+                   "sample": "1 optimizer step at batch %d x %d time steps through the reference training arithmetic with autograd (%.1f s): "
                              "%.2f HF snapshots/s vs %.0f here" % (args.ref_train_batch, tb, sec, args.ref_train_batch * tb / sec,
                                                                   GB * tb * args.steps / (ms * 1e-3)),
                    "hf_snapshots_per_sec": args.ref_train_batch * tb / sec}
@@ -424,7 +518,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32", "f16x3", "f16"],
                     help="f16x3 (default): tcgen05 with the fp16 hi+lo operand split, fp32-grade (same tolerance as fp32)")
-    ap.add_argument("--ref-batch", type=int, default=16)
+    ap.add_argument("--ref-batch", type=int, default=0, help="batch of the CPU reference arm; 0 = where samples/s saturates (sweep 16/64/256)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
@@ -463,7 +557,6 @@ def main():
     from tmglow_b200 import _lib
     lib = _lib.load()
     model = build_model()
-    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     model = model.to(dev)
     model.precision = args.precision
     S, K, W = args.samples, args.steps, args.warmup
@@ -617,9 +710,11 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, ncalls, el = cpu_port_samples_per_s(sd_cpu, model._cfg_dict, args.ref_batch, args.cpu_seconds)
-        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "%d x oracle.sample() of %d HF samples (%.1f s) on %d host threads" % (ncalls, args.ref_batch, el, cores)}
+        v, smp, cb, ncalls, el, sweep = cpu_samples_per_s(args.cpu_seconds)
+        cpu = {"value": v, "unit": "samples/s", "cores": smp.threads, "kind": smp.kind,
+               "sample": "%d x %s of %d HF samples (%.1f s) on %d host threads; samples/s by batch: %s" % (
+                   ncalls, "the unmodified reference TMGlow.sample (oracle/_ref)" if smp.kind == "reference" else "oracle.sample()",
+                   cb, el, smp.threads, {k: round(x_, 1) for k, x_ in sweep.items()})}
 
     # ---------------- the other half of BASELINE.json's metric: data-parallel train steps/s (configs[2]), short run
     train = None

@@ -148,8 +148,13 @@ struct tmg_model {
   int64_t n_replays = 0, n_eager = 0;
   cudaStream_t gstream = nullptr;   // capture / replay stream (stream capture is not allowed on the legacy default stream)
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
-  std::vector<std::vector<char>> tape_emit;
-  int tape_sig[4] = {0, 0, 0, -1};  // B, h, w, precision
+  // What a training forward recorded, keyed by the TAPE BUFFER it recorded into (a backward may run on an older tape
+  // after later forwards under another precision / shape: the per-step emit flags and the configuration belong to the
+  // tape, not to the model).  An entry is replaced when its buffer is recorded into again.
+  struct TapeInfo { int sig[4] = {0, 0, 0, -1}; std::vector<std::vector<char>> emit; uint64_t serial = 0; };
+  std::unordered_map<const void*, TapeInfo> tapes;
+  uint64_t tape_serial = 0;
+  std::mutex tape_mu;               // the backward runs on autograd's thread
 };
 
 namespace tmg {
@@ -1241,10 +1246,13 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
   TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)B * ldstride * sizeof(float), c.st));
   TMG_TRY(run_encoder(c, x, flags & TMG_FLAG_BN_TRAIN));
   if (prec_f16(m->precision)) TMG_TRY(run_hoist(c));
+  tmg_model::TapeInfo tinfo;
   if (tape) {
-    m->tape_emit.resize(L);
-    for (int l = 0; l < L; ++l) m->tape_emit[l].assign(m->levels[l].steps.size(), 0);
-    m->tape_sig[0] = B; m->tape_sig[1] = h; m->tape_sig[2] = w; m->tape_sig[3] = m->precision;
+    tinfo.emit.resize(L);
+    for (int l = 0; l < L; ++l) tinfo.emit[l].assign(m->levels[l].steps.size(), 0);
+    tinfo.sig[0] = B; tinfo.sig[1] = h; tinfo.sig[2] = w; tinfo.sig[3] = m->precision;
+    std::lock_guard<std::mutex> lk(m->tape_mu);
+    m->tapes.erase(tape);            // until this forward is fully issued the buffer holds no valid record
   }
 
   // top latent: z = cmean + exp(clamp(clog_std)) * eps[L]   (tmGlow.py:460-463); no log-prob term
@@ -1282,7 +1290,7 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
       TMG_TRY(run_step(c, l, st, &st, true, B, Hl, Wl, Y, Y2, ws + p.cond[l], h_in ? h_in[l] : nullptr,
                        c_in ? c_in[l] : nullptr, h_out[l], c_out[l], ws + p.ldp + (size_t)(slot++) * p.ctas));
       if (tape) {
-        m->tape_emit[l][s] = c.emitted ? 1 : 0;
+        tinfo.emit[l][s] = c.emitted ? 1 : 0;
         c.emit_d = c.emit_h = nullptr;
       }
     }
@@ -1298,6 +1306,15 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
       pa.dst = y;
     }
     TMG_TRY(launch_permute(pa, c.st));
+  }
+  if (tape) {
+    std::lock_guard<std::mutex> lk(m->tape_mu);
+    if (m->tapes.size() >= 512) {      // forget the oldest records (their backward, if any, recomputes the intermediates)
+      uint64_t cut = m->tape_serial > 256 ? m->tape_serial - 256 : 0;
+      for (auto it = m->tapes.begin(); it != m->tapes.end();) it = it->second.serial <= cut ? m->tapes.erase(it) : std::next(it);
+    }
+    tinfo.serial = ++m->tape_serial;
+    m->tapes[tape] = std::move(tinfo);
   }
   return finish_logdet(c, log_det);
 }
@@ -2019,8 +2036,14 @@ static int reconstruct_backward_impl(tmg_model* m, int B, int h, int w, const fl
   const float* tape = (const float*)tape_v;
   // the recorded coupling-network intermediates are used only when this backward runs under the configuration the tape
   // was recorded with; otherwise every step recomputes them from its taped input
-  const bool tape_ok = (int)m->tape_emit.size() == m->cfg.n_levels && m->tape_sig[0] == B && m->tape_sig[1] == h &&
-                       m->tape_sig[2] == w && m->tape_sig[3] == m->precision;
+  tmg_model::TapeInfo tinfo;
+  {
+    std::lock_guard<std::mutex> lk(m->tape_mu);
+    auto it = m->tapes.find(tape_v);
+    if (it != m->tapes.end()) tinfo = it->second;
+  }
+  const bool tape_ok = (int)tinfo.emit.size() == m->cfg.n_levels && tinfo.sig[0] == B && tinfo.sig[1] == h &&
+                       tinfo.sig[2] == w && tinfo.sig[3] == m->precision;
   const int L = p.L;
   Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
   float* ws = c.ws;
@@ -2048,7 +2071,7 @@ static int reconstruct_backward_impl(tmg_model* m, int B, int h, int w, const fl
       const StepW& st = lv.steps[s];
       StepBwdIO io{};
       io.Y = tape + tape_off(*m, p, l, s); io.COND = ws + p.cond[l]; io.GO = Gc; io.g_ld = g_log_det;
-      if (tape_ok && m->tape_emit[l][s]) { io.D_tape = tape + tape_off_d(*m, p, l, s); io.HR_tape = tape + tape_off_h(*m, p, l, s); }
+      if (tape_ok && tinfo.emit[l][s]) { io.D_tape = tape + tape_off_d(*m, p, l, s); io.HR_tape = tape + tape_off_h(*m, p, l, s); }
       io.GY = Gn; io.GC = rb + rx.gcond[l]; io.grads = grads;
       io.defer_lu = true;
       if (st.kind == STEP_LSTM) {
@@ -2135,8 +2158,12 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
   }
   {   // which steps read their intermediates from the tape (host-side state of the last training forward)
     uint64_t hsh = 1469598103934665603ull;
-    for (int q = 0; q < 4; ++q) hsh = (hsh ^ (uint64_t)(uint32_t)m->tape_sig[q]) * 1099511628211ull;
-    for (const auto& v : m->tape_emit) for (char ch : v) hsh = (hsh ^ (uint64_t)(unsigned char)ch) * 1099511628211ull;
+    std::lock_guard<std::mutex> lk(m->tape_mu);
+    auto it = m->tapes.find(tape_v);
+    if (it != m->tapes.end()) {
+      for (int q = 0; q < 4; ++q) hsh = (hsh ^ (uint64_t)(uint32_t)it->second.sig[q]) * 1099511628211ull;
+      for (const auto& v : it->second.emit) for (char ch : v) hsh = (hsh ^ (uint64_t)(unsigned char)ch) * 1099511628211ull;
+    }
     key.push_back(hsh);
   }
   if (m->bwd_graphs.size() > 1024) {       // keys that never repeated (unstable buffer addresses): forget them

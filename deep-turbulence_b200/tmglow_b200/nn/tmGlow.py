@@ -8,7 +8,9 @@ checkpoints load unchanged.  The compute is NOT PyTorch: every call goes through
 ``libtmglow_b200.so`` (hand-written sm_100a CUDA); the sub-modules only hold parameters.  There
 is no CPU fallback -- tensors must live on a CUDA device.
 
-Inference/likelihood only in this round: outputs carry no autograd graph.
+``forward`` / ``sample`` / ``reconstruct`` return plain tensors (no autograd graph); training runs through
+``sample_train`` / ``reconstruct_train``, whose backward is hand-written CUDA for EVERY parameter (flow and encoder,
+BatchNorm batch statistics included) and accumulates into the flat gradient buffer ``flat_grad``.
 """
 import math
 import re
@@ -19,7 +21,11 @@ import scipy.linalg
 import torch
 import torch.nn as nn
 
+from operator import attrgetter
+
 from .. import _lib
+
+_VERSION = attrgetter("_version")
 
 _BUFFER_SUFFIXES = ("running_mean", "running_var", "conv.p", "conv.sign_s", "conv.l_mask", "conv.u_mask",
                     "conv.eye", "conv.log_s_old")
@@ -106,7 +112,14 @@ class TMGlow(nn.Module):
         self.always_refresh_weights = False
         self._refreshed_for = None
         self._precision = "fp32"
+        self.register_load_state_dict_post_hook(TMGlow._after_load_state_dict)
         print('Total number of parameters: {}'.format(self._num_parameters()))
+
+    @staticmethod
+    def _after_load_state_dict(module, incompatible_keys):
+        module.__dict__["_layout_ok_for"] = None      # load_state_dict(assign=True) replaces the leaf tensors
+        module.__dict__["_leaf_tuple"] = None
+        module.__dict__["_leaf_cache"] = None
 
     @property
     def precision(self):
@@ -198,18 +211,70 @@ class TMGlow(nn.Module):
                     b.uniform_(-bound, bound)
 
     # ------------------------------------------------------------------ flat parameter buffer
+    def _leaf_modules(self):
+        """The container module of every table entry, resolved through THIS object's module tree: a replica made by
+        ``nn.DataParallel.replicate`` (utils/parallel.py:166-169) shares ``__dict__`` entries with the original but owns
+        re-wired children holding the per-device copies, so nothing is cached across objects."""
+        cache = self.__dict__.get("_leaf_cache")
+        if cache is None or cache[0] is not self:
+            mods = []
+            for name, _, _, _ in self._table:
+                mod = self
+                for p in name.split(".")[:-1]:
+                    mod = mod._modules[p]
+                mods.append(mod)
+            cache = (self, mods)
+            self.__dict__["_leaf_cache"] = cache
+        return cache[1]
+
     def _leaf_tensor(self, i):
-        mod, attr, is_param = self._leaves[i]
-        return mod._parameters[attr] if is_param else mod._buffers[attr]
+        # parameters of a replica are plain attributes (no longer leaves), buffers stay in _buffers: getattr covers both
+        return getattr(self._leaf_modules()[i], self._leaves[i][1])
 
     def _leaf_tensors(self):
-        return [mod._parameters[attr] if is_param else mod._buffers[attr] for mod, attr, is_param in self._leaves]
+        mods = self._leaf_modules()
+        return [getattr(mods[i], self._leaves[i][1]) for i in range(len(mods))]
+
+    def _replicate_for_data_parallel(self):
+        """``nn.DataParallel.replicate`` support (the reference's ``DataParallelINNModel``, utils/parallel.py:150-169, calls
+        replicas from one Python thread per GPU): a replica gets its OWN library handles, flat buffer and workspace --
+        derived-weight caches are never shared between objects, because each object refreshes its handle from its own
+        flat buffer."""
+        replica = super()._replicate_for_data_parallel()
+        d = replica.__dict__
+        d["_handles"] = {}
+        d["_flat"] = None
+        d["_ws"] = {}
+        d["_refreshed_for"] = None
+        d["_param_epoch"] = None
+        for k in ("_flat_param", "_train_mask", "_scratch_pool", "_leaf_cache", "_leaf_tuple", "_layout_ok_for", "flat_grad"):
+            d.pop(k, None)
+        return replica
+
+    def _apply(self, fn, *a, **k):
+        # .to() / .cuda() / .float() may replace the storage of every leaf: re-validate the flat layout on the next call
+        self.__dict__["_layout_ok_for"] = None
+        return super()._apply(fn, *a, **k)
 
     def _sync_flat(self, device):
         """All floating-point state lives in ONE flat buffer (the layout libtmglow_b200 reads);
         the module's parameters/buffers are views into it.  Rebuilt whenever ``.to()``/
-        ``load_state_dict(assign=True)`` replaced the storage."""
-        ok = self._flat is not None and self._flat.device == device
+        ``load_state_dict(assign=True)`` replaced the storage.  The full check (873 pointer comparisons, ~1.4 ms of
+        host time) runs after an event that can move storage; otherwise two canary leaves are checked."""
+        flat = self._flat
+        ok = flat is not None and flat.device == device
+        if ok and self.__dict__.get("_is_replica", False):
+            return False                   # a replica lives for one scatterModel(): its flat copy was made on first use
+        if ok and self.__dict__.get("_layout_ok_for") == (device, flat.data_ptr()):
+            base, n = flat.data_ptr(), len(self._table)
+            for i in (0, n // 2, n - 1):
+                t = self._leaf_tensor(i)
+                if t.data_ptr() != base + 4 * self._table[i][1] or t.dtype != torch.float32:
+                    ok = False
+                    break
+            if ok:
+                return False
+            ok = True
         if ok:
             base = self._flat.data_ptr()
             for i, (name, off, numel, shape) in enumerate(self._table):
@@ -218,17 +283,31 @@ class TMGlow(nn.Module):
                     ok = False
                     break
         if ok:
+            self.__dict__["_layout_ok_for"] = (device, self._flat.data_ptr())
             return False
         flat = torch.empty(self._n_flat, dtype=torch.float32, device=device)
+        replica = bool(self.__dict__.get("_is_replica", False))
         with torch.no_grad():
             for i, (name, off, numel, shape) in enumerate(self._table):
                 t = self._leaf_tensor(i)
                 view = flat[off:off + numel].view(t.shape)
                 view.copy_(t.detach().to(device=device, dtype=torch.float32))
-                t.data = view
+                if not replica:
+                    t.data = view          # a replica's tensors are broadcast copies owned by autograd: left alone
         self._flat = flat
         self._refreshed_for = None
+        self.__dict__["_leaf_tuple"] = None
+        self.__dict__["_layout_ok_for"] = (device, flat.data_ptr())
         return True
+
+    def _version_sum(self):
+        """Sum of the leaves' version counters (in-place writes by optimizers, ``load_state_dict``, ``copy_`` bump them; the
+        sum only grows).  The tensor objects are cached while the flat layout stands."""
+        tup = self.__dict__.get("_leaf_tuple")
+        if tup is None or tup[0] is not self:
+            tup = (self, tuple(self._leaf_tensors()))
+            self.__dict__["_leaf_tuple"] = tup
+        return sum(map(_VERSION, tup[1]))
 
     def _prepare(self, device):
         if device.type != "cuda":
@@ -241,7 +320,7 @@ class TMGlow(nn.Module):
         # (optimizers, load_state_dict, copy_ bump the tensors' version counters; their sum only grows).
         # Writes through ``p.data`` bypass the counter: call ``refresh_weights()`` after those, or set
         # ``always_refresh_weights = True``.
-        key = (h.value, self._flat.data_ptr(), sum(t._version for t in self._leaf_tensors()))
+        key = (h.value, self._flat.data_ptr(), self._version_sum())
         if changed or self.always_refresh_weights or self._refreshed_for != key:
             st = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.tmg_model_refresh(h, self._flat.data_ptr(), st))
@@ -454,8 +533,8 @@ class TMGlow(nn.Module):
         and records the input of every flow step; ``backward`` (hand-written CUDA, exact fp32) returns the gradients
         w.r.t. the incoming LSTM states and ACCUMULATES the parameter gradients into ``self.flat_grad`` (a flat
         buffer laid out like ``flat_parameters()``; ``zero_flat_grad()`` clears it, ``scatter_flat_grad()`` exposes it
-        as ``p.grad`` of every parameter).  Round 1: gradients of the flow (decoder) parameters; the encoder's are the
-        next step."""
+        as ``p.grad`` of every parameter).  All parameters are covered: the flow steps, split priors, ConvLSTM cells
+        and the encoder (tests/test_gpu_backward.py checks every one against oracle autograd)."""
         # the flat parameter is passed so that the outputs carry a graph even without incoming states; its gradient
         # is accumulated into ``flat_grad`` by the backward kernel (autograd gets None for it)
         return _ReconstructFn.apply(self, x, eps, self.flat_parameter_for_optimizer(), *([t for hc in (h_in or []) for t in hc]))

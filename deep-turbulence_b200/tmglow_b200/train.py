@@ -92,11 +92,12 @@ def mix_states(h_out: list, h_key: list) -> list:
 
 
 def train_series(model, optimizer, criterion, input0: torch.Tensor, target0: torch.Tensor, lstm_seeds: torch.Tensor,
-                 tback: int = 10, max_norm: Optional[float] = 1.0, group=None):
+                 tback: int = 10, max_norm: Optional[float] = 1.0, group=None, weight_decay: float = 1e-8):
     """One mini-batch of ``TrainFlow.trainParallel`` (trainFlowParallel.py:225-303): a time series ``input0
     [B,Tmax,nic,h,w]`` / ``target0 [B,Tmax,noc,H,W]`` is cut into ``Tmax // tback`` BPTT blocks, one optimizer step
-    each; LSTM states start from ``initLSTMStates(lstm_seeds)`` and are mixed with them between blocks.  Returns the
-    summed loss (``total_loss``) and the final states."""
+    each; LSTM states start from ``initLSTMStates(lstm_seeds)`` and are mixed with them between blocks.
+    ``weight_decay`` is the reference's Adam weight decay (1e-8, main.py:78), applied by ``train_block`` to the trainable
+    entries of the flat buffer only.  Returns the summed loss (``total_loss``) and the final states."""
     dev = model.flat_parameter_for_optimizer().device
     a_key = [(a.to(dev), c.to(dev)) for a, c in model.initLSTMStates(lstm_seeds, [target0.size(-2), target0.size(-1)])]
     a0 = a_key
@@ -108,7 +109,7 @@ def train_series(model, optimizer, criterion, input0: torch.Tensor, target0: tor
         xb = input0[:, i * tback:(i + 1) * tback].to(dev, non_blocking=True)
         tb = target0[:, i * tback:(i + 1) * tback]
         loss, _, a_out = train_block(model, optimizer, xb, tb, a0, max_norm=max_norm, group=group, criterion=criterion,
-                                     target_mean=t_mean, target_rms=t_rms)
+                                     target_mean=t_mean, target_rms=t_rms, weight_decay=weight_decay)
         a0 = mix_states(a_out, a_key)
         total = total + loss
     return total, a0

@@ -68,6 +68,9 @@ def sample_sequence(model, x_seq: torch.Tensor, samples: int, *, base_seed: int 
     sampler = sampler or model.sample
     init_states = init_states or model.initLSTMStates
     T = x_seq.shape[0]
+    # checked on EVERY rank before any work: an empty shard would leave the other ranks waiting in the all-reduce
+    if samples < world:
+        raise ValueError("samples (%d) < world (%d): every rank needs at least one sample" % (samples, world))
     lo, hi = shard_range(samples, rank, world)
     S = hi - lo
     dev = x_seq.device
@@ -103,8 +106,7 @@ def sample_sequence(model, x_seq: torch.Tensor, samples: int, *, base_seed: int 
             s2 = torch.zeros_like(s1)
         if m1 is not None:
             s1[t], s2[t] = m1, m2
-    if s1 is None:       # a rank without samples still takes part in the reduction
-        raise ValueError("rank %d of %d has no samples: use samples >= world" % (rank, world))
+    assert s1 is not None      # samples >= world: every rank has a shard
     mean, var, ntot = combine_moments(s1, s2, S, group)
     return mean.float(), var.float(), ntot, (torch.stack(kept, 1) if keep_samples else None)
 

@@ -46,12 +46,20 @@ def flat_optimizer_state_to_reference(model, optimizer):
             state[i] = ent
     group = {k: copy.deepcopy(v) for k, v in sd["param_groups"][0].items() if k != "params"}
     group["params"] = list(range(len(slices)))
+    # the flat optimizer itself always runs with weight_decay = 0 (see load_flat_optimizer_state); the file carries the
+    # decay the trainer applies to the trainable entries (main.py:78)
+    group["weight_decay"] = float(getattr(optimizer, "reference_weight_decay", group.get("weight_decay", 0.0)))
     return {"state": state, "param_groups": [group]}
 
 
 def load_flat_optimizer_state(model, optimizer, reference_state_dict):
     """Inverse: scatter a reference-layout Adam state (one entry per parameter) into the flat-parameter optimizer; the
-    non-trainable entries of the flat buffer keep zero moments.  Hyper-parameters (lr, betas, ...) follow the file."""
+    non-trainable entries of the flat buffer keep zero moments.  Hyper-parameters (lr, betas, ...) follow the file,
+    EXCEPT the weight decay: the flat parameter also holds non-trainable buffers (permutations, masks, BatchNorm running
+    statistics), and Adam's normalisation would turn ``wd * p`` on their zero gradient into a step of about ``lr``, so the
+    flat optimizer is forced to ``weight_decay = 0``.  The file's value (1e-8 for reference checkpoints, main.py:78) is
+    kept as ``optimizer.reference_weight_decay`` and returned: pass it to ``train.train_block(weight_decay=...)``, which
+    applies it to the trainable entries only.  Returns ``(optimizer, weight_decay)``."""
     flat = model.flat_parameter_for_optimizer()
     slices = _param_slices(model)
     ref_state = reference_state_dict["state"]
@@ -70,12 +78,15 @@ def load_flat_optimizer_state(model, optimizer, reference_state_dict):
         new_state[0] = ent
     group = {k: copy.deepcopy(v) for k, v in reference_state_dict["param_groups"][0].items() if k != "params"}
     group["params"] = [0]
+    file_wd = float(group.get("weight_decay", 0.0) or 0.0)
+    group["weight_decay"] = 0.0
     # keys a newer torch expects but an old file lacks keep the optimizer's current values
     cur = optimizer.state_dict()["param_groups"][0]
     for k, v in cur.items():
         group.setdefault(k, v)
     optimizer.load_state_dict({"state": new_state, "param_groups": [group]})
-    return optimizer
+    optimizer.reference_weight_decay = file_wd
+    return optimizer, file_wd
 
 
 def saveWorkspace(args, model, optimizer, file_name="nsWorkspace", file_id=0):
@@ -99,9 +110,11 @@ def saveWorkspace(args, model, optimizer, file_name="nsWorkspace", file_id=0):
     return zip_file_name
 
 
-def loadWorkspace(args, file_dir, file_name="nsWorkspace", file_id=0):
+def loadWorkspace(args, file_dir, file_name="nsWorkspace", file_id=0, trusted_pickle=False):
     """``utils/utils.py:95-148``: returns ``(args, model_state_dict, optimizer_state_dict)`` or ``None`` when the zip does
-    not exist; arguments in the file overwrite ``args`` except the black-listed run-control ones."""
+    not exist; arguments in the file overwrite ``args`` except the black-listed run-control ones.  The payload holds only
+    tensors, dicts, lists and numbers, so it is read with ``weights_only=True`` (no arbitrary code from an untrusted file);
+    ``trusted_pickle=True`` opts into full unpickling for files that carry other objects."""
     path = os.path.join(file_dir, file_name + "{:d}.zip".format(file_id))
     if not os.path.exists(path):
         return None
@@ -115,5 +128,5 @@ def loadWorkspace(args, file_dir, file_name="nsWorkspace", file_id=0):
         torch_name = 'torchModel{:d}.pth'.format(file_id)
         with zipObj.open(torch_name) as f:
             import io
-            param_dict = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=False)
+            param_dict = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=not trusted_pickle)
     return args, param_dict['state_dict'], param_dict['optimizer']

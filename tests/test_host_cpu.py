@@ -117,7 +117,10 @@ def test_bench_reference_arm_contract_sampling():
     d = _run_bench(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-batch", "2"])
     assert d["impl"] == "reference" and d["metric"] == "hf_samples_per_sec" and d["unit"] == "samples/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the unmodified reference package (oracle/_ref, made by oracle/make_ref.py); "port" only without that copy
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "tmglow", "nn", "tmGlow.py")) or os.path.exists("/root/reference/tmglow/nn/tmGlow.py")
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None
 
@@ -126,7 +129,7 @@ def test_bench_reference_arm_contract_training():
     d = _run_bench(["--impl", "reference", "--workload", "train", "--steps", "1", "--warmup", "0", "--ref-train-batch", "1",
                     "--tback", "2"])
     assert d["impl"] == "reference" and d["metric"] == "train_steps_per_sec" and d["unit"] == "steps/s"
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["value"] == d["value"]
     assert d["config"]["tback"] == 2 and d["config"]["global_batch"] == 1 and d["hf_snapshots_per_sec"] > 0
 
 
@@ -148,3 +151,35 @@ def test_trainable_mask_and_scratch_pool_cpu():
     c = m._scratch("g_y", (3, 3, 4, 4), torch.float32, torch.device("cpu"))
     assert a.data_ptr() == b.data_ptr() and c.shape[0] == 3
     assert len([k for k in m._scratch_pool if k[0] == "g_y"]) == 1        # one buffer per name is kept alive
+
+
+def test_replica_owns_its_handles_and_resolves_its_own_leaves():
+    """nn.DataParallel.replicate support (reference caller: utils/parallel.py:150-169, one thread per replica): a replica
+    gets its own library handles / flat buffer / workspace, and the flat buffer is assembled from the tensors of the
+    REPLICA's module tree (the per-device copies), never from the original's."""
+    import torch
+    from tmglow_b200 import TMGlow
+    m = TMGlow(2, 3, [1], [2], cond_features=4, cglow_upscale=1, growth_rate=2, init_features=4, rec_features=4)
+    # what torch.nn.parallel.replicate does, for one replica on the CPU: shallow replicas of every module, re-wired
+    mods = list(m.modules())
+    idx = {mod: i for i, mod in enumerate(mods)}
+    reps = [mod._replicate_for_data_parallel() for mod in mods]
+    for i, mod in enumerate(mods):
+        for key, child in mod._modules.items():
+            setattr(reps[i], key, reps[idx[child]])
+        for key, p in mod._parameters.items():
+            setattr(reps[i], key, p.detach().clone() + 1.0)          # a distinguishable "broadcast copy"
+        for key, b in mod._buffers.items():
+            setattr(reps[i], key, b.detach().clone())
+    r = reps[0]
+    assert r._handles is not m._handles and r._handles == {} and r._flat is None and r._ws == {}
+    name0 = next(n for n, _ in m.named_parameters())
+    i0 = [n for n, _, _, _ in m._table].index(name0)
+    assert torch.equal(r._leaf_tensor(i0), m._leaf_tensor(i0) + 1.0)
+    assert r._sync_flat(torch.device("cpu")) is True
+    off, numel = m._table[i0][1], m._table[i0][2]
+    assert torch.equal(r._flat[off:off + numel], (m._leaf_tensor(i0) + 1.0).reshape(-1))
+    # the original is untouched: its tensors were not re-bound to the replica's flat buffer
+    m._sync_flat(torch.device("cpu"))
+    assert m._leaf_tensor(i0).data_ptr() == m._flat.data_ptr() + 4 * off
+    assert m._flat.data_ptr() != r._flat.data_ptr()

@@ -143,3 +143,42 @@ def test_target_statistics_matches_reference_expression():
     mean, rms = L.target_statistics(t)
     assert torch.equal(mean, torch.mean(t, axis=1))
     assert torch.equal(rms, torch.sqrt(torch.mean((t - mean.unsqueeze(1)) ** 2, dim=1)))
+
+
+def test_oracle_equals_the_reference_copy_on_the_default_model():
+    """When the unmodified reference package is available (oracle/_ref, made by oracle/make_ref.py; /root/reference in the
+    build container) the oracle is checked against it directly on the default 1.75 M-parameter cylinder model -- the
+    configuration bench.py trains: forward, reconstruct and the LSTM states, max-abs difference 0.0."""
+    import numpy as np
+    import pytest
+    import torch
+    from oracle import ref_loader
+    from oracle import tmglow_oracle as O
+    if ref_loader.ref_root() is None:
+        pytest.skip("no copy of the reference package on this machine")
+    import bench
+    ns = ref_loader.load()
+    torch.manual_seed(3); np.random.seed(3)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ns.TMGlow(bench.TRAIN_GEOM["nic"], bench.TRAIN_GEOM["noc"], [4, 4, 4], [16, 16, 16], **bench.TRAIN_KW)
+    bench.perturb_(ref, 11)
+    ref.eval()
+    cfg = O.OracleConfig(in_features=3, out_features=3, enc_blocks=[4, 4, 4], glow_blocks=[16, 16, 16], **bench.TRAIN_KW)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    gen = torch.Generator().manual_seed(8)
+    B, G = 2, bench.TRAIN_GEOM
+    x = torch.randn(B, G["nic"], G["h"], G["w"], generator=gen)
+    y = torch.randn(B, G["noc"], G["H"], G["W"], generator=gen)
+    h = ref.initLSTMStates(torch.arange(B), [G["H"], G["W"]])
+    with torch.no_grad():
+        z_r, lp_r, h_r, eps_r = ref(x, y, h, return_eps=True)
+        z_o, lp_o, h_o, eps_o = O.forward(sd, cfg, x, y, h, return_eps=True)
+        assert torch.equal(z_r, z_o) and torch.equal(lp_r, lp_o)
+        for e_r, e_o in zip(eps_r, eps_o):
+            assert torch.equal(e_r, e_o)
+        y_r, ld_r, h2_r = ref.reconstruct(x, h, eps_r)
+        y_o, ld_o, h2_o = O.reconstruct(sd, cfg, x, h, eps_o)
+        assert torch.equal(y_r, y_o) and torch.equal(ld_r, ld_o)
+        for (a, c), (ao, co) in zip(h2_r, h2_o):
+            assert torch.equal(a, ao) and torch.equal(c, co)

@@ -39,9 +39,11 @@ def test_reference_workspace_loads_into_flat_optimizer(tmp_path):
     names = [n for n, _ in m.named_parameters()]
     assert len(osd["state"]) == len(names) == len(osd["param_groups"][0]["params"])
     opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1.0, amsgrad=True)
-    W.load_flat_optimizer_state(m, opt, osd)
+    _, wd = W.load_flat_optimizer_state(m, opt, osd)
     g = opt.param_groups[0]
-    assert abs(g["lr"] - 1e-3 * 0.995 ** 7) < 1e-12 and g["amsgrad"] and g["weight_decay"] == 1e-8
+    # the file's weight decay (main.py:78) is handed back for train_block; the flat optimizer itself must run without it
+    assert abs(g["lr"] - 1e-3 * 0.995 ** 7) < 1e-12 and g["amsgrad"] and g["weight_decay"] == 0.0
+    assert wd == 1e-8 and opt.reference_weight_decay == 1e-8
     st = opt.state[m.flat_parameter_for_optimizer()]
     assert float(st["step"]) == 2.0
     table = {name: (off, numel) for name, off, numel, shape in m._table}
@@ -54,6 +56,27 @@ def test_reference_workspace_loads_into_flat_optimizer(tmp_path):
     # the flat parameter holds the loaded weights
     off, numel = table[names[3]]
     assert torch.equal(m.flat_parameters()[off:off + numel], msd[names[3]].reshape(-1))
+
+
+def test_resumed_optimizer_leaves_buffers_untouched(tmp_path):
+    """Resuming from a reference checkpoint must not move the non-trainable entries of the flat buffer (permutations, masks,
+    BatchNorm running statistics): with the file's weight decay inside Adam they drifted by ~lr per step."""
+    from tmglow_b200 import workspace as W
+    args, msd, osd = W.loadWorkspace(_args(tmp_path), GOLDEN, file_id=7)
+    m = _model()
+    m.load_state_dict(msd)
+    fp = m.flat_parameter_for_optimizer()
+    opt = torch.optim.Adam([fp], lr=1.0, amsgrad=True)
+    W.load_flat_optimizer_state(m, opt, osd)
+    mask = m.trainable_mask()
+    before = fp.detach().clone()
+    for _ in range(20):
+        fp.grad = torch.zeros_like(fp)
+        opt.step()
+    after = fp.detach()
+    assert torch.equal(after[mask == 0], before[mask == 0])
+    # and the decay written back to a file is the reference's, not the 0 the flat optimizer runs with
+    assert W.flat_optimizer_state_to_reference(m, opt)["param_groups"][0]["weight_decay"] == 1e-8
 
 
 def test_workspace_round_trip_in_reference_layout(tmp_path):
