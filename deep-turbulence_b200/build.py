@@ -17,6 +17,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 FLAGS = [f for f in FLAGS if not f.startswith("--use_fast_math")]   # IEEE division / accurate expf on purpose
+if os.environ.get("TMG_LV_PROFILE"):                                 # developer build: role cycle counters in flow_level_f16.cu
+    FLAGS += ["-DTMG_LV_PROFILE"]
 if os.environ.get("TMG_MBAR_SLEEP"):                                 # experiment: nanosleep back-off in mbarrier waits
     FLAGS += ["-DTMG_MBAR_SLEEP=" + os.environ["TMG_MBAR_SLEEP"]]
 

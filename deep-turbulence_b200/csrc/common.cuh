@@ -60,7 +60,8 @@ enum ProfTag {
   PROF_PERMUTE = 9,
   PROF_MISC = 10,
   PROF_STEP_FUSED = 11,  // coupling net + coupling + 1x1 + ActNorm in one launch (coupling_tc.cu)
-  PROF_NTAGS = 12
+  PROF_LEVEL_RES = 12,   // all plain steps of a level in one launch, state resident on the SM (flow_level_f16.cu)
+  PROF_NTAGS = 13
 };
 struct ProfScope {
   cudaStream_t st;
@@ -246,6 +247,42 @@ int step2_ld_slots(int H, int W);   // log-det partial slots per sample: 8 (epil
 void step2_klayout(int nch0, int nch1, int& KSy, int& KS1, int& kd);
 size_t step2_wE_floats(int nch0, int nch1);
 size_t step2_wZ_floats(int nch0, int nch1, int C);
+
+// Level-resident fused flow steps (flow_level_f16.cu): ONE launch runs every plain step of a level in the reverse
+// (sampling) direction with the flow state resident on the SM -- fp32 state in registers, fp16 hi/lo operand planes of the
+// coupling-net input in shared memory --, so the state makes one HBM round trip per level instead of one per step.
+// Requires the hoisted conditioning tables (dc / hc).  Offsets are in floats from the parameter / packed bases.
+struct LevelStep {
+  int64_t wE, wZ, misc, gain, W;   // packed buffer: fp16 weights of flow_step_f16 (same packing), misc[12], gain, 1x1 mix W [C][C]
+  int64_t wEc, wZc;                // packed buffer: compact / tap-paired weights (JOB_STEP2C) or -1
+  int64_t bias, nw, nb;            // parameter buffer: Conv2dZeros bias, ActNorm weight / bias (-1: step without ActNorm)
+  int dc_off, hc_off;              // this step's index inside the (transposed) hoisted tables
+};
+struct LevelArgs {
+  const LevelStep* steps;          // device, in execution order (steps n-1 .. 1 of the block, reversed)
+  int nsteps;
+  const float* params;
+  const float* packed;
+  const float* y_in;               // [B,HW,C]
+  float* y_out;                    // [B,HW,C] (may alias y_in: every sample is read and written by one CTA)
+  const float* dc;                 // hoisted tables in the plane-transposed layout (launch_hoist_transpose):
+  const float* hc;                 //   dc [Bx][nsteps_tab][HW] float2, hc [Bx][nsteps_tab][C/4][HW] float4
+  int nsteps_tab;
+  int hoist_bstride;               // 0: tables shared by all samples; 1: per sample
+  float* ld_part;                  // [B][ld_stride]: sum over the steps and pixels of the coupling log-det -> entry 0
+  int ld_stride;
+  int B, H, W, C;
+  int x3;
+  int nch1;                        // conditioning channels (needed for the strides of the packed weights)
+  int compact;                     // 1: every step of the table carries the compact / tap-paired weights (wEc, wZc)
+  unsigned* overflow;              // sticky flag: set when an activation exceeded the fp16 operand range (+-6e4)
+  long long* prof;                 // developer profiling (TMG_LV_PROF=n): per-CTA cycle counters per role and phase, else null
+};
+bool level_resident_supported(const LevelArgs& a);
+// dc_all [Bx][HW][dstride] (cols 2s, 2s+1) / hc_all [Bx][HW][hstride] (cols s*C + n) -> the transposed layouts above
+int launch_hoist_transpose(const float* dc_all, int dstride, const float* hc_all, int hstride, float* dcT, float* hcT,
+                           int Bx, int HW, int nsteps, int C, cudaStream_t st);
+int launch_level_resident(const LevelArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ pointwise flow step
 struct PointArgs {
@@ -493,7 +530,7 @@ int gauss_bwd_blocks(int B, int HW);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
-                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10 };
+                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10, JOB_STEP2C = 11 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n

@@ -86,6 +86,7 @@ struct StepW {
   // fp16 fused step (flow_step_f16.cu)
   int64_t s2_wE = -1, s2_wZ = -1, s2_misc = -1;
   int s2_nch0 = 0, s2_nch1 = 0;
+  int64_t s2c_wE = -1, s2c_wZ = -1;   // compact / tap-paired variant for the level-resident kernel (narrow levels)
   // parameter offsets needed by the backward pass
   int64_t lu[8] = {-1, -1, -1, -1, -1, -1, -1, -1};     // l, u, log_s, p, sign_s, l_mask, u_mask, eye
   int64_t zc_scale = -1;
@@ -139,7 +140,9 @@ struct tmg_model {
   // intermediates, and the configuration it ran under (a backward under another configuration is refused)
   std::vector<LuTabEntry> lu_tab;   // deferred LU backward: one entry per flow step
   LuTabEntry* lu_tab_dev = nullptr;
-  unsigned* sync_dev = nullptr;     // zero-initialised, self-resetting words for single-launch reductions (absmax)
+  unsigned* sync_dev = nullptr;     // zero-initialised, self-resetting words for single-launch reductions (absmax);
+                                    // word 32: sticky fp16-operand overflow flag of the level-resident flow kernel
+  LevelStep* lvsteps_dev[TMG_MAX_LEVELS] = {nullptr};   // per level: the plain steps in reverse execution order
   // CUDA graphs of the per-time-step backward (~1 400 launches each): keyed by every pointer / shape the launch sequence
   // depends on; a key is run eagerly the first time it is seen, captured the second time, replayed from then on
   struct BwdGraph { int seen = 0; cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
@@ -260,6 +263,14 @@ struct Builder {
     j.src[0] = st.d1.w_param; j.src[1] = st.d2.w_param; j.src[2] = st.zc.w_param;
     j.dst[0] = st.s2_wE; j.dst[1] = st.s2_wZ; j.dst[2] = st.s2_misc;
     m.jobs.push_back(j);
+    if (nch0 + 2 <= 8 && nch1 > 0) {     // plain step of a narrow level: compact operand unit, two taps per MMA
+      st.s2c_wE = pack_alloc((int64_t)2 * 2 * 32 * 16 / 4);
+      st.s2c_wZ = pack_alloc((int64_t)5 * 2 * 2 * tc_npad(C) * 16 / 4);
+      PackJob k = j;
+      k.type = JOB_STEP2C;
+      k.dst[0] = st.s2c_wE; k.dst[1] = st.s2c_wZ; k.dst[2] = -1;
+      m.jobs.push_back(k);
+    }
   }
   int64_t gain(int64_t scale_param) {
     int64_t o = pack_alloc(1);
@@ -482,6 +493,7 @@ struct Plan {
   size_t bn_mean, bn_var, bn_scale, bn_shift;
   size_t y[TMG_MAX_LEVELS], y2[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
   size_t dc_all[TMG_MAX_LEVELS], hc_all[TMG_MAX_LEVELS];
+  size_t dcT[TMG_MAX_LEVELS], hcT[TMG_MAX_LEVELS];   // the same tables, plane-transposed for the level-resident kernel
 };
 
 static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shared = false) {
@@ -519,6 +531,8 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
     p.cond[l] = take(Bx * p.Hl[l] * p.Wl[l] * c.cond_features);
     p.dc_all[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.hoist_opd);
     p.hc_all[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.hoist_oph);
+    p.dcT[l] = take(Bx * p.Hl[l] * p.Wl[l] * 2 * lv.steps.size());
+    p.hcT[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.C * lv.steps.size());
     p.y[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
     p.y2[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
     cc_max = std::max(cc_max, Bx * p.eh[l] * p.ew[l] * c.cond_features);
@@ -552,6 +566,11 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
 }
 
 static inline bool prec_tc(int p) { return p != TMG_PREC_FP32; }
+// TMG_NO_RESIDENT=1: one launch per flow step (flow_step_f16.cu) even where the level-resident kernel applies (A/B runs)
+static inline bool resident_off() {
+  static const bool off = [] { const char* e = getenv("TMG_NO_RESIDENT"); return e && e[0] == '1'; }();
+  return off;
+}
 static inline bool prec_split(int p) { return p == TMG_PREC_TF32X3 || p == TMG_PREC_F16X3; }
 static inline bool prec_f16(int p) { return p == TMG_PREC_F16X3 || p == TMG_PREC_F16; }
 
@@ -1024,7 +1043,7 @@ int tmg_device_count(void) {
 
 static const char* kProfNames[PROF_NTAGS] = {"conv_lstm_gates", "conv_lstm_out", "conv_zero", "conv_dense_cout1",
                                               "conv_split_prior", "conv_encoder", "flow_pointwise", "lstm_pointwise",
-                                              "gaussian", "permute", "misc", "flow_step_fused"};
+                                              "gaussian", "permute", "misc", "flow_step_fused", "flow_level_resident"};
 
 int tmg_profile_enable(int on) {
   for (auto& r : tmg::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1068,6 +1087,7 @@ void tmg_model_destroy(tmg_model* m) {
   if (m->jobs2_dev) cudaFree(m->jobs2_dev);
   if (m->lu_tab_dev) cudaFree(m->lu_tab_dev);
   if (m->sync_dev) cudaFree(m->sync_dev);
+  for (auto* p_ : m->lvsteps_dev) if (p_) cudaFree(p_);
   for (auto& kv : m->bwd_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (m->gstream) cudaStreamDestroy(m->gstream);
   if (m->gev_in) cudaEventDestroy(m->gev_in);
@@ -1126,6 +1146,24 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
       TMG_CUDA_OK(cudaMemset(m->sync_dev, 0, 64 * sizeof(unsigned)));
       TMG_CUDA_OK(cudaMalloc(&m->lu_tab_dev, m->lu_tab.size() * sizeof(LuTabEntry)));
       TMG_CUDA_OK(cudaMemcpy(m->lu_tab_dev, m->lu_tab.data(), m->lu_tab.size() * sizeof(LuTabEntry), cudaMemcpyHostToDevice));
+    }
+    for (int l = 0; l < m->cfg.n_levels; ++l) {        // step tables of the level-resident flow kernel (offsets only: static)
+      const LevelW& lv = m->levels[l];
+      std::vector<LevelStep> tab;
+      for (int s = (int)lv.steps.size() - 2; s >= 0; --s) {
+        const StepW& sw = lv.steps[s];
+        LevelStep e{};
+        e.wE = sw.s2_wE; e.wZ = sw.s2_wZ; e.misc = sw.s2_misc; e.gain = sw.zc_gain; e.W = sw.W;
+        e.wEc = sw.s2c_wE; e.wZc = sw.s2c_wZ;
+        e.bias = sw.zc.b_param;
+        e.nw = sw.kind != STEP_UNNORMED ? sw.norm_w : -1; e.nb = sw.kind != STEP_UNNORMED ? sw.norm_b : -1;
+        e.dc_off = s; e.hc_off = s;
+        tab.push_back(e);
+      }
+      if (!tab.empty()) {
+        TMG_CUDA_OK(cudaMalloc(&m->lvsteps_dev[l], tab.size() * sizeof(LevelStep)));
+        TMG_CUDA_OK(cudaMemcpy(m->lvsteps_dev[l], tab.data(), tab.size() * sizeof(LevelStep), cudaMemcpyHostToDevice));
+      }
     }
     if (!m->jobs2.empty()) {
       TMG_CUDA_OK(cudaMalloc(&m->jobs2_dev, m->jobs2.size() * sizeof(PackJob)));
@@ -1283,6 +1321,33 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
     // steps n..1 reversed (flowLSTMBlock.py:348-359)
     for (int s = (int)lv.steps.size() - 1; s >= 0; --s) {
       const StepW& st = lv.steps[s];
+      if (!tape && s == (int)lv.steps.size() - 2 && s >= 0 && prec_f16(m->precision) && c.hoist_ready && m->lvsteps_dev[l] &&
+          !resident_off()) {
+        // all plain steps of the level in one launch with the state resident on the SM (flow_level_f16.cu)
+        LevelArgs la{};
+        la.steps = m->lvsteps_dev[l]; la.nsteps = s + 1;
+        la.params = c.P(); la.packed = c.Q();
+        la.y_in = Y; la.y_out = Y;
+        la.dc = ws + p.dcT[l]; la.hc = ws + p.hcT[l]; la.nsteps_tab = (int)lv.steps.size();
+        la.hoist_bstride = p.shared ? 0 : 1;
+        la.ld_part = ws + p.ldp + (size_t)slot * p.ctas; la.ld_stride = ldstride;
+        la.B = B; la.H = Hl; la.W = Wl; la.C = lv.C; la.x3 = prec_split(m->precision) ? 1 : 0;
+        la.nch1 = m->cfg.cond_features;
+        la.compact = lv.steps[0].s2c_wE >= 0 ? 1 : 0;
+        la.overflow = m->sync_dev + 32;
+        if (level_resident_supported(la)) {
+          TMG_TRY(launch_hoist_transpose(ws + p.dc_all[l], lv.hoist_opd, ws + p.hc_all[l], lv.hoist_oph, ws + p.dcT[l], ws + p.hcT[l],
+                                         p.Bx, HW, (int)lv.steps.size(), lv.C, c.st));
+          const double px = (double)B * HW;
+          const int cin_t = lv.C / 2 + m->cfg.cond_features;
+          ProfScope ps(c.st, PROF_LEVEL_RES,
+                       la.nsteps * (2.0 * px * 9.0 * (cin_t + (cin_t + 1) + (double)lv.C * (cin_t + 2)) + 2.0 * px * lv.C * lv.C),
+                       la.nsteps * 4.0 * px * (2.0 * lv.C + m->cfg.cond_features));
+          TMG_TRY(launch_level_resident(la, c.st));
+          slot += la.nsteps;
+          break;
+        }
+      }
       if (tape) {
         TMG_CUDA_OK(cudaMemcpyAsync(tape + tape_off(*m, p, l, s), Y, (size_t)B * HW * lv.C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
         c.emit_d = tape + tape_off_d(*m, p, l, s); c.emit_h = tape + tape_off_h(*m, p, l, s); c.emitted = false;

@@ -145,6 +145,66 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
     float* dm = Q + j.dst[2];
     if (tid < 9) dm[tid] = w2[(size_t)I1 * 9 + tid];
     if (tid >= 9 && tid < 12) dm[tid] = 1.f / sc[tid - 9];
+  } else if (j.type == JOB_STEP2C) {
+    // Compact weights of the level-resident flow kernel (flow_level_f16.cu) for narrow levels (C/2 + 2 <= 8): the whole
+    // coupling-net input of a position -- x1 channels, d1 (slot 6), d2 (slot 7) -- is ONE 16-byte operand unit, and a
+    // K = 16 MMA contracts TWO filter taps at once (its second K half reads another position through the descriptor's
+    // leading-dimension offset).  Same power-of-two scales as JOB_STEP2 (its misc block carries their inverses).
+    //   wE [hl][2 planes][32][8]: plane 0 = taps of dense layers 1 (cols 0-8) / 2 (cols 9-17), plane 1 = zeros
+    //   wZ [pair 0..4][hl][2 planes][NP][8]: plane 0 = tap 2*pair, plane 1 = tap 2*pair + 1 (zeros for pair 4)
+    const int C = j.a, I1 = j.b, NP = j.opad, nch0 = j.nch0, nch1 = j.nch1;
+    const float* w1 = P + j.src[0]; const float* w2 = P + j.src[1]; const float* w3 = P + j.src[2];
+    const int n1 = 9 * I1, n2 = 9 * (I1 + 1), n3 = 9 * C * (I1 + 2);
+    float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    for (int i = tid; i < n1; i += blockDim.x) m1 = fmaxf(m1, fabsf(w1[i]));
+    for (int i = tid; i < n2; i += blockDim.x) m2 = fmaxf(m2, fabsf(w2[i]));
+    for (int i = tid; i < n3; i += blockDim.x) m3 = fmaxf(m3, fabsf(w3[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+    }
+    if ((tid & 31) == 0) { sm[(tid >> 5) * 3] = m1; sm[(tid >> 5) * 3 + 1] = m2; sm[(tid >> 5) * 3 + 2] = m3; }
+    __syncthreads();
+    float sc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float m = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sm[w * 3 + q]);
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
+      sc[q] = m > 0.f ? ldexpf(1.f, min(max(11 - e, -20), 40)) : 1.f;
+    }
+    auto chan = [&](int k) -> int {          // slot inside the 8-channel unit -> concatenated input channel (or -1)
+      if (k < nch0) return k;
+      if (k == 6) return nch0 + nch1;
+      if (k == 7) return nch0 + nch1 + 1;
+      return -1;
+    };
+    __half* dE = reinterpret_cast<__half*>(Q + j.dst[0]);
+    for (int i = tid; i < 2 * 2 * 32 * 8; i += blockDim.x) {
+      const int e = i & 7; int t = i >> 3; const int n = t & 31; t >>= 5; const int plane = t & 1, hl = t >> 1;
+      const int c = plane == 0 ? chan(e) : -1;
+      float v = 0.f;
+      if (c >= 0 && c < I1) {          // compact columns: 0-8 dense layer 1, 9-17 dense layer 2 (18 TMEM columns are read back)
+        if (n < 9) v = w1[(size_t)c * 9 + n] * sc[0];
+        else if (n < 18) v = w2[(size_t)c * 9 + (n - 9)] * sc[1];
+      }
+      const __half hi = __float2half_rn(v);
+      dE[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    __half* dZ = reinterpret_cast<__half*>(Q + j.dst[1]);
+    for (int i = tid; i < 5 * 2 * 2 * NP * 8; i += blockDim.x) {
+      const int e = i & 7; int t = i >> 3; const int n = t % NP; t /= NP; const int plane = t & 1; t >>= 1;
+      const int hl = t & 1, pair = t >> 1;
+      const int tap = 2 * pair + plane;
+      const int c = chan(e);
+      float v = 0.f;
+      if (tap < 9 && c >= 0 && c < I1 + 2 && n < C) v = w3[((size_t)n * (I1 + 2) + c) * 9 + tap] * sc[2];
+      const __half hi = __float2half_rn(v);
+      dZ[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
   } else if (j.type == JOB_HOIST) {
     // Conditioning-only weight slices of every plain step of one level, concatenated along Cout, tap-major
     // [9][cond][opad] for conv3x3_ffma: the cond contribution to d1/d2 (kind 0: col 2s, 2s+1) or to the
