@@ -2280,6 +2280,284 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x, 
   return replay();
 }
 
+// ===================================================================== time-batched BPTT block
+// TrainFlow.trainParallel runs `tback` sample() calls in a row and back-propagates through all of them
+// (nn/trainFlowParallel.py:248-277).  Inside a level only the LSTM step couples the time steps (its ConvLSTM state);
+// everything else of a time step depends on that time step's own input, noise and LSTM output.  So a BPTT block is
+// restructured level by level: the LSTM step of the level runs T times in sequence on batch B, then the level's n-1 plain
+// steps, its split prior and the squeeze run ONCE on batch T*B (time-major: slice t = samples [t*B, (t+1)*B)).  Same
+// arithmetic per sample, 1/T of the launches for everything but the LSTM steps and the encoder (whose BatchNorm batch
+// statistics are per sample() call in the reference, so it still runs per time step).
+static Plan slice_plan(const tmg_model& m, const Plan& p, int t, int B) {
+  Plan q = p;
+  const tmg_config& g = m.cfg;
+  const size_t tb = (size_t)t * B;
+  q.B = B; q.Bx = B;
+  q.xn += tb * p.h * p.w * g.in_features;
+  q.e0 += tb * p.h * p.w * (g.init_features / 2);
+  for (int l = 0; l < p.L; ++l) {
+    q.db[l] += tb * p.eh[l] * p.ew[l] * m.levels[l].nf_out;
+    q.cond[l] += tb * p.Hl[l] * p.Wl[l] * g.cond_features;
+  }
+  q.zout += tb * p.Hl[p.L - 1] * p.Wl[p.L - 1] * 2 * m.Cz;
+  return q;      // cc / zo_pre / bn_* are scratch shared by the slices
+}
+// tape of a block: the per-step tape for batch T*B, then the ConvLSTM states after every time step [L][2][T*B,HW_l,R]
+static size_t bptt_state_off(const tmg_model& m, const Plan& p, int l, int which) {
+  size_t off = tape_floats(m, p);
+  for (int q = 0; q < l; ++q) off += (size_t)2 * p.B * p.Hl[q] * p.Wl[q] * m.cfg.rec_features;
+  return off + (size_t)which * p.B * p.Hl[l] * p.Wl[l] * m.cfg.rec_features;
+}
+static size_t bptt_tape_floats(const tmg_model& m, const Plan& p) { return bptt_state_off(m, p, p.L, 0); }
+
+size_t tmg_bptt_tape_bytes(const tmg_model* m, int T, int B, int h, int w) {
+  if (!m || T < 1) return 0;
+  Plan p;
+  if (make_plan(*m, T * B, h, w, p) != TMG_OK) return 0;
+  return bptt_tape_floats(*m, p) * sizeof(float);
+}
+size_t tmg_bptt_workspace_bytes(const tmg_model* m, int T, int B, int h, int w) {
+  if (!m || T < 1) return 0;
+  Plan p;
+  if (make_plan(*m, T * B, h, w, p) != TMG_OK) return 0;
+  size_t mxs = 0;                                    // gradients w.r.t. the carried LSTM states: two (h, c) pairs
+  for (int l = 0; l < p.L; ++l) mxs = std::max(mxs, (size_t)B * p.Hl[l] * p.Wl[l] * m->cfg.rec_features);
+  return tmg_reconstruct_backward_workspace_bytes(m, T * B, h, w) + 4 * mxs * sizeof(float) + 256;
+}
+
+int tmg_bptt_forward(tmg_model* m, int T, int B, int h, int w, const float* x, const float* const* h_in,
+                     const float* const* c_in, const float* const* eps, float* y, float* log_det, float* const* h_out,
+                     float* const* c_out, void* tape_v, size_t tape_bytes, void* workspace, size_t workspace_bytes,
+                     uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (T < 1) { set_error("bad block length"); return TMG_ERR_BAD_SHAPE; }
+  if (flags & TMG_FLAG_SHARED_X) { set_error("TMG_FLAG_SHARED_X is an inference option"); return TMG_ERR_BAD_CONFIG; }
+  Plan p;
+  const int BT = T * B;
+  TMG_TRY(make_plan(*m, BT, h, w, p, false));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !eps || !y || !log_det || !h_out || !c_out || !tape_v) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (tape_bytes < bptt_tape_floats(*m, p) * sizeof(float)) { set_error("tape too small"); return TMG_ERR_WORKSPACE; }
+  const int L = p.L, R = m->cfg.rec_features;
+  for (int l = 0; l <= L; ++l) if (!eps[l]) { set_error("eps[%d] is null", l); return TMG_ERR_NULL; }
+  float* tape = (float*)tape_v;
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const int ldstride = p.nslots * p.ctas;
+  TMG_CUDA_OK(cudaMemsetAsync(ws + p.ldp, 0, (size_t)BT * ldstride * sizeof(float), c.st));
+  // encoder: once per time step (BatchNorm batch statistics and running-stat updates per sample() call, as in the reference)
+  for (int t = 0; t < T; ++t) {
+    Ctx ct{*m, slice_plan(*m, p, t, B), ws, c.st};
+    TMG_TRY(run_encoder(ct, x + (size_t)t * B * m->cfg.in_features * h * w, flags & TMG_FLAG_BN_TRAIN));
+  }
+  if (prec_f16(m->precision)) TMG_TRY(run_hoist(c));
+  tmg_model::TapeInfo tinfo;
+  tinfo.emit.resize(L);
+  for (int l = 0; l < L; ++l) tinfo.emit[l].assign(m->levels[l].steps.size(), 0);
+  tinfo.sig[0] = BT; tinfo.sig[1] = h; tinfo.sig[2] = w; tinfo.sig[3] = m->precision;
+  { std::lock_guard<std::mutex> lk(m->tape_mu); m->tapes.erase(tape); }
+  {
+    const LevelW& lv = m->levels[L - 1];
+    GaussArgs ga{};
+    ga.prm = ws + p.zout; ga.prm_cstride = 2 * m->Cz;
+    ga.val = ws + p.y[L - 1]; ga.val_cstride = lv.C; ga.val_coff = 0;
+    ga.eps_in = eps[L]; ga.reverse = 1;
+    ga.B = BT; ga.HW = p.Hl[L - 1] * p.Wl[L - 1]; ga.n = m->Cz;
+    ga.ld_part = nullptr; ga.ld_stride = ldstride;
+    TMG_TRY(launch_gaussian(ga, c.st));
+  }
+  int slot = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const LevelW& lv = m->levels[l];
+    const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl, n = (int)lv.steps.size();
+    float* Y = ws + p.y[l];
+    float* Y2 = ws + p.y2[l];
+    TMG_TRY(run_split_prior(c, l, BT, Hl, Wl, Y));
+    GaussArgs ga{};
+    ga.prm = ws + p.hr; ga.prm_cstride = lv.C;
+    ga.val = Y; ga.val_cstride = lv.C; ga.val_coff = lv.C / 2;
+    ga.eps_in = eps[l]; ga.reverse = 1; ga.B = BT; ga.HW = HW; ga.n = lv.C / 2;
+    ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
+    TMG_TRY(launch_gaussian(ga, c.st));
+    for (int s = n - 1; s >= 0; --s) {
+      const StepW& st = lv.steps[s];
+      TMG_CUDA_OK(cudaMemcpyAsync(tape + tape_off(*m, p, l, s), Y, (size_t)BT * HW * lv.C * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+      float* ldp = ws + p.ldp + (size_t)(slot++) * p.ctas;
+      if (st.kind == STEP_LSTM) {
+        // the only step that couples the time steps: T launches sequences on batch B, states carried through the tape
+        float* hs = tape + bptt_state_off(*m, p, l, 0);
+        float* cs = tape + bptt_state_off(*m, p, l, 1);
+        const size_t sst = (size_t)B * HW * R, yst = (size_t)B * HW * lv.C, cst = (size_t)B * HW * m->cfg.cond_features;
+        bool swapped = false;                            // fused kernels write the other buffer, the fp32 path works in place
+        for (int t = 0; t < T; ++t) {
+          float* Yt = Y + t * yst; float* Y2t = Y2 + t * yst;
+          TMG_TRY(run_step(c, l, st, &st, true, B, Hl, Wl, Yt, Y2t, ws + p.cond[l] + t * cst,
+                           t ? hs + (t - 1) * sst : (h_in ? h_in[l] : nullptr), t ? cs + (t - 1) * sst : (c_in ? c_in[l] : nullptr),
+                           hs + t * sst, cs + t * sst, ldp + (size_t)t * B * ldstride));
+          const bool sw = Yt == Y2 + t * yst;
+          if (t && sw != swapped) { set_error("bptt: inconsistent buffer use of the LSTM step"); return TMG_ERR_UNSUPPORTED; }
+          swapped = sw;
+        }
+        if (swapped) { float* tmp = Y; Y = Y2; Y2 = tmp; }
+        TMG_CUDA_OK(cudaMemcpyAsync(h_out[l], hs + (size_t)(T - 1) * sst, sst * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+        TMG_CUDA_OK(cudaMemcpyAsync(c_out[l], cs + (size_t)(T - 1) * sst, sst * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+      } else {
+        c.emit_d = tape + tape_off_d(*m, p, l, s); c.emit_h = tape + tape_off_h(*m, p, l, s); c.emitted = false;
+        TMG_TRY(run_step(c, l, st, &st, true, BT, Hl, Wl, Y, Y2, ws + p.cond[l], nullptr, nullptr, nullptr, nullptr, ldp));
+        tinfo.emit[l][s] = c.emitted ? 1 : 0;
+        c.emit_d = c.emit_h = nullptr;
+      }
+    }
+    PermArgs pa{};
+    pa.src = Y; pa.src_cstride = lv.C; pa.src_coff = 0;
+    pa.B = BT; pa.C = lv.C / 4; pa.H = 2 * Hl; pa.W = 2 * Wl;
+    if (l > 0) {
+      pa.mode = PERM_UNSQUEEZE_NHWC_TO_NHWC;
+      pa.dst = ws + p.y[l - 1]; pa.dst_cstride = m->levels[l - 1].C; pa.dst_coff = 0;
+    } else {
+      pa.mode = PERM_UNSQUEEZE_NHWC_TO_NCHW;
+      pa.dst = y;
+    }
+    TMG_TRY(launch_permute(pa, c.st));
+  }
+  {
+    std::lock_guard<std::mutex> lk(m->tape_mu);
+    tinfo.serial = ++m->tape_serial;
+    m->tapes[tape] = std::move(tinfo);
+  }
+  return finish_logdet(c, log_det);
+}
+
+int tmg_bptt_backward(tmg_model* m, int T, int B, int h, int w, const float* x, const float* const* h_in,
+                      const float* const* c_in, const float* const* eps, const void* tape_v, const float* g_y,
+                      const float* g_log_det, const float* const* g_h_out, const float* const* g_c_out,
+                      float* const* g_h_in, float* const* g_c_in, float* grads, void* workspace, size_t workspace_bytes,
+                      uint32_t flags, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (T < 1) { set_error("bad block length"); return TMG_ERR_BAD_SHAPE; }
+  Plan p;
+  const int BT = T * B;
+  TMG_TRY(make_plan(*m, BT, h, w, p, false));
+  TMG_TRY(check_common(m, workspace, workspace_bytes, p));
+  if (!x || !eps || !tape_v || !g_y || !g_log_det || !grads) { set_error("null argument"); return TMG_ERR_NULL; }
+  if (workspace_bytes < tmg_bptt_workspace_bytes(m, T, B, h, w)) { set_error("workspace too small for the backward pass"); return TMG_ERR_WORKSPACE; }
+  const float* tape = (const float*)tape_v;
+  tmg_model::TapeInfo tinfo;
+  {
+    std::lock_guard<std::mutex> lk(m->tape_mu);
+    auto it = m->tapes.find(tape_v);
+    if (it != m->tapes.end()) tinfo = it->second;
+  }
+  const bool tape_ok = (int)tinfo.emit.size() == m->cfg.n_levels && tinfo.sig[0] == BT && tinfo.sig[1] == h &&
+                       tinfo.sig[2] == w && tinfo.sig[3] == m->precision;
+  const int L = p.L, R = m->cfg.rec_features, cf = m->cfg.cond_features;
+  Ctx c{*m, p, (float*)workspace, (cudaStream_t)stream};
+  float* ws = c.ws;
+  const RbExtra rx = rb_extra(*m, p);
+  float* ex = (float*)((char*)workspace + align_up(p.total, 256));
+  float* rb = ex + rx.e.total;
+  float* carry = rb + rx.total;                      // gradients w.r.t. the carried LSTM states: two (h, c) pairs, ping-pong
+  size_t mxs = 0;
+  for (int l = 0; l < L; ++l) mxs = std::max(mxs, (size_t)B * p.Hl[l] * p.Wl[l] * R);
+  if ((size_t)((char*)(carry + 4 * mxs) - (char*)workspace) > workspace_bytes) { set_error("workspace too small for the state gradients"); return TMG_ERR_WORKSPACE; }
+  const bool bn_train = (flags & TMG_FLAG_BN_TRAIN) != 0;
+  for (int t = 0; t < T; ++t) {                       // conditioning maps and top prior parameters of every time step
+    Ctx ct{*m, slice_plan(*m, p, t, B), ws, c.st};
+    TMG_TRY(run_encoder(ct, x + (size_t)t * B * m->cfg.in_features * h * w, bn_train, 0.f));
+  }
+  for (int l = 0; l < L; ++l)
+    TMG_CUDA_OK(cudaMemsetAsync(rb + rx.gcond[l], 0, (size_t)BT * p.Hl[l] * p.Wl[l] * cf * sizeof(float), c.st));
+  float* Gc = rb + rx.ga;
+  float* Gn = rb + rx.gb;
+  {
+    PermArgs pa{};
+    pa.mode = PERM_SQUEEZE_NCHW_TO_NHWC; pa.src = g_y; pa.dst = Gc; pa.dst_cstride = m->levels[0].C; pa.dst_coff = 0;
+    pa.B = BT; pa.C = m->cfg.out_features; pa.H = p.H; pa.W = p.W;
+    TMG_TRY(launch_permute(pa, c.st));
+  }
+  const int prec = m->precision;
+  for (int l = 0; l < L; ++l) {
+    const LevelW& lv = m->levels[l];
+    const int Hl = p.Hl[l], Wl = p.Wl[l], HW = Hl * Wl, C = lv.C, n = (int)lv.steps.size();
+    const BwdExtra e = bwd_extra(*m, l, BT, Hl, Wl);
+    for (int s = 0; s < n; ++s) {
+      const StepW& st = lv.steps[s];
+      if (st.kind != STEP_LSTM) {
+        StepBwdIO io{};
+        io.Y = tape + tape_off(*m, p, l, s); io.COND = ws + p.cond[l]; io.GO = Gc; io.g_ld = g_log_det;
+        if (tape_ok && tinfo.emit[l][s]) { io.D_tape = tape + tape_off_d(*m, p, l, s); io.HR_tape = tape + tape_off_h(*m, p, l, s); }
+        io.GY = Gn; io.GC = rb + rx.gcond[l]; io.grads = grads; io.defer_lu = true;
+        TMG_TRY(step_backward(c, l, st, BT, Hl, Wl, io, ex, e));
+      } else {
+        const float* hs = tape + bptt_state_off(*m, p, l, 0);
+        const float* cs = tape + bptt_state_off(*m, p, l, 1);
+        const size_t sst = (size_t)B * HW * R, yst = (size_t)B * HW * C, cst = (size_t)B * HW * cf;
+        for (int t = T - 1; t >= 0; --t) {
+          StepBwdIO io{};
+          io.Y = tape + tape_off(*m, p, l, s) + t * yst; io.COND = ws + p.cond[l] + t * cst;
+          io.GO = Gc + t * yst; io.g_ld = g_log_det + (size_t)t * B;
+          io.GY = Gn + t * yst; io.GC = rb + rx.gcond[l] + t * cst; io.grads = grads; io.defer_lu = true;
+          io.h_prev = t ? hs + (t - 1) * sst : (h_in ? h_in[l] : nullptr);
+          io.c_prev = t ? cs + (t - 1) * sst : (c_in ? c_in[l] : nullptr);
+          float* ch_in = carry + (size_t)((t + 1) & 1) * 2 * mxs;        // written by time step t + 1
+          float* ch_out = carry + (size_t)(t & 1) * 2 * mxs;
+          io.g_hn = t == T - 1 ? (g_h_out ? g_h_out[l] : nullptr) : ch_in;
+          io.g_cn = t == T - 1 ? (g_c_out ? g_c_out[l] : nullptr) : ch_in + mxs;
+          io.g_hprev = t ? ch_out : ((g_h_in && io.h_prev) ? g_h_in[l] : nullptr);
+          io.g_cprev = t ? ch_out + mxs : ((g_c_in && io.c_prev) ? g_c_in[l] : nullptr);
+          TMG_TRY(step_backward(c, l, st, B, Hl, Wl, io, ex, e));
+        }
+      }
+      float* tsw = Gc; Gc = Gn; Gn = tsw;
+    }
+    const float* Ysplit = tape + tape_off(*m, p, l, n - 1);
+    m->precision = TMG_PREC_FP32;
+    int rc = run_split_prior(c, l, BT, Hl, Wl, Ysplit);
+    m->precision = prec;
+    TMG_TRY(rc);
+    GaussBwdArgs ga{};
+    ga.prm = ws + p.hr; ga.prm_cstride = C;
+    ga.g_val = Gc; ga.gv_cstride = C; ga.gv_coff = C / 2;
+    ga.eps = eps[l]; ga.g_ld = g_log_det; ga.gain = c.Q() + lv.split_gain; ga.hardtanh = 1;
+    ga.g_prm = ex + e.gz; ga.gp_cstride = C; ga.part = rb + rx.gpart;
+    ga.B = BT; ga.HW = HW; ga.n = C / 2;
+    TMG_TRY(launch_gauss_bwd(ga, c.st));
+    TMG_TRY(launch_reduce_cols(rb + rx.gpart, gauss_bwd_blocks(BT, HW), 1, 0, 1, ex + e.tmp, 0, c.st));
+    TMG_TRY(launch_scale_grad(ex + e.tmp, c.P() + lv.split_scale, grads + lv.split_scale, c.st));
+    {
+      const ConvSrc fs[1] = {{Ysplit, C, 0, C / 2, 0}};
+      const BwdDest ds[1] = {{Gc, nullptr, C, 0, C / 2, 1}};
+      TMG_TRY(conv_backward(c, BT, Hl, Wl, lv.split, 1, fs, true, ex + e.gz, C, 0, ds, 1, grads, ex + e.wt, ex + e.wscr, ex + e.gscale));
+    }
+    if (l + 1 < L) {
+      PermArgs pa{};
+      pa.mode = PERM_SQUEEZE_NHWC_TO_NHWC; pa.src = Gc; pa.src_cstride = C; pa.src_coff = 0;
+      pa.dst = Gn; pa.dst_cstride = m->levels[l + 1].C; pa.dst_coff = 0;
+      pa.B = BT; pa.C = C / 2; pa.H = Hl; pa.W = Wl;
+      TMG_TRY(launch_permute(pa, c.st));
+      float* tsw = Gc; Gc = Gn; Gn = tsw;
+    } else {
+      GaussBwdArgs gt{};
+      gt.prm = ws + p.zout; gt.prm_cstride = 2 * m->Cz;
+      gt.g_val = Gc; gt.gv_cstride = C; gt.gv_coff = 0;
+      gt.eps = eps[L]; gt.g_ld = nullptr; gt.gain = nullptr; gt.hardtanh = 0;
+      gt.g_prm = rb + rx.gzout; gt.gp_cstride = 2 * m->Cz; gt.part = nullptr;
+      gt.B = BT; gt.HW = HW; gt.n = m->Cz;
+      TMG_TRY(launch_gauss_bwd(gt, c.st));
+    }
+  }
+  // encoder parameters: per time step (batch statistics of that sample() call)
+  for (int t = 0; t < T; ++t) {
+    Ctx ct{*m, slice_plan(*m, p, t, B), ws, c.st};
+    RbExtra rxt = rx;
+    const size_t tb = (size_t)t * B;
+    for (int l = 0; l < L; ++l) rxt.gcond[l] += tb * p.Hl[l] * p.Wl[l] * cf;
+    rxt.gzout += tb * p.Hl[L - 1] * p.Wl[L - 1] * 2 * m->Cz;
+    TMG_TRY(run_encoder_backward(ct, bn_train, rb, rxt, grads));
+  }
+  return TMG_OK;
+}
+
 // how the backward calls of this model ran so far: captured graphs, graph replays, eager launch sequences
 int tmg_backward_graph_stats(const tmg_model* m, int64_t* graphs, int64_t* replays, int64_t* eager) {
   if (!m) { set_error("null model"); return TMG_ERR_NULL; }

@@ -64,6 +64,10 @@ SIGNATURES = {
     "tmg_reconstruct_train": (_I, [_P, _I, _I, _I, _P, _PP, _PP, _PP, _P, _P, _PP, _PP, _P, _SZ, _P, _SZ, _U32, _P]),
     "tmg_reconstruct_backward_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "tmg_reconstruct_backward": (_I, [_P, _I, _I, _I, _P, _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _PP, _P, _P, _SZ, _U32, _P]),
+    "tmg_bptt_tape_bytes": (_SZ, [_P, _I, _I, _I, _I]),
+    "tmg_bptt_workspace_bytes": (_SZ, [_P, _I, _I, _I, _I]),
+    "tmg_bptt_forward": (_I, [_P, _I, _I, _I, _I, _P, _PP, _PP, _PP, _P, _P, _PP, _PP, _P, _SZ, _P, _SZ, _U32, _P]),
+    "tmg_bptt_backward": (_I, [_P, _I, _I, _I, _I, _P, _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _PP, _P, _P, _SZ, _U32, _P]),
     "tmg_backward_finalize": (_I, [_P, _P, _P]),
     "tmg_backward_graph_stats": (_I, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "tmg_forward": (_I, [_P, _I, _I, _I, _P, _P, _PP, _PP, _P, _P, _PP, _PP, _PP, _P, _SZ, _U32, _P]),

@@ -547,6 +547,27 @@ class TMGlow(nn.Module):
             eps[i] = torch.randn(shapes[i], dtype=torch.float32, device=x.device)
         return self.reconstruct_train(x, h_in, eps)
 
+    def reconstruct_block_train(self, x_block, h_in, eps_block):
+        """A whole BPTT block (the ``tback`` chained ``sample()`` calls of nn/trainFlowParallel.py:248-277) as ONE
+        differentiable call: ``x_block [B,T,nic,h,w]``, ``eps_block`` = list over the T time steps of the per-call noise
+        lists (as ``reconstruct`` takes them).  Returns ``y [B,T,out,H,W]``, ``log_det [B,T]`` and the LSTM states after the
+        last time step.  Same results as T chained ``reconstruct_train`` calls; inside the library the time steps are
+        coupled only through the LSTM step of each level, everything else runs once on batch T*B (tmg_bptt_forward)."""
+        return _BlockFn.apply(self, x_block, eps_block, self.flat_parameter_for_optimizer(), *([t for hc in (h_in or []) for t in hc]))
+
+    def sample_block_train(self, x_block, h_in=None):
+        """``reconstruct_block_train`` with the noise drawn like T successive ``sample()`` calls (same RNG consumption)."""
+        B, T = x_block.shape[0], x_block.shape[1]
+        H, W = x_block.shape[-2] * self._cfg.cglow_upscale, x_block.shape[-1] * self._cfg.cglow_upscale
+        shapes = self.latent_shapes(B, H, W)
+        eps_block = []
+        for _ in range(T):
+            eps = [None] * len(shapes)
+            for i in [len(shapes) - 1] + list(range(len(shapes) - 2, -1, -1)):
+                eps[i] = torch.randn(shapes[i], dtype=torch.float32, device=x_block.device)
+            eps_block.append(eps)
+        return self.reconstruct_block_train(x_block, h_in, eps_block)
+
     def zero_flat_grad(self):
         flat = self.flat_parameters()
         if getattr(self, "flat_grad", None) is None or self.flat_grad.shape != flat.shape or self.flat_grad.device != flat.device:
@@ -660,6 +681,92 @@ class TMGlow(nn.Module):
             _lib.check(lib.tmg_model_get_conv1x1(h, level, step, int(inverse), out.data_ptr(),
                                                  torch.cuda.current_stream(device).cuda_stream))
         return out
+
+
+class _BlockFn(torch.autograd.Function):
+    """autograd bridge of a BPTT block: tmg_bptt_forward / tmg_bptt_backward (time-major tensors inside)."""
+
+    @staticmethod
+    def forward(ctx, model, x_block, eps_block, flat_param, *states):
+        device = x_block.device
+        lib, h = model._prepare(device)
+        L = len(model.glow_blocks)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            B, T = x_block.shape[0], x_block.shape[1]
+            x = x_block.detach().to(torch.float32).transpose(0, 1).contiguous()           # [T,B,nic,h,w]
+            hh, ww = x.shape[-2], x.shape[-1]
+            H, W = hh * model._cfg.cglow_upscale, ww * model._cfg.cglow_upscale
+            shapes = model.latent_shapes(B, H, W)
+            assert len(eps_block) == T and all(len(e) == len(shapes) for e in eps_block)
+            eps_c = [torch.stack([model._f32c(eps_block[t][l], device) for t in range(T)], 0) for l in range(len(shapes))]
+            for e, s in zip(eps_c, shapes):
+                assert tuple(e.shape[1:]) == tuple(s)
+            dims = model._state_dims(B, H, W)
+            h_in = [(states[2 * l], states[2 * l + 1]) for l in range(L)] if states else None
+            hp, cp, keep = model._states_in(lib, h_in, dims, device, st)
+            ho, co = model._states_out(dims, device)
+            y = torch.empty((T, B, model._cfg.out_features, H, W), dtype=torch.float32, device=device)
+            log_det = torch.empty((T, B), dtype=torch.float32, device=device)
+            n_ws = lib.tmg_bptt_workspace_bytes(h, T, B, hh, ww)
+            if n_ws == 0:
+                raise AssertionError(lib.tmg_last_error().decode("utf-8", "replace"))
+            ws = model._scratch("bptt_ws", (n_ws,), torch.uint8, device)
+            tape = torch.empty(lib.tmg_bptt_tape_bytes(h, T, B, hh, ww), dtype=torch.uint8, device=device)
+            _lib.check(lib.tmg_bptt_forward(
+                h, T, B, hh, ww, x.data_ptr(), hp, cp, _lib.ptr_array([t.data_ptr() for t in eps_c]),
+                y.data_ptr(), log_det.data_ptr(), _lib.ptr_array([t.data_ptr() for t in ho]),
+                _lib.ptr_array([t.data_ptr() for t in co]), tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(),
+                model._flags(), st))
+            if model.training:
+                for name, b in model.named_buffers():
+                    if name.endswith("num_batches_tracked"):
+                        b += T
+        ctx.model, ctx.x, ctx.eps, ctx.tape, ctx.keep, ctx.has_states = model, x, eps_c, tape, keep, bool(states)
+        ctx.state_ptrs, ctx.dims, ctx.TB = (hp, cp), dims, (T, B)
+        outs = [y.transpose(0, 1), log_det.transpose(0, 1)]
+        for a, b in zip(ho, co):
+            outs += [a, b]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_y, g_ld, *g_states):
+        model, x = ctx.model, ctx.x
+        device = x.device
+        lib, h = model._prepare(device)
+        L = len(model.glow_blocks)
+        T, B = ctx.TB
+        if getattr(model, "flat_grad", None) is None:
+            model.zero_flat_grad()
+        cl = lambda t: None if t is None else t.detach().float().contiguous(memory_format=torch.channels_last)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            H, W = x.shape[-2] * model._cfg.cglow_upscale, x.shape[-1] * model._cfg.cglow_upscale
+            gy_buf = model._scratch("g_yb", (T, B, model._cfg.out_features, H, W), torch.float32, device)
+            gld_buf = model._scratch("g_ldb", (T, B), torch.float32, device)
+            if g_y is None:
+                gy_buf.zero_()
+            else:
+                gy_buf.copy_(g_y.transpose(0, 1))
+            if g_ld is None:
+                gld_buf.zero_()
+            else:
+                gld_buf.copy_(g_ld.transpose(0, 1))
+            gh = [cl(g_states[2 * l]) for l in range(L)]
+            gc = [cl(g_states[2 * l + 1]) for l in range(L)]
+            g_in = [(_empty_channels_last(d, device), _empty_channels_last(d, device)) for d in ctx.dims] if ctx.has_states else []
+            ws = model._scratch("bptt_ws", (lib.tmg_bptt_workspace_bytes(h, T, B, x.shape[-2], x.shape[-1]),), torch.uint8, device)
+            hp, cp = ctx.state_ptrs
+            pa = lambda ts: _lib.ptr_array([None if t is None else t.data_ptr() for t in ts])
+            _lib.check(lib.tmg_bptt_backward(
+                h, T, B, x.shape[-2], x.shape[-1], x.data_ptr(), hp, cp, _lib.ptr_array([t.data_ptr() for t in ctx.eps]),
+                ctx.tape.data_ptr(), gy_buf.data_ptr(), gld_buf.data_ptr(), pa(gh), pa(gc),
+                pa([a for a, _ in g_in]) if g_in else None, pa([b for _, b in g_in]) if g_in else None,
+                model.flat_grad.data_ptr(), ws.data_ptr(), ws.numel(), model._flags(), st))
+        grads = [None, None, None, None]
+        for a, b in g_in:
+            grads += [a, b]
+        return tuple(grads)
 
 
 class _ReconstructFn(torch.autograd.Function):

@@ -48,25 +48,34 @@ def reverse_kl_loss(y_pred: torch.Tensor, log_det: torch.Tensor, target: torch.T
 def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h_in: Optional[list],
                 loss_fn: Callable = reverse_kl_loss, max_norm: Optional[float] = 1.0, group=None,
                 criterion=None, target_mean: Optional[torch.Tensor] = None, target_rms: Optional[torch.Tensor] = None,
-                weight_decay: float = 0.0):
+                weight_decay: float = 0.0, block_call: bool = True):
     """One optimizer step on a BPTT block (trainFlowParallel.py:248-293).  ``x_block [B,T,nic,h,w]``, ``target
     [B,T,noc,H,W]``, ``h_in`` list of (h, c) or None; ``optimizer`` must have been built on
     ``[model.flat_parameter_for_optimizer()]``.  With ``criterion`` (a ``TMGLowLoss``) the loss is the reference's
     ``criterion(yPred, logp, target, target_mean, target_rms)`` with the statistics of the full series
     (``loss.target_statistics``); otherwise ``loss_fn(yPred, logp, target)``.
+    ``block_call``: evaluate the block through ``model.sample_block_train`` (one library call, time-batched); ``False`` runs
+    the ``T`` chained ``sample_train`` calls of round 1 (same results, ~5x the launches).
     Returns ``(loss, grad_norm, h_out)`` with ``h_out`` detached (truncated BPTT, trainFlowParallel.py:296-300)."""
     T = x_block.shape[1]
     model.zero_flat_grad()
-    ys, lds = [], []
-    h = h_in
-    for t in range(T):
-        outs = model.sample_train(x_block[:, t], h)
-        ys.append(outs[0]); lds.append(outs[1])
+    if block_call and hasattr(model, "sample_block_train"):
+        # the whole block in one library call: time steps are coupled only through the LSTM step of each level
+        outs = model.sample_block_train(x_block, h_in)
+        y_pred, logp = outs[0], outs[1]
         h = [(outs[2 + 2 * l], outs[3 + 2 * l]) for l in range(len(model.glow_blocks))]
-    if criterion is not None:
-        loss = criterion(torch.stack(ys, 1), torch.stack(lds, 1), target, target_mean, target_rms)
     else:
-        loss = loss_fn(torch.stack(ys, 1), torch.stack(lds, 1), target)
+        ys, lds = [], []
+        h = h_in
+        for t in range(T):
+            outs = model.sample_train(x_block[:, t], h)
+            ys.append(outs[0]); lds.append(outs[1])
+            h = [(outs[2 + 2 * l], outs[3 + 2 * l]) for l in range(len(model.glow_blocks))]
+        y_pred, logp = torch.stack(ys, 1), torch.stack(lds, 1)
+    if criterion is not None:
+        loss = criterion(y_pred, logp, target, target_mean, target_rms)
+    else:
+        loss = loss_fn(y_pred, logp, target)
     loss.backward()
     g = model.flat_grad
     if hasattr(model, "finalize_flat_grad"):

@@ -158,6 +158,27 @@ int tmg_reconstruct_backward(tmg_model* m, int B, int h, int w, const float* x,
  * cleared.  tmg_flow_step_backward is not deferred. */
 int tmg_backward_finalize(tmg_model* m, float* grads, void* stream);
 
+/* One BPTT block of the reference trainer in ONE call (the `tback` sample() calls of nn/trainFlowParallel.py:248-277 and the
+ * loss.backward() through all of them, :277).  Inside a flow level only the LSTM step couples the time steps, so the block is
+ * evaluated level by level: the level's LSTM step T times in sequence on batch B, its plain steps / split prior / squeeze
+ * ONCE on batch T*B.  Same results as T chained tmg_reconstruct_train calls (per-sample arithmetic is unchanged), about a
+ * fifth of the launches, ten times the work per launch.  All tensors are TIME-MAJOR: x [T,B,nic,h,w], eps[l] [T,B,...],
+ * y [T,B,out,H,W], log_det [T,B]; h_in / c_in: states before the first time step (NULL = zeros), h_out / c_out: states after
+ * the last one (channels-last).  The encoder runs per time step (BatchNorm batch statistics per sample() call).
+ * Backward: g_y [T,B,out,H,W], g_log_det [T,B], g_h_out / g_c_out w.r.t. the final states (entries may be NULL); ACCUMULATES
+ * into `grads` like tmg_reconstruct_backward (call tmg_backward_finalize once per optimizer step) and returns g_h_in / g_c_in. */
+size_t tmg_bptt_tape_bytes(const tmg_model* m, int T, int B, int h, int w);
+size_t tmg_bptt_workspace_bytes(const tmg_model* m, int T, int B, int h, int w);
+int tmg_bptt_forward(tmg_model* m, int T, int B, int h, int w, const float* x, const float* const* h_in,
+                     const float* const* c_in, const float* const* eps, float* y, float* log_det, float* const* h_out,
+                     float* const* c_out, void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
+                     uint32_t flags, void* stream);
+int tmg_bptt_backward(tmg_model* m, int T, int B, int h, int w, const float* x, const float* const* h_in,
+                      const float* const* c_in, const float* const* eps, const void* tape, const float* g_y,
+                      const float* g_log_det, const float* const* g_h_out, const float* const* g_c_out,
+                      float* const* g_h_in, float* const* g_c_in, float* grads, void* workspace, size_t workspace_bytes,
+                      uint32_t flags, void* stream);
+
 /* With TMG_BWD_GRAPH=1 in the environment tmg_reconstruct_backward replays a CUDA graph of its ~1 400 launches when it is
  * called again with the same buffers (same pointers, shapes, precision): a key is run eagerly the first time it is seen,
  * captured the second time and replayed from then on.  Off by default: it pays only for callers with stable buffer

@@ -36,8 +36,8 @@ def _cyl_model():
     return m
 
 
-@pytest.mark.parametrize("precision", ["f16x3", "fp32"])
-def test_default_cylinder_training_gradients(precision):
+@pytest.mark.parametrize("precision,block", [("f16x3", True), ("f16x3", False), ("fp32", False)])
+def test_default_cylinder_training_gradients(precision, block):
     """configs[2] as benchmarked: default cylinder model, x[2,3,16,16] -> y[2,3,64,64], two BPTT time steps with carried
     LSTM states, training-mode BatchNorm, TMGLowLoss -> backward: the gradient of EVERY parameter against torch autograd
     through the oracles.  Exercises what the small golden model does not: C = 48 level, rec 64 (N = 256 gate conv with two
@@ -76,7 +76,10 @@ def test_default_cylinder_training_gradients(precision):
     m.zero_flat_grad()
     hh = [(a.to(dev), c.to(dev)) for a, c in h0]
     ys_c, lds_c = [], []
-    for t in range(Tn):
+    if block:         # what bench.py --workload train runs: the whole BPTT block in one library call
+        outs = m.reconstruct_block_train(x.to(dev), hh, [[e.to(dev) for e in eps[t]] for t in range(Tn)])
+        ys_c = [outs[0][:, t] for t in range(Tn)]; lds_c = [outs[1][:, t] for t in range(Tn)]
+    for t in range(Tn if not block else 0):
         outs = m.reconstruct_train(x[:, t].to(dev), hh, [e.to(dev) for e in eps[t]])
         ys_c.append(outs[0]); lds_c.append(outs[1])
         hh = [(outs[2 + 2 * l], outs[3 + 2 * l]) for l in range(len(hh))]
