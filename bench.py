@@ -398,7 +398,8 @@ def measure_train(args, rank, world, dev, dist, steps, warmup, e2e_steps=0):
     h_key = h
     # main.py:78 (Adam, amsgrad, weight_decay 1e-8 -- applied by train_block on the trainable entries only); lr below the
     # reference's 1e-3 start because the synthetic targets are white noise -- the arithmetic per step is identical
-    opt = torch.optim.Adam([m.flat_parameter_for_optimizer()], lr=1e-4, amsgrad=True)
+    from tmglow_b200 import FlatAdam
+    opt = FlatAdam(m, lr=1e-4, amsgrad=True)          # clip + decay + AMSGrad fused, no host synchronisation per step
     # the reference loss: TMGLowLoss(beta=200, dx=dy=5/64) with the PDE-residual terms (args.py:61-63), one fused kernel
     import types
     from tmglow_b200.loss import TMGLowLoss, target_statistics
@@ -455,7 +456,7 @@ def measure_train(args, rank, world, dev, dist, steps, warmup, e2e_steps=0):
         out.update({"e2e_ms": ms_e, "e2e_steps": e2e_steps, "h2d_bytes": xh.numel() * 4 + th.numel() * 4, "d2h_bytes": 4})
     assert torch.isfinite(state["loss"]).all(), "non-finite loss"
     gs = m.backward_graph_stats()
-    out.update({"loss": float(state["loss"]), "norm": state["norm"],
+    out.update({"loss": float(state["loss"]), "norm": float(state["norm"]),
                 "backward_graphs": {"captured": gs[0], "replays": gs[1], "eager_calls": gs[2]}})
     return out
 

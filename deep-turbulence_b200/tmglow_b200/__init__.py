@@ -8,5 +8,6 @@ C ABI of include/tmglow_b200.h.  No CPU fallback.
 """
 from . import _lib  # noqa: F401
 from .nn.tmGlow import TMGlow  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
 
-__all__ = ["TMGlow"]
+__all__ = ["TMGlow", "FlatAdam"]

@@ -69,6 +69,8 @@ SIGNATURES = {
     "tmg_bptt_forward": (_I, [_P, _I, _I, _I, _I, _P, _PP, _PP, _PP, _P, _P, _PP, _PP, _P, _SZ, _P, _SZ, _U32, _P]),
     "tmg_bptt_backward": (_I, [_P, _I, _I, _I, _I, _P, _PP, _PP, _PP, _P, _P, _P, _PP, _PP, _PP, _PP, _P, _P, _SZ, _U32, _P]),
     "tmg_backward_finalize": (_I, [_P, _P, _P]),
+    "tmg_adam_workspace_bytes": (_SZ, []),
+    "tmg_adam_step": (_I, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "tmg_backward_graph_stats": (_I, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "tmg_forward": (_I, [_P, _I, _I, _I, _P, _P, _PP, _PP, _P, _P, _PP, _PP, _PP, _P, _SZ, _U32, _P]),
     "tmg_encoder_forward": (_I, [_P, _I, _I, _I, _P, _PP, _P, _P, _SZ, _U32, _P]),

@@ -54,6 +54,8 @@ def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h
     ``[model.flat_parameter_for_optimizer()]``.  With ``criterion`` (a ``TMGLowLoss``) the loss is the reference's
     ``criterion(yPred, logp, target, target_mean, target_rms)`` with the statistics of the full series
     (``loss.target_statistics``); otherwise ``loss_fn(yPred, logp, target)``.
+    With a ``tmglow_b200.optim.FlatAdam`` optimizer the clip / decay / AMSGrad update is one fused library call without a
+    host synchronisation and ``grad_norm`` is returned as a 0-dim device tensor; with a plain ``torch.optim.Adam`` it is a float.
     ``block_call``: evaluate the block through ``model.sample_block_train`` (one library call, time-batched); ``False`` runs
     the ``T`` chained ``sample_train`` calls of round 1 (same results, ~5x the launches).
     Returns ``(loss, grad_norm, h_out)`` with ``h_out`` detached (truncated BPTT, trainFlowParallel.py:296-300)."""
@@ -81,6 +83,10 @@ def train_block(model, optimizer, x_block: torch.Tensor, target: torch.Tensor, h
     if hasattr(model, "finalize_flat_grad"):
         model.finalize_flat_grad()                  # deferred LU-parameter gradients, once per optimizer step
     allreduce_mean_(g, group)                       # the one collective of data-parallel training
+    if hasattr(optimizer, "fused_step"):
+        # clip + weight decay (trainable entries) + AMSGrad in one library call; the norm stays on the device (no sync)
+        out = optimizer.fused_step(g, max_norm=max_norm, weight_decay=weight_decay, mask=model.trainable_mask())
+        return loss.detach(), out[0], [(a.detach(), b.detach()) for a, b in h]
     norm = clip_flat_grad_(g, max_norm)
     flat = model.flat_parameter_for_optimizer()
     if weight_decay:

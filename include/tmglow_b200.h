@@ -277,6 +277,16 @@ int tmg_tmglow_loss(const float* y_pred, const float* logp, const float* target,
                     double beta, float* loss, float* terms, float* g_y, float* g_logp, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Optimizer step of the reference trainer on the flat parameter buffer: torch.nn.utils.clip_grad_norm_ followed by
+ * torch.optim.Adam(..., weight_decay, amsgrad).step() (nn/trainFlowParallel.py:290-291, main.py:78) as two launches with no host
+ * synchronisation.  `mask` (0/1 per entry, may be NULL): entries with 0 -- the buffers that share the flat layout: permutations,
+ * masks, BatchNorm running statistics -- are left untouched.  hyper (device, 8 floats): lr, beta1, beta2, eps, weight_decay,
+ * max_norm (<= 0: no clipping), step counter (incremented by the call), amsgrad flag; out (device, 2 floats): gradient norm
+ * before clipping, clip coefficient.  max_exp_avg_sq may be NULL when amsgrad is off.  Deterministic. */
+size_t tmg_adam_workspace_bytes(void);
+int tmg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, const float* mask,
+                  int64_t n, float* hyper, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* layout helpers for the LSTM states at the API boundary */
 int tmg_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 int tmg_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
