@@ -433,30 +433,54 @@ def measure_train(args, rank, world, dev, dist, steps, warmup, e2e_steps=0):
         return ms, int(launches)
 
     state = {"h": h, "loss": None, "norm": None}
+    graphed = None
+    if not getattr(args, "no_graph", False):
+        try:      # the whole optimizer step as CUDA graphs (tmglow_b200.train.GraphedTrainBlock); eager when capture fails
+            graphed = T.GraphedTrainBlock(m, opt, crit, x, tgt, t_mean, t_rms, h_key, max_norm=1.0, weight_decay=1e-8)
+        except Exception as ex:
+            sys.stderr.write("CUDA-graph capture of the training step failed (%r): running eagerly\n" % (ex,))
+            graphed = None
 
     def resident():
-        state["loss"], state["norm"], state["h"] = block(state["h"], x, tgt, t_mean, t_rms)
+        if graphed is not None:
+            state["loss"], state["norm"] = graphed.step()
+        else:
+            state["loss"], state["norm"], state["h"] = block(state["h"], x, tgt, t_mean, t_rms)
 
     for _ in range(max(warmup, 1)):
         resident()
+    if graphed is not None:
+        graphed.time_allreduce = True
+        graphed.allreduce_ms()
     ms, launches = timed(resident, steps)
-    out = {"ms": ms, "launches": launches}
+    out = {"ms": ms, "launches": launches + (graphed.kernels_per_step * steps if graphed is not None else 0)}
+    if graphed is not None:
+        ar_ms, ar_n = graphed.allreduce_ms()
+        graphed.time_allreduce = False
+        out["allreduce_ms_per_step"] = ar_ms / max(ar_n, 1) if ar_n else 0.0
     if e2e_steps > 0:
         # end to end: every step copies its inputs (LF block + HF targets) from pinned host memory, recomputes the target
         # statistics and reads the loss back
         xh, th = x.cpu().pin_memory(), tgt.cpu().pin_memory()
 
         def e2e():
-            xb, tb_ = xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)
-            tm, tr = target_statistics(tb_)
-            state["loss"], state["norm"], state["h"] = block(state["h"], xb, tb_, tm, tr)
+            if graphed is not None:
+                graphed.load(x_block=xh, target=th)                      # pinned host -> static device buffers
+                tm, tr = target_statistics(graphed.target)
+                graphed.load(target_mean=tm, target_rms=tr)
+                state["loss"], state["norm"] = graphed.step()
+            else:
+                xb, tb_ = xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)
+                tm, tr = target_statistics(tb_)
+                state["loss"], state["norm"], state["h"] = block(state["h"], xb, tb_, tm, tr)
             state["loss_host"] = float(state["loss"])
         e2e()
         ms_e, _ = timed(e2e, e2e_steps)
         out.update({"e2e_ms": ms_e, "e2e_steps": e2e_steps, "h2d_bytes": xh.numel() * 4 + th.numel() * 4, "d2h_bytes": 4})
     assert torch.isfinite(state["loss"]).all(), "non-finite loss"
     gs = m.backward_graph_stats()
-    out.update({"loss": float(state["loss"]), "norm": float(state["norm"]),
+    out.update({"flat_numel": int(m._n_flat), "cuda_graph": {"captured": graphed is not None, "replays": graphed.replays if graphed is not None else 0},
+                "loss": float(state["loss"]), "norm": float(state["norm"]),
                 "backward_graphs": {"captured": gs[0], "replays": gs[1], "eager_calls": gs[2]}})
     return out
 
@@ -503,7 +527,10 @@ def run_train(args, rank, world, local):
                 "clocks": clk, "gpu_launches": int(launches), "loss": loss, "grad_norm": norm,
                 "e2e": {"value": r["e2e_steps"] / (r["e2e_ms"] * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": r["h2d_bytes"],
                         "d2h_bytes_per_step": r["d2h_bytes"]},
-                "cpu_baseline": cpu, "backward_graphs": r["backward_graphs"],
+                "cpu_baseline": cpu, "backward_graphs": r["backward_graphs"], "cuda_graph": r["cuda_graph"],
+                "allreduce": {"ms_per_step": r.get("allreduce_ms_per_step", 0.0),
+                              "share_of_step": r.get("allreduce_ms_per_step", 0.0) / (ms / args.steps),
+                              "bytes": 4 * r.get("flat_numel", 0), "note": "CUDA events around dist.all_reduce of the flat gradient on rank 0 (one per optimizer step)"},
                 "hf_snapshots_per_sec": GB * tb * args.steps / (ms * 1e-3)}
         print(json.dumps(line))
     if dist is not None:
@@ -528,6 +555,7 @@ def main():
     ap.add_argument("--tback", type=int, default=10)
     ap.add_argument("--ref-train-batch", type=int, default=4, help="batch of the CPU training baseline (bounded sample)")
     ap.add_argument("--no-train", action="store_true", help="skip the short training measurement of the default line")
+    ap.add_argument("--no-graph", action="store_true", help="training: launch eagerly instead of replaying the captured CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -128,3 +128,113 @@ def train_series(model, optimizer, criterion, input0: torch.Tensor, target0: tor
         a0 = mix_states(a_out, a_key)
         total = total + loss
     return total, a0
+
+
+class GraphedTrainBlock:
+    """One optimizer step of the reference trainer's inner loop (``nn/trainFlowParallel.py:248-303``: BPTT block through
+    ``sample()``, ``TMGLowLoss``, backward, gradient all-reduce, clip, Adam-amsgrad, LSTM-state mixing) captured ONCE as CUDA
+    graphs and replayed: the ~4 000 kernel launches of a step become two ``cudaGraphLaunch`` calls and the Python thread does
+    no per-launch work -- what limits the step when the per-GPU batch is small (strong scaling).
+
+    Static buffers: ``x`` [B,T,nic,h,w], ``target`` [B,T,noc,H,W], ``target_mean`` / ``target_rms`` [B,noc,H,W] and the LSTM
+    states; ``step(x, target, ...)`` copies into them (device-to-device or pinned host-to-device, asynchronous) and replays.
+    Graph A = zero the gradient, forward block, loss, backward, deferred LU gradients; then the gradient all-reduce (eager NCCL,
+    only when a process group is active); graph B = ``FlatAdam.fused_step`` + state mixing with the key states.  The noise is
+    drawn inside graph A by ``torch.randn`` (graph-safe CUDA generator: every replay consumes fresh offsets).
+    Needs a ``FlatAdam`` optimizer (no host synchronisation inside the step)."""
+
+    def __init__(self, model, optimizer, criterion, x_block, target, target_mean, target_rms, h_key, max_norm=1.0,
+                 weight_decay=1e-8, group=None, warmup=2):
+        assert hasattr(optimizer, "fused_step"), "GraphedTrainBlock needs tmglow_b200.optim.FlatAdam"
+        self.model, self.opt, self.crit, self.group = model, optimizer, criterion, group
+        self.max_norm, self.wd = max_norm, weight_decay
+        dev = x_block.device
+        self.x = x_block.clone(); self.target = target.clone()
+        self.t_mean = target_mean.clone(); self.t_rms = target_rms.clone()
+        self.h_key = [(a.clone(), c.clone()) for a, c in h_key]
+        self.h_in = [(a.clone(), c.clone()) for a, c in h_key]
+        self.loss = torch.zeros((), device=dev)
+        self.norm = None
+        self.replays = 0
+        import torch.distributed as dist
+        self._dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 2)):          # allocator, derived weights, optimizer state, kernel attributes
+                self._part_a()
+                self._allreduce()
+                self._part_b()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        lib = _lib.load()
+        n0 = lib.tmg_launch_count(0)
+        self.ga, self.gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.ga):
+            self._part_a()
+        with torch.cuda.graph(self.gb, pool=self.ga.pool()):
+            self._part_b()
+        self.kernels_per_step = int(lib.tmg_launch_count(0) - n0)     # library kernels inside the two graphs (torch's not counted)
+        self.time_allreduce = False
+        self._ar_events = []
+
+    def _part_a(self):
+        m = self.model
+        m.zero_flat_grad()
+        outs = m.sample_block_train(self.x, self.h_in)
+        L = len(m.glow_blocks)
+        self._h_out = [(outs[2 + 2 * l].detach(), outs[3 + 2 * l].detach()) for l in range(L)]
+        loss = self.crit(outs[0], outs[1], self.target, self.t_mean, self.t_rms)
+        loss.backward()
+        m.finalize_flat_grad()
+        self.loss.copy_(loss.detach())
+
+    def _allreduce(self):
+        if self._dist is not None:
+            if getattr(self, "time_allreduce", False):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                allreduce_mean_(self.model.flat_grad, self.group)
+                e1.record()
+                self._ar_events.append((e0, e1))
+            else:
+                allreduce_mean_(self.model.flat_grad, self.group)
+
+    def allreduce_ms(self):
+        """Device time of the gradient all-reduces recorded since ``time_allreduce`` was switched on (synchronises)."""
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._ar_events)
+        n = len(self._ar_events)
+        self._ar_events = []
+        return ms, n
+
+    def _part_b(self):
+        out = self.opt.fused_step(self.model.flat_grad, max_norm=self.max_norm, weight_decay=self.wd, mask=self.model.trainable_mask())
+        self.norm = out
+        for (hi, ci), (ho, co), (hk, ck) in zip(self.h_in, self._h_out, self.h_key):      # trainFlowParallel.py:296-300
+            hi.copy_(0.5 * ho + 0.5 * hk)
+            ci.copy_(0.5 * co + 0.5 * ck)
+
+    def load(self, x_block=None, target=None, target_mean=None, target_rms=None, h_key=None):
+        """Asynchronous copies into the static buffers (pinned host tensors or device tensors)."""
+        for dst, src in ((self.x, x_block), (self.target, target), (self.t_mean, target_mean), (self.t_rms, target_rms)):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        if h_key is not None:                         # a new series: states restart from its key states
+            for (hk, ck), (hi, ci), (a, c) in zip(self.h_key, self.h_in, h_key):
+                hk.copy_(a, non_blocking=True); ck.copy_(c, non_blocking=True)
+                hi.copy_(hk); ci.copy_(ck)
+
+    def step(self):
+        """Replays the captured step; returns ``(loss, grad_norm)`` as device tensors (no synchronisation)."""
+        self.ga.replay()
+        self._allreduce()
+        self.gb.replay()
+        self.replays += 1
+        st = self.opt.state[self.opt.param_groups[0]["params"][0]]
+        st["step"] += 1.0                             # host mirror of the device-side step counter
+        if self.opt._hyper_host is not None:
+            hh = list(self.opt._hyper_host); hh[6] += 1.0; self.opt._hyper_host = tuple(hh)
+        self.model.refresh_weights()                  # the parameters changed inside the graph
+        return self.loss, self.norm[0]
