@@ -554,7 +554,9 @@ def main():
     ap.add_argument("--global-batch", type=int, default=64)
     ap.add_argument("--tback", type=int, default=10)
     ap.add_argument("--ref-train-batch", type=int, default=4, help="batch of the CPU training baseline (bounded sample)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed configuration")
     ap.add_argument("--no-train", action="store_true", help="skip the short training measurement of the default line")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed optimizer steps of the training legs of the default line")
     ap.add_argument("--no-graph", action="store_true", help="training: launch eagerly instead of replaying the captured CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -667,6 +669,29 @@ def main():
     e2e = {"value": world * S * K / (ms_e2e * 1e-3), "unit": "samples/s",
            "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (y_host[0].numel() + ld_host[0].numel()) * 4}
 
+    # ---------------- parity of what was just timed (rank 0, outside the timed region): the same S samples of the same LF input
+    # once more with EXPLICIT noise through reconstruct(), a handful of them against the pinned oracle on the CPU
+    # (fields 2e-4 abs, log-dets 1e-5 rel: the fp32 tolerance of the test-suite); the sticky fp16-overflow flag must be clear
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import tmglow_oracle as O
+        ocfg = O.OracleConfig.from_dict(model._cfg_dict)
+        sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        gp = torch.Generator(device=dev).manual_seed(4242)
+        eps_p = [torch.randn(sh, generator=gp, device=dev) for sh in model.latent_shapes(S, GEOM["H"], GEOM["W"])]
+        y_p, ld_p, _ = model.reconstruct(x_dev, h0, eps_p)
+        pick = torch.tensor(sorted({0, 1, S // 3, S // 2, S - 2, S - 1}))
+        with torch.no_grad():
+            y_o, ld_o, _ = O.reconstruct(sd_cpu, ocfg, x_host.expand(len(pick), -1, -1, -1).contiguous(),
+                                         [(a[pick].cpu(), c[pick].cpu()) for a, c in h0], [e[pick.to(dev)].cpu() for e in eps_p])
+        e_y = (y_p[pick.to(dev)].cpu() - y_o).abs().max().item()
+        e_l = ((ld_p[pick.to(dev)].cpu() - ld_o).abs() / ld_o.abs()).max().item()
+        ovf = model.activation_overflow()
+        parity = {"checked": True, "samples": [int(i) for i in pick], "of": S, "max_abs_y": e_y, "max_rel_log_det": e_l,
+                  "tolerance": {"y_abs": 2e-4, "log_det_rel": 1e-5}, "fp16_overflow_flag": bool(ovf)}
+        assert e_y < 2e-4 and e_l < 1e-5 and not ovf, "bench parity check failed: %r" % (parity,)
+        del eps_p, y_p, ld_p
+
     # ---------------- the single-pass fp16 mode, reported separately with its own tolerance (tests/test_gpu_parity.py)
     fast = None
     if args.precision == "f16x3":
@@ -745,21 +770,36 @@ def main():
                    ncalls, "the unmodified reference TMGlow.sample (oracle/_ref)" if smp.kind == "reference" else "oracle.sample()",
                    cb, el, smp.threads, {k: round(x_, 1) for k, x_ in sweep.items()})}
 
-    # ---------------- the other half of BASELINE.json's metric: data-parallel train steps/s (configs[2]), short run
-    train = None
+    # ---------------- the other half of BASELINE.json's metric: data-parallel train steps/s (configs[2]) -- the path with
+    # the collective: one all-reduce of the flat gradient per optimizer step.  Strong scaling (global batch 64 split over the
+    # ranks, BASELINE configs[2]) and, for N > 1, weak scaling (64 per GPU); >= 10 timed optimizer steps each.
+    train, train_weak = None, None
     if not args.no_train:
         del y, ld, h
         model = None
         torch.cuda.empty_cache()
-        try:
-            r_t = measure_train(args, rank, world, dev, dist, steps=2, warmup=1)
-            ms_t, loss_t, norm_t = r_t["ms"], r_t["loss"], r_t["norm"]
-            train = {"metric": "train_steps_per_sec", "value": 2 / (ms_t * 1e-3), "unit": "steps/s", "ms_per_step": ms_t / 2,
-                     "global_batch": args.global_batch, "tback": args.tback, "scaling": "strong",
-                     "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world,
-                     "workload": "TM-Glow cylinder-array training (configs[2]); see bench.py --workload train", "loss": loss_t}
-        except Exception as ex:        # the sampling line must not be lost to a training failure
-            train = {"error": repr(ex)[:200]}
+
+        def train_leg(global_batch, scaling):
+            a2 = argparse.Namespace(**vars(args))
+            a2.global_batch = global_batch
+            try:
+                r_t = measure_train(a2, rank, world, dev, dist, steps=args.train_steps, warmup=2)
+                ms_t = r_t["ms"]
+                return {"metric": "train_steps_per_sec", "value": args.train_steps / (ms_t * 1e-3), "unit": "steps/s",
+                        "ms_per_step": ms_t / args.train_steps, "steps": args.train_steps, "global_batch": global_batch, "tback": args.tback,
+                        "scaling": scaling, "hf_snapshots_per_sec": global_batch * args.tback * args.train_steps / (ms_t * 1e-3),
+                        "parallelism": "dp%d, one all-reduce of the flat gradient per step" % world,
+                        "allreduce_ms_per_step": r_t.get("allreduce_ms_per_step", 0.0),
+                        "allreduce_share_of_step": r_t.get("allreduce_ms_per_step", 0.0) / (ms_t / args.train_steps),
+                        "allreduce_bytes": 4 * r_t.get("flat_numel", 0), "cuda_graph": r_t["cuda_graph"],
+                        "gpu_launches": r_t["launches"], "loss": r_t["loss"],
+                        "workload": "TM-Glow cylinder-array training (configs[2]); see bench.py --workload train"}
+            except Exception as ex:        # the sampling line must not be lost to a training failure
+                return {"error": repr(ex)[:300]}
+        train = train_leg(args.global_batch, "strong")
+        if world > 1:
+            torch.cuda.empty_cache()
+            train_weak = train_leg(args.global_batch * world, "weak")
 
     if rank == 0:
         line = {
@@ -767,7 +807,8 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": dict(workload_config(S, world), precision=args.precision),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "fast_mode": fast, "train": train,
+            "parity_checked": bool(parity and parity["checked"]), "parity": parity,
+            "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "fast_mode": fast, "train": train, "train_weak": train_weak,
             "whole_path": {"alg_tflops": value * ALG_FLOP_PER_SAMPLE / 1e12 / world,
                            "alg_gbs": value * ALG_BYTES_PER_SAMPLE / 1e9 / world, "per": "GPU"},
             "kernel_classes": classes,

@@ -172,6 +172,7 @@ struct ConvF16Args {
                            // the fp16 normal range) and its inverse, applied in the epilogue; null = none
   int ndst;                // > 0: the output columns are routed to up to 3 destinations (the sources of the forward
   ConvDst dst[3];          // conv), each optionally gated by the sign of the forward input and accumulated
+  unsigned* overflow;      // sticky flag (or null): set when a staged operand left the fp16 range (+-6e4) and was clamped
 };
 int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st);
 // scale[0] = 2^k with max|g| * 2^k in [2^10, 2^11) (1 when g == 0), scale[1] = 2^-k; scratch: 1024 floats
@@ -240,6 +241,7 @@ struct Step2Args {
   long long* prof;         // developer profiling (TMG_STEP2_PROF=1): per-CTA cycle counters per role, else null
   float* d_emit;           // training forward: relu(d1), relu(d2) [B,HW,2] and ...
   float* h_emit;           // ... h [B,HW,C] written for the backward pass (both or neither)
+  unsigned* overflow;      // sticky flag (or null): set when a staged operand left the fp16 range (+-6e4) and was clamped
 };
 int launch_step2(const Step2Args& a, cudaStream_t st);
 bool step2_supported(const Step2Args& a);

@@ -314,6 +314,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
   } else {
     // =========================================================== producers (128 threads): activation K-steps
     const int ptid = tid - 11 * 32;
+    bool ovf = false;
     CvTileIt it;
     it.init(blockIdx.x, tiles_img);
     int ja = 0;
@@ -373,16 +374,21 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
           for (int q = 0; q < 2; ++q) {
             if (pos[q] < 0) continue;
             uint32_t ph[4], pl[4];
+            float umax = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float y0 = fminf(v[q][2 * e] * isc, 60000.f), y1 = fminf(v[q][2 * e + 1] * isc, 60000.f);
-              y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
+              const float u0 = v[q][2 * e] * isc, u1 = v[q][2 * e + 1] * isc;
+              const float lo_ = relu[q] ? 0.f : -60000.f;
+              umax = fmaxf(umax, relu[q] ? fmaxf(u0, u1) : fmaxf(fabsf(u0), fabsf(u1)));      // overflow detection: one compare per unit
+              float y0 = fminf(u0, 60000.f), y1 = fminf(u1, 60000.f);
+              y0 = fmaxf(y0, lo_); y1 = fmaxf(y1, lo_);
               const __half2 h2 = __floats2half2_rn(y0, y1);
               const float2 hf = __half22float2(h2);
               const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
               ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
               pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
             }
+            ovf = ovf || umax > 60000.f;
             uint8_t* dst = Ab + (size_t)pln[q] * kCvPLB + (size_t)pos[q] * 16;
             *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
             if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -392,6 +398,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
         mbar_arrive(a_full + ua);
       }
     }
+    if (ovf && a.overflow) atomicOr(a.overflow, 1u);       // an operand left the fp16 range and was clamped: sticky flag
   }
 
   tc_fence_before();

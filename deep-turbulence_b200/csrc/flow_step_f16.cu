@@ -575,6 +575,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
   } else {
     // =========================================================== producers (128 threads): stage relu(t) as fp16 hi/lo
     const int ptid = tid - kProdWarp * 32;
+    bool ovf = false;
     const int npl0 = 2 * g.KSy;
     const int nsrc1 = g.KS - g.KSy;
     TileIt it;
@@ -635,9 +636,12 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
           for (int q = 0; q < 4; ++q) {
             if (pos[q] < 0) continue;
             uint32_t ph[4], pl[4];
+            float umax = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float y0 = fminf(v[q][2 * e], 60000.f), y1 = fminf(v[q][2 * e + 1], 60000.f);
+              const float u0 = v[q][2 * e], u1 = v[q][2 * e + 1];
+              umax = fmaxf(umax, relu[q] ? fmaxf(u0, u1) : fmaxf(fabsf(u0), fabsf(u1)));      // overflow detection: one compare per unit
+              float y0 = fminf(u0, 60000.f), y1 = fminf(u1, 60000.f);
               y0 = fmaxf(y0, relu[q] ? 0.f : -60000.f); y1 = fmaxf(y1, relu[q] ? 0.f : -60000.f);
               const __half2 h2 = __floats2half2_rn(y0, y1);
               const float2 hf = __half22float2(h2);
@@ -645,6 +649,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
               ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
               pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
             }
+            ovf = ovf || umax > 60000.f;
             // the d slots (last 32-bit word of their plane) are owned by the epilogue warps
             uint8_t* dst = Ab + (size_t)lpl[q] * kPLB + (size_t)pos[q] * 16;
             if (hasd[q]) {
@@ -666,6 +671,7 @@ flow_step_f16_kernel(Step2Args a, Step2Geom g) {
       }
     }
     if (ptid == 0) { PROF_FLUSH(16) }
+    if (ovf && a.overflow) atomicOr(a.overflow, 1u);       // an operand left the fp16 range and was clamped: sticky flag
   }
 
   tc_fence_before();

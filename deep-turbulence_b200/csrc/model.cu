@@ -613,7 +613,7 @@ static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int ns
     t.wpk = c.Q() + w.w_pack_f16; t.inv_scale = c.Q() + w.inv_f16; t.npad = w.NP;
     t.bias = a.bias; t.gain = a.gain; t.act = act;
     t.out = out; t.out_cstride = out_cstride; t.out_coff = out_coff; t.cout = w.O;
-    t.B = B; t.H = Hin; t.W = Win; t.pad_replicate = a.pad_replicate; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+    t.B = B; t.H = Hin; t.W = Win; t.pad_replicate = a.pad_replicate; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
     if (match && convf16_supported(t)) {
       const double M = (double)B * Hin * Win;
       ProfScope ps(c.st, tag, 2.0 * M * w.O * 9.0 * w.I, 4.0 * ((double)B * Hin * Win * w.I + M * w.O));
@@ -696,7 +696,7 @@ static int run_encoder(Ctx& c, const float* x, bool bn_train, float bn_momentum 
       t.src[0] = sc; t.nsrc = 1;
       t.wpk = c.Q() + w.w_pack_f16; t.inv_scale = c.Q() + w.inv_f16; t.npad = w.NP; t.cout = w.O;
       t.out = out; t.out_cstride = cstride; t.out_coff = 0;
-      t.B = B; t.H = eh; t.W = ew; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+      t.B = B; t.H = eh; t.W = ew; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
       if (!convf16_supported(t)) return 0;
       const double M = (double)B * eh * ew;
       ProfScope ps(c.st, PROF_CONV_ENC, 2.0 * M * w.O * 9.0 * w.I, 4.0 * M * (w.I + w.O));
@@ -756,7 +756,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       t.nsrc = 3; (void)ns;
       t.wpk = c.Q() + s.gate.w_pack_f16; t.inv_scale = c.Q() + s.gate.inv_f16; t.npad = s.gate.NP;
       t.bias = c.P() + s.gate.b_param; t.cout = s.gate.O;
-      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
       t.lstm_R = R; t.c_prev = c_in; t.h_out = h_out; t.c_out = c_out;
       if (convf16_supported(t)) {
         const double M = (double)B * Hl * Wl;
@@ -773,7 +773,7 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       t.wpk = c.Q() + s.outc.w_pack_f16; t.inv_scale = c.Q() + s.outc.inv_f16; t.npad = s.outc.NP;
       t.bias = c.P() + s.outc.b_param; t.cout = s.outc.O; t.act = 1;
       t.out = ws + p.u0; t.out_cstride = u0s_f; t.out_coff = 0;
-      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
       if (s.outc.w_pack_f16 >= 0 && convf16_supported(t)) {
         const double M = (double)B * Hl * Wl;
         ProfScope ps(c.st, PROF_CONV_OUT, 2.0 * M * s.outc.O * 9.0 * s.outc.I, 4.0 * (M * s.outc.I + M * s.outc.O));
@@ -882,6 +882,7 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
     a.reverse = reverse ? 1 : 0;
     a.ld_part = ld_slot; a.ld_stride = c.p.nslots * c.p.ctas;
     a.B = B; a.H = Hl; a.W = Wl; a.x3 = prec_split(c.m.precision) ? 1 : 0;
+    a.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
     if (st.kind != STEP_LSTM && c.emit_d && c.emit_h) { a.d_emit = c.emit_d; a.h_emit = c.emit_h; }
     if (step2_supported(a)) {
       if (st.kind == STEP_LSTM) TMG_TRY(run_coupling_nn(c, level, st, B, Hl, Wl, Y, cond, h_in, c_in, h_out, c_out, true));
@@ -938,7 +939,7 @@ static int run_split_prior(Ctx& c, int level, int B, int Hl, int Wl, const float
     t.wpk = c.Q() + lv.split.w_pack_f16; t.inv_scale = c.Q() + lv.split.inv_f16; t.npad = lv.split.NP;
     t.bias = c.P() + lv.split.b_param; t.gain = c.Q() + lv.split_gain; t.act = 2; t.cout = lv.split.O;
     t.out = c.ws + c.p.hr; t.out_cstride = lv.C; t.out_coff = 0;
-    t.B = B; t.H = Hl; t.W = Wl; t.pad_replicate = 1; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+    t.B = B; t.H = Hl; t.W = Wl; t.pad_replicate = 1; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
     if (convf16_supported(t)) {
       const double M = (double)B * Hl * Wl;
       ProfScope ps(c.st, PROF_CONV_SPLIT, 2.0 * M * lv.split.O * 9.0 * lv.split.I, 4.0 * (M * lv.split.I + M * lv.split.O));
@@ -970,7 +971,7 @@ static int run_hoist(Ctx& c) {
           t.out = c.ws + (kind ? c.p.hc_all[l] : c.p.dc_all[l]);
           t.out_cstride = kind ? lv.hoist_oph : lv.hoist_opd; t.out_coff = hc.col0;
           t.B = c.p.B; t.H = c.p.Hl[l]; t.W = c.p.Wl[l]; t.pad_replicate = kind;
-          t.x3 = prec_split(c.m.precision) ? 1 : 0;
+          t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
           if (!convf16_supported(t)) { set_error("hoisted conditioning conv: unsupported shape"); return TMG_ERR_UNSUPPORTED; }
           const double M = (double)t.B * t.H * t.W;
           ProfScope ps(c.st, PROF_MISC, 2.0 * M * cw.O * 9.0 * cw.I, 4.0 * M * (cw.I + cw.O));
@@ -1105,6 +1106,22 @@ int tmg_model_set_precision(tmg_model* m, int mode) {
   return TMG_OK;
 }
 int tmg_model_get_precision(const tmg_model* m) { return m ? m->precision : -1; }
+
+// Sticky overflow flag of the fp16-operand kernels (modes f16x3 / f16): the fp32 activations are clamped to +-6e4 when they
+// are split into fp16 hi/lo halves; a clamp that actually changed a value -- outside the reference's semantics, it means
+// ill-conditioned weights -- raises the flag.  Synchronises the stream.  Returns 1 (and sets tmg_last_error) when raised.
+int tmg_model_overflow(tmg_model* m, int clear, void* stream) {
+  if (!m) { set_error("null model"); return TMG_ERR_NULL; }
+  if (!m->sync_dev) return 0;
+  unsigned v = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  TMG_CUDA_OK(cudaMemcpyAsync(&v, m->sync_dev + 32, sizeof(v), cudaMemcpyDeviceToHost, st));
+  TMG_CUDA_OK(cudaStreamSynchronize(st));
+  if (v && clear) TMG_CUDA_OK(cudaMemsetAsync(m->sync_dev + 32, 0, sizeof(unsigned), st));
+  if (v) set_error("an activation exceeded the fp16 operand range (|v| > 6e4) and was clamped: results are outside the "
+                   "reference's fp32 semantics (ill-conditioned weights?); use precision \"fp32\"");
+  return v ? 1 : 0;
+}
 
 int64_t tmg_model_param_entries(const tmg_model* m) { return m ? (int64_t)m->entries.size() : 0; }
 const char* tmg_model_param_name(const tmg_model* m, int64_t i) {
@@ -1757,7 +1774,7 @@ static int conv_backward(Ctx& c, int B, int Hl, int Wl, const ConvW& w, int nsrc
     ConvF16Args t{};
     t.src[0] = ConvSrc{g, g_cs, g_co, w.O, 0}; t.nsrc = 1;
     t.wpk = c.Q() + w.w_pack_f16t; t.inv_scale = c.Q() + w.inv_f16t; t.npad = w.NPt; t.cout = w.I;
-    t.B = B; t.H = Hl; t.W = Wl; t.pad_replicate = 0; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+    t.B = B; t.H = Hl; t.W = Wl; t.pad_replicate = 0; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
     t.in_scale = gscale;
     t.ndst = ndest;
     int tot = 0;

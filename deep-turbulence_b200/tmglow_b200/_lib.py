@@ -50,6 +50,7 @@ SIGNATURES = {
     "tmg_conv3x3_wgrad_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "tmg_flow_step_backward_workspace_bytes": (_SZ, [_P, _I, _I, _I, _I]),
     "tmg_flow_step_backward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "tmg_model_overflow": (_I, [_P, _I, _P]),
     "tmg_model_param_entries": (_I64, [_P]),
     "tmg_model_param_name": (C.c_char_p, [_P, _I64]),
     "tmg_model_param_offset": (_I64, [_P, _I64]),

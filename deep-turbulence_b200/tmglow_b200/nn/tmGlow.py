@@ -651,6 +651,23 @@ class TMGlow(nn.Module):
             self._bump_bn_counters()
         return z_out, c_out
 
+    def activation_overflow(self, clear=True):
+        """True when a kernel of the fp16-operand modes (``f16x3`` / ``f16``) had to clamp an activation to the fp16 range
+        (|v| > 6e4) since the flag was last cleared -- the result then deviates from the reference's fp32 arithmetic
+        (ill-conditioned weights; rerun in ``precision = "fp32"``).  Synchronises the device."""
+        device = next(self.parameters()).device
+        lib, h = self._prepare(device)
+        with torch.cuda.device(device):
+            r = lib.tmg_model_overflow(h, int(clear), torch.cuda.current_stream(device).cuda_stream)
+        if r < 0:
+            _lib.check(r)
+        return r == 1
+
+    def check_overflow(self):
+        """Raises ``FloatingPointError`` (text of ``tmg_last_error``) when ``activation_overflow()``."""
+        if self.activation_overflow(clear=True):
+            raise FloatingPointError(_lib.load().tmg_last_error().decode("utf-8", "replace"))
+
     def _num_parameters(self):
         """Number of trainable parameters (reference nn/tmGlow.py:469-479)."""
         return sum(p.numel() for p in self.parameters())

@@ -91,6 +91,12 @@ void tmg_model_destroy(tmg_model* m);
 int tmg_model_set_precision(tmg_model* m, int mode);
 int tmg_model_get_precision(const tmg_model* m);
 
+/* Sticky overflow flag of the fp16-operand modes (TMG_PREC_F16X3 / TMG_PREC_F16): activations are staged as fp16 hi/lo halves
+ * and clamped to +-6e4; a clamp that changed a value (never with well-conditioned weights; the reference would carry the value
+ * in fp32) raises the flag.  Returns 1 when raised (text in tmg_last_error), 0 otherwise, < 0 on error; `clear` resets it.
+ * Synchronises `stream`. */
+int tmg_model_overflow(tmg_model* m, int clear, void* stream);
+
 /* Parameter table: the flat fp32 parameter buffer holds every floating-point state_dict entry
  * (parameters AND buffers, reference names) back to back in the order reported here. */
 int64_t     tmg_model_param_entries(const tmg_model* m);

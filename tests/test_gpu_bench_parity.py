@@ -148,3 +148,30 @@ def test_shared_input_many_samples_vs_oracle(S):
     for l, (a, c) in enumerate(hh):
         assert (a[pick.to(dev)].cpu() - h[l][0]).abs().max().item() < 2e-4
         assert (c[pick.to(dev)].cpu() - h[l][1]).abs().max().item() < 2e-4
+
+
+def test_fp16_operand_overflow_is_flagged_not_silent():
+    """The fp16-operand modes clamp staged activations to +-6e4 (the reference carries them in fp32): the clamp must not be
+    silent.  Well-conditioned inputs leave the sticky flag clear; a latent blown up far beyond the fp16 range raises it, is
+    reported through tmg_last_error (check_overflow -> FloatingPointError) and clears on request."""
+    import json
+    from conftest import load_golden
+    from tmglow_b200 import TMGlow
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    m.load_state_dict(g["state_dict"])
+    dev = _dev()
+    m = m.to(dev).eval()
+    m.precision = "f16x3"
+    h_in = [(a.to(dev), c.to(dev)) for a, c in g["h_in"]]
+    eps = [e.to(dev) for e in g["rec2"]["eps"]]
+    m.reconstruct(g["x"].to(dev), h_in, eps)
+    assert m.activation_overflow() is False
+    m.reconstruct(g["x"].to(dev), h_in, [e * 1e7 for e in eps])
+    assert m.activation_overflow(clear=False) is True
+    with pytest.raises(FloatingPointError):
+        m.check_overflow()
+    assert m.activation_overflow() is False          # cleared
