@@ -58,8 +58,13 @@ def mix_states(states, key, weight=0.5):
 def sample_sequence(model, x_seq: torch.Tensor, samples: int, *, base_seed: int = 0, sequence: int = 0,
                     state_mix_every: int = 10, rank: int = 0, world: int = 1, group=None,
                     unnormalise: bool = True, keep_samples: bool = False,
-                    sampler: Optional[Callable] = None, init_states: Optional[Callable] = None):
+                    sampler: Optional[Callable] = None, init_states: Optional[Callable] = None,
+                    key_states: Optional[list] = None):
     """S stochastic HF samples of one LF sequence ``x_seq [T, nic, h, w]``.
+
+    ``key_states``: this rank's initial LSTM states when the caller prepared them ahead of time (``initLSTMStates`` is the
+    reference's seeded HOST generator, one per sample: seconds of CPU time for thousands of samples); default: drawn here
+    from ``sample_seeds`` of the rank's global sample indices.
 
     Returns ``(mean [T,C,H,W], var [T,C,H,W], n_total, samples or None)``; ``samples`` ([S_rank,T,C,H,W], this rank's
     shard) only when ``keep_samples``.  ``sampler(x, h) -> (y, log_det, h)`` and ``init_states(seeds, [H,W])`` default
@@ -85,7 +90,7 @@ def sample_sequence(model, x_seq: torch.Tensor, samples: int, *, base_seed: int 
     if S > 0:
         up = getattr(getattr(model, "_cfg", None), "cglow_upscale", None)
         H, W = (x_seq.shape[-2] * up, x_seq.shape[-1] * up) if up else (None, None)
-        key = init_states(sample_seeds(base_seed, sequence, lo, hi), [H, W])
+        key = key_states if key_states is not None else init_states(sample_seeds(base_seed, sequence, lo, hi), [H, W])
         h = key
     for t in range(T):
         if S > 0:
@@ -158,3 +163,70 @@ def test_error(model, input_seq: torch.Tensor, target_seq: torch.Tensor, samples
     ``ntest * tmax * H * W`` (``:377``).  ``target_seq [B, >= tmax + 1, C, H, W]`` already un-normalised."""
     yp = model_pred(model, input_seq, samples, tmax + 1, state_mix_every=kw.pop("state_mix_every", 10), **kw)
     return torch.pow(yp[:, :, 1:tmax + 1].mean(0) - target_seq[:, 1:tmax + 1], 2).sum()
+
+
+class GraphedSampler:
+    """``model.sample`` captured once as CUDA graphs and replayed (reference loop: the 48 flow steps of
+    ``LSTMCFlowDecoder.reverse``, nn/tmGlow.py:269-303, called once per time step by every prediction loop).  One replay =
+    one ``cudaGraphLaunch`` instead of ~100 kernel launches plus the Python work of a call -- what bounds the latency of a
+    small batch.  The ConvLSTM states chain from call to call inside the object (two graphs ping-pong between two state
+    buffers, so no state is ever copied); the noise is drawn inside the graph (graph-safe CUDA generator: fresh draws every
+    replay, same distribution and order as ``sample``).
+
+    ``x``: the LF input of the first call -- ``[B,nic,h,w]``, or a batch-expanded view ``x1.expand(S, ...)`` for S samples
+    of one input (shared-input fast path).  ``sample(x_new)`` copies ``x_new`` (same shape; for the shared case ``[1,nic,h,w]``)
+    into the static input and replays; it returns ``(y, log_det, states)`` -- STATIC tensors, overwritten by the next call.
+    ``states`` / ``set_states`` give access to the carried LSTM states (e.g. for the reference's periodic state mixing)."""
+
+    def __init__(self, model, x, h_in, warmup=2):
+        assert not model.training, "GraphedSampler is an inference tool (eval mode)"
+        self.model = model
+        dev = x.device
+        shared = x.dim() == 4 and x.shape[0] > 1 and x.stride(0) == 0
+        self._S = x.shape[0]
+        self._shared = shared
+        self._x = (x[:1] if shared else x).detach().clone()
+        cl = lambda t: t.detach().clone(memory_format=torch.channels_last) if t.dim() == 4 else t.detach().clone()
+        self._h = [[(cl(a), cl(c)) for a, c in h_in], None]
+        self._cur = 0
+        self.replays = 0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):
+                y, ld, h1 = model.sample(self._xin(), self._h[0])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._h[1] = [(torch.empty_like(a), torch.empty_like(c)) for a, c in h1]
+        self._g, self._out = [], []
+        pool = None
+        for k in (0, 1):                    # graph k reads state buffer k and leaves the new states in buffer 1 - k
+            g = torch.cuda.CUDAGraph()
+            with torch.no_grad(), (torch.cuda.graph(g) if pool is None else torch.cuda.graph(g, pool=pool)):
+                y, ld, hn = model.sample(self._xin(), self._h[k])
+                for (dh, dc), (sh, sc) in zip(self._h[1 - k], hn):
+                    dh.copy_(sh); dc.copy_(sc)
+            pool = g.pool()
+            self._g.append(g); self._out.append((y, ld))
+
+    def _xin(self):
+        return self._x.expand(self._S, -1, -1, -1) if self._shared else self._x
+
+    @property
+    def states(self):
+        return self._h[self._cur]
+
+    def set_states(self, h):
+        for (dh, dc), (sh, sc) in zip(self._h[self._cur], h):
+            dh.copy_(sh); dc.copy_(sc)
+
+    @torch.no_grad()
+    def sample(self, x=None):
+        if x is not None:
+            self._x.copy_(x[:1] if (self._shared and x.shape[0] != 1) else x, non_blocking=True)
+        k = self._cur
+        self._g[k].replay()
+        self._cur = 1 - k
+        self.replays += 1
+        y, ld = self._out[k]
+        return y, ld, self._h[self._cur]
