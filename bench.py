@@ -743,6 +743,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=64)
     ap.add_argument("--tback", type=int, default=10)
     ap.add_argument("--ref-train-batch", type=int, default=4, help="batch of the CPU training baseline (bounded sample)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the small-batch eager vs CUDA-graph latency leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed configuration")
     ap.add_argument("--no-train", action="store_true", help="skip the short training measurement of the default line")
     ap.add_argument("--train-steps", type=int, default=10, help="timed optimizer steps of the training legs of the default line")
@@ -906,6 +907,40 @@ def main():
                 "tolerance": "5e-2 abs on fields, 1e-3 rel on log_det (fp32-grade modes: 2e-4 / 1e-5)"}
         model.precision = args.precision
 
+    # ---------------- small-batch latency: 64 DISTINCT LF inputs per call, eager launches vs one CUDA-graph replay
+    # (uq.GraphedSampler: ~100 launches + the Python work of a call become one cudaGraphLaunch)
+    latency = None
+    if rank == 0 and not args.no_latency:
+        from tmglow_b200 import uq
+        Bq = 64
+        xq = torch.randn(Bq, GEOM["nic"], GEOM["h"], GEOM["w"], generator=torch.Generator().manual_seed(9)).to(dev)
+        hq = model.initLSTMStates(torch.arange(Bq), [GEOM["H"], GEOM["W"]])
+        stq = {"h": hq}
+
+        def eager_call():
+            yq, lq, stq["h"] = model.sample(xq, stq["h"])
+        for _ in range(5):
+            eager_call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(30):
+            eager_call()
+        torch.cuda.synchronize()
+        eager_ms = (time.perf_counter() - t0) / 30 * 1e3
+        gsamp = uq.GraphedSampler(model, xq, hq)
+        for _ in range(5):
+            gsamp.sample()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(30):
+            gsamp.sample()
+        torch.cuda.synchronize()
+        graph_ms = (time.perf_counter() - t0) / 30 * 1e3
+        latency = {"batch": Bq, "inputs": "distinct", "eager_ms_per_call": eager_ms, "graph_ms_per_call": graph_ms,
+                   "graph_replays": gsamp.replays, "samples_per_sec_graph": Bq / (graph_ms * 1e-3),
+                   "note": "wall clock per sample() call incl. host work, 30 calls after 5 warm-ups, synchronised at both ends"}
+        del gsamp, xq, hq, stq
+
     # ---------------- per-kernel-class device times (CUDA events on the launching stream)
     pk = peaks()
     roof, roof_tensor, classes = None, None, []
@@ -1004,7 +1039,7 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": dict(workload_config(S, world), precision=args.precision),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "parity_checked": bool(parity and parity["checked"]), "parity": parity,
+            "parity_checked": bool(parity and parity["checked"]), "parity": parity, "latency_small_batch": latency,
             "roofline": roof, "roofline_tensor": roof_tensor, "cpu_baseline": cpu, "fast_mode": fast, "train": train, "train_weak": train_weak,
             "whole_path": {"alg_tflops": value * ALG_FLOP_PER_SAMPLE / 1e12 / world,
                            "alg_gbs": value * ALG_BYTES_PER_SAMPLE / 1e9 / world, "per": "GPU"},

@@ -178,9 +178,12 @@ class GraphedSampler:
     into the static input and replays; it returns ``(y, log_det, states)`` -- STATIC tensors, overwritten by the next call.
     ``states`` / ``set_states`` give access to the carried LSTM states (e.g. for the reference's periodic state mixing)."""
 
-    def __init__(self, model, x, h_in, warmup=2):
+    def __init__(self, model, x, h_in, warmup=2, eps=None):
+        """``eps``: optional explicit noise (list as ``reconstruct`` takes it): the graphs then replay ``model.reconstruct`` on
+        static noise buffers that ``sample(eps=...)`` refreshes -- deterministic, bit-comparable with the eager call."""
         assert not model.training, "GraphedSampler is an inference tool (eval mode)"
         self.model = model
+        self._eps = [e.detach().clone() for e in eps] if eps is not None else None
         dev = x.device
         shared = x.dim() == 4 and x.shape[0] > 1 and x.stride(0) == 0
         self._S = x.shape[0]
@@ -194,7 +197,7 @@ class GraphedSampler:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(max(warmup, 1)):
-                y, ld, h1 = model.sample(self._xin(), self._h[0])
+                y, ld, h1 = self._call(self._h[0])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._h[1] = [(torch.empty_like(a), torch.empty_like(c)) for a, c in h1]
@@ -203,11 +206,16 @@ class GraphedSampler:
         for k in (0, 1):                    # graph k reads state buffer k and leaves the new states in buffer 1 - k
             g = torch.cuda.CUDAGraph()
             with torch.no_grad(), (torch.cuda.graph(g) if pool is None else torch.cuda.graph(g, pool=pool)):
-                y, ld, hn = model.sample(self._xin(), self._h[k])
+                y, ld, hn = self._call(self._h[k])
                 for (dh, dc), (sh, sc) in zip(self._h[1 - k], hn):
                     dh.copy_(sh); dc.copy_(sc)
             pool = g.pool()
             self._g.append(g); self._out.append((y, ld))
+
+    def _call(self, h):
+        if self._eps is not None:
+            return self.model.reconstruct(self._xin(), h, self._eps)
+        return self.model.sample(self._xin(), h)
 
     def _xin(self):
         return self._x.expand(self._S, -1, -1, -1) if self._shared else self._x
@@ -221,7 +229,10 @@ class GraphedSampler:
             dh.copy_(sh); dc.copy_(sc)
 
     @torch.no_grad()
-    def sample(self, x=None):
+    def sample(self, x=None, eps=None):
+        if eps is not None:
+            for d, e in zip(self._eps, eps):
+                d.copy_(e, non_blocking=True)
         if x is not None:
             self._x.copy_(x[:1] if (self._shared and x.shape[0] != 1) else x, non_blocking=True)
         k = self._cur

@@ -82,3 +82,43 @@ def test_replicate_and_one_thread_per_device(precision):
     outs = _parallel_apply(replicas, [(i[0], i[1]) for i in inputs], devices, "sample")
     for (lo, hi), (y, ld, h) in zip(cuts, outs):
         assert tuple(y.shape) == (hi - lo,) + tuple(y_o.shape[1:]) and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_graphed_sampler_replays_equal_eager_calls(shared):
+    """uq.GraphedSampler: the whole sample()/reconstruct() call captured as CUDA graphs (two graphs ping-pong between two LSTM
+    state buffers).  With explicit noise the replays must reproduce the eager calls bit for bit over several chained time
+    steps (same kernels, same order); with internal noise the states chain and every replay draws fresh noise."""
+    from tmglow_b200 import TMGlow, uq
+    g = load_golden("caseA_states")
+    cfg = json.loads(g["config"])
+    m = TMGlow(cfg["in_features"], cfg["out_features"], cfg["enc_blocks"], cfg["glow_blocks"],
+               cond_features=cfg["cond_features"], cglow_upscale=cfg["cglow_upscale"], growth_rate=cfg["growth_rate"],
+               init_features=cfg["init_features"], rec_features=cfg["rec_features"])
+    m.load_state_dict(g["state_dict"])
+    dev = torch.device("cuda:0")
+    m = m.to(dev).eval()
+    m.precision = "f16x3"
+    B = g["x"].shape[0]
+    x = g["x"].to(dev)
+    xs = [x[:1].expand(B, -1, -1, -1) if shared else x, (1.3 * x[:1]).expand(B, -1, -1, -1) if shared else 1.3 * x, 0.7 * x[:1] if shared else 0.7 * x]
+    if shared:
+        xs[2] = xs[2].expand(B, -1, -1, -1)
+    h0 = [(a.to(dev), c.to(dev)) for a, c in g["h_in"]]
+    eps = [[(e * (1.0 + 0.2 * t)).to(dev) for e in g["rec2"]["eps"]] for t in range(3)]
+    ref, h = [], h0
+    for t in range(3):
+        y, ld, h = m.reconstruct(xs[t], h, eps[t])
+        ref.append((y.clone(), ld.clone()))
+    gs = uq.GraphedSampler(m, xs[0], h0, eps=eps[0])
+    gs.set_states(h0)                                   # the warm-up calls advanced nothing: states restart from h0
+    for t in range(3):
+        y, ld, hs = gs.sample(xs[t][:1] if shared else xs[t], eps=eps[t])
+        assert torch.equal(y, ref[t][0]) and torch.equal(ld, ref[t][1])
+    for (a, c), (ar, cr) in zip(hs, h):
+        assert torch.equal(a, ar) and torch.equal(c, cr)
+    assert gs.replays == 3
+    gn = uq.GraphedSampler(m, xs[0], h0)                # internal noise
+    y1 = gn.sample()[0].clone()
+    y2 = gn.sample()[0].clone()
+    assert torch.isfinite(y1).all() and torch.isfinite(y2).all() and not torch.equal(y1, y2)
