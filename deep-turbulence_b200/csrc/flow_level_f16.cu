@@ -89,6 +89,15 @@ __device__ __forceinline__ void lv_split2(float y0, float y1, uint32_t& hi, uint
 #define LVP_FLUSH(base)
 #endif
 
+// packed fp32 FMA (FFMA2 on sm_100a): (d.x, d.y) = (a.x, a.y) * (b, b) + (c.x, c.y) -- two outputs of the 1x1 mix per issue slot
+__device__ __forceinline__ float2 lv_ffma2(float2 a, float b, float2 c) {
+  const float2 bb = make_float2(b, b);
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a), rb = *reinterpret_cast<const unsigned long long*>(&bb),
+                     rc = *reinterpret_cast<const unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // flag bits of an owned position
 constexpr uint32_t kFValid = 1u, kFLeft = 2u, kFRight = 4u, kFTop = 8u, kFBottom = 16u, kFOk = 32u;   // bits 8..: sample in the pass
 
@@ -487,18 +496,27 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
             if (OKJ(j)) {
               ldacc[j] += ldsum;
               // u = W v, out = (u - nb) / nw     (glowConv.py:219, actNorm.py:82)
+              // (W is staged TRANSPOSED, Wt[k][r]: four consecutive outputs of one input channel per 16-byte load, two
+              // outputs per packed FMA; C/2 independent accumulation chains)
+              float2 acc2[C / 2];
+#pragma unroll
+              for (int r2 = 0; r2 < C / 2; ++r2) acc2[r2] = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < C; ++k) {
+                const float4* w4 = reinterpret_cast<const float4*>(sm + k * C);
+                const float vk = v[k];
+#pragma unroll
+                for (int r4 = 0; r4 < C / 4; ++r4) {
+                  const float4 w = w4[r4];
+                  acc2[2 * r4] = lv_ffma2(make_float2(w.x, w.y), vk, acc2[2 * r4]);
+                  acc2[2 * r4 + 1] = lv_ffma2(make_float2(w.z, w.w), vk, acc2[2 * r4 + 1]);
+                }
+              }
               float o[C];
 #pragma unroll
-              for (int r = 0; r < C; ++r) {
-                const float4* w4 = reinterpret_cast<const float4*>(sm + r * C);
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int kk = 0; kk < C / 4; ++kk) {
-                  const float4 w = w4[kk];
-                  if (kk & 1) { s1 = fmaf(w.x, v[4 * kk], s1); s1 = fmaf(w.y, v[4 * kk + 1], s1); s1 = fmaf(w.z, v[4 * kk + 2], s1); s1 = fmaf(w.w, v[4 * kk + 3], s1); }
-                  else { s0 = fmaf(w.x, v[4 * kk], s0); s0 = fmaf(w.y, v[4 * kk + 1], s0); s0 = fmaf(w.z, v[4 * kk + 2], s0); s0 = fmaf(w.w, v[4 * kk + 3], s0); }
-                }
-                o[r] = ((s0 + s1) - s_nb[r]) * s_rnw[r];
+              for (int r2 = 0; r2 < C / 2; ++r2) {
+                o[2 * r2] = (acc2[r2].x - s_nb[2 * r2]) * s_rnw[2 * r2];
+                o[2 * r2 + 1] = (acc2[r2].y - s_nb[2 * r2 + 1]) * s_rnw[2 * r2 + 1];
               }
 #pragma unroll
               for (int r = 0; r < NSR; ++r) st[j][r] = o[r];
@@ -569,7 +587,7 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
         if (gs >= 2) mbar_wait_sleep(we_free + stg, (uint32_t)(((gs >> 1) - 1) & 1));
         float* sm = reinterpret_cast<float*>(SM + (size_t)stg * g.sm_stage);
         const int64_t oW = S->W, oNw = S->nw, oNb = S->nb, oB = S->bias, oM = S->misc, oG = S->gain;
-        for (int i = lane; i < CC; i += 32) sm[i] = __ldg(a.packed + oW + i);
+        for (int i = lane; i < CC; i += 32) sm[(i % C) * C + i / C] = __ldg(a.packed + oW + i);      // Wt[k][r] = W[r][k]
         for (int i = lane; i < C; i += 32) {
           const float nw = oNw >= 0 ? __ldg(a.params + oNw + i) : 1.f;
           sm[CC + i] = nw;
