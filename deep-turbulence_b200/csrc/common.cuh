@@ -173,6 +173,8 @@ struct ConvF16Args {
   int ndst;                // > 0: the output columns are routed to up to 3 destinations (the sources of the forward
   ConvDst dst[3];          // conv), each optionally gated by the sign of the forward input and accumulated
   unsigned* overflow;      // sticky flag (or null): set when a staged operand left the fp16 range (+-6e4) and was clamped
+  const float* addend;     // optional per-pixel term added before bias / activation: [H*W][addend_stride], the SAME for every
+  int addend_stride;       // sample (conditioning contribution hoisted out of the convolution when all samples share one input)
 };
 int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st);
 // scale[0] = 2^k with max|g| * 2^k in [2^10, 2^11) (1 when g == 0), scale[1] = 2^-k; scratch: 1024 floats
@@ -532,7 +534,7 @@ int gauss_bwd_blocks(int B, int HW);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
-                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10, JOB_STEP2C = 11 };
+                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10, JOB_STEP2C = 11, JOB_SLICE = 12 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n

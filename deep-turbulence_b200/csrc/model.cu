@@ -87,6 +87,11 @@ struct StepW {
   int64_t s2_wE = -1, s2_wZ = -1, s2_misc = -1;
   int s2_nch0 = 0, s2_nch1 = 0;
   int64_t s2c_wE = -1, s2c_wZ = -1;   // compact / tap-paired variant for the level-resident kernel (narrow levels)
+  // LSTM step, one LF input shared by all samples: gate / output convolutions WITHOUT their conditioning rows (fp16 packing
+  // over the sources [x1 | h]) + the conditioning rows as tap-major fp32 slices for the once-per-call hoisted tables
+  ConvW gate_nc, outc_nc;
+  int64_t gate_hw = -1, outc_hw = -1;
+  int gate_hop = 0, outc_hop = 0;
   // parameter offsets needed by the backward pass
   int64_t lu[8] = {-1, -1, -1, -1, -1, -1, -1, -1};     // l, u, log_s, p, sign_s, l_mask, u_mask, eye
   int64_t zc_scale = -1;
@@ -217,6 +222,32 @@ struct Builder {
     for (auto& s : j.src) s = -1;
     j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16; j.dst[1] = c.inv_f16;
     m.jobs.push_back(j);
+  }
+  // fp16 packing of `full` over the sources [first n0 input channels | n1 channels after skipping `skip`]
+  ConvW conv_f16_skip_job(const ConvW& full, int n0, int skip, int n1) {
+    ConvW c = full;
+    c.w_pack = c.w_pack_tc = c.w_pack_f16t = -1;
+    const int nch[3] = {n0, n1, 0};
+    c.NP = tc_npad(c.O);
+    c.f16_nch[0] = n0; c.f16_nch[1] = n1; c.f16_nch[2] = 0;
+    c.w_pack_f16 = pack_alloc((int64_t)convf16_packed_floats(nch, 2, c.NP));
+    c.inv_f16 = pack_alloc(1);
+    PackJob j{};
+    j.type = JOB_CONV_F16; j.a = c.O; j.b = c.I; j.opad = c.NP; j.nch0 = n0; j.nch1 = n1; j.nd = 0; j.part = skip;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16; j.dst[1] = c.inv_f16;
+    m.jobs.push_back(j);
+    return c;
+  }
+  int64_t slice_job(const ConvW& full, int c0, int n, int& op) {
+    op = (full.O + 3) / 4 * 4;
+    const int64_t dst = pack_alloc((int64_t)9 * n * op);
+    PackJob j{};
+    j.type = JOB_SLICE; j.a = full.O; j.b = full.I; j.opad = op; j.nch0 = c0; j.nch1 = n;
+    for (auto& s : j.src) s = -1;
+    j.src[0] = full.w_param; j.dst[0] = dst;
+    m.jobs.push_back(j);
+    return dst;
   }
   void conv_f16t_job(ConvW& c) {             // data-gradient weights: K = O, N = I (each forward source padded to 4 columns)
     if (c.f16_nch[0] + c.f16_nch[1] + c.f16_nch[2] != c.I) return;
@@ -407,6 +438,12 @@ static int build_model(tmg_model& m) {
         B.step2_jobs(st, cin_t, 0, C);
         B.conv_f16_job(st.d1, cin_t, 0, 0); B.conv_f16_job(st.d2, cin_t, 1, 0); B.conv_f16_job(st.zc, cin_t, 2, 0);
         B.conv_f16t_job(st.gate); B.conv_f16t_job(st.outc);
+        if (4 * R <= 256) {
+          st.gate_nc = B.conv_f16_skip_job(st.gate, C / 2, c.cond_features, R);
+          st.gate_hw = B.slice_job(st.gate, C / 2, c.cond_features, st.gate_hop);
+          st.outc_nc = B.conv_f16_skip_job(st.outc, C / 2, c.cond_features, R);
+          st.outc_hw = B.slice_job(st.outc, C / 2, c.cond_features, st.outc_hop);
+        }
       } else {
         st.d1 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer1.conv1", 1, cin_t, false);
         st.d2 = B.conv(sp + "coupling.coupling_nn.dense_block.denselayer2.conv1", 1, cin_t + 1, false);
@@ -494,6 +531,7 @@ struct Plan {
   size_t y[TMG_MAX_LEVELS], y2[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
   size_t dc_all[TMG_MAX_LEVELS], hc_all[TMG_MAX_LEVELS];
   size_t dcT[TMG_MAX_LEVELS], hcT[TMG_MAX_LEVELS];   // the same tables, plane-transposed for the level-resident kernel
+  size_t gc[TMG_MAX_LEVELS], oc[TMG_MAX_LEVELS];     // shared LF input: conditioning part of the ConvLSTM gate / output convs
 };
 
 static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shared = false) {
@@ -531,6 +569,11 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
     p.cond[l] = take(Bx * p.Hl[l] * p.Wl[l] * c.cond_features);
     p.dc_all[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.hoist_opd);
     p.hc_all[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.hoist_oph);
+    {
+      const StepW& ls = lv.steps.back();
+      p.gc[l] = take(shared && ls.gate_hw >= 0 ? (size_t)p.Hl[l] * p.Wl[l] * ls.gate_hop : 16);
+      p.oc[l] = take(shared && ls.outc_hw >= 0 ? (size_t)p.Hl[l] * p.Wl[l] * ls.outc_hop : 16);
+    }
     p.dcT[l] = take(Bx * p.Hl[l] * p.Wl[l] * 2 * lv.steps.size());
     p.hcT[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.C * lv.steps.size());
     p.y[l] = take(Bz * p.Hl[l] * p.Wl[l] * lv.C);
@@ -567,6 +610,11 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
 
 static inline bool prec_tc(int p) { return p != TMG_PREC_FP32; }
 // TMG_NO_RESIDENT=1: one launch per flow step (flow_step_f16.cu) even where the level-resident kernel applies (A/B runs)
+// TMG_NO_LSTM_HOIST=1: keep the conditioning rows inside the ConvLSTM convolutions (A/B runs)
+static inline bool nc_off() {
+  static const bool off = [] { const char* e = getenv("TMG_NO_LSTM_HOIST"); return e && e[0] == '1'; }();
+  return off;
+}
 static inline bool resident_off() {
   static const bool off = [] { const char* e = getenv("TMG_NO_RESIDENT"); return e && e[0] == '1'; }();
   return off;
@@ -748,6 +796,9 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
     ConvSrc gs[3] = {{Y, C, 0, C / 2, 0}, {cond, cf, 0, cf, 0, sh}, {h_in, R, 0, R, 0}};
     bool gate_done = false, out_done = false;
     const int u0s_f = (cin_t + 3) / 4 * 4;
+    // one LF input shared by all samples: the conditioning rows leave the two convolutions (K shrinks by the 32 conditioning
+    // channels: 7 -> 5 K-steps at level 0) and come back as a per-pixel addend evaluated once per call (run_hoist)
+    const bool nc = sh && c.hoist_ready && s.gate_nc.w_pack_f16 >= 0 && s.gate_hw >= 0 && !c.unfused && !nc_off();
     if (prec_f16(c.m.precision) && s.gate.w_pack_f16 >= 0 && !c.unfused) {
       ConvF16Args t{};
       const int ns = h_in ? 3 : 2;
@@ -755,6 +806,11 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       if (!h_in) t.src[2].p = nullptr;        // zero states: the plane is staged as zeros
       t.nsrc = 3; (void)ns;
       t.wpk = c.Q() + s.gate.w_pack_f16; t.inv_scale = c.Q() + s.gate.inv_f16; t.npad = s.gate.NP;
+      if (nc) {
+        t.src[1] = t.src[2]; t.src[2] = ConvSrc{}; t.nsrc = 2;
+        t.wpk = c.Q() + s.gate_nc.w_pack_f16; t.inv_scale = c.Q() + s.gate_nc.inv_f16;
+        t.addend = ws + p.gc[level]; t.addend_stride = s.gate_hop;
+      }
       t.bias = c.P() + s.gate.b_param; t.cout = s.gate.O;
       t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
       t.lstm_R = R; t.c_prev = c_in; t.h_out = h_out; t.c_out = c_out;
@@ -771,6 +827,11 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
       for (int i = 0; i < 3; ++i) t.src[i] = os2[i];
       t.nsrc = 3;
       t.wpk = c.Q() + s.outc.w_pack_f16; t.inv_scale = c.Q() + s.outc.inv_f16; t.npad = s.outc.NP;
+      if (nc) {
+        t.src[1] = t.src[2]; t.src[2] = ConvSrc{}; t.nsrc = 2;
+        t.wpk = c.Q() + s.outc_nc.w_pack_f16; t.inv_scale = c.Q() + s.outc_nc.inv_f16;
+        t.addend = ws + p.oc[level]; t.addend_stride = s.outc_hop;
+      }
       t.bias = c.P() + s.outc.b_param; t.cout = s.outc.O; t.act = 1;
       t.out = ws + p.u0; t.out_cstride = u0s_f; t.out_coff = 0;
       t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0; t.overflow = c.m.sync_dev ? c.m.sync_dev + 32 : nullptr;
@@ -998,6 +1059,23 @@ static int run_hoist(Ctx& c) {
       ProfScope ps(c.st, PROF_MISC, 2.0 * M * a.cout * 9.0 * a.cin_w, 4.0 * M * (a.cin_w + a.cout));
       TMG_TRY(launch_conv3x3(a, c.st));
     }
+    // conditioning rows of the ConvLSTM gate and output convolutions (zero padding, no ReLU: convLSTM.py:44,129)
+    const StepW& ls = lv.steps.back();
+    if (ls.kind == STEP_LSTM && ls.gate_hw >= 0) {
+      for (int kind = 0; kind < 2; ++kind) {
+        ConvArgs a{};
+        a.src[0] = ConvSrc{c.ws + c.p.cond[l], g.cond_features, 0, g.cond_features, 0, 1};
+        a.nsrc = 1;
+        a.w = c.Q() + (kind ? ls.outc_hw : ls.gate_hw);
+        a.cin_w = g.cond_features; a.cout_w = kind ? ls.outc_hop : ls.gate_hop;
+        a.out = c.ws + (kind ? c.p.oc[l] : c.p.gc[l]);
+        a.out_cstride = a.cout_w; a.out_coff = 0; a.cout = a.cout_w;
+        a.B = 1; a.Hin = c.p.Hl[l]; a.Win = c.p.Wl[l]; a.Hout = a.Hin; a.Wout = a.Win; a.stride = 1;
+        const double M = (double)a.Hin * a.Win;
+        ProfScope ps(c.st, PROF_MISC, 2.0 * M * a.cout * 9.0 * a.cin_w, 4.0 * M * (a.cin_w + a.cout));
+        TMG_TRY(launch_conv3x3(a, c.st));
+      }
+    }
   }
   c.hoist_ready = true;
   return TMG_OK;
@@ -1209,9 +1287,10 @@ int tmg_model_get_conv1x1(const tmg_model* m, int level, int step, int inverse, 
 
 size_t tmg_workspace_bytes(const tmg_model* m, int B, int h, int w) {
   if (!m) return 0;
-  Plan p;
+  Plan p, q;
   if (make_plan(*m, B, h, w, p) != TMG_OK) return 0;
-  return p.total;
+  if (make_plan(*m, B, h, w, q, true) != TMG_OK) return 0;     // TMG_FLAG_SHARED_X: smaller encoder buffers, extra hoisted tables
+  return std::max(p.total, q.total);
 }
 
 int tmg_encoder_forward(tmg_model* m, int B, int h, int w, const float* x, float* const* c_out, float* z_out,

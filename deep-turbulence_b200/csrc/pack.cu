@@ -263,6 +263,7 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       for (int q = 0, base = 0; q < 3; ++q) {
         if (plane >= pl0[q] && plane < pl0[q + 1]) { const int ch = (plane - pl0[q]) * 8 + e; if (ch < nch[q]) c = base + ch; }
         base += nch[q];
+        if (q == 0) base += j.part;          // j.part: input channels skipped after source 0 (conditioning hoisted out of the conv)
       }
       float v = 0.f;
       if (c >= 0 && c < I && n < O) v = w[((size_t)n * I + c) * 9 + tap] * sc;
@@ -270,6 +271,17 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
     }
     if (tid == 0) Q[j.dst[1]] = 1.f / sc;
+  } else if (j.type == JOB_SLICE) {
+    // Input-channel slice [nch0, nch0 + nch1) of an OIHW weight as tap-major fp32 [9][nch1][opad] for conv3x3_ffma: the
+    // conditioning rows of the ConvLSTM gate / output convolutions, whose contribution is the same for every sample of one
+    // low-fidelity input and is evaluated once per call (run_hoist).
+    const int O = j.a, I = j.b, OP = j.opad, c0 = j.nch0, n = j.nch1;
+    const float* w = P + j.src[0];
+    float* d = Q + j.dst[0];
+    for (int i = tid; i < 9 * n * OP; i += blockDim.x) {
+      const int o = i % OP; int t = i / OP; const int c = t % n, tap = t / n;
+      d[i] = o < O ? w[((size_t)o * I + c0 + c) * 9 + tap] : 0.f;
+    }
   } else if (j.type == JOB_CONV_F16_T) {
     // Data-gradient weights for conv3x3_f16.cu: the gradient w.r.t. the input of a 3x3 convolution is the convolution
     // of the output gradient with the transposed, tap-flipped kernel: K = forward output channel o (one source of O
