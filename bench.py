@@ -981,10 +981,11 @@ def main():
                         "unit": "GB/s", "frac": top["gbs"] / pk["hbm"], "traffic": traffic,
                         "peak_source": pk["source"], "share_of_step": top["share"],
                         "avg_launch_ms": top["ms_per_step"] / top["launches_per_step"],
-                        "note": "algorithmic bytes = 4*px*(2C+cond) per step (SURVEY 8d, un-hoisted definition); with one LF "
-                                "input shared by all samples the conditioning map is served from L2 / hoisted tables; traffic = ncu dram bytes of ONE "
-                                "level-0 launch (the largest of the three levels; its algorithmic bytes are 1.88 GB), achieved / avg_launch_ms "
-                                "average over the 48 launches of a step"}
+                        "note": "algorithmic bytes = 4*px*(2C+cond) per flow step (SURVEY 8d, un-hoisted definition) x the steps a launch "
+                                "runs; flow_level_resident = one launch per level with all 15 plain steps, the state resident on the SM: its "
+                                "DRAM traffic (ncu, level-0 launch: 761 MB for 4096 samples = the state read once + written once) is 37x "
+                                "below the algorithmic bytes of the 15 steps it replaces (28.2 GB); achieved / avg_launch_ms average over the "
+                                "launches of the class in a step"}
             gate = [c for c in classes if c["class"] == "conv_lstm_gates"]
             if gate:
                 x3 = args.precision in ("f16x3", "tf32x3")
