@@ -19,6 +19,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 FLAGS = [f for f in FLAGS if not f.startswith("--use_fast_math")]   # IEEE division / accurate expf on purpose
 if os.environ.get("TMG_LV_PROFILE"):                                 # developer build: role cycle counters in flow_level_f16.cu
     FLAGS += ["-DTMG_LV_PROFILE"]
+if os.environ.get("TMG_GT_PROFILE"):                                 # developer build: wait-time counters in lstm_gate_f16.cu
+    FLAGS += ["-DTMG_GT_PROFILE"]
 if os.environ.get("TMG_MBAR_SLEEP"):                                 # experiment: nanosleep back-off in mbarrier waits
     FLAGS += ["-DTMG_MBAR_SLEEP=" + os.environ["TMG_MBAR_SLEEP"]]
 

@@ -186,6 +186,12 @@ int launch_absmax_scale(const float* g, int64_t npix, int cstride, int coff, int
 bool convf16_supported(const ConvF16Args& a);
 int convf16_ksteps(const int* nch, int nsrc);
 size_t convf16_packed_floats(const int* nch, int nsrc, int npad);
+// lstm_gate_f16.cu: ConvLSTM gate conv + cell update as a two-pass N-split implicit GEMM (R = 64).  Same argument block;
+// wpk = JOB_GATE2P packing, addend (optional) = plane-transposed table [4R / 4][H*W] float4 in pass order WITH the bias.
+bool lstm_gate_f16_supported(const ConvF16Args& a);
+int launch_lstm_gate_f16(const ConvF16Args& a, cudaStream_t st);
+size_t lstm_gate_packed_floats(const int* nch, int nsrc);
+int launch_gate_addend_transpose(const float* src, const float* bias, float* dst, int HW, int ncol, int R, cudaStream_t st);
 
 // Fused flow step on tensor cores (coupling_tc.cu): coupling net + coupling + 1x1 + ActNorm + log-det
 struct CouplingArgs {
@@ -534,7 +540,7 @@ int gauss_bwd_blocks(int B, int HW);
 
 // ------------------------------------------------------------------ weight packing jobs
 enum PackJobType { JOB_CONVW = 0, JOB_1X1 = 1, JOB_GAIN = 2, JOB_BN = 3, JOB_CONVW_TC = 4, JOB_CPL_W12 = 5, JOB_CPL_W3 = 6,
-                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10, JOB_STEP2C = 11, JOB_SLICE = 12 };
+                   JOB_STEP2 = 7, JOB_HOIST = 8, JOB_CONV_F16 = 9, JOB_CONV_F16_T = 10, JOB_STEP2C = 11, JOB_SLICE = 12, JOB_GATE2P = 13 };
 struct PackJob {
   int type;
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n

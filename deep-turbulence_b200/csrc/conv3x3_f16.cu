@@ -24,7 +24,7 @@ namespace tmg {
 
 constexpr int kCvRP = 18;                 // staged tile pitch: 16 + 2
 constexpr int kCvNPOS = 324;
-constexpr int kCvNPOSA = 328;
+constexpr int kCvNPOSA = 332;               // plane pitch 5312 B = 16 banks mod 32: the two planes of a K-step do not collide
 constexpr uint32_t kCvPLB = kCvNPOSA * 16;        // bytes of one 8-channel plane of a K-step
 // warps 0-7 epilogue, 8-9 MMA, 10 weights, 11.. producers (NPW warps: 4 when the MMAs dominate (wide N), 8 when the
 // activation staging does (narrow N))
@@ -43,19 +43,6 @@ struct ConvF16Geom {
   int plane0[3];          // first 8-channel plane of each source
   int nplanes[3];
 };
-
-__device__ __forceinline__ uint32_t cv_idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
-__device__ __forceinline__ void cv_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// sigmoid / tanh from ex2.approx + rcp.approx (2 ulp each): abs error ~2e-7, far inside the stated 2e-4
-__device__ __forceinline__ float fast_sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 struct CvTileIt {
   int b, timg;
@@ -244,7 +231,6 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
             tmem_ld16(trow + n0, v);
             if (valid) {
               float* op = a.out + pix * a.out_cstride + a.out_coff + n0;
-#pragma unroll
               float ad[16];
               if (a.addend) {          // hoisted per-pixel term (rows padded to a multiple of 4 columns: 16-byte loads)
                 const float* ap_ = a.addend + ((size_t)ir * a.W + ic) * a.addend_stride + n0;
@@ -352,69 +338,67 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
       it.advance(g, tiles_img);
       for (int ks = 0; ks < g.KS; ++ks, ++ja) {
         const int ua = ja % kCvNA, use = ja / kCvNA;
-        if (use >= 1) mbar_wait(a_free + ua, (uint32_t)((use - 1) & 1));
-        uint8_t* Ab = As + (size_t)ua * g.bufA;
-        // 2 planes x 324 positions; batches of up to 2 items per thread, loads first
-        for (int it0 = ptid; it0 < 2 * kCvNPOS; it0 += 2 * kNPT) {
-          float v[2][8];
-          int pos[2], pln[2];
-          bool relu[2];
+        // item = (tile position, 16-byte quarter q of the K-step's 16 channels): 4 consecutive lanes read 64 contiguous bytes
+        // of a pixel (8 pixels per request instead of 32 lines).  q = ptid & 3 is fixed per thread, so the source and channel
+        // offset are chosen once per K-step, and ALL positions of the thread are requested before the first conversion: one
+        // DRAM round trip per K-step (lstm_gate_f16.cu measured 10k -> 4k cycles per K-step with the same change).
+        const int q = ptid & 3, plane = 2 * ks + (q >> 1);
+        int si = 0;
+        if (a.nsrc > 1 && plane >= g.plane0[1]) si = 1;
+        if (a.nsrc > 2 && plane >= g.plane0[2]) si = 2;
+        // (field-wise select: a dynamically indexed kernel parameter is copied to local memory)
+        const float* sp = si == 0 ? a.src[0].p : (si == 1 ? a.src[1].p : a.src[2].p);
+        const int s_cstride = si == 0 ? a.src[0].cstride : (si == 1 ? a.src[1].cstride : a.src[2].cstride);
+        const int s_coff = si == 0 ? a.src[0].coff : (si == 1 ? a.src[1].coff : a.src[2].coff);
+        const int s_nch = si == 0 ? a.src[0].nch : (si == 1 ? a.src[1].nch : a.src[2].nch);
+        const bool s_relu = (si == 0 ? a.src[0].relu : (si == 1 ? a.src[1].relu : a.src[2].relu)) != 0;
+        const bool s_shared = (si == 0 ? a.src[0].bshared : (si == 1 ? a.src[1].bshared : a.src[2].bshared)) != 0;
+        const int ch = (plane - (si == 0 ? 0 : (si == 1 ? g.plane0[1] : g.plane0[2]))) * 8 + (q & 1) * 4;
+        const int nv = min(4, s_nch - ch);
+        const float* sbase = sp ? sp + (s_shared ? 0 : (size_t)b * HW) * s_cstride + s_coff + ch : nullptr;
+        const bool live = sbase != nullptr && nv > 0;
+        const bool vec4 = nv == 4 && (s_cstride & 3) == 0 && (reinterpret_cast<uintptr_t>(sbase) & 15) == 0;
+        const bool vec2 = nv == 2 && (s_cstride & 1) == 0 && (reinterpret_cast<uintptr_t>(sbase) & 7) == 0;
+        constexpr int kItems = (kCvNPOS + kNPT / 4 - 1) / (kNPT / 4);       // positions per thread: 11 (4 warps) or 6 (8 warps)
+        float4 v[kItems];
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int itx = it0 + q * kNPT;
-            pos[q] = -1; pln[q] = 0; relu[q] = false;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
-            if (itx < 2 * kCvNPOS) {
-              const int lp = itx >= kCvNPOS ? 1 : 0, p = itx - lp * kCvNPOS;
-              const int plane = 2 * ks + lp;
-              pos[q] = p; pln[q] = lp;
-              const int rr = p / kCvRP, rc = p - rr * kCvRP;
-              int r = r0 - 1 + rr, c = c0 - 1 + rc;
-              bool inb = r >= 0 && r < a.H && c >= 0 && c < a.W;
-              if (a.pad_replicate) { r = min(max(r, 0), a.H - 1); c = min(max(c, 0), a.W - 1); inb = true; }
-              // which source owns this plane
-              int si = 0;
-              if (a.nsrc > 1 && plane >= g.plane0[1]) si = 1;
-              if (a.nsrc > 2 && plane >= g.plane0[2]) si = 2;
-              const ConvSrc& sc = a.src[si];
-              const int ch = (plane - g.plane0[si]) * 8;
-              const int nv = min(8, sc.nch - ch);
-              relu[q] = sc.relu != 0;
-              if (inb && nv > 0 && sc.p != nullptr) {
-                const size_t pixi = (sc.bshared ? 0 : (size_t)b * HW) + (size_t)r * a.W + c;
-                const float* ptr = sc.p + pixi * sc.cstride + sc.coff + ch;
-                if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (nv & 1) == 0) {
-                  if (nv >= 4) { const float4 t0 = __ldg(reinterpret_cast<const float4*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; v[q][2] = t0.z; v[q][3] = t0.w; }
-                  else { const float2 t0 = __ldg(reinterpret_cast<const float2*>(ptr)); v[q][0] = t0.x; v[q][1] = t0.y; }
-                  if (nv == 8) { const float4 t1 = __ldg(reinterpret_cast<const float4*>(ptr) + 1); v[q][4] = t1.x; v[q][5] = t1.y; v[q][6] = t1.z; v[q][7] = t1.w; }
-                  else if (nv == 6) { const float2 t1 = __ldg(reinterpret_cast<const float2*>(ptr) + 2); v[q][4] = t1.x; v[q][5] = t1.y; }
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) if (e < nv) v[q][e] = __ldg(ptr + e);
-                }
-              }
+        for (int u = 0; u < kItems; ++u) {
+          const int p = (ptid >> 2) + u * (kNPT / 4);
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int rr = p / kCvRP, rc = p - rr * kCvRP;
+          int r = r0 - 1 + rr, c = c0 - 1 + rc;
+          bool inb = r >= 0 && r < a.H && c >= 0 && c < a.W;
+          if (a.pad_replicate) { r = min(max(r, 0), a.H - 1); c = min(max(c, 0), a.W - 1); inb = true; }
+          if (live && p < kCvNPOS && inb) {
+            const float* ptr = sbase + ((size_t)r * a.W + c) * s_cstride;
+            if (vec4) {
+              v[u] = __ldg(reinterpret_cast<const float4*>(ptr));
+            } else if (vec2) {
+              const float2 t = __ldg(reinterpret_cast<const float2*>(ptr)); v[u].x = t.x; v[u].y = t.y;
+            } else {
+              v[u].x = __ldg(ptr);
+              if (nv > 1) v[u].y = __ldg(ptr + 1);
+              if (nv > 2) v[u].z = __ldg(ptr + 2);
+              if (nv > 3) v[u].w = __ldg(ptr + 3);
             }
           }
+        }
+        if (use >= 1) mbar_wait(a_free + ua, (uint32_t)((use - 1) & 1));
+        uint8_t* Ab = As + (size_t)ua * g.bufA + (q >> 1) * kCvPLB + (q & 1) * 8;
+        const float lo_ = s_relu ? 0.f : -60000.f;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (pos[q] < 0) continue;
-            uint32_t ph[4], pl[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float u0 = v[q][2 * e] * isc, u1 = v[q][2 * e + 1] * isc;
-              const float lo_ = relu[q] ? 0.f : -60000.f;
-              float y0 = fminf(u0, 60000.f), y1 = fminf(u1, 60000.f);
-              y0 = fmaxf(y0, lo_); y1 = fmaxf(y1, lo_);
-              const __half2 h2 = __floats2half2_rn(y0, y1);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
-              ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
-              pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            uint8_t* dst = Ab + (size_t)pln[q] * kCvPLB + (size_t)pos[q] * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            if (X3) *reinterpret_cast<uint4*>(dst + g.hlA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        for (int u = 0; u < kItems; ++u) {
+          const int p = (ptid >> 2) + u * (kNPT / 4);
+          if (p >= kCvNPOS) continue;
+          const float y0 = fmaxf(fminf(v[u].x * isc, 60000.f), lo_), y1 = fmaxf(fminf(v[u].y * isc, 60000.f), lo_);
+          const float y2 = fmaxf(fminf(v[u].z * isc, 60000.f), lo_), y3 = fmaxf(fminf(v[u].w * isc, 60000.f), lo_);
+          const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+          uint8_t* dst = Ab + p * 16;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          if (X3) {
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y), l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
+            *reinterpret_cast<uint2*>(dst + g.hlA) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
           }
         }
         fence_proxy_async();

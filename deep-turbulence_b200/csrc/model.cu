@@ -73,6 +73,12 @@ struct ConvW {
 
 enum StepKind { STEP_UNNORMED = 0, STEP_PLAIN = 1, STEP_LSTM = 2 };
 
+// TMG_NO_GATE2P=1 (read when the model is built): ConvLSTM gate conv through conv3x3_f16.cu instead of lstm_gate_f16.cu (A/B runs)
+static inline bool gate2p_off() {
+  static const bool off = [] { const char* e = getenv("TMG_NO_GATE2P"); return e && e[0] == '1'; }();
+  return off;
+}
+
 struct StepW {
   int kind = STEP_PLAIN;
   int64_t norm_w = -1, norm_b = -1;
@@ -92,6 +98,10 @@ struct StepW {
   ConvW gate_nc, outc_nc;
   int64_t gate_hw = -1, outc_hw = -1;
   int gate_hop = 0, outc_hop = 0;
+  // two-pass gate kernel (lstm_gate_f16.cu, R = 64): weights over the sources [h | cond | x1] and [h | x1], gate rows in pass
+  // order; gate2p_hw >= 0: gate_hw holds the conditioning slice in pass order (the hoisted table is then kept plane-transposed)
+  ConvW gate2p, gate2p_nc;
+  int64_t gate2p_hw = -1;
   // parameter offsets needed by the backward pass
   int64_t lu[8] = {-1, -1, -1, -1, -1, -1, -1, -1};     // l, u, log_s, p, sign_s, l_mask, u_mask, eye
   int64_t zc_scale = -1;
@@ -239,11 +249,28 @@ struct Builder {
     m.jobs.push_back(j);
     return c;
   }
-  int64_t slice_job(const ConvW& full, int c0, int n, int& op) {
+  // two-pass gate packing over `nsrc` sources given as (first input channel, channels), in staging order
+  ConvW gate2p_job(const ConvW& full, const int* c0, const int* nch, int nsrc) {
+    ConvW c = full;
+    c.w_pack = c.w_pack_tc = c.w_pack_f16t = -1;
+    c.NP = 128;
+    int n3[3] = {0, 0, 0};
+    for (int i = 0; i < nsrc; ++i) { n3[i] = nch[i]; c.f16_nch[i] = nch[i]; }
+    c.w_pack_f16 = pack_alloc((int64_t)lstm_gate_packed_floats(n3, nsrc));
+    c.inv_f16 = pack_alloc(1);
+    PackJob j{};
+    j.type = JOB_GATE2P; j.a = c.O; j.b = c.I; j.opad = 128; j.nch0 = n3[0]; j.nch1 = n3[1]; j.nd = n3[2];
+    for (auto& s : j.src) s = -1;
+    j.src[0] = c.w_param; j.dst[0] = c.w_pack_f16; j.dst[1] = c.inv_f16;
+    for (int i = 0; i < nsrc; ++i) j.src[1 + i] = c0[i];
+    m.jobs.push_back(j);
+    return c;
+  }
+  int64_t slice_job(const ConvW& full, int c0, int n, int& op, int pass_rh = 0) {
     op = (full.O + 3) / 4 * 4;
     const int64_t dst = pack_alloc((int64_t)9 * n * op);
     PackJob j{};
-    j.type = JOB_SLICE; j.a = full.O; j.b = full.I; j.opad = op; j.nch0 = c0; j.nch1 = n;
+    j.type = JOB_SLICE; j.a = full.O; j.b = full.I; j.opad = op; j.nch0 = c0; j.nch1 = n; j.part = pass_rh;
     for (auto& s : j.src) s = -1;
     j.src[0] = full.w_param; j.dst[0] = dst;
     m.jobs.push_back(j);
@@ -440,7 +467,16 @@ static int build_model(tmg_model& m) {
         B.conv_f16t_job(st.gate); B.conv_f16t_job(st.outc);
         if (4 * R <= 256) {
           st.gate_nc = B.conv_f16_skip_job(st.gate, C / 2, c.cond_features, R);
-          st.gate_hw = B.slice_job(st.gate, C / 2, c.cond_features, st.gate_hop);
+          if (R == 64 && !gate2p_off()) {
+            // staging order of the two-pass kernel: h first (its 8-channel planes pair up into aligned 64-byte reads)
+            const int c0a[3] = {cin_t, C / 2, 0}, na[3] = {R, c.cond_features, C / 2};
+            const int c0b[2] = {cin_t, 0}, nb[2] = {R, C / 2};
+            st.gate2p = B.gate2p_job(st.gate, c0a, na, 3);
+            st.gate2p_nc = B.gate2p_job(st.gate, c0b, nb, 2);
+            st.gate_hw = st.gate2p_hw = B.slice_job(st.gate, C / 2, c.cond_features, st.gate_hop, R / 2);
+          } else {
+            st.gate_hw = B.slice_job(st.gate, C / 2, c.cond_features, st.gate_hop);
+          }
           st.outc_nc = B.conv_f16_skip_job(st.outc, C / 2, c.cond_features, R);
           st.outc_hw = B.slice_job(st.outc, C / 2, c.cond_features, st.outc_hop);
         }
@@ -531,6 +567,7 @@ struct Plan {
   size_t y[TMG_MAX_LEVELS], y2[TMG_MAX_LEVELS], hr, d, gates, u0, ldp, scratch_in, scratch_cond, scratch_out;
   size_t dc_all[TMG_MAX_LEVELS], hc_all[TMG_MAX_LEVELS];
   size_t dcT[TMG_MAX_LEVELS], hcT[TMG_MAX_LEVELS];   // the same tables, plane-transposed for the level-resident kernel
+  size_t gcT[TMG_MAX_LEVELS];                         // gate table, plane-transposed + bias (two-pass gate kernel)
   size_t gc[TMG_MAX_LEVELS], oc[TMG_MAX_LEVELS];     // shared LF input: conditioning part of the ConvLSTM gate / output convs
 };
 
@@ -573,6 +610,7 @@ static int make_plan(const tmg_model& m, int B, int h, int w, Plan& p, bool shar
       const StepW& ls = lv.steps.back();
       p.gc[l] = take(shared && ls.gate_hw >= 0 ? (size_t)p.Hl[l] * p.Wl[l] * ls.gate_hop : 16);
       p.oc[l] = take(shared && ls.outc_hw >= 0 ? (size_t)p.Hl[l] * p.Wl[l] * ls.outc_hop : 16);
+      p.gcT[l] = take(shared && ls.gate2p_hw >= 0 ? (size_t)p.Hl[l] * p.Wl[l] * ls.gate_hop : 16);
     }
     p.dcT[l] = take(Bx * p.Hl[l] * p.Wl[l] * 2 * lv.steps.size());
     p.hcT[l] = take(Bx * p.Hl[l] * p.Wl[l] * lv.C * lv.steps.size());
@@ -799,7 +837,32 @@ static int run_coupling_nn(Ctx& c, int level, const StepW& s, int B, int Hl, int
     // one LF input shared by all samples: the conditioning rows leave the two convolutions (K shrinks by the 32 conditioning
     // channels: 7 -> 5 K-steps at level 0) and come back as a per-pixel addend evaluated once per call (run_hoist)
     const bool nc = sh && c.hoist_ready && s.gate_nc.w_pack_f16 >= 0 && s.gate_hw >= 0 && !c.unfused && !nc_off();
-    if (prec_f16(c.m.precision) && s.gate.w_pack_f16 >= 0 && !c.unfused) {
+    if (prec_f16(c.m.precision) && s.gate2p.w_pack_f16 >= 0 && !c.unfused) {
+      // two-pass kernel: the cell-update epilogue of one half of the gate columns overlaps the MMAs of the other half
+      ConvF16Args t{};
+      const bool nc2 = nc && s.gate2p_hw >= 0;
+      t.src[0] = ConvSrc{h_in, R, 0, R, 0};             // zero states: null -> staged as zeros
+      if (nc2) {
+        t.src[1] = gs[0]; t.nsrc = 2;
+        t.wpk = c.Q() + s.gate2p_nc.w_pack_f16; t.inv_scale = c.Q() + s.gate2p_nc.inv_f16;
+        t.addend = ws + p.gcT[level]; t.addend_stride = 0;      // bias folded into the table
+      } else {
+        t.src[1] = gs[1]; t.src[2] = gs[0]; t.nsrc = 3;
+        t.wpk = c.Q() + s.gate2p.w_pack_f16; t.inv_scale = c.Q() + s.gate2p.inv_f16;
+        t.bias = c.P() + s.gate.b_param;
+      }
+      t.npad = 256; t.cout = s.gate.O;
+      t.B = B; t.H = Hl; t.W = Wl; t.x3 = prec_split(c.m.precision) ? 1 : 0;
+      t.lstm_R = R; t.c_prev = c_in; t.h_out = h_out; t.c_out = c_out;
+      if (lstm_gate_f16_supported(t)) {
+        const double M = (double)B * Hl * Wl;
+        ProfScope ps(c.st, PROF_CONV_GATE, 2.0 * M * s.gate.O * 9.0 * s.gate.I, 4.0 * (M * s.gate.I + M * R * (c_in ? 3.0 : 2.0)));
+        TMG_TRY(launch_lstm_gate_f16(t, c.st));
+        gate_done = true;
+      }
+    }
+    if (!gate_done && prec_f16(c.m.precision) && s.gate.w_pack_f16 >= 0 && !c.unfused) {
+      const bool nc = sh && c.hoist_ready && s.gate_nc.w_pack_f16 >= 0 && s.gate_hw >= 0 && s.gate2p_hw < 0 && !c.unfused && !nc_off();
       ConvF16Args t{};
       const int ns = h_in ? 3 : 2;
       for (int i = 0; i < 3; ++i) t.src[i] = gs[i];
@@ -1075,6 +1138,9 @@ static int run_hoist(Ctx& c) {
         ProfScope ps(c.st, PROF_MISC, 2.0 * M * a.cout * 9.0 * a.cin_w, 4.0 * M * (a.cin_w + a.cout));
         TMG_TRY(launch_conv3x3(a, c.st));
       }
+      if (ls.gate2p_hw >= 0)      // pass-ordered columns -> [column group of 4][pixel] float4, bias folded in
+        TMG_TRY(launch_gate_addend_transpose(c.ws + c.p.gc[l], c.P() + ls.gate.b_param, c.ws + c.p.gcT[l], c.p.Hl[l] * c.p.Wl[l],
+                                             ls.gate_hop, g.rec_features, c.st));
     }
   }
   c.hoist_ready = true;

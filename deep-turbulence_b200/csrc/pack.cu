@@ -271,6 +271,45 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
     }
     if (tid == 0) Q[j.dst[1]] = 1.f / sc;
+  } else if (j.type == JOB_GATE2P) {
+    // ConvLSTM gate weights for lstm_gate_f16.cu: OIHW (O = 4 R gate rows) -> fp16 [pass][kstep][tap][hl][2 planes][4 RH][8],
+    // RH = R / 2; column n of pass p is gate row (n / RH) R + RH p + n % RH (i, f, o, g of recurrent channels [RH p, RH p + RH)).
+    // The K planes are the sources (first input channel src[1 + q], channels nch0 / nch1 / nd), each padded to a multiple
+    // of 8 channels, in the order given -- not necessarily the concatenation order of the reference.  Same power-of-two scale.
+    const int O = j.a, I = j.b, R = O / 4, RH = R / 2, NPP = 4 * RH;
+    const int nch[3] = {j.nch0, j.nch1, j.nd};
+    int pl0[4]; pl0[0] = 0;
+    for (int q = 0; q < 3; ++q) pl0[q + 1] = pl0[q] + (nch[q] + 7) / 8;
+    const int KS = (pl0[3] + 1) / 2;
+    const float* w = P + j.src[0];
+    float m = 0.f;
+    for (int i = tid; i < O * I * 9; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) sm[tid >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm[q]);
+    int ex = 0;
+    if (m > 0.f && m < 3.0e38f) frexpf(m, &ex);
+    const float sc = m > 0.f ? ldexpf(1.f, min(max(11 - ex, -20), 40)) : 1.f;
+    __half* d = reinterpret_cast<__half*>(Q + j.dst[0]);
+    const size_t total = (size_t)2 * KS * 9 * 2 * 2 * NPP * 8;
+    for (size_t i = tid; i < total; i += blockDim.x) {
+      const int e = (int)(i & 7); size_t t = i >> 3; const int n = (int)(t % NPP); t /= NPP;
+      const int lp = (int)(t & 1); t >>= 1; const int hl = (int)(t & 1); t >>= 1;
+      const int tap = (int)(t % 9); t /= 9; const int ks = (int)(t % KS); const int p = (int)(t / KS);
+      const int plane = 2 * ks + lp;
+      int c = -1;
+      for (int q = 0; q < 3; ++q)
+        if (plane >= pl0[q] && plane < pl0[q + 1]) { const int ch = (plane - pl0[q]) * 8 + e; if (ch < nch[q]) c = (int)j.src[1 + q] + ch; }
+      const int o = (n / RH) * R + p * RH + n % RH;
+      float v = 0.f;
+      if (c >= 0 && c < I && o < O) v = w[((size_t)o * I + c) * 9 + tap] * sc;
+      const __half hi = __float2half_rn(v);
+      d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    if (tid == 0) Q[j.dst[1]] = 1.f / sc;
   } else if (j.type == JOB_SLICE) {
     // Input-channel slice [nch0, nch0 + nch1) of an OIHW weight as tap-major fp32 [9][nch1][opad] for conv3x3_ffma: the
     // conditioning rows of the ConvLSTM gate / output convolutions, whose contribution is the same for every sample of one
@@ -278,8 +317,11 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
     const int O = j.a, I = j.b, OP = j.opad, c0 = j.nch0, n = j.nch1;
     const float* w = P + j.src[0];
     float* d = Q + j.dst[0];
+    // j.part = RH > 0: the columns come in the pass order of lstm_gate_f16.cu (column 4 RH p + RH g + jj <- gate row g R + RH p + jj)
+    const int RH = j.part;
     for (int i = tid; i < 9 * n * OP; i += blockDim.x) {
-      const int o = i % OP; int t = i / OP; const int c = t % n, tap = t / n;
+      int o = i % OP; int t = i / OP; const int c = t % n, tap = t / n;
+      if (RH > 0 && o < O) { const int p = o / (4 * RH), nn = o % (4 * RH); o = (nn / RH) * 2 * RH + p * RH + nn % RH; }
       d[i] = o < O ? w[((size_t)o * I + c0 + c) * 9 + tap] : 0.f;
     }
   } else if (j.type == JOB_CONV_F16_T) {
