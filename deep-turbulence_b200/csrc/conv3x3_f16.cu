@@ -44,6 +44,18 @@ struct ConvF16Geom {
   int nplanes[3];
 };
 
+#ifdef TMG_GT_PROFILE
+// developer build (-DTMG_GT_PROFILE, TMG_CV_PROF=n at run time): cycles per role spent in each wait
+__device__ long long cv_prof[148 * 16];
+#define CVP_T0() const long long cvp_t0 = clock64()
+#define CVP_ADD(slot) cvp_acc[slot] += clock64() - cvp_t0
+#define CVP_DECL() long long cvp_acc[4] = {0, 0, 0, 0}; const long long cvp_start = clock64()
+#else
+#define CVP_T0()
+#define CVP_ADD(slot)
+#define CVP_DECL()
+#endif
+
 struct CvTileIt {
   int b, timg;
   __device__ __forceinline__ void init(int t, int tiles_img) { b = t / tiles_img; timg = t - b * tiles_img; }
@@ -61,7 +73,11 @@ template <bool X3, int NPW>
 __global__ void __launch_bounds__((11 + NPW) * 32, 1)
 conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
   constexpr int kCvThreads = (11 + NPW) * 32;
-  constexpr int kNPT = NPW * 32;
+  // Producer warps work in groups of 4 (128 threads): group gi stages the K-steps with (running index) % groups == gi, so
+  // with 8 warps two K-steps are in flight at once -- at narrow N the kernel is bound by the DRAM round trip of a K-step,
+  // not by the tensor pipe.
+  constexpr int kNPG = NPW / 4;           // producer groups
+  constexpr int kNPT = 128;               // threads staging one K-step
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W;
@@ -76,14 +92,17 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
   uint64_t* a_free = bars + 3;               // [3]  2 commits
   uint64_t* b_full = bars + 6;               // [8]  tx
   uint64_t* b_free = bars + 14;              // [8]  2 commits
-  uint64_t* acc_full = bars + 22;            // 2 commits
-  uint64_t* acc_free = bars + 23;            // epilogue (256)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* acc_full = bars + 22;            // [2] 2 commits
+  uint64_t* acc_free = bars + 24;            // [2] epilogue (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  // N <= 128: two accumulator sets (2 x 2 M tiles x 128 columns), the MMAs of tile k + 1 run under the epilogue of tile k
+  // (measured at N = 48, 5 K-steps: the issuer waited 44 % of a tile for the epilogue, the epilogue 57 % for the MMAs)
+  const bool acc2 = NP <= 128;
 
   if (tid == 0) {
     for (int i = 0; i < kCvNA; ++i) { mbar_init(a_full + i, kNPT); mbar_init(a_free + i, 2); }
     for (int i = 0; i < kCvMaxNB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_free + i, 2); }
-    mbar_init(acc_full, 2); mbar_init(acc_free, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 2); mbar_init(acc_free + i, 256); }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -108,6 +127,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     const float inv = (a.inv_scale ? __ldg(a.inv_scale) : 1.f) * (a.in_scale ? __ldg(a.in_scale + 1) : 1.f);
     const float gain = a.gain ? __ldg(a.gain) : 1.f;
     const bool vec_ok = (a.out_cstride & 3) == 0 && (a.out_coff & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    CVP_DECL();
     CvTileIt it;
     it.init(blockIdx.x, tiles_img);
     for (int k = 0; k < nmy; ++k) {
@@ -115,14 +135,15 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
       it.origin(g, r0, c0);
       const int b = it.b;
       it.advance(g, tiles_img);
-      mbar_wait(acc_full, (uint32_t)(k & 1));
+      const int ai = acc2 ? (k & 1) : 0, an = acc2 ? (k >> 1) : k;       // accumulator set, its use count
+      { CVP_T0(); mbar_wait(acc_full + ai, (uint32_t)(an & 1)); CVP_ADD(0); }
       tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < 2; ++mt) {
         const int ir = r0 + (el >> 3), ic = c0 + 8 * mt + (el & 7);
         const bool valid = ir < a.H && ic < a.W;
         const size_t pix = valid ? (size_t)b * HW + (size_t)ir * a.W + ic : 0;
-        const uint32_t trow = tmem_base + lane_base + (uint32_t)(mt * 256);
+        const uint32_t trow = tmem_base + lane_base + (uint32_t)(acc2 ? ai * 256 + mt * 128 : mt * 256);
         if (a.lstm_R > 0) {
           // fused ConvLSTM cell (convLSTM.py:76-83): gates i,f,o,g at columns [0,R),[R,2R),[2R,3R),[3R,4R);
           // this thread owns recurrent channels [half*R/2, (half+1)*R/2) of its pixel
@@ -182,8 +203,11 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
           // accesses when the destination allows), gated by the ReLU of the forward input, optionally accumulated
           const int pb1 = (a.dst[0].nch + 3) & ~3, pb2 = pb1 + (a.ndst > 1 ? (a.dst[1].nch + 3) & ~3 : 0);
           const int pb3 = pb2 + (a.ndst > 2 ? (a.dst[2].nch + 3) & ~3 : 0);
-          for (int n0 = half * 16; n0 < NP; n0 += 32) {
+          // 16-column chunks alternate between the two halves of the epilogue, continuing across the M tiles (odd chunk
+          // counts stay balanced)
+          for (int n0 = 0; n0 < NP; n0 += 16) {
             if (n0 >= pb3) break;
+            if ((((n0 >> 4) + mt * (NP >> 4)) & 1) != half) continue;
             float v[16];
             tmem_ld16(trow + n0, v);
             if (valid) {
@@ -225,8 +249,8 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
             }
           }
         } else {
-          // columns split between the two halves in chunks of 16
-          for (int n0 = half * 16; n0 < NP; n0 += 32) {
+          for (int n0 = 0; n0 < NP; n0 += 16) {
+            if ((((n0 >> 4) + mt * (NP >> 4)) & 1) != half) continue;
             float v[16];
             tmem_ld16(trow + n0, v);
             if (valid) {
@@ -251,9 +275,15 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
                 else if (a.act == 2) t = fminf(fmaxf(t, -2.f), kLog5);
                 v[e] = t;
               }
-              if (vec_ok && n0 + 16 <= a.cout) {
+              if (vec_ok) {      // 16-byte stores for every complete group of 4 columns, scalars only for a ragged tail
 #pragma unroll
-                for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                for (int e = 0; e < 16; e += 4) {
+                  if (n0 + e + 4 <= a.cout) *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                  else {
+#pragma unroll
+                    for (int e1 = e; e1 < e + 4; ++e1) if (n0 + e1 < a.cout) op[e1] = v[e1];
+                  }
+                }
               } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) if (n0 + e < a.cout) op[e] = v[e];
@@ -263,46 +293,61 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_free);
+      mbar_arrive(acc_free + ai);
     }
+#ifdef TMG_GT_PROFILE
+    if (tid == 0) { cv_prof[blockIdx.x * 16 + 4] = clock64() - cvp_start; cv_prof[blockIdx.x * 16 + 5] = cvp_acc[0]; }
+#endif
   } else if (warp < 10) {
     // =========================================================== MMA issue: warp 8 -> M tile 0, warp 9 -> M tile 1
     const int mt = warp - 8;
     if (elect_one()) {
       const uint32_t idesc = cv_idesc_f16(NP);
       const uint64_t hlA16 = g.hlA >> 4, hlB16 = g.hlB >> 4, tapB16 = (uint64_t)(g.nhl * g.hlB) >> 4;
-      const uint32_t tacc = tmem_base + (uint32_t)(mt * 256);
-      int ja = 0, jb = 0;                      // running K-step / weight-stage counters
+      // ring slots / phase parities are carried incrementally and the tap loop is unrolled over the 9 taps: at narrow N one
+      // MMA occupies the tensor pipe for ~24 cycles and the issue path (runtime div / mod, descriptor arithmetic) was longer
+      int ua = 0, ub = 0; uint32_t pa = 0, pb = 0;
+      CVP_DECL();
       for (int k = 0; k < nmy; ++k) {
-        if (k >= 1) mbar_wait(acc_free, (uint32_t)((k - 1) & 1));
+        const int ai = acc2 ? (k & 1) : 0, an = acc2 ? (k >> 1) : k;
+        const uint32_t tacc = tmem_base + (uint32_t)(acc2 ? ai * 256 + mt * 128 : mt * 256);
+        { CVP_T0(); if (an >= 1) mbar_wait(acc_free + ai, (uint32_t)((an - 1) & 1)); CVP_ADD(0); }
         tc_fence_after();
-        for (int ks = 0; ks < g.KS; ++ks, ++ja) {
-          const int ua = ja % kCvNA;
-          mbar_wait(a_full + ua, (uint32_t)((ja / kCvNA) & 1));
+        for (int ks = 0; ks < g.KS; ++ks) {
+          { CVP_T0(); mbar_wait(a_full + ua, pa); CVP_ADD(1); }
           tc_fence_after();
           const uint64_t a0 = make_desc(smem_u32(As + (size_t)ua * g.bufA), kCvPLB, kCvRP * 16) + (uint64_t)(8 * mt);
-          for (int sg = 0; sg < 9; sg += g.tps, ++jb) {
-            const int ub = jb % g.nb;
-            mbar_wait(b_full + ub, (uint32_t)((jb / g.nb) & 1));
-            tc_fence_after();
-            const uint64_t bd0 = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)NP * 16u, 128);
-            for (int t = 0; t < g.tps; ++t) {
-              const int tap = sg + t;
-              const int dr = tap / 3, dc = tap - 3 * dr;
-              const uint64_t ad = a0 + (uint64_t)(dr * kCvRP + dc);
-              const uint64_t bd = bd0 + (uint64_t)t * tapB16;
-              cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
-              if (X3) {
-                cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
-                cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
-              }
+          uint64_t bd = 0;
+          int left = 0;                          // taps left in the current weight stage
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            if (left == 0) {
+              { CVP_T0(); mbar_wait(b_full + ub, pb); CVP_ADD(2); }
+              tc_fence_after();
+              bd = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)NP * 16u, 128);
+              left = g.tps;
             }
-            mma_commit(b_free + ub);
+            const int dr = tap / 3, dc = tap - 3 * dr;
+            const uint64_t ad = a0 + (uint64_t)(dr * kCvRP + dc);
+            cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+            if (X3) {
+              cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
+              cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
+            }
+            bd += tapB16;
+            if (--left == 0) {
+              mma_commit(b_free + ub);
+              if (++ub == g.nb) { ub = 0; pb ^= 1u; }
+            }
           }
           mma_commit(a_free + ua);
+          if (++ua == kCvNA) { ua = 0; pa ^= 1u; }
         }
-        mma_commit(acc_full);
+        mma_commit(acc_full + ai);
       }
+#ifdef TMG_GT_PROFILE
+      if (mt == 0) { cv_prof[blockIdx.x * 16 + 0] = clock64() - cvp_start; for (int i = 0; i < 3; ++i) cv_prof[blockIdx.x * 16 + 1 + i] = cvp_acc[i]; }
+#endif
     }
   } else if (warp == 10) {
     // =========================================================== weight streaming (one lane, cp.async.bulk)
@@ -326,10 +371,11 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
     }
   } else {
     // =========================================================== producers (128 threads): activation K-steps
-    const int ptid = tid - 11 * 32;
+    const int ptid = (tid - 11 * 32) & 127, pgrp = (tid - 11 * 32) >> 7;
     CvTileIt it;
     it.init(blockIdx.x, tiles_img);
     int ja = 0;
+    CVP_DECL();
     const float isc = a.in_scale ? __ldg(a.in_scale) : 1.f;
     for (int k = 0; k < nmy; ++k) {
       int r0, c0;
@@ -337,6 +383,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
       const int b = it.b;
       it.advance(g, tiles_img);
       for (int ks = 0; ks < g.KS; ++ks, ++ja) {
+        if (kNPG > 1 && (ja % kNPG) != pgrp) continue;
         const int ua = ja % kCvNA, use = ja / kCvNA;
         // item = (tile position, 16-byte quarter q of the K-step's 16 channels): 4 consecutive lanes read 64 contiguous bytes
         // of a pixel (8 pixels per request instead of 32 lines).  q = ptid & 3 is fixed per thread, so the source and channel
@@ -359,7 +406,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
         const bool live = sbase != nullptr && nv > 0;
         const bool vec4 = nv == 4 && (s_cstride & 3) == 0 && (reinterpret_cast<uintptr_t>(sbase) & 15) == 0;
         const bool vec2 = nv == 2 && (s_cstride & 1) == 0 && (reinterpret_cast<uintptr_t>(sbase) & 7) == 0;
-        constexpr int kItems = (kCvNPOS + kNPT / 4 - 1) / (kNPT / 4);       // positions per thread: 11 (4 warps) or 6 (8 warps)
+        constexpr int kItems = (kCvNPOS + kNPT / 4 - 1) / (kNPT / 4);       // positions per thread: 324 / 32 -> 11
         float4 v[kItems];
 #pragma unroll
         for (int u = 0; u < kItems; ++u) {
@@ -383,7 +430,7 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
             }
           }
         }
-        if (use >= 1) mbar_wait(a_free + ua, (uint32_t)((use - 1) & 1));
+        { CVP_T0(); if (use >= 1) mbar_wait(a_free + ua, (uint32_t)((use - 1) & 1)); CVP_ADD(0); }
         uint8_t* Ab = As + (size_t)ua * g.bufA + (q >> 1) * kCvPLB + (q & 1) * 8;
         const float lo_ = s_relu ? 0.f : -60000.f;
 #pragma unroll
@@ -405,6 +452,9 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
         mbar_arrive(a_full + ua);
       }
     }
+#ifdef TMG_GT_PROFILE
+    if (ptid == 0 && pgrp == 0) { cv_prof[blockIdx.x * 16 + 6] = clock64() - cvp_start; cv_prof[blockIdx.x * 16 + 7] = cvp_acc[0]; }
+#endif
     // (no overflow detection here: the staging loop of this kernel is its bottleneck at N <= 64 -- measured +0.6 ms per
     // call for one compare per 8 values; the only unbounded input of these convolutions is the flow state, which the step
     // kernels that produce and consume it check: flow_step_f16.cu, flow_level_f16.cu)
@@ -609,7 +659,7 @@ static bool cv_geom(const ConvF16Args& a, ConvF16Geom& g, int grid) {
   auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
   g.oA = take((uint32_t)kCvNA * g.bufA);
   g.oMisc = take((uint32_t)a.npad * 4);
-  g.oBar = take(25 * 8 + 16);
+  g.oBar = take(27 * 8 + 16);
   const uint32_t fixed = off;
   int nb = (int)((220u * 1024u - fixed) / ((g.stageB + 127) / 128 * 128));
   nb = std::min(nb, g.tps == 1 ? kCvMaxNB : 4);
@@ -644,6 +694,22 @@ int launch_conv3x3_f16(const ConvF16Args& a, cudaStream_t st) {
   else { if (wide) TMG_CV(false, 4) else TMG_CV(false, 8) }
 #undef TMG_CV
   TMG_LAUNCH_CHECK();
+#ifdef TMG_GT_PROFILE
+  if (getenv("TMG_CV_PROF") && tiles >= 8 * grid) {
+    static int left = atoi(getenv("TMG_CV_PROF"));
+    if (left > 0) {
+      --left;
+      cudaStreamSynchronize(st);
+      static long long h[148 * 16];
+      cudaMemcpyFromSymbol(h, cv_prof, sizeof(h));
+      double s8[8] = {0};
+      for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) s8[i] += (double)h[b * 16 + i] / grid;
+      const double nt = (double)tiles / grid;
+      fprintf(stderr, "conv_f16 %dx%d B=%d N=%d KS=%d nb=%d tps=%d lstm=%d: cycles/tile issuer %.0f (acc_free %.0f a_full %.0f b_full %.0f) | epilogue %.0f (acc_full %.0f) | producer %.0f (a_free %.0f)\n",
+              a.H, a.W, a.B, a.npad, g.KS, g.nb, g.tps, a.lstm_R, s8[0] / nt, s8[1] / nt, s8[2] / nt, s8[3] / nt, s8[4] / nt, s8[5] / nt, s8[6] / nt, s8[7] / nt);
+    }
+  }
+#endif
   return TMG_OK;
 }
 

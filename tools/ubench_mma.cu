@@ -8,7 +8,7 @@
 #include <cuda_fp16.h>
 #include "../deep-turbulence_b200/csrc/tc_ptx.cuh"
 using namespace tmg;
-namespace tmg { void set_error(const char*, ...) {} thread_local int64_t g_launches = 0; }
+namespace tmg { void set_error(const char*, ...) {} std::atomic<int64_t> g_launches{0}; }
 
 __device__ __forceinline__ uint32_t make_idesc(int n, int f16) {
   // D=F32 (bit4), A/B format bits 7-9 / 10-12: tf32 = 2, f16 = 0 (bf16 = 1)
@@ -179,6 +179,56 @@ void run_real(long long* d) {
          (double)h[0] / n, (double)h[1] / n);
 }
 
+// fold pattern of conv3x3_f16.cu: per tap [A_hi x (B_hi|B_lo), N' = 2N] + [A_lo x B_hi, N] against three N-wide MMAs
+template <int N, int FOLD>
+__global__ void __launch_bounds__(128, 1) k_fold(int iters, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) tmem_alloc(&slot, 512);
+  fence_proxy_async();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (tid < 32 && elect_one()) {
+    const uint32_t idesc = make_idesc(N, 1), idesc2 = make_idesc(2 * N, 1);
+    const uint64_t a0 = make_desc(smem_u32(smem), 5312, 288), b0 = make_desc(smem_u32(smem + 64 * 1024), (uint32_t)(2 * N) * 16u, 128);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += 18) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint64_t ad = a0 + (uint64_t)((tap / 3) * 18 + 8 * mt + tap % 3);
+          const uint64_t bd = b0 + (uint64_t)(tap * 2 * 2 * N);
+          if (FOLD) { mma_f16(tm + mt * 128, ad, bd, idesc2, 1); mma_f16(tm + mt * 128, ad + 664, bd, idesc, 1); }
+          else { mma_f16(tm + mt * 128, ad, bd, idesc, 1); mma_f16(tm + mt * 128, ad + 664, bd, idesc, 1); mma_f16(tm + mt * 128, ad, bd + N, idesc, 1); }
+        }
+      }
+    }
+    long long t1 = clock64();
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (tid < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+template <int N, int FOLD>
+void run_fold(long long* d) {
+  long long h[2];
+  const int iters = 18 * 40;
+  cudaFuncSetAttribute(k_fold<N, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_fold<N, FOLD><<<1, 128, 160 * 1024>>>(iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+  cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  printf("fold N=%3d fold=%d : %.1f cycles per tap (issue), %.1f (complete)\n", N, FOLD, (double)h[0] / iters, (double)h[1] / iters);
+}
+
 // truncation test: D = A*B with A row r = (1 + r*2^-20) in channel 0, B col 0 = 1 at k=0
 __global__ void __launch_bounds__(128, 1) k_trunc(float* out) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -236,6 +286,8 @@ int main() {
   run_lean<128, 1, 4>(d);
   run_real<16, 128, 0, 0>(d); run_real<16, 352, 0, 0>(d); run_real<16, 352, 1, 0>(d);
   run_real<16, 352, 1, 8>(d); run_real<16, 352, 1, 20>(d); run_real<32, 352, 1, 20>(d); run_real<16, 128, 1, 20>(d);
+  run_lean<96, 1, 1>(d);
+  run_fold<48, 0>(d); run_fold<48, 1>(d); run_fold<16, 0>(d); run_fold<16, 1>(d); run_fold<32, 0>(d); run_fold<32, 1>(d); run_fold<64, 0>(d); run_fold<64, 1>(d);
   float* o; cudaMalloc(&o, 512);
   k_trunc<<<1, 128, 16 * 1024>>>(o);
   cudaDeviceSynchronize();
