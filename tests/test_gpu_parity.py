@@ -339,6 +339,39 @@ def test_shared_input_equals_materialised_batch(mode):
     _field_close(z_s, z_o, what="shared z"); _logp_close(lp_s, lp_o, "shared logp")
 
 
+@pytest.mark.parametrize("mode", ["f16x3", "f16"])
+@pytest.mark.parametrize("shared", [True, False])
+def test_ragged_geometry_lstm_gate_kernel(mode, shared):
+    """lstm_gate_f16.cu (two-pass ConvLSTM gate conv, R = 64) and the double-buffered conv3x3_f16.cu on a geometry whose
+    level images are not multiples of the 16 x 16 tile / 8-pixel M-tile column (48 x 80 -> 24 x 40, 12 x 20, 6 x 10): ragged
+    tiles, cooperative 4-lanes-per-pixel state I/O at image edges, hoisted (shared) and in-GEMM (distinct inputs) conditioning,
+    two chained time steps (the second reads the states the first wrote)."""
+    from oracle import tmglow_oracle as O
+    dev = _dev()
+    m = _default_model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = O.OracleConfig.from_dict(m._cfg_dict)
+    g = torch.Generator().manual_seed(17)
+    S, H, W = 3, 48, 80
+    xs_cpu = [torch.randn(1 if shared else S, 4, H // 2, W // 2, generator=g) for _ in range(2)]
+    h_in = O.init_lstm_states(cfg, torch.arange(S), [H, W])
+    m = m.to(dev)
+    m.precision = mode
+    eps = [[torch.randn(s, generator=g) for s in m.latent_shapes(S, H, W)] for _ in range(2)]
+    tol_y, tol_h = (FIELD_TOL, FIELD_TOL) if mode == "f16x3" else (5e-2, 5e-2)
+    ho_o, hd = h_in, [(h.to(dev), c.to(dev)) for h, c in h_in]
+    for t in range(2):
+        xo = xs_cpu[t].expand(S, -1, -1, -1).contiguous()
+        y_o, ld_o, ho_o = O.reconstruct(sd, cfg, xo, ho_o, eps[t])
+        xd = xs_cpu[t].to(dev).expand(S, -1, -1, -1) if shared else xs_cpu[t].to(dev)
+        y, ld, hd = m.reconstruct(xd, hd, [e.to(dev) for e in eps[t]])
+        _field_close(y, y_o, tol=tol_y, what="y step %d" % t)
+        if mode == "f16x3":
+            _logp_close(ld, ld_o, "log_det step %d" % t)
+        for (h, c), (hr, cr) in zip(hd, ho_o):
+            _field_close(h, hr, tol=tol_h, what="h step %d" % t); _field_close(c, cr, tol=tol_h, what="c step %d" % t)
+
+
 def test_f16x3_full_size_properties():
     """The persistent fp16x3 step kernel at a bench-like batch: many tiles per CTA, all pipeline stages
     wrap around; invertibility, bit-reproducibility and batch independence."""
