@@ -4,7 +4,8 @@ BASELINE.json configs[1] (backward-step sampling, ONE LF input shared by S sampl
 
 Stated tolerances: fields / latents 2e-4 abs, log-dets 1e-5 rel (the fp32 tolerance of the whole suite); gradients of the
 benchmarked f16x3 mode within 2e-4 of the largest entry of each parameter's gradient (measured 7.5e-5 against a float64
-evaluation of the oracle); the fp32 leg carries a documented looser bound (see the comment at the tolerance)."""
+evaluation of the oracle); the same bound for the exact-fp32 leg except on the four tensors behind one ReLU mask bit that is
+inside fp32 rounding noise on these inputs (see the comment at the tolerance)."""
 import types
 
 import pytest
@@ -92,12 +93,16 @@ def test_default_cylinder_training_gradients(precision, block):
     m.scatter_flat_grad()
     params = dict(m.named_parameters())
     # Measured on B200 against a float64 evaluation of the oracle (tools/dbg_grads.py; the fp32 oracle itself is within
-    # 1.2e-5 of it): f16x3 -- the mode bench.py trains in -- worst parameter 7.5e-5.  The exact-fp32 mode is within 6e-5 on
-    # every parameter EXCEPT the four ConvLSTM tensors of the level-0 LSTM step (LSTM_out_conv.weight 2.7e-3, convLSTM.conv.weight
-    # 7e-4, their biases 3e-4 / 1e-4) when the encoder BatchNorm runs on batch statistics; the step's own backward is exact
-    # in isolation (tools/dbg_stepbwd.py: 5e-7), so the defect is in the composition of the fp32-mode BPTT chain -- open,
-    # recorded in DESIGN.md section 9; the tolerance of the fp32 leg is set above it so that the other 535 tensors stay pinned.
-    tol = 2e-4 if precision == "f16x3" else 5e-3
+    # 1.2e-5 of it): f16x3 -- the mode bench.py trains in -- worst parameter 7.5e-5; exact fp32 within 6e-5 on every parameter
+    # except the four ConvLSTM tensors of the level-0 LSTM step (LSTM_out_conv.weight 2.7e-3, its bias 3e-4, convLSTM.conv
+    # 7e-4 / 1e-4).  That is a ReLU kink, not arithmetic: on these inputs ONE pre-activation of LSTM_out_conv (t = 0, output
+    # channel 35) is 1.6e-7 in float64 and 2.9e-7 in the fp32 oracle (tools/chk_relu_kink.py) -- inside the rounding noise of
+    # any fp32 evaluation -- the fp32 CUDA path lands on the other side of zero, and the gradient of exactly that channel moves
+    # by that pixel's share (bias gradient: channel 35 off by 1.0e-3 absolute, the other 37 channels by < 1e-6).  The tensors
+    # downstream of that one mask bit get the looser bound, everything else the 2e-4 of the suite.
+    kink = ("glow.flow_blocks.0.revlayers.affine_layer16.coupling.resid_lstm.",)
+    def tol_of(k):
+        return 5e-3 if (precision != "f16x3" and k.startswith(kink)) else 2e-4
     checked, worst = 0, (0.0, "")
     for k in sorted(trainable):
         if sd[k].grad is None:
@@ -106,7 +111,7 @@ def test_default_cylinder_training_gradients(precision, block):
         err = (params[k].grad.cpu() - r).abs().max().item()
         rel = err / max(r.abs().max().item(), 1e-3)
         worst = max(worst, (rel, k))
-        assert rel <= tol, "%s: %.3e vs max %.3e" % (k, err, r.abs().max().item())
+        assert rel <= tol_of(k), "%s: %.3e vs max %.3e" % (k, err, r.abs().max().item())
         checked += 1
     print("default cylinder model, %s: %d parameters checked, worst relative gradient error %.2e (%s)" % ((precision, checked) + worst))
     assert checked >= 530, checked            # 545 trainable tensors, 6 of them (norm2.*) unused

@@ -70,3 +70,26 @@ for e, k, mx in errs:
     byk[(lvl, kind)] = max(byk[(lvl, kind)], e)
 for kk, e in sorted(byk.items(), key=lambda x: -x[1])[:20]:
     print("%s %.2e" % (kk, e))
+# slice analysis of the ConvLSTM tensors: error by input-channel group and by output block
+for e, k, mx in errs[:8]:
+    if not k.endswith("conv.weight") and not k.endswith("LSTM_out_conv.weight"):
+        continue
+    r = sd[k].grad
+    d = (params[k].grad.cpu().double() - r).abs()
+    O_, I_ = r.shape[0], r.shape[1]
+    C = ocfg.out_features * 4 * (2 ** int(k.split(".")[2])) if k.startswith("glow.flow_blocks") else 0
+    print(k, tuple(r.shape), "max|g| %.3e" % r.abs().max().item())
+    cuts = [0, C // 2, C // 2 + 32, I_] if I_ > C // 2 + 32 else [0, I_]
+    for a0, a1 in zip(cuts[:-1], cuts[1:]):
+        print("   in[%3d:%3d]  err %.3e  max|g| %.3e" % (a0, a1, d[:, a0:a1].max().item(), r[:, a0:a1].abs().max().item()))
+    nb = 4 if O_ % 4 == 0 and O_ >= 64 else 1
+    for q in range(nb):
+        s0, s1 = q * O_ // nb, (q + 1) * O_ // nb
+        print("   out[%3d:%3d] err %.3e  max|g| %.3e" % (s0, s1, d[s0:s1].max().item(), r[s0:s1].abs().max().item()))
+    for tap in range(9):
+        print("   tap %d err %.3e" % (tap, d[:, :, tap // 3, tap % 3].max().item()), end="")
+    print()
+for k in [kk for _, kk, _ in errs[:4] if kk.endswith("bias")]:
+    r = sd[k].grad; g_ = params[k].grad.cpu().double()
+    print(k, "err per channel:", ["%.1e" % v for v in (g_ - r).abs().tolist()[:48]])
+    print("   ref:", ["%.2f" % v for v in r.tolist()[:48]])
