@@ -17,6 +17,8 @@
 //     so staging is vector loads + cvt, no per-channel source selection.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -313,36 +315,41 @@ conv3x3_f16_kernel(ConvF16Args a, ConvF16Geom g) {
         const uint32_t tacc = tmem_base + (uint32_t)(acc2 ? ai * 256 + mt * 128 : mt * 256);
         { CVP_T0(); if (an >= 1) mbar_wait(acc_free + ai, (uint32_t)((an - 1) & 1)); CVP_ADD(0); }
         tc_fence_after();
-        for (int ks = 0; ks < g.KS; ++ks) {
+        // One K-step = 9 taps, unrolled and branch-free for each of the three "taps per weight stage" layouts (the stage
+        // boundaries are compile-time): a data-dependent branch per tap doubles the cycles per issued MMA (measured in
+        // lstm_gate_f16.cu: 55 -> 120), and at narrow N the issue path, not the tensor pipe, is what is saturated.
+        auto kstep = [&](auto tps_c, uint32_t acc0) {
+          constexpr int TPS = decltype(tps_c)::value;
           { CVP_T0(); mbar_wait(a_full + ua, pa); CVP_ADD(1); }
           tc_fence_after();
           const uint64_t a0 = make_desc(smem_u32(As + (size_t)ua * g.bufA), kCvPLB, kCvRP * 16) + (uint64_t)(8 * mt);
           uint64_t bd = 0;
-          int left = 0;                          // taps left in the current weight stage
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if (left == 0) {
+            if (tap % TPS == 0) {
               { CVP_T0(); mbar_wait(b_full + ub, pb); CVP_ADD(2); }
               tc_fence_after();
               bd = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)NP * 16u, 128);
-              left = g.tps;
             }
             const int dr = tap / 3, dc = tap - 3 * dr;
             const uint64_t ad = a0 + (uint64_t)(dr * kCvRP + dc);
-            cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+            cv_mma_f16(tacc, ad, bd, idesc, tap > 0 ? 1u : acc0);
             if (X3) {
               cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
               cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
             }
             bd += tapB16;
-            if (--left == 0) {
+            if (tap % TPS == TPS - 1) {
               mma_commit(b_free + ub);
               if (++ub == g.nb) { ub = 0; pb ^= 1u; }
             }
           }
           mma_commit(a_free + ua);
           if (++ua == kCvNA) { ua = 0; pa ^= 1u; }
-        }
+        };
+        if (g.tps == 9) { for (int ks = 0; ks < g.KS; ++ks) kstep(std::integral_constant<int, 9>{}, ks > 0 ? 1u : 0u); }
+        else if (g.tps == 3) { for (int ks = 0; ks < g.KS; ++ks) kstep(std::integral_constant<int, 3>{}, ks > 0 ? 1u : 0u); }
+        else { for (int ks = 0; ks < g.KS; ++ks) kstep(std::integral_constant<int, 1>{}, ks > 0 ? 1u : 0u); }
         mma_commit(acc_full + ai);
       }
 #ifdef TMG_GT_PROFILE

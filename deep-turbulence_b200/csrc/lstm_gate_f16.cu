@@ -18,6 +18,8 @@
 //     K-step are 64 contiguous, aligned bytes).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -45,6 +47,7 @@ struct GateGeom {
   uint32_t oA, oB, oStage, oMisc, oBar, total;
   int plane0[3];
   int nplanes[3];
+  int odd;                 // X3 and an odd number of K planes: the last K-step carries [x_hi | x_lo] / [x_hi | 0] (2 MMAs, see the issuer)
 };
 
 struct GtTileIt {
@@ -297,7 +300,11 @@ lstm_gate_f16_kernel(ConvF16Args a, GateGeom g) {
           { GTP_T0(); if (k >= 1) mbar_wait(acc_free + p, (uint32_t)((k - 1) & 1)); GTP_ADD(0); }
           tc_fence_after();
           int ua = ua0; uint32_t pa = pa0;
-          for (int ks = 0; ks < g.KS; ++ks) {
+          // One K-step = 9 taps, unrolled and branch-free: the issue path is as critical as the tensor pipe (a data-dependent
+          // branch per tap doubled the cycles per issued MMA, 55 -> 120, and made the kernel issue-bound).  PAIR = the spare
+          // plane variant of the last K-step: [x_hi | x_lo] x [W_hi ; W_hi] = hi*hi + lo*hi, [x_hi | 0] x [W_lo ; 0] = hi*lo.
+          auto kstep = [&](auto pair_c, uint32_t acc0) {
+            constexpr bool PAIR = decltype(pair_c)::value;
             { GTP_T0(); mbar_wait(a_full + ua, pa); GTP_ADD(1); }
             tc_fence_after();
             const uint64_t a0 = make_desc(smem_u32(As + (size_t)ua * g.bufA), kGtPLB, kGtRP * 16) + (uint64_t)(8 * mt);
@@ -308,17 +315,24 @@ lstm_gate_f16_kernel(ConvF16Args a, GateGeom g) {
               const uint64_t bd = make_desc(smem_u32(Bs + (size_t)ub * g.stageB), (uint32_t)kGtNP * 16u, 128);
               const int dr = tap / 3, dc = tap - 3 * dr;
               const uint64_t ad = a0 + (uint64_t)(dr * kGtRP + dc);
-              cv_mma_f16(tacc, ad, bd, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+              cv_mma_f16(tacc, ad, bd, idesc, tap > 0 ? 1u : acc0);
               if (X3) {
-                cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
-                cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
+                if (PAIR) {
+                  cv_mma_f16(tacc, ad + hlA16, bd + hlB16, idesc, 1u);
+                } else {
+                  cv_mma_f16(tacc, ad + hlA16, bd, idesc, 1u);
+                  cv_mma_f16(tacc, ad, bd + hlB16, idesc, 1u);
+                }
               }
               mma_commit(b_free + ub);
               if (++ub == g.NB) { ub = 0; pb ^= 1u; }
             }
             if (p == 1) mma_commit(a_free + ua);
             if (++ua == g.NA) { ua = 0; pa ^= 1u; }
-          }
+          };
+          const int ks_full = g.odd ? g.KS - 1 : g.KS;
+          for (int ks = 0; ks < ks_full; ++ks) kstep(std::false_type{}, ks > 0 ? 1u : 0u);
+          if (g.odd) kstep(std::true_type{}, ks_full > 0 ? 1u : 0u);
           mma_commit(acc_full + p);
           if (p == 1) { ua0 = ua; pa0 = pa; }
         }
@@ -370,7 +384,10 @@ lstm_gate_f16_kernel(ConvF16Args a, GateGeom g) {
         // this thread's quarter q = ptid & 3 of the K-step's 16 channels is fixed (128 threads, 4 quarters per position):
         // one source, one channel offset per K-step; ALL its positions are loaded before the first conversion, so a K-step
         // costs one DRAM round trip (the states do not fit L2) instead of one per batch
-        const int q = ptid & 3, plane = 2 * ks + (q >> 1);
+        // odd plane count: the spare plane of the last K-step is fed from the same channels as its real plane -- the hi part
+        // of the buffer holds [x_hi | x_lo], the lo part [x_hi | 0] (two MMAs instead of three, see the issuer)
+        const bool dup = g.odd && ks == g.KS - 1;
+        const int q = ptid & 3, plane = 2 * ks + (dup ? 0 : (q >> 1));
         int si = 0;
         if (a.nsrc > 1 && plane >= g.plane0[1]) si = 1;
         if (a.nsrc > 2 && plane >= g.plane0[2]) si = 2;
@@ -420,11 +437,23 @@ lstm_gate_f16_kernel(ConvF16Args a, GateGeom g) {
           const float y2 = fmaxf(fminf(v[u].z, 60000.f), lo_), y3 = fmaxf(fminf(v[u].w, 60000.f), lo_);
           const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
           uint8_t* dst = Ab + p * 16;
-          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          const uint2 hi2 = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
           if (X3) {
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y), l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
-            *reinterpret_cast<uint2*>(dst + g.hlA) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            const uint2 lo2 = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            if (!dup) {
+              *reinterpret_cast<uint2*>(dst) = hi2;
+              *reinterpret_cast<uint2*>(dst + g.hlA) = lo2;
+            } else if ((q >> 1) == 0) {        // real plane: x_hi in both parts
+              *reinterpret_cast<uint2*>(dst) = hi2;
+              *reinterpret_cast<uint2*>(dst + g.hlA) = hi2;
+            } else {                           // spare plane: x_lo in the hi part, zeros in the lo part
+              *reinterpret_cast<uint2*>(dst) = lo2;
+              *reinterpret_cast<uint2*>(dst + g.hlA) = make_uint2(0u, 0u);
+            }
+          } else {
+            *reinterpret_cast<uint2*>(dst) = hi2;
           }
         }
         fence_proxy_async();
@@ -497,6 +526,8 @@ static bool gt_geom(const ConvF16Args& a, GateGeom& g, int grid) {
   }
   g.KS = (pl + 1) / 2;
   g.nhl = a.x3 ? 2 : 1;
+  static const bool no_odd = [] { const char* e = getenv("TMG_GT_NO_ODD"); return e && e[0] == '1'; }();   // A/B runs
+  g.odd = (a.x3 && (pl & 1) && !no_odd) ? 1 : 0;
   g.hlA = 2 * kGtPLB; g.bufA = g.hlA * g.nhl;
   g.hlB = (uint32_t)2 * kGtNP * 16; g.stageB = g.hlB * g.nhl;
   g.tiles_x = cdiv(a.W, 16); g.tiles_y = cdiv(a.H, 16);

@@ -653,6 +653,11 @@ static inline bool nc_off() {
   static const bool off = [] { const char* e = getenv("TMG_NO_LSTM_HOIST"); return e && e[0] == '1'; }();
   return off;
 }
+// TMG_TAIL_TC=1: LSTM tails the fused fp16 step kernel does not fit through coupling_tc_kernel as before (A/B runs)
+static inline bool tail_tc() {
+  static const bool on = [] { const char* e = getenv("TMG_TAIL_TC"); return e && e[0] == '1'; }();
+  return on;
+}
 static inline bool resident_off() {
   static const bool off = [] { const char* e = getenv("TMG_NO_RESIDENT"); return e && e[0] == '1'; }();
   return off;
@@ -667,6 +672,7 @@ struct Ctx {
   cudaStream_t st;
   bool hoist_ready = false;     // the per-step conditioning tables dc_all / hc_all of this call are filled
   bool unfused = false;         // backward recompute: every conv on its own (the intermediates are needed), no fused epilogues
+  bool f16_small = false;   // route the Cout = 1 / zero convs of a step through conv3x3_f16.cu (LSTM tail the fused step kernel does not fit)
   float* emit_d = nullptr;      // training forward: where the fused step kernel records relu(d1), relu(d2) ...
   float* emit_h = nullptr;      // ... and the coupling-network output h of the current step (tape)
   bool emitted = false;         // set by run_step when the launch recorded them
@@ -690,7 +696,7 @@ static int run_conv(Ctx& c, int tag, const ConvW& w, const ConvSrc* srcs, int ns
   a.Hout = stride == 1 ? Hin : (Hin + 1) / 2;
   a.Wout = stride == 1 ? Win : (Win + 1) / 2;
   a.pad_replicate = replicate ? 1 : 0;
-  if (c.unfused && prec_f16(c.m.precision) && w.w_pack_f16 >= 0 && stride == 1 && !bn_scale) {
+  if ((c.unfused || c.f16_small) && prec_f16(c.m.precision) && w.w_pack_f16 >= 0 && stride == 1 && !bn_scale) {
     bool match = true;
     for (int i = 0; i < 3; ++i) match = match && (i < nsrc ? srcs[i].nch : 0) == w.f16_nch[i];
     ConvF16Args t{};
@@ -1018,6 +1024,16 @@ static int run_step(Ctx& c, int level, const StepW& st, const StepW* mix, bool r
       if (rc == TMG_OK) { float* t = Y; Y = Y2; Y2 = t; c.emitted = a.d_emit != nullptr; }
       return rc;
     }
+  }
+  if (prec_f16(c.m.precision) && st.kind == STEP_LSTM && st.d1.w_pack_f16 >= 0 && st.zc.w_pack_f16 >= 0 && !c.unfused && !tail_tc()) {
+    // LSTM tail the fused fp16 step kernel has no room for (C = 48: 4 K-steps of u0 + all 9 taps of the Z weights exceed the
+    // shared memory of an SM): the three convolutions of the coupling net through conv3x3_f16.cu + the pointwise step, instead
+    // of the first-generation TF32 kernel (one CTA per sample: 1.5 ms at S = 4096, level 2)
+    c.f16_small = true;
+    int rc = run_coupling_nn(c, level, st, B, Hl, Wl, Y, cond, h_in, c_in, h_out, c_out);
+    c.f16_small = false;
+    TMG_TRY(rc);
+    return run_pointwise(c, level, Y, true, mix, reverse, B, HW, ld_slot);
   }
   if (c.m.precision != TMG_PREC_FP32 && st.cpl_w3 >= 0) {
     CouplingArgs a{};

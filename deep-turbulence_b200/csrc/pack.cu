@@ -299,7 +299,10 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       const int e = (int)(i & 7); size_t t = i >> 3; const int n = (int)(t % NPP); t /= NPP;
       const int lp = (int)(t & 1); t >>= 1; const int hl = (int)(t & 1); t >>= 1;
       const int tap = (int)(t % 9); t /= 9; const int ks = (int)(t % KS); const int p = (int)(t / KS);
-      const int plane = 2 * ks + lp;
+      // odd plane count: the spare plane of the last K-step repeats the real one in the hi part ([W_hi ; W_hi]) and is zero in
+      // the lo part ([W_lo ; 0]) -- the kernel feeds it [x_hi | x_lo] / [x_hi | 0] and issues two MMAs instead of three
+      const bool dup = (pl0[3] & 1) && ks == KS - 1;
+      const int plane = 2 * ks + (dup ? 0 : lp);
       int c = -1;
       for (int q = 0; q < 3; ++q)
         if (plane >= pl0[q] && plane < pl0[q + 1]) { const int ch = (plane - pl0[q]) * 8 + e; if (ch < nch[q]) c = (int)j.src[1 + q] + ch; }
@@ -307,7 +310,7 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       float v = 0.f;
       if (c >= 0 && c < I && o < O) v = w[((size_t)o * I + c) * 9 + tap] * sc;
       const __half hi = __float2half_rn(v);
-      d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+      d[i] = hl ? ((dup && lp == 1) ? __float2half_rn(0.f) : __float2half_rn(v - __half2float(hi))) : hi;
     }
     if (tid == 0) Q[j.dst[1]] = 1.f / sc;
   } else if (j.type == JOB_SLICE) {
