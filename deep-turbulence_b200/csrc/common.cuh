@@ -288,11 +288,17 @@ struct LevelArgs {
   unsigned* overflow;              // sticky flag: set when an activation exceeded the fp16 operand range (+-6e4)
   long long* prof;                 // developer profiling (TMG_LV_PROF=n): per-CTA cycle counters per role and phase, else null
 };
-bool level_resident_supported(const LevelArgs& a);
+// wmx: device [nsteps] offsets (floats, packed buffer) of each step's mix W as fp16 hi/lo MMA operand (JOB_1X1, dst[3]) or
+// null -- the 1x1 mix then runs on the CUDA cores.  (Passed beside LevelArgs, not inside: the kernel argument block must keep
+// its layout -- the register allocation of the C = 12 kernel, at its 80-register cap, changed with the size of LevelArgs /
+// LevelStep: spills 88 -> 182 bytes, +9 % time.)
+bool level_resident_supported(const LevelArgs& a, bool mix_mma = false);
 // dc_all [Bx][HW][dstride] (cols 2s, 2s+1) / hc_all [Bx][HW][hstride] (cols s*C + n) -> the transposed layouts above
 int launch_hoist_transpose(const float* dc_all, int dstride, const float* hc_all, int hstride, float* dcT, float* hcT,
                            int Bx, int HW, int nsteps, int C, cudaStream_t st);
-int launch_level_resident(const LevelArgs& a, cudaStream_t st);
+int launch_level_resident(const LevelArgs& a, const int64_t* wmx, cudaStream_t st);
+// floats of the fp16 hi/lo mix operand of one step: [4: 1/scale, pad][hl 2][K planes, even][NP rows][8 halves]
+inline int64_t level_mix_floats(int C) { const int PM = (C / 8 + 1) / 2 * 2, NP = (C + 15) / 16 * 16; return 4 + (int64_t)2 * PM * NP * 8 / 2; }
 
 // ------------------------------------------------------------------ pointwise flow step
 struct PointArgs {
@@ -546,7 +552,7 @@ struct PackJob {
   int a, b;              // JOB_CONVW: O, I ; JOB_1X1: C ; JOB_BN: n
   int64_t src[9];        // offsets (floats) into the flat parameter buffer, -1 = absent
                          // JOB_1X1: l,u,log_s,p,sign_s,l_mask,u_mask,eye,norm.weight
-  int64_t dst[3];        // offsets (floats) into the packed buffer
+  int64_t dst[4];        // offsets (floats) into the packed buffer (JOB_1X1: W, W^-1, step constant, fp16 hi/lo W for the MMA mix or -1)
   int opad;              // JOB_CONVW: padded O ; JOB_CONVW_TC: npad
   int part, nparts;      // JOB_CONVW_TC: this CTA packs elements [part*chunk, (part+1)*chunk)
   int nch0, nch1, nd;    // JOB_CPL_*: channels of source 0 / source 1 / d channels (concat order: src0, src1, d)

@@ -39,6 +39,11 @@ struct LevelGeom {
   uint32_t wE_hl, wZ_hl, wZ_tap;         // shared-memory strides of the weight copies
   uint32_t gE_hl, gZ_hl, gZ_tap;         // strides of the packed (global) weights
   uint32_t wE_stage, wZ_stage, sm_stage; // bytes per stage
+  // MMA mix (C >= 24): NMX staging buffers for the state as fp16 hi/lo A operand [hl][K plane][128 rows][16 B], two stages of
+  // the per-step W operand [hl][K plane][NP rows][16 B]
+  int NMX;
+  uint32_t oMXA, oMXW, mxa_bytes, mxw_stage;
+  const int64_t* wmx;                    // device [nsteps]: packed-buffer offsets of the steps' mix operands
 };
 
 __device__ __forceinline__ uint32_t lv_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
@@ -77,6 +82,17 @@ __device__ __forceinline__ void lv_split2(float y0, float y1, uint32_t& hi, uint
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
+// signed variant (the flow state itself): clamped to +-6e4, flagged
+__device__ __forceinline__ void lv_split2s(float y0, float y1, uint32_t& hi, uint32_t& lo, bool& ovf) {
+  ovf = ovf || fabsf(y0) > 60000.f || fabsf(y1) > 60000.f;
+  y0 = fmaxf(fminf(y0, 60000.f), -60000.f); y1 = fmaxf(fminf(y1, 60000.f), -60000.f);
+  const __half2 h2 = __floats2half2_rn(y0, y1);
+  const float2 hf = __half22float2(h2);
+  const __half2 l2 = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
 // developer profiling: cycles between marks, accumulated per role (one thread per role writes at the end)
 // (compiled in only with -DTMG_LV_PROFILE: the counters cost 24 registers per thread)
 #ifdef TMG_LV_PROFILE
@@ -107,7 +123,11 @@ constexpr uint32_t kFValid = 1u, kFLeft = 2u, kFRight = 4u, kFTop = 8u, kFBottom
 // matrices overlap) -- so Conv2dZeros takes 5 MMAs per M tile and operand pass instead of 9, the operand planes take 32
 // instead of 64 bytes per position, and the tap partials of the dense layers are reduced along the row with warp shuffles
 // before they go to shared memory (24 instead of 72 bytes per position): a whole 32 x 64 sample of level 0 fits on one SM.
-template <int C, bool X3, int NTG, int NT, bool CP>
+// MX: the 1x1 mix u = W v as a tensor-core GEMM (M = 128 pixels of a tile, N = C, K = C, fp16 hi/lo split like the
+// convolutions) instead of C^2 FMAs per pixel: each thread writes its state row as an A operand, the E issuer (idle most of
+// a step) issues the MMAs into the tile's (already consumed) Conv2dZeros accumulator columns, the thread reads its row back.
+// (A fifth service warp would take the kernel from 128 to 96 registers per thread: register allocation is per 4 warps.)
+template <int C, bool X3, int NTG, int NT, bool CP, bool MX>
 __global__ void __launch_bounds__((4 * NTG + 4) * 32, 1)
 flow_level_kernel(LevelArgs a, LevelGeom g) {
   constexpr int NP = (C + 15) / 16 * 16;
@@ -119,6 +139,9 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
   constexpr int kEpi = NE * 32;
   constexpr int kThreads = (NE + 4) * 32;
   constexpr int CC = C * C;
+  constexpr int CCs = MX ? 0 : CC;               // floats of W in the small-vector stage (MX: W lives in its own operand stage)
+  constexpr int PM = (C / 8 + 1) / 2 * 2;        // MX: K planes of the mix operands (even)
+  static_assert(!MX || (!CP && C % 8 == 0), "MMA mix: wide levels only");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W, P = g.P, T = g.T;
@@ -132,6 +155,8 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
   uint8_t* WE = smem + g.oWE;
   uint8_t* WZ = smem + g.oWZ;
   uint8_t* SM = smem + g.oSm;
+  uint8_t* MXA = smem + g.oMXA;
+  uint8_t* MXW = smem + g.oMXW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.oBar);
   uint64_t* we_full = bars;                      // [2] E weights + small per-step vectors: loader
   uint64_t* we_free = bars + 2;                  // [2] E issuer commit + every epilogue thread
@@ -142,12 +167,15 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
   uint64_t* e_full = a_ready + kLvMaxTiles;      // [NES] commit
   uint64_t* e_free = e_full + kLvMaxTiles;       // [NES] 128
   uint64_t* z_full = e_free + kLvMaxTiles;       // [T] commit
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_full + kLvMaxTiles);
+  uint64_t* mx_ready = z_full + kLvMaxTiles;     // [T] MX: the 128 threads of a tile wrote their state rows
+  uint64_t* mx_full = mx_ready + kLvMaxTiles;    // [T] MX: commit of the tile's mix MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mx_full + kLvMaxTiles);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(we_full + i, 1); mbar_init(we_free + i, 1 + kEpi); mbar_init(wz_full + i, 1); mbar_init(wz_free + i, 2); }
     mbar_init(d_ready, kEpi);
     for (int i = 0; i < kLvMaxTiles; ++i) { mbar_init(a_ready + i, 128); mbar_init(e_full + i, 1); mbar_init(e_free + i, 128); mbar_init(z_full + i, 1); }
+    if constexpr (MX) { for (int i = 0; i < kLvMaxTiles; ++i) { mbar_init(mx_ready + i, 128); mbar_init(mx_full + i, 1); } }
     fence_barrier_init();
   }
   if (warp == NE + 1) tmem_alloc(tmem_slot, 512);
@@ -300,10 +328,10 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
         const LevelStep* S = a.steps + is;
         const uint32_t par = (uint32_t)(gs & 1);
         const float* sm = reinterpret_cast<const float*>(SM + (size_t)(gs & 1) * g.sm_stage);
-        const float* s_nb = sm + CC + C;
-        const float* s_rnw = sm + CC + 2 * C;
-        const float* s_b3 = sm + CC + 3 * C;
-        const float* s_w2d = sm + CC + 4 * C;
+        const float* s_nb = sm + CCs + C;
+        const float* s_rnw = sm + CCs + 2 * C;
+        const float* s_b3 = sm + CCs + 3 * C;
+        const float* s_w2d = sm + CCs + 4 * C;
         const int dc_off = __ldg(&S->dc_off), hc_off = __ldg(&S->hc_off);          // step index inside the hoisted tables
         // hoisted conditioning terms of d1 / d2 ([sample][step][pixel] float2): issued now, used after the gather barriers
         float2 dcv[NT];
@@ -493,6 +521,41 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
 #pragma unroll
               for (int c4 = 0; c4 < NHC; ++c4) hcn[c4] = __ldg(hpn + (size_t)c4 * HW);
             }
+            if constexpr (MX) {
+              if (OKJ(j)) ldacc[j] += ldsum;
+              // u = W v on the tensor cores: this thread's row of the A operand (fp16 hi / lo, 8 channels per 16-byte unit)
+              const int row = q * 32 + lane;
+              if (mt >= g.NMX) mbar_wait_sleep(mx_full + (mt - g.NMX), par);       // the MMAs that read this buffer last are done
+              uint8_t* mb = MXA + (size_t)(mt % g.NMX) * g.mxa_bytes + (size_t)row * 16;
+              const bool okj = OKJ(j);
+#pragma unroll
+              for (int pl = 0; pl < C / 8; ++pl) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) lv_split2s(okj ? v[8 * pl + 2 * e] : 0.f, okj ? v[8 * pl + 2 * e + 1] : 0.f, hi[e], lo[e], ovf);
+                *reinterpret_cast<uint4*>(mb + (size_t)pl * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (X3) *reinterpret_cast<uint4*>(mb + (size_t)(PM + pl) * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+              fence_proxy_async();
+              mbar_arrive(mx_ready + mt);
+              mbar_wait_sleep(mx_full + mt, par);
+              tc_fence_after();
+              const float invw = s_w2d[13];
+#pragma unroll
+              for (int n0 = 0; n0 < NP; n0 += 16) {
+                float u[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(mt * NP + n0), u);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const int r = n0 + e;
+                  if (r < C) {
+                    const float o = (u[e] * invw - s_nb[r]) * s_rnw[r];      // out = (u - nb) / nw   (glowConv.py:219, actNorm.py:82)
+                    if (okj) st[j][r < NSR ? r : 0] = o;
+                  }
+                }
+              }
+              tc_fence_before();
+            } else
             if (OKJ(j)) {
               ldacc[j] += ldsum;
               // u = W v, out = (u - nb) / nw     (glowConv.py:219, actNorm.py:82)
@@ -586,17 +649,21 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
         const int stg = gs & 1;
         if (gs >= 2) mbar_wait_sleep(we_free + stg, (uint32_t)(((gs >> 1) - 1) & 1));
         float* sm = reinterpret_cast<float*>(SM + (size_t)stg * g.sm_stage);
-        const int64_t oW = S->W, oNw = S->nw, oNb = S->nb, oB = S->bias, oM = S->misc, oG = S->gain;
-        for (int i = lane; i < CC; i += 32) sm[(i % C) * C + i / C] = __ldg(a.packed + oW + i);      // Wt[k][r] = W[r][k]
+        [[maybe_unused]] const int64_t oW = S->W; const int64_t oNw = S->nw, oNb = S->nb, oB = S->bias, oM = S->misc, oG = S->gain;
+        if constexpr (!MX) {
+          for (int i = lane; i < CC; i += 32) sm[(i % C) * C + i / C] = __ldg(a.packed + oW + i);      // Wt[k][r] = W[r][k]
+        }
         for (int i = lane; i < C; i += 32) {
           const float nw = oNw >= 0 ? __ldg(a.params + oNw + i) : 1.f;
-          sm[CC + i] = nw;
-          sm[CC + C + i] = oNw >= 0 ? __ldg(a.params + oNb + i) : 0.f;
-          sm[CC + 2 * C + i] = 1.f / nw;
-          sm[CC + 3 * C + i] = __ldg(a.params + oB + i);
+          sm[CCs + i] = nw;
+          sm[CCs + C + i] = oNw >= 0 ? __ldg(a.params + oNb + i) : 0.f;
+          sm[CCs + 2 * C + i] = 1.f / nw;
+          sm[CCs + 3 * C + i] = __ldg(a.params + oB + i);
         }
-        if (lane < 12) sm[CC + 4 * C + lane] = __ldg(a.packed + oM + lane);
-        if (lane == 12) sm[CC + 4 * C + 12] = __ldg(a.packed + oG);
+        if (lane < 12) sm[CCs + 4 * C + lane] = __ldg(a.packed + oM + lane);
+        if (lane == 12) sm[CCs + 4 * C + 12] = __ldg(a.packed + oG);
+        const int64_t oX = MX ? __ldg(g.wmx + is) : 0;
+        if (MX && lane == 13) sm[CCs + 4 * C + 13] = __ldg(a.packed + oX);            // 1 / (power-of-two scale of the mix operand)
         __syncwarp();
         // NOTE: the copies are issued from rolled loops with a running source pointer.  With the (tap, hl) loops unrolled,
         // ptxas 12.9 formed the 64-bit source of some UBLKCP from a stale upper register (the mbarrier address): an
@@ -604,9 +671,11 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
         if (lane == 0) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed + (CP ? S->wEc : S->wE));
           uint8_t* dst = WE + (size_t)stg * g.wE_stage;
-          mbar_expect_tx(we_full + stg, g.cpE_n * g.cpE_bytes);
+          mbar_expect_tx(we_full + stg, g.cpE_n * g.cpE_bytes + (MX ? g.mxw_stage : 0u));
 #pragma unroll 1
           for (uint32_t i = 0; i < g.cpE_n; ++i, src += g.cpE_sstep, dst += g.cpE_bytes) bulk_g2s(dst, src, g.cpE_bytes, we_full + stg);
+          if constexpr (MX)      // mix operand: hi (and lo) planes are contiguous behind the 16-byte header of the block
+            bulk_g2s(MXW + (size_t)stg * g.mxw_stage, reinterpret_cast<const uint8_t*>(a.packed + oX + 4), g.mxw_stage, we_full + stg);
         }
         const int zs = gs % g.nzs, zuse = gs / g.nzs;
         if (zuse >= 1) mbar_wait_sleep(wz_free + zs, (uint32_t)((zuse - 1) & 1));
@@ -657,6 +726,29 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
               }
             }
             mma_commit(e_full + slot);
+          }
+          if constexpr (MX) {
+            // the mixes of this step, tile by tile as their state rows arrive (the next step's a_ready follows each of them)
+            const uint32_t idM = lv_idesc(NP);
+            const uint64_t loA16 = (uint64_t)(PM * 2048) >> 4, loB16 = (uint64_t)(PM * NP * 16) >> 4;
+            const uint64_t bW0 = make_desc(smem_u32(MXW + (size_t)stg * g.mxw_stage), (uint32_t)NP * 16u, 128);
+            for (int mt = 0; mt < T; ++mt) {
+              mbar_wait_sleep(mx_ready + mt, (uint32_t)(gs & 1));
+              tc_fence_after();
+              const uint32_t tM = tmem_base + (uint32_t)(mt * NP);
+              const uint64_t aM0 = make_desc(smem_u32(MXA + (size_t)(mt % g.NMX) * g.mxa_bytes), 2048, 128);
+#pragma unroll
+              for (int ks = 0; ks < PM / 2; ++ks) {
+                const uint64_t ad = aM0 + (uint64_t)ks * (uint64_t)((2 * 2048) >> 4);
+                const uint64_t bd = bW0 + (uint64_t)ks * (uint64_t)(2 * NP);
+                lv_mma(tM, ad, bd, idM, ks > 0 ? 1u : 0u);
+                if (X3) {
+                  lv_mma(tM, ad + loA16, bd, idM, 1u);
+                  lv_mma(tM, ad, bd + loB16, idM, 1u);
+                }
+              }
+              mma_commit(mx_full + mt);
+            }
           }
           mma_commit(we_free + stg);
         }
@@ -740,7 +832,7 @@ template <> struct LvCfg<12> { static constexpr int NTG = 5, NT = 4; static cons
 template <> struct LvCfg<24> { static constexpr int NTG = 3, NT = 2; static constexpr bool CP = false; };
 template <> struct LvCfg<48> { static constexpr int NTG = 3, NT = 1; static constexpr bool CP = false; };
 
-static bool lv_geom(const LevelArgs& a, LevelGeom& g, int ntg, int nt, bool cp) {
+static bool lv_geom(const LevelArgs& a, LevelGeom& g, int ntg, int nt, bool cp, bool mx) {
   const int C = a.C;
   const int NP = (C + 15) / 16 * 16;
   const int KSy = cp ? 1 : (C / 2 + 2 + 15) / 16, KS1 = (a.nch1 + 15) / 16;
@@ -765,7 +857,10 @@ static bool lv_geom(const LevelArgs& a, LevelGeom& g, int ntg, int nt, bool cp) 
   }
   g.cpE_n = nhl; g.cpE_bytes = g.wE_hl; g.cpE_sstep = g.gE_hl;
   g.cpZ_bytes = g.wZ_hl; g.cpZ_sstep = a.x3 ? g.gZ_hl : g.gZ_tap;
-  g.sm_stage = (uint32_t)((C * C + 4 * C + 16) * 4 + 127) / 128 * 128;
+  const int PM = (C / 8 + 1) / 2 * 2;
+  g.sm_stage = (uint32_t)(((mx ? 0 : C * C) + 4 * C + 16) * 4 + 127) / 128 * 128;
+  g.mxa_bytes = mx ? (uint32_t)nhl * PM * 2048u : 0u;
+  g.mxw_stage = mx ? (uint32_t)nhl * PM * NP * 16u : 0u;
   const int maxT = std::min(ntg * nt, kLvMaxTiles);
   double best = -1.0;
   LevelGeom bg{};
@@ -781,28 +876,34 @@ static bool lv_geom(const LevelArgs& a, LevelGeom& g, int ntg, int nt, bool cp) 
     c.G = G; c.T = T; c.NES = NES; c.zcols = zcols;
     c.NA = (c.M0 + T * 128 + c.M0 + 7) / 8 * 8;
     c.PLB = (uint32_t)c.NA * 16; c.hlA = (uint32_t)NPL * c.PLB;
+    bool placed = false;
+    for (int nmx = mx ? std::min(T, 3) : 0; nmx >= (mx ? 1 : 0) && !placed; --nmx) {
     for (int nzs = 2; nzs >= 1; --nzs) {
       uint32_t off = 0;
       auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
-      c.nzs = nzs;
+      c.nzs = nzs; c.NMX = nmx;
       c.oA = take((uint32_t)nhl * c.hlA);
       c.oS1 = take((uint32_t)c.NA * (cp ? 12 : 36));
       c.oS2 = take((uint32_t)c.NA * (cp ? 12 : 36));
       c.oD1 = take((uint32_t)c.NA * 4);
       c.oEdge = take(cp ? (uint32_t)(T * 4 + 2) * 48 : 16u);
       c.oY2 = take(cp ? (uint32_t)c.NA * (uint32_t)(C / 2) * 4 : 16u);
+      c.oMXA = take(mx ? (uint32_t)nmx * c.mxa_bytes : 16u);       // inside the range zeroed at kernel start (padding K plane)
       c.oWE = take(2u * c.wE_stage);
       c.oWZ = take((uint32_t)nzs * c.wZ_stage);
       c.oSm = take(2u * c.sm_stage);
-      c.oBar = take((10 + 4 * kLvMaxTiles) * 8 + 16);
+      c.oMXW = take(mx ? 2u * c.mxw_stage : 16u);
+      c.oBar = take((10 + 6 * kLvMaxTiles) * 8 + 16);
       c.total = off;
       if (c.total <= 227u * 1024u) {
         // fill of the M tiles by real pixels; larger groups amortise the per-step weight traffic (tie-break), two weight
         // stages for the Conv2dZeros weights hide their load
-        const double fill = (double)G * a.H * a.W / (T * 128.0) + 0.02 * (nzs - 1) + 1e-4 * G;
+        const double fill = (double)G * a.H * a.W / (T * 128.0) + 0.02 * (nzs - 1) + 0.01 * nmx + 1e-4 * G;
         if (fill > best) { best = fill; bg = c; }
+        placed = true;
         break;
       }
+    }
     }
   }
   if (best < 0.0) return false;
@@ -822,18 +923,18 @@ static int lv_sm_count() {
   return nsm;
 }
 
-bool level_resident_supported(const LevelArgs& a) {
+bool level_resident_supported(const LevelArgs& a, bool mix_mma) {
   LevelGeom g{};
   switch (a.C) {
-    case 12: return lv_geom(a, g, LvCfg<12>::NTG, LvCfg<12>::NT, LvCfg<12>::CP);
-    case 24: return lv_geom(a, g, LvCfg<24>::NTG, LvCfg<24>::NT, LvCfg<24>::CP);
-    case 48: return lv_geom(a, g, LvCfg<48>::NTG, LvCfg<48>::NT, LvCfg<48>::CP);
+    case 12: return lv_geom(a, g, LvCfg<12>::NTG, LvCfg<12>::NT, LvCfg<12>::CP, false);
+    case 24: return lv_geom(a, g, LvCfg<24>::NTG, LvCfg<24>::NT, LvCfg<24>::CP, mix_mma);
+    case 48: return lv_geom(a, g, LvCfg<48>::NTG, LvCfg<48>::NT, LvCfg<48>::CP, mix_mma);
     default: return false;
   }
 }
 
 template <int C>
-static int lv_launch(const LevelArgs& a_in, cudaStream_t st) {
+static int lv_launch(const LevelArgs& a_in, const int64_t* wmx, cudaStream_t st) {
   constexpr int NTG = LvCfg<C>::NTG, NT = LvCfg<C>::NT;
   constexpr bool CP = LvCfg<C>::CP;
   LevelArgs a = a_in;
@@ -843,16 +944,22 @@ static int lv_launch(const LevelArgs& a_in, cudaStream_t st) {
   if (prof_env && !prof_buf) { cudaMalloc(&prof_buf, 148 * 48 * sizeof(long long)); prof_left = atoi(getenv("TMG_LV_PROF")); }
   if (prof_env && prof_left > 0) { cudaMemsetAsync(prof_buf, 0, 148 * 48 * sizeof(long long), st); a.prof = prof_buf; }
   LevelGeom g{};
-  if (!lv_geom(a, g, NTG, NT, CP)) { set_error("level-resident flow kernel: unsupported shape (C=%d, %dx%d)", a.C, a.H, a.W); return TMG_ERR_UNSUPPORTED; }
+  const bool mx = !CP && wmx != nullptr;
+  if (!lv_geom(a, g, NTG, NT, CP, mx)) { set_error("level-resident flow kernel: unsupported shape (C=%d, %dx%d)", a.C, a.H, a.W); return TMG_ERR_UNSUPPORTED; }
+  g.wmx = wmx;
   const int grid = std::min(g.npass, lv_sm_count());
-  constexpr int threads = (4 * NTG + 4) * 32;
-  if (a.x3) {
-    TMG_SMEM_ATTR(flow_level_kernel<C, true, NTG, NT, CP>, 227 * 1024);
-    flow_level_kernel<C, true, NTG, NT, CP><<<grid, threads, g.total, st>>>(a, g);
-  } else {
-    TMG_SMEM_ATTR(flow_level_kernel<C, false, NTG, NT, CP>, 227 * 1024);
-    flow_level_kernel<C, false, NTG, NT, CP><<<grid, threads, g.total, st>>>(a, g);
+#define TMG_LVK(XX, MM)                                                                                  \
+  {                                                                                                      \
+    TMG_SMEM_ATTR((flow_level_kernel<C, XX, NTG, NT, CP, MM>), 227 * 1024);                              \
+    flow_level_kernel<C, XX, NTG, NT, CP, MM><<<grid, (4 * NTG + 4) * 32, g.total, st>>>(a, g);          \
   }
+  if constexpr (CP) {
+    if (a.x3) TMG_LVK(true, false) else TMG_LVK(false, false)
+  } else {
+    if (mx) { if (a.x3) TMG_LVK(true, true) else TMG_LVK(false, true) }
+    else { if (a.x3) TMG_LVK(true, false) else TMG_LVK(false, false) }
+  }
+#undef TMG_LVK
   TMG_LAUNCH_CHECK();
   if (a.prof) {      // developer profiling: average cycles per role and phase over the CTAs of this launch, per step
     --prof_left;
@@ -918,11 +1025,11 @@ int launch_hoist_transpose(const float* dc_all, int dstride, const float* hc_all
   return TMG_OK;
 }
 
-int launch_level_resident(const LevelArgs& a, cudaStream_t st) {
+int launch_level_resident(const LevelArgs& a, const int64_t* wmx, cudaStream_t st) {
   switch (a.C) {
-    case 12: return lv_launch<12>(a, st);
-    case 24: return lv_launch<24>(a, st);
-    case 48: return lv_launch<48>(a, st);
+    case 12: return lv_launch<12>(a, nullptr, st);
+    case 24: return lv_launch<24>(a, wmx, st);
+    case 48: return lv_launch<48>(a, wmx, st);
     default: set_error("level-resident flow kernel: %d channels not supported", a.C); return TMG_ERR_UNSUPPORTED;
   }
 }

@@ -79,10 +79,17 @@ static inline bool gate2p_off() {
   return off;
 }
 
+// TMG_NO_MIXMMA=1 (read when the model is built): the 1x1 mix of the level-resident kernel on the CUDA cores (A/B runs)
+static inline bool mixmma_off() {
+  static const bool off = [] { const char* e = getenv("TMG_NO_MIXMMA"); return e && e[0] == '1'; }();
+  return off;
+}
+
 struct StepW {
   int kind = STEP_PLAIN;
   int64_t norm_w = -1, norm_b = -1;
   int64_t W = -1, Wi = -1;        // packed
+  int64_t Wmx = -1;               // packed: W as fp16 hi/lo tensor-core operand (level-resident kernel, C >= 24)
   int const_idx = -1;             // index into step_const
   ConvW d1, d2, zc, gate, outc;
   int64_t zc_gain = -1;           // packed
@@ -158,6 +165,7 @@ struct tmg_model {
   unsigned* sync_dev = nullptr;     // zero-initialised, self-resetting words for single-launch reductions (absmax);
                                     // word 32: sticky fp16-operand overflow flag of the level-resident flow kernel
   LevelStep* lvsteps_dev[TMG_MAX_LEVELS] = {nullptr};   // per level: the plain steps in reverse execution order
+  int64_t* lvwmx_dev[TMG_MAX_LEVELS] = {nullptr};       // per level: offsets of the steps' tensor-core mix operands (or null)
   // CUDA graphs of the per-time-step backward (~1 400 launches each): keyed by every pointer / shape the launch sequence
   // depends on; a key is run eagerly the first time it is seen, captured the second time, replayed from then on
   struct BwdGraph { int seen = 0; cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
@@ -444,6 +452,10 @@ static int build_model(tmg_model& m) {
       j.src[8] = st.norm_w;
       st.W = B.pack_alloc((int64_t)C * C);
       st.Wi = B.pack_alloc((int64_t)C * C);
+      j.dst[3] = -1;
+      // tensor-core mix of the level-resident kernel: pays from C = 32 on (measured: C = 48 finish phase 14.9 k -> 6.8 k cycles per
+      // step; at C = 24 the 288 packed FMAs per pixel are cheaper than the round trip through the MMA issuer, 4.7 k -> 7.8 k)
+      if (C >= 32 && C % 8 == 0 && !mixmma_off()) { st.Wmx = B.pack_alloc(level_mix_floats(C)); j.dst[3] = st.Wmx; }
       st.const_idx = m.n_steps++;
       for (int q = 0; q < 8; ++q) st.lu[q] = j.src[q];
       j.dst[0] = st.W; j.dst[1] = st.Wi; j.dst[2] = -1;   // step_const offset patched below
@@ -1249,6 +1261,7 @@ void tmg_model_destroy(tmg_model* m) {
   if (m->lu_tab_dev) cudaFree(m->lu_tab_dev);
   if (m->sync_dev) cudaFree(m->sync_dev);
   for (auto* p_ : m->lvsteps_dev) if (p_) cudaFree(p_);
+  for (auto* p_ : m->lvwmx_dev) if (p_) cudaFree(p_);
   for (auto& kv : m->bwd_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (m->gstream) cudaStreamDestroy(m->gstream);
   if (m->gev_in) cudaEventDestroy(m->gev_in);
@@ -1327,6 +1340,7 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
     for (int l = 0; l < m->cfg.n_levels; ++l) {        // step tables of the level-resident flow kernel (offsets only: static)
       const LevelW& lv = m->levels[l];
       std::vector<LevelStep> tab;
+      std::vector<int64_t> wmx;
       for (int s = (int)lv.steps.size() - 2; s >= 0; --s) {
         const StepW& sw = lv.steps[s];
         LevelStep e{};
@@ -1336,10 +1350,15 @@ int tmg_model_refresh(tmg_model* m, float* params, void* stream) {
         e.nw = sw.kind != STEP_UNNORMED ? sw.norm_w : -1; e.nb = sw.kind != STEP_UNNORMED ? sw.norm_b : -1;
         e.dc_off = s; e.hc_off = s;
         tab.push_back(e);
+        wmx.push_back(sw.Wmx);
       }
       if (!tab.empty()) {
         TMG_CUDA_OK(cudaMalloc(&m->lvsteps_dev[l], tab.size() * sizeof(LevelStep)));
         TMG_CUDA_OK(cudaMemcpy(m->lvsteps_dev[l], tab.data(), tab.size() * sizeof(LevelStep), cudaMemcpyHostToDevice));
+        if (wmx[0] >= 0) {
+          TMG_CUDA_OK(cudaMalloc(&m->lvwmx_dev[l], wmx.size() * sizeof(int64_t)));
+          TMG_CUDA_OK(cudaMemcpy(m->lvwmx_dev[l], wmx.data(), wmx.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        }
       }
     }
     if (!m->jobs2.empty()) {
@@ -1512,8 +1531,9 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
         la.B = B; la.H = Hl; la.W = Wl; la.C = lv.C; la.x3 = prec_split(m->precision) ? 1 : 0;
         la.nch1 = m->cfg.cond_features;
         la.compact = lv.steps[0].s2c_wE >= 0 ? 1 : 0;
+        const int64_t* wmx = m->lvwmx_dev[l];
         la.overflow = m->sync_dev + 32;
-        if (level_resident_supported(la)) {
+        if (level_resident_supported(la, wmx != nullptr)) {
           TMG_TRY(launch_hoist_transpose(ws + p.dc_all[l], lv.hoist_opd, ws + p.hc_all[l], lv.hoist_oph, ws + p.dcT[l], ws + p.hcT[l],
                                          p.Bx, HW, (int)lv.steps.size(), lv.C, c.st));
           const double px = (double)B * HW;
@@ -1521,7 +1541,7 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
           ProfScope ps(c.st, PROF_LEVEL_RES,
                        la.nsteps * (2.0 * px * 9.0 * (cin_t + (cin_t + 1) + (double)lv.C * (cin_t + 2)) + 2.0 * px * lv.C * lv.C),
                        la.nsteps * 4.0 * px * (2.0 * lv.C + m->cfg.cond_features));
-          TMG_TRY(launch_level_resident(la, c.st));
+          TMG_TRY(launch_level_resident(la, wmx, c.st));
           slot += la.nsteps;
           break;
         }

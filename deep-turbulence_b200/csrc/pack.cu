@@ -434,6 +434,37 @@ pack_kernel(const PackJob* jobs, const float* __restrict__ P, float* __restrict_
       }
       Wi[i] = (float)acc2;
     }
+    if (j.dst[3] >= 0) {
+      // the same W as a tensor-core B operand for the level-resident kernel's mix (u = W v per pixel: M = pixels, N = output
+      // row r, K = input channel k): fp16 hi + lo, K-major [hl][K plane of 8, padded to an even count][NP rows][8 halves],
+      // scaled by a power of two so that max|w| lands in [2^10, 2^11); word 0 of the block = 1 / scale
+      __syncthreads();
+      __threadfence_block();
+      float m = 0.f;
+      for (int i = tid; i < C * C; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      __syncthreads();
+      if ((tid & 31) == 0) sm[tid >> 5] = m;
+      __syncthreads();
+      m = 0.f;
+      for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, sm[q]);
+      int ex = 0;
+      if (m > 0.f && m < 3.0e38f) frexpf(m, &ex);
+      const float sc = m > 0.f ? ldexpf(1.f, min(max(11 - ex, -20), 40)) : 1.f;
+      const int PM = (C / 8 + 1) / 2 * 2, NPm = (C + 15) / 16 * 16;
+      float* blk = Q + j.dst[3];
+      __half* d = reinterpret_cast<__half*>(blk + 4);
+      const int total = 2 * PM * NPm * 8;
+      for (int i = tid; i < total; i += blockDim.x) {
+        const int e = i & 7; int t = i >> 3; const int n = t % NPm; t /= NPm; const int pl = t % PM; const int hl = t / PM;
+        const int k = pl * 8 + e;
+        const float v = (n < C && k < C) ? W[n * C + k] * sc : 0.f;
+        const __half hi = __float2half_rn(v);
+        d[i] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+      }
+      if (tid == 0) { blk[0] = 1.f / sc; blk[1] = 0.f; blk[2] = 0.f; blk[3] = 0.f; }
+    }
     if (tid == 0) {    // step constant: sum log|w_actnorm| - sum log_s   (multiplied by H*W at run time)
       double s = 0.0;
       for (int c = 0; c < C; ++c) s -= (double)pls[c];
