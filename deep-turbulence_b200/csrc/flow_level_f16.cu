@@ -21,6 +21,8 @@
 // order differs.  Reference: AffineCouplingLayer.reverse flowAffine.py:84-109, InvertibleConv1x1LU.reverse glowConv.py:196-222,
 // ActNorm.reverse actNorm.py:69-85, step wrappers flowLSTMBlock.py:71-86,132-146.
 #include <cuda_fp16.h>
+
+#include <type_traits>
 #include <algorithm>
 #include <cstdlib>
 
@@ -463,11 +465,15 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
 #pragma unroll
           for (int c4 = 0; c4 < NHC; ++c4) hcn[c4] = __ldg(hp0 + (size_t)c4 * HW);
         }
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
+        // One tile of the F phase.  PH = 0: everything; PH = 1 / 2 (tensor-core mix with several tiles per thread): first the
+        // coupling and the state rows of ALL tiles, then, per tile, the mix result and the next step's operand planes -- the round
+        // trip through the MMA issuer of one tile runs under the coupling of the next.
+        auto finish_tile = [&](int j, auto ph_c) {
+          constexpr int PH = decltype(ph_c)::value;
           const int mt = tg + j * NTG;
           if (mt < T) {
             const int ap = g.M0 + mt * 128 + q * 32 + lane;
+            if constexpr (PH != 2) {
             const float4* hcp = hc_ptr(j);
             // v = [y1 | y2]: registers (and shared memory for the second half in the CP layout)
             float v[C];
@@ -538,24 +544,8 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
               }
               fence_proxy_async();
               mbar_arrive(mx_ready + mt);
-              mbar_wait_sleep(mx_full + mt, par);
-              tc_fence_after();
-              const float invw = s_w2d[13];
-#pragma unroll
-              for (int n0 = 0; n0 < NP; n0 += 16) {
-                float u[16];
-                tmem_ld16(tmem_base + lane_base + (uint32_t)(mt * NP + n0), u);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const int r = n0 + e;
-                  if (r < C) {
-                    const float o = (u[e] * invw - s_nb[r]) * s_rnw[r];      // out = (u - nb) / nw   (glowConv.py:219, actNorm.py:82)
-                    if (okj) st[j][r < NSR ? r : 0] = o;
-                  }
-                }
-              }
-              tc_fence_before();
-            } else
+            }
+            if constexpr (!MX) {
             if (OKJ(j)) {
               ldacc[j] += ldsum;
               // u = W v, out = (u - nb) / nw     (glowConv.py:219, actNorm.py:82)
@@ -589,6 +579,29 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
                 for (int c2 = 0; c2 < C / 4; ++c2) y2p[c2] = make_float2(o[C / 2 + 2 * c2], o[C / 2 + 2 * c2 + 1]);
               }
             }
+            }
+            }   // PH != 2
+            if constexpr (PH != 1) {
+            if constexpr (MX) {
+              const bool okj = OKJ(j);
+              mbar_wait_sleep(mx_full + mt, par);
+              tc_fence_after();
+              const float invw = s_w2d[13];
+#pragma unroll
+              for (int n0 = 0; n0 < NP; n0 += 16) {
+                float u[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(mt * NP + n0), u);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const int r = n0 + e;
+                  if (r < C) {
+                    const float o = (u[e] * invw - s_nb[r]) * s_rnw[r];      // out = (u - nb) / nw   (glowConv.py:219, actNorm.py:82)
+                    if (okj) st[j][r < NSR ? r : 0] = o;
+                  }
+                }
+              }
+              tc_fence_before();
+            }
             // the Z MMAs of the following tiles read this tile's positions as neighbours: wait for them before overwriting
             LVP_MARK(9)
             for (int k = mt + 1; k <= mt + g.Dt && k < T; ++k) mbar_wait_sleep(z_full + k, par);
@@ -598,7 +611,17 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
               fence_proxy_async();
               mbar_arrive(a_ready + mt);
             }
+            }   // PH != 1
           }
+        };
+        if constexpr (MX && NT > 1) {
+#pragma unroll
+          for (int j = 0; j < NT; ++j) finish_tile(j, std::integral_constant<int, 1>{});
+#pragma unroll
+          for (int j = 0; j < NT; ++j) finish_tile(j, std::integral_constant<int, 2>{});
+        } else {
+#pragma unroll
+          for (int j = 0; j < NT; ++j) finish_tile(j, std::integral_constant<int, 0>{});
         }
         mbar_arrive(we_free + (gs & 1));           // this thread is done with the step's small vectors
       }

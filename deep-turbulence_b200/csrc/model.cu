@@ -85,6 +85,11 @@ static inline bool mixmma_off() {
   return off;
 }
 
+static inline int mixmma_min_c() {       // TMG_MIXMMA_MINC=n (A/B runs): smallest C with the tensor-core mix
+  static const int c = [] { const char* e = getenv("TMG_MIXMMA_MINC"); return e ? atoi(e) : 24; }();
+  return c;
+}
+
 struct StepW {
   int kind = STEP_PLAIN;
   int64_t norm_w = -1, norm_b = -1;
@@ -453,9 +458,9 @@ static int build_model(tmg_model& m) {
       st.W = B.pack_alloc((int64_t)C * C);
       st.Wi = B.pack_alloc((int64_t)C * C);
       j.dst[3] = -1;
-      // tensor-core mix of the level-resident kernel: pays from C = 32 on (measured: C = 48 finish phase 14.9 k -> 6.8 k cycles per
-      // step; at C = 24 the 288 packed FMAs per pixel are cheaper than the round trip through the MMA issuer, 4.7 k -> 7.8 k)
-      if (C >= 32 && C % 8 == 0 && !mixmma_off()) { st.Wmx = B.pack_alloc(level_mix_floats(C)); j.dst[3] = st.Wmx; }
+      // tensor-core mix of the level-resident kernel (wide levels; with several tiles per thread the round trip through the MMA
+      // issuer of one tile runs under the coupling of the next)
+      if (C >= mixmma_min_c() && C % 8 == 0 && !mixmma_off()) { st.Wmx = B.pack_alloc(level_mix_floats(C)); j.dst[3] = st.Wmx; }
       st.const_idx = m.n_steps++;
       for (int q = 0; q < 8; ++q) st.lu[q] = j.src[q];
       j.dst[0] = st.W; j.dst[1] = st.Wi; j.dst[2] = -1;   // step_const offset patched below
