@@ -866,6 +866,20 @@ def main():
     assert torch.isfinite(y_host[(K - 1) & 1]).all()
     e2e = {"value": world * S * K / (ms_e2e * 1e-3), "unit": "samples/s",
            "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (y_host[0].numel() + ld_host[0].numel()) * 4}
+    # the device->host link of this box, measured alone (one copy of the step's result into the pinned buffer): the copy of
+    # step k overlaps the compute of step k + 1, so a step costs max(compute, copy) -- on a box whose link is slower than
+    # d2h_bytes / ms_per_step the end-to-end number is the link's, not the kernels'
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    c0.record()
+    for _ in range(2):
+        y_host[0].copy_(y, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize(dev)
+    d2h_ms = c0.elapsed_time(c1) / 2
+    e2e["d2h_alone_ms"] = d2h_ms
+    e2e["d2h_gb_per_s"] = y_host[0].numel() * 4 / (d2h_ms * 1e-3) / 1e9
+    e2e["bound"] = "d2h link" if d2h_ms > ms / K else "compute"
 
     # ---------------- parity of what was just timed (rank 0, outside the timed region): the same S samples of the same LF input
     # once more with EXPLICIT noise through reconstruct(), a handful of them against the pinned oracle on the CPU
