@@ -32,6 +32,7 @@ constexpr uint32_t kWfPLB = kWfPosBA * 16;
 constexpr int kWfProd = 8;                         // producer warps (1..8); warp 0 issues the MMAs
 constexpr int kWfThreads = (1 + kWfProd) * 32;
 constexpr int kWfNPT = kWfProd * 32;
+constexpr int kWfBatch = 5;                        // staged items (8 channels of one position) per thread and load batch
 
 struct WgF16Geom {
   int NPl;               // x planes (even): MMA N = 8 * NPl
@@ -168,14 +169,17 @@ wgrad_f16_kernel(WgradArgs a, WgF16Geom g, const float* __restrict__ gscale, flo
       const int r0 = ty * kWfRows, c0 = tx * 16;
       uint8_t* sA = smem + (size_t)sidx * g.stageBytes;
       uint8_t* sB = sA + g.oB;
-      for (int it0 = ptid; it0 < items; it0 += 2 * kWfNPT) {
-        float v[2][8];
-        uint8_t* dst[2];
-        uint32_t hl[2];
-        float sc[2];
-        bool relu[2];
+      // batches of kWfBatch items per thread, all loads of a batch before its first conversion: the operands of a large batch
+      // come from DRAM, and a tile staged in batches of 2 waited five round trips (measured on the forward convolutions:
+      // conv3x3_f16.cu, lstm_gate_f16.cu)
+      for (int it0 = ptid; it0 < items; it0 += kWfBatch * kWfNPT) {
+        float v[kWfBatch][8];
+        uint8_t* dst[kWfBatch];
+        uint32_t hl[kWfBatch];
+        float sc[kWfBatch];
+        bool relu[kWfBatch];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < kWfBatch; ++q) {
           const int it = it0 + q * kWfNPT;
           dst[q] = nullptr; hl[q] = 0; sc[q] = 1.f; relu[q] = false;
 #pragma unroll
@@ -208,7 +212,7 @@ wgrad_f16_kernel(WgradArgs a, WgF16Geom g, const float* __restrict__ gscale, flo
           }
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < kWfBatch; ++q)
           if (dst[q]) wf_store_hl(dst[q], hl[q], v[q], sc[q], relu[q]);
       }
       fence_proxy_async();
