@@ -21,6 +21,8 @@ if os.environ.get("TMG_LV_PROFILE"):                                 # developer
     FLAGS += ["-DTMG_LV_PROFILE"]
 if os.environ.get("TMG_GT_PROFILE"):                                 # developer build: wait-time counters in lstm_gate_f16.cu
     FLAGS += ["-DTMG_GT_PROFILE"]
+if os.environ.get("TMG_NVCC_DEFS"):                                  # experiments: extra -D flags (e.g. tile configurations)
+    FLAGS += os.environ["TMG_NVCC_DEFS"].split()
 if os.environ.get("TMG_MBAR_SLEEP"):                                 # experiment: nanosleep back-off in mbarrier waits
     FLAGS += ["-DTMG_MBAR_SLEEP=" + os.environ["TMG_MBAR_SLEEP"]]
 
