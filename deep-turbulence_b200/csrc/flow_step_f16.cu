@@ -728,7 +728,11 @@ static bool make_geom2(const Step2Args& a, Step2Geom& g, int grid) {
   g.scratch = (uint32_t)(2 * (kNPOSA + 64) * 9 + kNPOSA) * 4;
   // preference: two epilogue groups (narrow levels only: register budget) with the deepest K-step ring that fits
   // (at most 4 slots; at least KS so that a whole tile can be resident)
-  for (int ng = (a.C <= 24 ? 2 : 1); ng >= 1; --ng) {
+  // one epilogue group by default: what this kernel runs today (LSTM tails with 3 K-steps of per-sample input, the training
+  // forward) is bound by its 4 staging warps, and a second group of 8 epilogue warps takes issue slots from them (LSTM tails of
+  // a S = 4096 call 3.04 -> 2.80 ms, training unchanged); TMG_STEP2_NG2=1 restores round 1's two groups at C <= 24 (A/B runs)
+  static const bool ng2 = [] { const char* e = getenv("TMG_STEP2_NG2"); return e && e[0] == '1'; }();
+  for (int ng = ((a.C <= 24 && ng2) ? 2 : 1); ng >= 1; --ng) {
     for (int nbuf = 4; nbuf >= std::max(g.KS, 2); --nbuf) {
       uint32_t off = 0;
       auto take = [&](uint32_t n) { uint32_t o = off; off += (n + 127) / 128 * 128; return o; };
