@@ -372,6 +372,27 @@ def test_ragged_geometry_lstm_gate_kernel(mode, shared):
             _field_close(h, hr, tol=tol_h, what="h step %d" % t); _field_close(c, cr, tol=tol_h, what="c step %d" % t)
 
 
+@pytest.mark.parametrize("shared", [True, False])
+def test_absent_states_equal_zero_states_default_model(shared):
+    """h_in = None (null state pointers at the C ABI: the h planes of the ConvLSTM gate conv are staged as zeros, c_prev is
+    skipped) must give what explicit zero states give -- through lstm_gate_f16.cu (R = 64), which the small goldens never reach."""
+    dev = _dev()
+    m = _default_model().to(dev)
+    m.precision = "f16x3"
+    g = torch.Generator().manual_seed(23)
+    S = 3
+    x = torch.randn(1 if shared else S, 4, 32, 64, generator=g).to(dev)
+    if shared:
+        x = x.expand(S, -1, -1, -1)
+    eps = [torch.randn(s, generator=g).to(dev) for s in m.latent_shapes(S, 64, 128)]
+    zeros = [(torch.zeros(d, device=dev), torch.zeros(d, device=dev)) for d in m._state_dims(S, 64, 128)]
+    y0, ld0, h0 = m.reconstruct(x, None, eps)
+    y1, ld1, h1 = m.reconstruct(x, zeros, eps)
+    assert torch.equal(y0, y1) and torch.equal(ld0, ld1)
+    for (a, c), (a1, c1) in zip(h0, h1):
+        assert torch.equal(a, a1) and torch.equal(c, c1)
+
+
 def test_f16x3_full_size_properties():
     """The persistent fp16x3 step kernel at a bench-like batch: many tiles per CTA, all pipeline stages
     wrap around; invertibility, bit-reproducibility and batch independence."""
