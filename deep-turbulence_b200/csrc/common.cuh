@@ -296,7 +296,9 @@ bool level_resident_supported(const LevelArgs& a, bool mix_mma = false);
 // dc_all [Bx][HW][dstride] (cols 2s, 2s+1) / hc_all [Bx][HW][hstride] (cols s*C + n) -> the transposed layouts above
 int launch_hoist_transpose(const float* dc_all, int dstride, const float* hc_all, int hstride, float* dcT, float* hcT,
                            int Bx, int HW, int nsteps, int C, cudaStream_t st);
-int launch_level_resident(const LevelArgs& a, const int64_t* wmx, cudaStream_t st);
+// unsq (wide levels, or null): the result goes un-squeezed into the next level's state [B, 2H, 2W, unsq_cstride] (channels
+// [0, C/4)) instead of y_out -- CheckerSqueeze.reverse fused into the kernel's final store
+int launch_level_resident(const LevelArgs& a, const int64_t* wmx, float* unsq, int unsq_cstride, cudaStream_t st);
 // floats of the fp16 hi/lo mix operand of one step: [4: 1/scale, pad][hl 2][K planes, even][NP rows][8 halves]
 inline int64_t level_mix_floats(int C) { const int PM = (C / 8 + 1) / 2 * 2, NP = (C + 15) / 16 * 16; return 4 + (int64_t)2 * PM * NP * 8 / 2; }
 

@@ -46,6 +46,8 @@ struct LevelGeom {
   int NMX;
   uint32_t oMXA, oMXW, mxa_bytes, mxw_stage;
   const int64_t* wmx;                    // device [nsteps]: packed-buffer offsets of the steps' mix operands
+  float* unsq;                           // wide levels, optional: write the level's result un-squeezed (CheckerSqueeze.reverse,
+  int unsq_cstride;                      //   flowUtils.py:124-145) into the next level's state [B, 2H, 2W, unsq_cstride] instead of y_out
 };
 
 __device__ __forceinline__ uint32_t lv_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
@@ -628,6 +630,27 @@ flow_level_kernel(LevelArgs a, LevelGeom g) {
       // ---- end of pass: state back to HBM, per-sample log-det
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
+        if constexpr (!CP) {
+          if (OKJ(j) && g.unsq != nullptr) {
+            // channel group k of this pixel is pixel (2y + dr, 2x + dc) of the next level: (0,0),(1,0),(1,1),(0,1) (flowUtils.py:117-120)
+            constexpr int C4 = C / 4;
+            const int b = SAMPLE(j), py = pix[j] / a.W, px = pix[j] - py * a.W;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int dr = (k == 1 || k == 2) ? 1 : 0, dc = k >= 2 ? 1 : 0;
+              float* d = g.unsq + (((size_t)b * (2 * a.H) + 2 * py + dr) * (size_t)(2 * a.W) + 2 * px + dc) * g.unsq_cstride;
+              if constexpr (C4 % 4 == 0) {
+#pragma unroll
+                for (int c = 0; c < C4; c += 4) *reinterpret_cast<float4*>(d + c) = make_float4(st[j][k * C4 + c], st[j][k * C4 + c + 1], st[j][k * C4 + c + 2], st[j][k * C4 + c + 3]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < C4; c += 2) *reinterpret_cast<float2*>(d + c) = make_float2(st[j][k * C4 + c], st[j][k * C4 + c + 1]);
+              }
+            }
+            D1[g.M0 + (tg + j * NTG) * 128 + q * 32 + lane] = ldacc[j];
+            continue;
+          }
+        }
         if (OKJ(j)) {
           const int b = SAMPLE(j);
           float4* y4 = reinterpret_cast<float4*>(a.y_out + ((size_t)b * HW + pix[j]) * C);
@@ -958,7 +981,7 @@ bool level_resident_supported(const LevelArgs& a, bool mix_mma) {
 }
 
 template <int C>
-static int lv_launch(const LevelArgs& a_in, const int64_t* wmx, cudaStream_t st) {
+static int lv_launch(const LevelArgs& a_in, const int64_t* wmx, float* unsq, int unsq_cstride, cudaStream_t st) {
   constexpr int NTG = LvCfg<C>::NTG, NT = LvCfg<C>::NT;
   constexpr bool CP = LvCfg<C>::CP;
   LevelArgs a = a_in;
@@ -971,6 +994,11 @@ static int lv_launch(const LevelArgs& a_in, const int64_t* wmx, cudaStream_t st)
   const bool mx = !CP && wmx != nullptr;
   if (!lv_geom(a, g, NTG, NT, CP, mx)) { set_error("level-resident flow kernel: unsupported shape (C=%d, %dx%d)", a.C, a.H, a.W); return TMG_ERR_UNSUPPORTED; }
   g.wmx = wmx;
+  g.unsq = CP ? nullptr : unsq; g.unsq_cstride = unsq_cstride;
+  if (unsq && (CP || (unsq_cstride & 1) || (reinterpret_cast<uintptr_t>(unsq) & 15) || ((a.C / 4) % 4 == 0 && (unsq_cstride & 3)))) {
+    set_error("level-resident flow kernel: un-squeezed output not supported for C=%d, stride %d", a.C, unsq_cstride);
+    return TMG_ERR_UNSUPPORTED;
+  }
   const int grid = std::min(g.npass, lv_sm_count());
 #define TMG_LVK(XX, MM)                                                                                  \
   {                                                                                                      \
@@ -1049,11 +1077,11 @@ int launch_hoist_transpose(const float* dc_all, int dstride, const float* hc_all
   return TMG_OK;
 }
 
-int launch_level_resident(const LevelArgs& a, const int64_t* wmx, cudaStream_t st) {
+int launch_level_resident(const LevelArgs& a, const int64_t* wmx, float* unsq, int unsq_cstride, cudaStream_t st) {
   switch (a.C) {
-    case 12: return lv_launch<12>(a, nullptr, st);
-    case 24: return lv_launch<24>(a, wmx, st);
-    case 48: return lv_launch<48>(a, wmx, st);
+    case 12: return lv_launch<12>(a, nullptr, nullptr, 0, st);
+    case 24: return lv_launch<24>(a, wmx, unsq, unsq_cstride, st);
+    case 48: return lv_launch<48>(a, wmx, unsq, unsq_cstride, st);
     default: set_error("level-resident flow kernel: %d channels not supported", a.C); return TMG_ERR_UNSUPPORTED;
   }
 }

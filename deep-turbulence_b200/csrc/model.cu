@@ -675,6 +675,11 @@ static inline bool tail_tc() {
   static const bool on = [] { const char* e = getenv("TMG_TAIL_TC"); return e && e[0] == '1'; }();
   return on;
 }
+// TMG_NO_FUSED_UNSQ=1: CheckerSqueeze.reverse as its own launch after the level-resident kernel (A/B runs)
+static inline bool unsq_off() {
+  static const bool off = [] { const char* e = getenv("TMG_NO_FUSED_UNSQ"); return e && e[0] == '1'; }();
+  return off;
+}
 static inline bool resident_off() {
   static const bool off = [] { const char* e = getenv("TMG_NO_RESIDENT"); return e && e[0] == '1'; }();
   return off;
@@ -1521,6 +1526,7 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
     ga.ld_part = ws + p.ldp + (size_t)(slot++) * p.ctas; ga.ld_stride = ldstride;
     TMG_TRY(launch_gaussian(ga, c.st));
     // steps n..1 reversed (flowLSTMBlock.py:348-359)
+    bool unsq_done = false;
     for (int s = (int)lv.steps.size() - 1; s >= 0; --s) {
       const StepW& st = lv.steps[s];
       if (!tape && s == (int)lv.steps.size() - 2 && s >= 0 && prec_f16(m->precision) && c.hoist_ready && m->lvsteps_dev[l] &&
@@ -1546,7 +1552,10 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
           ProfScope ps(c.st, PROF_LEVEL_RES,
                        la.nsteps * (2.0 * px * 9.0 * (cin_t + (cin_t + 1) + (double)lv.C * (cin_t + 2)) + 2.0 * px * lv.C * lv.C),
                        la.nsteps * 4.0 * px * (2.0 * lv.C + m->cfg.cond_features));
-          TMG_TRY(launch_level_resident(la, wmx, c.st));
+          // CheckerSqueeze.reverse of wide levels inside the kernel's final store (the level's result feeds nothing else)
+          float* unsq = (l > 0 && lv.C != 12 && lv.C % 8 == 0 && !unsq_off()) ? ws + p.y[l - 1] : nullptr;
+          TMG_TRY(launch_level_resident(la, wmx, unsq, unsq ? m->levels[l - 1].C : 0, c.st));
+          unsq_done = unsq != nullptr;
           slot += la.nsteps;
           break;
         }
@@ -1573,7 +1582,7 @@ static int reconstruct_impl(tmg_model* m, int B, int h, int w, const float* x, c
       pa.mode = PERM_UNSQUEEZE_NHWC_TO_NCHW;
       pa.dst = y;
     }
-    TMG_TRY(launch_permute(pa, c.st));
+    if (!unsq_done) TMG_TRY(launch_permute(pa, c.st));
   }
   if (tape) {
     std::lock_guard<std::mutex> lk(m->tape_mu);
