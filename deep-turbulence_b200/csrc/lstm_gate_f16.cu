@@ -568,8 +568,12 @@ int launch_lstm_gate_f16(const ConvF16Args& a, cudaStream_t st) {
   const int tiles = cdiv(a.W, 16) * cdiv(a.H, 16) * a.B;
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = std::min(tiles, nsm > 0 ? nsm : 148);
+  static int cached[64] = {0};                  // SM count per device, queried once
+  if (dev >= 0 && dev < 64) {
+    if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (cached[dev] > 0) nsm = cached[dev];
+  }
+  const int grid = std::min(tiles, nsm);
   GateGeom g{};
   if (!gt_geom(a, g, grid) || !a.h_out || !a.c_out) {
     set_error("two-pass ConvLSTM gate kernel: unsupported shape (R=%d, %dx%d, %d sources)", a.lstm_R, a.H, a.W, a.nsrc);
